@@ -1,0 +1,65 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG_DIR = os.path.join(ROOT, "pydrobert-pytorch_b200")
+for p in (ROOT, PKG_DIR):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+
+        has_cuda = torch.cuda.is_available()
+    except Exception:  # pragma: no cover
+        has_cuda = False
+    if has_cuda:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+class Golden:
+    """Accessor for one tests/golden/*.npz fixture (written by make_golden.py)."""
+
+    def __init__(self, name):
+        self.z = np.load(os.path.join(GOLDEN, name))
+        self.params = json.loads(str(self.z["params"])) if "params" in self.z.files else {}
+
+    def names(self, prefix=""):
+        return [k for k in self.params if k.startswith(prefix)]
+
+    def has(self, case, field):
+        return f"{case}.{field}" in self.z.files
+
+    def get(self, case, field):
+        return self.z[f"{case}.{field}"]
+
+
+@pytest.fixture(scope="session")
+def golden_sm():
+    return Golden("string_matching.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_loss():
+    return Golden("losses.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_sclite():
+    return np.load(os.path.join(GOLDEN, "sclite.npz"))
