@@ -1,0 +1,434 @@
+"""Host side of the custom-op layer: tensor plumbing around the C ABI.
+
+Each public call of the reference's string-matching family maps to ONE registered
+torch op (``torch.ops.b200lev.*``) whose body allocates the outputs/workspace with
+torch, hands raw device pointers, strides and the current CUDA stream to
+``libb200lev.so`` and returns.  PyTorch is used for device memory, streams and
+autograd wiring only; every number is produced by the hand-written kernels.
+
+There is no CPU fallback: tensors must live on a CUDA device (host tensors are
+accepted by the *functional* layer, which copies them to the current device and the
+result back -- see ``functional._offload``).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _abi
+
+_INT_DTYPES = (torch.int64, torch.int32, torch.int16, torch.int8)
+_FLOAT_CODES = {torch.float32: _abi.F32, torch.float16: _abi.F16, torch.bfloat16: _abi.BF16,
+                torch.float64: _abi.F64}
+
+
+def _as_tokens(t: Tensor) -> Tensor:
+    """Token tensors are "long tensors" in the reference (_string.py:588-596) but its
+    tests also trace with float placeholders; normalise without copying when the dtype
+    is already a signed integer type the kernels read directly."""
+    t = t.detach()  # _string.py:186-187
+    if t.dtype in _INT_DTYPES:
+        return t
+    if t.dtype == torch.uint8:
+        return t.to(torch.int16)
+    return t.to(torch.long)
+
+
+def _check_device(*ts: Tensor) -> torch.device:
+    dev = ts[0].device
+    for t in ts:
+        if t.device != dev:
+            raise RuntimeError(f"expected all tensors on {dev}, got one on {t.device}")
+    if dev.type != "cuda" and not _abi.EMULATED:
+        raise _abi.B200LevError(
+            f"b200lev kernels need CUDA tensors (got {dev}); there is no CPU fallback")
+    return dev
+
+
+def _stream(dev: torch.device) -> int:
+    if dev.type == "cuda":
+        return torch.cuda.current_stream(dev).cuda_stream
+    return 0
+
+
+class _DeviceGuard:
+    def __init__(self, dev: torch.device):
+        self.g = torch.cuda.device(dev) if dev.type == "cuda" else None
+
+    def __enter__(self):
+        if self.g is not None:
+            self.g.__enter__()
+
+    def __exit__(self, *a):
+        if self.g is not None:
+            self.g.__exit__(*a)
+
+
+def _tok_struct(t: Tensor, batch_first: bool) -> _abi.Tokens:
+    if batch_first:  # the transpose of _string.py:181-183, as a stride swap
+        n, T = t.shape
+        sn, st = t.stride()
+    else:
+        T, n = t.shape
+        st, sn = t.stride()
+    return _abi.Tokens(t.data_ptr(), t.element_size(), T, n, st, sn)
+
+
+def _opts(eos: Optional[int], include_eos: bool, ins: float, del_: float, sub: float, norm: bool,
+          exclude_last: bool, padding: int, return_mistakes: bool, ref_group: int) -> _abi.Opts:
+    return _abi.Opts(int(eos is not None), 0 if eos is None else int(eos), int(include_eos),
+                     float(ins), float(del_), float(sub), int(norm), int(exclude_last),
+                     int(padding), int(return_mistakes), int(ref_group))
+
+
+def _shapes(ref: Tensor, hyp: Tensor, batch_first: bool, ref_group: int) -> Tuple[int, int, int]:
+    if ref.dim() != 2 or hyp.dim() != 2:
+        raise RuntimeError("ref and hyp must be 2 dimensional")  # _string.py:166-167
+    if batch_first:
+        (nr, R), (n, H) = ref.shape, hyp.shape
+    else:
+        (R, nr), (H, n) = ref.shape, hyp.shape
+    if nr * ref_group != n:  # _string.py:191-194
+        raise RuntimeError(f"ref has batch size {nr * ref_group}, but hyp has {n}")
+    return R, H, n
+
+
+# ---------------------------------------------------------------------------------------
+# string matching: final / prefix
+# ---------------------------------------------------------------------------------------
+@torch.library.custom_op("b200lev::string_matching", mutates_args=())
+def string_matching(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: bool,
+                    batch_first: bool, ins_cost: float, del_cost: float, sub_cost: float,
+                    norm: bool, prefix: bool, exclude_last: bool, padding: int,
+                    return_mistakes: bool, ref_group: int) -> Tuple[Tensor, Tensor]:
+    """``_string_matching`` (_string.py:146-406) minus the mask mode.
+
+    Returns ``(out, flags)``: fp32 ``(N,)`` or ``(H', N)`` / ``(N, H')`` and the int32[1]
+    warning flags (``_abi.FLAG_*``)."""
+    R, H, n = _shapes(ref, hyp, batch_first, ref_group)
+    ref, hyp = _as_tokens(ref), _as_tokens(hyp)
+    dev = _check_device(ref, hyp)
+    L = _abi.lib()
+    with _DeviceGuard(dev):
+        rt, ht = _tok_struct(ref, batch_first), _tok_struct(hyp, batch_first)
+        o = _opts(eos, include_eos, ins_cost, del_cost, sub_cost, norm, exclude_last, padding,
+                  return_mistakes, ref_group)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        nbytes = L.b200lev_workspace_bytes(ctypes.byref(rt), ctypes.byref(ht), 0, int(exclude_last))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        st = _stream(dev)
+        if not prefix:
+            out = torch.empty(n, dtype=torch.float32, device=dev)
+            _abi.check(L.b200lev_final(ctypes.byref(rt), ctypes.byref(ht), ctypes.byref(o),
+                                       out.data_ptr(), ws.data_ptr(), nbytes, flags.data_ptr(), st))
+        else:
+            hout = H + (0 if exclude_last else 1)
+            if batch_first:  # _string.py:387-388
+                out = torch.empty((n, hout), dtype=torch.float32, device=dev)
+                si, sn = 1, hout
+            else:
+                out = torch.empty((hout, n), dtype=torch.float32, device=dev)
+                si, sn = n, 1
+            _abi.check(L.b200lev_prefix(ctypes.byref(rt), ctypes.byref(ht), ctypes.byref(o),
+                                        out.data_ptr(), si, sn, ws.data_ptr(), nbytes,
+                                        flags.data_ptr(), st))
+    return out, flags
+
+
+@string_matching.register_fake
+def _(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost, sub_cost, norm, prefix,
+      exclude_last, padding, return_mistakes, ref_group):
+    if batch_first:
+        n, H = hyp.shape
+    else:
+        H, n = hyp.shape
+    flags = ref.new_empty((1,), dtype=torch.int32)
+    if not prefix:
+        return ref.new_empty((n,), dtype=torch.float32), flags
+    hout = H + (0 if exclude_last else 1)
+    shape = (n, hout) if batch_first else (hout, n)
+    return ref.new_empty(shape, dtype=torch.float32), flags
+
+
+# ---------------------------------------------------------------------------------------
+# optimal completion
+# ---------------------------------------------------------------------------------------
+@torch.library.custom_op("b200lev::optimal_completion", mutates_args=())
+def optimal_completion(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: bool,
+                       batch_first: bool, ins_cost: float, del_cost: float, sub_cost: float,
+                       padding: int, exclude_last: bool) -> Tuple[Tensor, Tensor]:
+    """``optimal_completion`` (_string.py:464-517): ``(targets, flags)`` with targets int64
+    ``(H', N, U)`` or ``(N, H', U)``.  One host read of U, as the reference has at :511."""
+    R, H, n = _shapes(ref, hyp, batch_first, 1)
+    ref, hyp = _as_tokens(ref), _as_tokens(hyp)
+    dev = _check_device(ref, hyp)
+    L = _abi.lib()
+    with _DeviceGuard(dev):
+        rt, ht = _tok_struct(ref, batch_first), _tok_struct(hyp, batch_first)
+        o = _opts(eos, include_eos, ins_cost, del_cost, sub_cost, False, exclude_last, padding,
+                  False, 1)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        umax = torch.zeros(1, dtype=torch.int32, device=dev)
+        nbytes = L.b200lev_workspace_bytes(ctypes.byref(rt), ctypes.byref(ht), 1, int(exclude_last))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        st = _stream(dev)
+        _abi.check(L.b200lev_completion_count(ctypes.byref(rt), ctypes.byref(ht), ctypes.byref(o),
+                                              ws.data_ptr(), nbytes, umax.data_ptr(),
+                                              flags.data_ptr(), st))
+        U = int(umax.item())  # _string.py:511
+        hout = max(H + (0 if exclude_last else 1), 1)  # _string.py:271-278
+        if batch_first:  # _string.py:515-516
+            out = torch.empty((n, hout, U), dtype=torch.long, device=dev)
+            si, sn = U, hout * U
+        else:
+            out = torch.empty((hout, n, U), dtype=torch.long, device=dev)
+            si, sn = n * U, U
+        _abi.check(L.b200lev_completion_fill(ctypes.byref(rt), ctypes.byref(ht), ctypes.byref(o),
+                                             ws.data_ptr(), nbytes, U, out.data_ptr(), si, sn, st))
+    return out, flags
+
+
+@optimal_completion.register_fake
+def _(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost, sub_cost, padding, exclude_last):
+    if batch_first:
+        n, H = hyp.shape
+    else:
+        H, n = hyp.shape
+    U = torch.library.get_ctx().new_dynamic_size()
+    hout = max(H + (0 if exclude_last else 1), 1)
+    shape = (n, hout, U) if batch_first else (hout, n, U)
+    return ref.new_empty(shape, dtype=torch.long), ref.new_empty((1,), dtype=torch.int32)
+
+
+# ---------------------------------------------------------------------------------------
+# OCD loss (forward / backward)
+# ---------------------------------------------------------------------------------------
+def _acc_dtype(t: Tensor) -> torch.dtype:
+    return torch.float64 if t.dtype == torch.float64 else torch.float32
+
+
+def _float_code(t: Tensor) -> int:
+    try:
+        return _FLOAT_CODES[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"unsupported floating dtype {t.dtype}") from None
+
+
+def _rowmajor_last(t: Tensor) -> Tensor:
+    return t if t.stride(-1) == 1 or t.size(-1) <= 1 else t.contiguous()
+
+
+@torch.library.custom_op("b200lev::ocd_loss", mutates_args=())
+def ocd_loss(logits: Tensor, targets: Tensor, weight: Optional[Tensor], ignore_index: int,
+             reduction: int, seq_axis: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """_string.py:1229-1251 given the optimal-completion targets.  Returns
+    ``(loss, lse, denom)`` (lse/denom are saved for the backward)."""
+    dev = _check_device(logits, targets)
+    A, B, V = logits.shape
+    U = targets.size(-1)
+    logits = _rowmajor_last(logits.detach())
+    targets = targets.contiguous()
+    acc = _acc_dtype(logits)
+    w = None if weight is None else weight.detach().to(device=dev, dtype=torch.float32).contiguous()
+    per = torch.empty((A, B), dtype=acc, device=dev)
+    lse = torch.empty((A, B), dtype=acc, device=dev)
+    denom = torch.empty(max(B if seq_axis == 0 else A, 1), dtype=acc, device=dev)
+    loss = torch.zeros((), dtype=acc, device=dev)
+    with _DeviceGuard(dev):
+        _abi.check(_abi.lib().b200lev_ocd_forward(
+            logits.data_ptr(), _float_code(logits), A, B, V, logits.stride(0), logits.stride(1),
+            targets.data_ptr(), U, targets.stride(0), targets.stride(1),
+            None if w is None else w.data_ptr(), ignore_index, reduction, seq_axis,
+            per.data_ptr(), lse.data_ptr(), denom.data_ptr(), loss.data_ptr(), _stream(dev)))
+    out = per if reduction == 0 else loss
+    return out.to(logits.dtype), lse, denom
+
+
+@ocd_loss.register_fake
+def _(logits, targets, weight, ignore_index, reduction, seq_axis):
+    A, B, _ = logits.shape
+    acc = _acc_dtype(logits)
+    out = logits.new_empty((A, B) if reduction == 0 else ())
+    return out, logits.new_empty((A, B), dtype=acc), logits.new_empty(
+        (max(B if seq_axis == 0 else A, 1),), dtype=acc)
+
+
+@torch.library.custom_op("b200lev::ocd_loss_backward", mutates_args=())
+def ocd_loss_backward(grad_out: Tensor, logits: Tensor, targets: Tensor, weight: Optional[Tensor],
+                      ignore_index: int, reduction: int, seq_axis: int, lse: Tensor,
+                      denom: Tensor) -> Tensor:
+    dev = _check_device(logits, targets)
+    A, B, V = logits.shape
+    U = targets.size(-1)
+    logits = _rowmajor_last(logits.detach())
+    targets = targets.contiguous()
+    acc = _acc_dtype(logits)
+    w = None if weight is None else weight.detach().to(device=dev, dtype=torch.float32).contiguous()
+    go = grad_out.detach().to(acc).contiguous()
+    grad = torch.empty((A, B, V), dtype=logits.dtype, device=dev)
+    with _DeviceGuard(dev):
+        _abi.check(_abi.lib().b200lev_ocd_backward(
+            logits.data_ptr(), _float_code(logits), A, B, V, logits.stride(0), logits.stride(1),
+            targets.data_ptr(), U, targets.stride(0), targets.stride(1),
+            None if w is None else w.data_ptr(), ignore_index, reduction, seq_axis,
+            lse.data_ptr(), denom.data_ptr(), go.data_ptr(), grad.data_ptr(), _stream(dev)))
+    return grad
+
+
+@ocd_loss_backward.register_fake
+def _(grad_out, logits, targets, weight, ignore_index, reduction, seq_axis, lse, denom):
+    return logits.new_empty(logits.shape)
+
+
+def _ocd_setup(ctx, inputs, output):
+    logits, targets, weight, ignore_index, reduction, seq_axis = inputs
+    _, lse, denom = output
+    ctx.save_for_backward(logits, targets, weight, lse, denom)
+    ctx.args = (ignore_index, reduction, seq_axis)
+
+
+def _ocd_backward(ctx, g_loss, g_lse, g_denom):
+    logits, targets, weight, lse, denom = ctx.saved_tensors
+    ignore_index, reduction, seq_axis = ctx.args
+    grad = ocd_loss_backward(g_loss, logits, targets, weight, ignore_index, reduction, seq_axis,
+                             lse, denom)
+    return grad, None, None, None, None, None
+
+
+ocd_loss.register_autograd(_ocd_backward, setup_context=_ocd_setup)
+
+
+# ---------------------------------------------------------------------------------------
+# MWER epilogue (forward / backward)
+# ---------------------------------------------------------------------------------------
+@torch.library.custom_op("b200lev::mwer_loss", mutates_args=())
+def mwer_loss(er: Tensor, log_probs: Tensor, sub_avg: bool, reduction: int) -> Tensor:
+    """_string.py:1463-1471 on the (N, M) error rates."""
+    dev = _check_device(er, log_probs)
+    N, M = log_probs.shape
+    er = er.detach().reshape(N, M).contiguous()
+    lp = log_probs.detach()
+    acc = _acc_dtype(lp)
+    per = torch.empty((N, M), dtype=acc, device=dev)
+    loss = torch.zeros((), dtype=acc, device=dev)
+    with _DeviceGuard(dev):
+        _abi.check(_abi.lib().b200lev_mwer_forward(
+            er.data_ptr(), lp.data_ptr(), _float_code(lp), N, M, lp.stride(0), lp.stride(1),
+            int(sub_avg), reduction, per.data_ptr(), loss.data_ptr(), _stream(dev)))
+    return per if reduction == 0 else loss
+
+
+@mwer_loss.register_fake
+def _(er, log_probs, sub_avg, reduction):
+    acc = _acc_dtype(log_probs)
+    return log_probs.new_empty(log_probs.shape if reduction == 0 else (), dtype=acc)
+
+
+@torch.library.custom_op("b200lev::mwer_loss_backward", mutates_args=())
+def mwer_loss_backward(grad_out: Tensor, er: Tensor, log_probs: Tensor, sub_avg: bool,
+                       reduction: int) -> Tensor:
+    dev = _check_device(er, log_probs)
+    N, M = log_probs.shape
+    er = er.detach().reshape(N, M).contiguous()
+    lp = log_probs.detach()
+    acc = _acc_dtype(lp)
+    go = grad_out.detach().to(acc).contiguous()
+    grad = torch.empty((N, M), dtype=lp.dtype, device=dev)
+    with _DeviceGuard(dev):
+        _abi.check(_abi.lib().b200lev_mwer_backward(
+            er.data_ptr(), lp.data_ptr(), _float_code(lp), N, M, lp.stride(0), lp.stride(1),
+            int(sub_avg), reduction, go.data_ptr(), grad.data_ptr(), _stream(dev)))
+    return grad
+
+
+@mwer_loss_backward.register_fake
+def _(grad_out, er, log_probs, sub_avg, reduction):
+    return log_probs.new_empty(log_probs.shape)
+
+
+def _mwer_setup(ctx, inputs, output):
+    er, log_probs, sub_avg, reduction = inputs
+    ctx.save_for_backward(er, log_probs)
+    ctx.args = (sub_avg, reduction)
+
+
+def _mwer_backward(ctx, g):
+    er, log_probs = ctx.saved_tensors
+    sub_avg, reduction = ctx.args
+    # autograd flows only through log_probs: er is built from detached integers
+    # (_string.py:186-187)
+    return None, mwer_loss_backward(g, er, log_probs, sub_avg, reduction), None, None
+
+
+mwer_loss.register_autograd(_mwer_backward, setup_context=_mwer_setup)
+
+
+# ---------------------------------------------------------------------------------------
+# fill_after_eos scan, bulk error sums, INT32 microbenchmark
+# ---------------------------------------------------------------------------------------
+@torch.library.custom_op("b200lev::after_eos_mask", mutates_args=())
+def after_eos_mask(tokens: Tensor, eos: int, dim: int) -> Tensor:
+    """bool mask, True strictly after the first ``eos`` along ``dim`` (_string.py:41)."""
+    dev = _check_device(tokens)
+    dim = dim % max(tokens.dim(), 1)
+    tok = tokens.detach()
+    tok = tok.to(torch.long) if tok.dtype != torch.long else tok
+    tok = tok.contiguous()
+    shape = tok.shape
+    T = shape[dim] if tok.dim() else 1
+    outer = 1
+    for s in shape[:dim]:
+        outer *= s
+    inner = 1
+    for s in shape[dim + 1:]:
+        inner *= s
+    mask = torch.zeros(shape, dtype=torch.uint8, device=dev)
+    with _DeviceGuard(dev):
+        _abi.check(_abi.lib().b200lev_after_eos_mask(tok.data_ptr(), outer, T, inner, int(eos),
+                                                     mask.data_ptr(), _stream(dev)))
+    return mask.bool()
+
+
+@after_eos_mask.register_fake
+def _(tokens, eos, dim):
+    return tokens.new_empty(tokens.shape, dtype=torch.bool)
+
+
+@torch.library.custom_op("b200lev::error_sums", mutates_args=())
+def error_sums(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: bool, batch_first: bool,
+               ins_cost: float, del_cost: float, sub_cost: float, norm: bool,
+               return_mistakes: bool, ref_group: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """Bulk scoring (command_line.py:1124-1147 without the per-utterance host reads):
+    ``(er, acc, flags)`` with ``er`` the per-pair values of ``string_matching`` and
+    ``acc = [sum(er), sum(ref_lens), #pairs]`` in fp64 on the device, ready for a single
+    all-reduce.  The reference lengths come from the same packing pass as the DP."""
+    R, H, n = _shapes(ref, hyp, batch_first, ref_group)
+    ref, hyp = _as_tokens(ref), _as_tokens(hyp)
+    dev = _check_device(ref, hyp)
+    L = _abi.lib()
+    with _DeviceGuard(dev):
+        rt, ht = _tok_struct(ref, batch_first), _tok_struct(hyp, batch_first)
+        o = _opts(eos, include_eos, ins_cost, del_cost, sub_cost, norm, False, 0,
+                  return_mistakes, ref_group)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        acc = torch.zeros(3, dtype=torch.float64, device=dev)
+        nbytes = L.b200lev_workspace_bytes(ctypes.byref(rt), ctypes.byref(ht), 0, 0)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        st = _stream(dev)
+        _abi.check(L.b200lev_final(ctypes.byref(rt), ctypes.byref(ht), ctypes.byref(o),
+                                   out.data_ptr(), ws.data_ptr(), nbytes, flags.data_ptr(), st))
+        lens = L.b200lev_workspace_ref_lens(ctypes.byref(rt), ctypes.byref(ht), ws.data_ptr())
+        _abi.check(L.b200lev_err_sum(out.data_ptr(), lens, n, ref_group, acc.data_ptr(), st))
+    return out, acc, flags
+
+
+@error_sums.register_fake
+def _(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost, sub_cost, norm,
+      return_mistakes, ref_group):
+    n = hyp.shape[0] if batch_first else hyp.shape[1]
+    return (ref.new_empty((n,), dtype=torch.float32), ref.new_empty((3,), dtype=torch.float64),
+            ref.new_empty((1,), dtype=torch.int32))

@@ -1,0 +1,59 @@
+"""Multi-GPU bulk scoring: shard the pair axis, all-reduce three scalars.
+
+The path shards naturally: pairs are independent, so each rank scores a
+contiguous block of (batch x n-best) pairs with no data-path communication; the only
+exchange is one ``all_reduce(sum)`` of ``[sum(err), sum(ref_tokens), #pairs]`` (fp64,
+24 bytes), the pattern of the reference's ``training.py:887-908`` applied to the
+accumulation of ``command_line.py:1135-1147``.  With the NCCL backend the buffer never
+leaves the device and the collective is enqueued behind the scoring kernels.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _ops
+from . import functional as F
+
+
+def shard_bounds(num_items: int, rank: int, world_size: int, group: int = 1) -> Tuple[int, int]:
+    """Contiguous block ``[lo, hi)`` of ``num_items`` for ``rank``; block edges are
+    multiples of ``group`` so an n-best group never straddles two ranks (the softmax
+    and mean of _string.py:1463-1465 are per group)."""
+    if num_items % group:
+        raise ValueError(f"{num_items} items are not a multiple of the group size {group}")
+    units = num_items // group
+    base, rem = divmod(units, world_size)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo * group, hi * group
+
+
+def bulk_error_rate(ref: torch.Tensor, hyp: torch.Tensor, eos: Optional[int] = None,
+                    include_eos: bool = False, batch_first: bool = False, ins_cost: float = 1.0,
+                    del_cost: float = 1.0, sub_cost: float = 1.0, distances: bool = False,
+                    process_group=None, warn: bool = False):
+    """Score this rank's pairs and reduce the totals over the process group.
+
+    ``ref`` / ``hyp`` are the LOCAL shard (see :func:`shard_bounds`).  Returns
+    ``(per_pair, totals)`` where ``totals = [sum(err), sum(ref_tokens), #pairs]`` is the
+    globally reduced fp64 tensor; the corpus-level rate of
+    ``compute-torch-token-data-dir-error-rates`` (command_line.py:1141-1147) is
+    ``totals[0] / totals[1]`` (or ``/ totals[2]`` with ``distances``).
+    """
+    (ref_d, hyp_d), back = F._offload(ref, hyp)
+    er, acc, flags = _ops.error_sums(ref_d, hyp_d, eos, include_eos, batch_first,
+                                     float(ins_cost), float(del_cost), float(sub_cost), False,
+                                     not distances, 1)
+    if warn:
+        F._warn_flags(flags, eos, include_eos, False, False)
+    if dist.is_available() and dist.is_initialized():
+        if dist.get_backend(process_group) == "gloo" and acc.is_cuda:
+            host = acc.cpu()
+            dist.all_reduce(host, op=dist.ReduceOp.SUM, group=process_group)
+            acc = host.to(acc.device)
+        else:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=process_group)
+    return back(er), acc

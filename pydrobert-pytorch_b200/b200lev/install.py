@@ -1,0 +1,42 @@
+"""Rebind the reference's string-matching names to the B200 kernels.
+
+``install()`` patches an importable ``pydrobert.torch`` in place -- ``_string``,
+``functional`` and ``modules`` (functional.py:49-58, modules.py:115-124 of the
+reference) -- so that existing user code and the reference's own
+``tests/test_string.py`` run on ``libb200lev.so`` without edits.
+"""
+from __future__ import annotations
+
+import importlib
+
+from . import functional as _F
+from . import modules as _M
+
+_FUNCS = tuple(_F.__all__)
+_CLASSES = tuple(_M.__all__)
+_saved = {}
+
+
+def install() -> bool:
+    """Returns False if ``pydrobert.torch`` is not importable (nothing to patch)."""
+    try:
+        mods = [importlib.import_module(f"pydrobert.torch.{m}")
+                for m in ("_string", "functional", "modules")]
+    except ImportError:
+        return False
+    for mod in mods:
+        for name in _FUNCS:
+            if hasattr(mod, name):
+                _saved.setdefault((mod.__name__, name), getattr(mod, name))
+                setattr(mod, name, getattr(_F, name))
+        for name in _CLASSES:
+            if hasattr(mod, name):
+                _saved.setdefault((mod.__name__, name), getattr(mod, name))
+                setattr(mod, name, getattr(_M, name))
+    return True
+
+
+def uninstall() -> None:
+    for (modname, name), obj in list(_saved.items()):
+        setattr(importlib.import_module(modname), name, obj)
+    _saved.clear()

@@ -1,0 +1,271 @@
+// lev_abi.cu -- the extern "C" boundary declared in include/b200lev.h: argument
+// checking, the uniform-cost shortcut (SM:168-174), int/float path selection, workspace
+// carving and kernel sequencing.  No device allocation, no host synchronisation.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+
+#include "lev_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void lev_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int lev_check_cuda(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        lev_set_error("%s: %s", what, cudaGetErrorString(e));
+        return B200LEV_ERR_CUDA;
+    }
+    return B200LEV_OK;
+}
+
+extern "C" int b200lev_abi_version(void) { return B200LEV_ABI_VERSION; }
+extern "C" const char* b200lev_last_error(void) { return g_err; }
+
+extern "C" int b200lev_device_count(void) {
+#ifdef B200LEV_EMU
+    return 1;
+#else
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+#endif
+}
+
+static int lev_check_tokens(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                            const b200lev_opts_t* o) {
+    if (!ref || !hyp || !o) {
+        lev_set_error("NULL argument");
+        return B200LEV_ERR_ARG;
+    }
+    if (ref->T < 0 || hyp->T < 0 || ref->N < 0 || hyp->N < 0) {
+        lev_set_error("negative dimension");
+        return B200LEV_ERR_ARG;
+    }
+    if (o->ref_group < 1 || ref->N * o->ref_group != hyp->N) {
+        // SM:191-194
+        lev_set_error("ref has batch size %lld, but hyp has %lld",
+                      (long long)(ref->N * (o->ref_group < 1 ? 1 : o->ref_group)), (long long)hyp->N);
+        return B200LEV_ERR_ARG;
+    }
+    if ((ref->N * ref->T > 0 && !ref->data) || (hyp->N * hyp->T > 0 && !hyp->data)) {
+        lev_set_error("NULL token data");
+        return B200LEV_ERR_ARG;
+    }
+    if (ref->T >= (1 << 24) || hyp->T >= (1 << 24) || hyp->N >= ((int64_t)1 << 31)) {
+        lev_set_error("dimension too large");
+        return B200LEV_ERR_UNSUPPORTED;
+    }
+    return B200LEV_OK;
+}
+
+extern "C" size_t b200lev_workspace_bytes(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                                          int32_t for_completion, int32_t exclude_last) {
+    if (!ref || !hyp) return 0;
+    return lev_layout(ref, hyp, for_completion, exclude_last).bytes + 128;
+}
+
+static inline char* lev_ws_base(const void* ws) {
+    return (char*)(((uintptr_t)ws + 127) & ~(uintptr_t)127);
+}
+
+extern "C" const int32_t* b200lev_workspace_ref_lens(const b200lev_tokens_t* ref,
+                                                     const b200lev_tokens_t* hyp, const void* ws) {
+    LevLayout L = lev_layout(ref, hyp, 0, 0);
+    return (const int32_t*)(lev_ws_base(ws) + L.off_ref_len);
+}
+extern "C" const int32_t* b200lev_workspace_hyp_lens(const b200lev_tokens_t* ref,
+                                                     const b200lev_tokens_t* hyp, const void* ws) {
+    LevLayout L = lev_layout(ref, hyp, 0, 0);
+    return (const int32_t*)(lev_ws_base(ws) + L.off_hyp_len);
+}
+
+// Fills the cost fields of `p`.  Returns count_mode / float_path through the out-params.
+static void lev_classify_costs(const b200lev_opts_t* o, int64_t R, int64_t H, LevParams* p,
+                               bool* count_mode, bool* float_path) {
+    float ins = o->ins_cost, del = o->del_cost, sub = o->sub_cost;
+    float mult = 1.0f;
+    bool cm = o->return_mistakes != 0;
+    if (ins == del && del == sub && sub > 0.0f) {  // SM:168-174
+        if (!cm) mult = ins;
+        ins = del = sub = 1.0f;
+        cm = false;
+    }
+    // integer path iff every cost is an integer and every reachable fp32 value of the
+    // reference is exact (< 2^24), so int32 arithmetic reproduces it bit for bit
+    const float amax = fmaxf(fabsf(ins), fmaxf(fabsf(del), fabsf(sub)));
+    const bool integral = floorf(ins) == ins && floorf(del) == del && floorf(sub) == sub &&
+                          (double)amax * (double)(R + H + 2) < 16777216.0;
+    p->ins_f = ins;
+    p->del_f = del;
+    p->sub_f = sub;
+    p->ins_i = integral ? (int)ins : 0;
+    p->del_i = integral ? (int)del : 0;
+    p->sub_i = integral ? (int)sub : 0;
+    p->mult = mult;
+    *count_mode = cm;
+    *float_path = !integral;
+}
+
+// pack both token tensors into the workspace and fill the common fields of `p`
+static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                       const b200lev_opts_t* o, const LevLayout& L, char* ws, int32_t* flags,
+                       cudaStream_t st, LevParams* p) {
+    int32_t* ref_tok = (int32_t*)(ws + L.off_ref_tok);
+    int32_t* hyp_tok = (int32_t*)(ws + L.off_hyp_tok);
+    int32_t* ref_len = (int32_t*)(ws + L.off_ref_len);
+    int32_t* hyp_len = (int32_t*)(ws + L.off_hyp_len);
+    int rc = lev_launch_pack(ref, o->has_eos, o->eos, o->include_eos, ref_tok, L.Rp, ref_len, flags,
+                             B200LEV_FLAG_REF_NO_EOS, st);
+    if (rc) return rc;
+    rc = lev_launch_pack(hyp, o->has_eos, o->eos, o->include_eos, hyp_tok, L.Hp, hyp_len, flags,
+                         B200LEV_FLAG_HYP_NO_EOS, st);
+    if (rc) return rc;
+    memset(p, 0, sizeof(*p));
+    p->ref_tok = ref_tok;
+    p->hyp_tok = hyp_tok;
+    p->ref_len = ref_len;
+    p->hyp_len = hyp_len;
+    p->Rp = L.Rp;
+    p->Hp = L.Hp;
+    p->R = (int)L.R;
+    p->H = (int)L.H;
+    p->P = (int)L.P;
+    p->ref_group = o->ref_group;
+    p->norm = o->norm;
+    p->exclude_last = o->exclude_last;
+    p->padding = (float)o->padding;
+    p->flags = flags;
+    return B200LEV_OK;
+}
+
+extern "C" int b200lev_final(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                             const b200lev_opts_t* opts, float* out, void* workspace,
+                             size_t workspace_bytes, int32_t* flags, void* stream) {
+    int rc = lev_check_tokens(ref, hyp, opts);
+    if (rc) return rc;
+    if (hyp->N == 0) return B200LEV_OK;
+    if (!out || !workspace) {
+        lev_set_error("NULL output/workspace");
+        return B200LEV_ERR_ARG;
+    }
+    const LevLayout L = lev_layout(ref, hyp, 0, 0);
+    if (workspace_bytes < L.bytes + 128) {
+        lev_set_error("workspace too small: %zu < %zu", workspace_bytes, L.bytes + 128);
+        return B200LEV_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    LevParams p;
+    b200lev_opts_t o = *opts;
+    o.exclude_last = 0;  // SM:165
+    rc = lev_prepare(ref, hyp, &o, L, lev_ws_base(workspace), flags, st, &p);
+    if (rc) return rc;
+    bool cm, fp;
+    lev_classify_costs(&o, L.R, L.H, &p, &cm, &fp);
+    p.out = out;
+    return lev_launch_dp(p, LEV_MODE_FINAL, cm, fp, st);
+}
+
+extern "C" int b200lev_prefix(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                              const b200lev_opts_t* opts, float* out, int64_t out_stride_i,
+                              int64_t out_stride_n, void* workspace, size_t workspace_bytes,
+                              int32_t* flags, void* stream) {
+    int rc = lev_check_tokens(ref, hyp, opts);
+    if (rc) return rc;
+    const LevLayout L = lev_layout(ref, hyp, 0, opts->exclude_last);
+    if (hyp->N == 0 || L.Hout <= 0) return B200LEV_OK;
+    if (!out || !workspace) {
+        lev_set_error("NULL output/workspace");
+        return B200LEV_ERR_ARG;
+    }
+    if (workspace_bytes < L.bytes + 128) {
+        lev_set_error("workspace too small: %zu < %zu", workspace_bytes, L.bytes + 128);
+        return B200LEV_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    LevParams p;
+    rc = lev_prepare(ref, hyp, opts, L, lev_ws_base(workspace), flags, st, &p);
+    if (rc) return rc;
+    bool cm, fp;
+    lev_classify_costs(opts, L.R, L.H, &p, &cm, &fp);
+    p.out = out;
+    p.out_si = out_stride_i;
+    p.out_sn = out_stride_n;
+    p.Hout = (int)L.Hout;
+    return lev_launch_dp(p, LEV_MODE_PREFIX, cm, fp, st);
+}
+
+extern "C" int b200lev_completion_count(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                                        const b200lev_opts_t* opts, void* workspace,
+                                        size_t workspace_bytes, int32_t* umax, int32_t* flags,
+                                        void* stream) {
+    int rc = lev_check_tokens(ref, hyp, opts);
+    if (rc) return rc;
+    if (!umax) {
+        lev_set_error("NULL umax");
+        return B200LEV_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(umax, 0, sizeof(int32_t), st) != cudaSuccess) return lev_check_cuda("memset");
+    if (hyp->N == 0) return B200LEV_OK;
+    if (!workspace) {
+        lev_set_error("NULL workspace");
+        return B200LEV_ERR_ARG;
+    }
+    const LevLayout L = lev_layout(ref, hyp, 1, opts->exclude_last);
+    if (workspace_bytes < L.bytes + 128) {
+        lev_set_error("workspace too small: %zu < %zu", workspace_bytes, L.bytes + 128);
+        return B200LEV_ERR_WORKSPACE;
+    }
+    char* ws = lev_ws_base(workspace);
+    LevParams p;
+    b200lev_opts_t o = *opts;
+    o.return_mistakes = 0;  // SM:479-491: the mask is always taken on the cost row
+    o.norm = 0;
+    rc = lev_prepare(ref, hyp, &o, L, ws, flags, st, &p);
+    if (rc) return rc;
+    bool cm, fp;
+    lev_classify_costs(&o, L.R, L.H, &p, &cm, &fp);
+    int32_t* uid = (int32_t*)(ws + L.off_uid);
+    int64_t* dtok = (int64_t*)(ws + L.off_dtok);
+    int32_t* ndist = (int32_t*)(ws + L.off_ndist);
+    uint32_t* dbits = (uint32_t*)(ws + L.off_dbits);
+    rc = lev_launch_uid(ref, p.ref_len, uid, dtok, ndist, L.Rp, st);
+    if (rc) return rc;
+    if (cudaMemsetAsync(dbits, 0, sizeof(uint32_t) * (size_t)L.Hout * L.P * L.Wd, st) != cudaSuccess)
+        return lev_check_cuda("memset");
+    p.uid = uid;
+    p.dbits = dbits;
+    p.Wd = (int)L.Wd;
+    p.umax = umax;
+    p.Hout = (int)L.Hout;
+    return lev_launch_dp(p, LEV_MODE_MASK, false, fp, st);
+}
+
+extern "C" int b200lev_completion_fill(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                                       const b200lev_opts_t* opts, const void* workspace,
+                                       size_t workspace_bytes, int64_t U, int64_t* out,
+                                       int64_t out_stride_i, int64_t out_stride_n, void* stream) {
+    int rc = lev_check_tokens(ref, hyp, opts);
+    if (rc) return rc;
+    if (hyp->N == 0 || U <= 0) return B200LEV_OK;
+    const LevLayout L = lev_layout(ref, hyp, 1, opts->exclude_last);
+    if (!workspace || !out || workspace_bytes < L.bytes + 128) {
+        lev_set_error("bad workspace/output");
+        return B200LEV_ERR_WORKSPACE;
+    }
+    const char* ws = lev_ws_base(workspace);
+    return lev_launch_completion_fill((const uint32_t*)(ws + L.off_dbits),
+                                      (const int64_t*)(ws + L.off_dtok), L.Rp, L.Hout, L.P, L.Wd,
+                                      opts->ref_group, U, opts->padding, out, out_stride_i,
+                                      out_stride_n, (cudaStream_t)stream);
+}

@@ -1,0 +1,105 @@
+// lev_common.cuh -- shared declarations for the Levenshtein kernels.
+//
+// "SM" in comments is src/pydrobert/torch/_string.py of the reference.
+#pragma once
+#include "simt.h"
+
+#include "../../include/b200lev.h"
+
+enum LevMode { LEV_MODE_FINAL = 0, LEV_MODE_PREFIX = 1, LEV_MODE_MASK = 2 };
+
+// "Infinity" for the int32 DP: virtual columns left of column 0 hold it so that
+// column 0 needs no special case.  Costs are bounded on the host so that BIG plus
+// any reachable path cost stays below 2^31.
+#define LEV_BIG_I32 (1 << 29)
+
+static inline int64_t lev_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// Workspace layout (device scratch supplied by the caller).  All offsets are
+// multiples of 128 bytes.
+struct LevLayout {
+    int64_t R, H, Nref, P;
+    int64_t Rp, Hp;  // padded row lengths of the packed int32 token tables
+    int64_t Hout;    // output rows of the prefix / mask modes
+    int64_t Wd;      // 32-bit words of one (prefix, pair) distinct-token bitmap
+    size_t off_ref_tok, off_hyp_tok, off_ref_len, off_hyp_len;
+    size_t off_uid, off_dtok, off_ndist, off_dbits;
+    size_t bytes;
+};
+
+static inline LevLayout lev_layout(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                                   int for_completion, int exclude_last) {
+    LevLayout L;
+    L.R = ref->T;
+    L.H = hyp->T;
+    L.Nref = ref->N;
+    L.P = hyp->N;
+    L.Rp = lev_round_up(L.R > 0 ? L.R : 1, 4);
+    L.Hp = lev_round_up(L.H > 0 ? L.H : 1, 4);
+    L.Hout = L.H + (exclude_last ? 0 : 1);
+    if (for_completion && L.Hout < 1) L.Hout = 1;  // SM:271-278
+    L.Wd = (L.R + 31) / 32;
+    if (L.Wd < 1) L.Wd = 1;
+    size_t o = 0;
+    auto take = [&](size_t n) {
+        size_t at = o;
+        o += (size_t)lev_round_up((int64_t)n, 128);
+        return at;
+    };
+    L.off_ref_tok = take(sizeof(int32_t) * (size_t)L.Nref * L.Rp);
+    L.off_hyp_tok = take(sizeof(int32_t) * (size_t)L.P * L.Hp);
+    L.off_ref_len = take(sizeof(int32_t) * (size_t)L.Nref);
+    L.off_hyp_len = take(sizeof(int32_t) * (size_t)L.P);
+    L.off_uid = L.off_dtok = L.off_ndist = L.off_dbits = 0;
+    if (for_completion) {
+        L.off_uid = take(sizeof(int32_t) * (size_t)L.Nref * L.Rp);
+        L.off_dtok = take(sizeof(int64_t) * (size_t)L.Nref * L.Rp);
+        L.off_ndist = take(sizeof(int32_t) * (size_t)L.Nref);
+        L.off_dbits = take(sizeof(uint32_t) * (size_t)L.Hout * L.P * L.Wd);
+    }
+    L.bytes = o;
+    return L;
+}
+
+// Everything the DP kernels need, by value.
+struct LevParams {
+    const int32_t* ref_tok;  // [Nref][Rp]
+    const int32_t* hyp_tok;  // [P][Hp]
+    const int32_t* ref_len;  // [Nref]
+    const int32_t* hyp_len;  // [P]
+    int64_t Rp, Hp;
+    int R, H, P, ref_group;
+    // costs: integer path uses the *_i fields, float path the *_f fields
+    int ins_i, del_i, sub_i;
+    float ins_f, del_f, sub_f;
+    float mult;  // SM:168-174
+    int norm, exclude_last;
+    float padding;
+    // FINAL: out[n];  PREFIX: out[i*out_si + n*out_sn]
+    float* out;
+    int64_t out_si, out_sn;
+    int Hout;
+    // MASK
+    const int32_t* uid;  // [Nref][Rp] rank of ref[j] among the pair's distinct tokens
+    uint32_t* dbits;     // [Hout][P][Wd]
+    int Wd;
+    int* umax;
+    int* flags;
+};
+
+// host-side status plumbing (lev_abi.cu)
+void lev_set_error(const char* fmt, ...);
+int lev_check_cuda(const char* what);
+
+// kernels' host launchers
+int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int include_eos,
+                    int32_t* packed, int64_t Tp, int32_t* lens, int32_t* flags,
+                    int missing_flag, cudaStream_t st);
+int lev_launch_dp(const LevParams& p, int mode, bool count_mode, bool float_path,
+                  cudaStream_t st);
+int lev_launch_uid(const b200lev_tokens_t* ref, const int32_t* ref_len, int32_t* uid,
+                   int64_t* dtok, int32_t* ndist, int64_t Rp, cudaStream_t st);
+int lev_launch_completion_fill(const uint32_t* dbits, const int64_t* dtok, int64_t Rp,
+                               int64_t Hout, int64_t P, int64_t Wd, int ref_group, int64_t U,
+                               int64_t padding, int64_t* out, int64_t out_si, int64_t out_sn,
+                               cudaStream_t st);

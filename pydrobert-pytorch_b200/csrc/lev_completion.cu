@@ -1,0 +1,119 @@
+// lev_completion.cu -- K4: the sorted-unique compaction of optimal_completion.
+//
+// The reference (SM:492-517) turns the (H', R, N) position mask into per-prefix token
+// sets by (i) OR-ing the mask across duplicate tokens with an (H', N, R, R) boolean
+// temporary, (ii) sorting the reference tokens, (iii) masked_select/masked_scatter.
+// Here the sort happens ONCE per reference instead of once per prefix:
+//   lev_uid_kernel      : for every reference position j its rank uid[j] among the
+//                         DISTINCT token values of that reference (ascending, as
+//                         int64), plus the table dtok[rank] -> token value;
+//   (lev_dp.cu, MASK)   : sets bit uid[j] of the (prefix, pair) bitmap for every
+//                         flagged position -- duplicates collapse onto one bit and
+//                         ascending bit order IS ascending token order;
+//   lev_completion_fill : enumerates the set bits into the (H', N, U) int64 output,
+//                         padding the tail (coalesced: consecutive threads own
+//                         consecutive U-element rows).
+#include "lev_common.cuh"
+
+template <typename TT>
+__global__ void __launch_bounds__(256)
+lev_uid_kernel(const TT* __restrict__ tok, int64_t st, int64_t sn, const int32_t* __restrict__ ref_len,
+               int32_t* __restrict__ uid, int64_t* __restrict__ dtok, int32_t* __restrict__ ndist,
+               int64_t Rp, int64_t R) {
+    LEV_DYN_SMEM(int64_t, t64);                                       // [R]
+    unsigned char* isfirst = reinterpret_cast<unsigned char*>(t64 + R);  // [R]
+    __shared__ int nfirst;
+    const int64_t n = blockIdx.x;
+    const int r = ref_len[n];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) nfirst = 0;
+    for (int j = tid; j < r; j += nt) t64[j] = (int64_t)tok[(int64_t)j * st + n * sn];
+    __syncthreads();
+    int mine = 0;
+    for (int j = tid; j < r; j += nt) {
+        const int64_t x = t64[j];
+        int f = 1;
+        for (int k = 0; k < j; ++k)
+            if (t64[k] == x) {
+                f = 0;
+                break;
+            }
+        isfirst[j] = (unsigned char)f;
+        mine += f;
+    }
+    if (mine) atomicAdd(&nfirst, mine);
+    __syncthreads();
+    for (int j = tid; j < r; j += nt) {
+        const int64_t x = t64[j];
+        int rank = 0;
+        for (int k = 0; k < r; ++k) rank += (isfirst[k] && t64[k] < x) ? 1 : 0;
+        uid[n * Rp + j] = rank;
+        if (isfirst[j]) dtok[n * Rp + rank] = x;
+    }
+    if (tid == 0) ndist[n] = nfirst;
+}
+
+int lev_launch_uid(const b200lev_tokens_t* ref, const int32_t* ref_len, int32_t* uid,
+                   int64_t* dtok, int32_t* ndist, int64_t Rp, cudaStream_t st) {
+    if (ref->N <= 0) return B200LEV_OK;
+    const size_t smem = (size_t)ref->T * (sizeof(int64_t) + 1) + 16;
+    if (smem > 200 * 1024) {
+        lev_set_error("reference length %lld too long for the completion path", (long long)ref->T);
+        return B200LEV_ERR_UNSUPPORTED;
+    }
+    dim3 grid((unsigned)ref->N), block(256);
+#define LEV_UID_CASE(TT)                                                                        \
+    {                                                                                           \
+        auto kern = lev_uid_kernel<TT>;                                                         \
+        if (smem > 48 * 1024)                                                                   \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        lev_launch(kern, grid, block, smem, st, (const TT*)ref->data, ref->stride_t,            \
+                   ref->stride_n, ref_len, uid, dtok, ndist, Rp, ref->T);                       \
+    }
+    switch (ref->elem_bytes) {
+        case 8: LEV_UID_CASE(int64_t) break;
+        case 4: LEV_UID_CASE(int32_t) break;
+        case 2: LEV_UID_CASE(int16_t) break;
+        case 1: LEV_UID_CASE(int8_t) break;
+        default:
+            lev_set_error("unsupported token element size %d", (int)ref->elem_bytes);
+            return B200LEV_ERR_ARG;
+    }
+#undef LEV_UID_CASE
+    return lev_check_cuda("lev_uid_kernel");
+}
+
+__global__ void __launch_bounds__(256)
+lev_completion_fill_kernel(const uint32_t* __restrict__ dbits, const int64_t* __restrict__ dtok,
+                           int64_t Rp, int64_t rows /* Hout*P */, int64_t P, int64_t Wd,
+                           int ref_group, int64_t U, int64_t padding, int64_t* __restrict__ out,
+                           int64_t out_si, int64_t out_sn) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows) return;
+    const int64_t i = idx / P, n = idx - i * P;
+    const uint32_t* __restrict__ w = dbits + idx * Wd;
+    const int64_t* __restrict__ dt = dtok + (n / ref_group) * Rp;
+    int64_t* __restrict__ o = out + i * out_si + n * out_sn;
+    int64_t k = 0;
+    for (int64_t q = 0; q < Wd && k < U; ++q) {
+        uint32_t bits = w[q];
+        while (bits && k < U) {
+            const int b = __ffs((int)bits) - 1;
+            bits &= bits - 1;
+            o[k++] = dt[q * 32 + b];
+        }
+    }
+    for (; k < U; ++k) o[k] = padding;
+}
+
+int lev_launch_completion_fill(const uint32_t* dbits, const int64_t* dtok, int64_t Rp,
+                               int64_t Hout, int64_t P, int64_t Wd, int ref_group, int64_t U,
+                               int64_t padding, int64_t* out, int64_t out_si, int64_t out_sn,
+                               cudaStream_t st) {
+    const int64_t rows = Hout * P;
+    if (rows <= 0 || U <= 0) return B200LEV_OK;
+    dim3 block(256), grid((unsigned)((rows + 255) / 256));
+    lev_launch(lev_completion_fill_kernel, grid, block, 0, st, dbits, dtok, Rp, rows, P, Wd,
+               ref_group, U, padding, out, out_si, out_sn);
+    return lev_check_cuda("lev_completion_fill_kernel");
+}

@@ -1,0 +1,371 @@
+// lev_dp.cu -- K1: warp-per-pair anti-diagonal wavefront for the Levenshtein DP.
+//
+// Replaces the Python hot loop SM:258-318 and the epilogues SM:340-406 of the
+// reference ("SM" = src/pydrobert/torch/_string.py).
+//
+// Geometry.  DP columns 0..r (r = valid reference length) are cut into strips of
+// W = 32*C columns, RIGHT-aligned so the last strip ends exactly at column r; the
+// columns of the first strip that fall left of column 0 are "virtual" and hold +BIG,
+// which makes column 0 (value i*ins) an ordinary cell and leaves no boundary special
+// case.  Inside a strip lane l owns C adjacent columns in registers and the warp is
+// skewed over hypothesis rows: at step s lane l updates row s-l, so the cells touched
+// in one step lie on an anti-diagonal (of C-wide column blocks).  The previous
+// diagonal lives in registers; the values a lane needs from its left neighbour (row
+// i, last column of lane l-1) move with __shfl_up_sync once per step, and the
+// matching diagonal value is simply last step's shuffle result.  Between strips the
+// boundary column is handed over through a per-warp shared-memory column (written by
+// lane 31 for row i, read by lane 0 of the next strip 31 steps earlier in its own
+// schedule, so one buffer per channel suffices).
+//
+// Per cell the integer path issues 4 INT32 instructions:
+//   ISETP (token compare), predicated IADD (diag + sub), VIADDMNMX (min(up+ins, .)),
+//   VIADDMNMX (min(left+del, .))            -- the DPX fused add+min of sm_90+/sm_100.
+//
+// Modes: FINAL (one value per pair), PREFIX (value at column r after every row),
+// MASK (row minima in pass A, equality bits in pass B; bits are set per DISTINCT
+// reference token so the compaction of SM:492-517 becomes a bit enumeration).
+// Arithmetic: int32 for integer costs (exact; converted to fp32 on store), fp32 for
+// the rest, in the reference's operation order (including its deletion term
+// min_k v[k] + (fl(j*d) - fl(k*d)), SM:263-266,317, tracked by run origin).
+#include <type_traits>
+
+#include "lev_common.cuh"
+
+template <typename V>
+struct LevArith;
+template <>
+struct LevArith<int> {
+    static __device__ __forceinline__ int big() { return LEV_BIG_I32; }
+    static __device__ __forceinline__ int ins(const LevParams& p) { return p.ins_i; }
+    static __device__ __forceinline__ int del(const LevParams& p) { return p.del_i; }
+    static __device__ __forceinline__ int sub(const LevParams& p) { return p.sub_i; }
+};
+template <>
+struct LevArith<float> {
+    static __device__ __forceinline__ float big() { return __int_as_float(0x7f800000); }
+    static __device__ __forceinline__ float ins(const LevParams& p) { return p.ins_f; }
+    static __device__ __forceinline__ float del(const LevParams& p) { return p.del_f; }
+    static __device__ __forceinline__ float sub(const LevParams& p) { return p.sub_f; }
+};
+
+// SM:390-405 (final) and SM:356-378 (prefix row i): scale, normalise, empty-ref rule.
+// `positive` is (hyp_len > 0) for the final value and (i > 0) for prefix row i.
+__device__ __forceinline__ float lev_finalize(float val, const LevParams& p, int r,
+                                              bool positive) {
+    float v = val * p.mult;
+    if (p.norm) v = (r == 0) ? (positive ? 1.0f : 0.0f) : v / (float)r;
+    return v;
+}
+
+// number of per-warp shared-memory columns (boundary channels + row minima)
+template <typename V, bool COUNT, int MODE>
+struct LevBufs {
+    static constexpr bool FLT_COST = !std::is_same<V, int>::value && !COUNT;
+    static constexpr int NB = (COUNT ? 2 : (FLT_COST ? 3 : 1)) + (MODE == LEV_MODE_MASK ? 1 : 0);
+};
+
+// One pair on one warp.  PASS: 0 = the only pass (FINAL/PREFIX) or the row-minimum
+// pass of MASK; 1 = the equality pass of MASK.
+template <typename V, bool COUNT, int MODE, int C, int PASS>
+__device__ __forceinline__ void lev_warp_pair(const LevParams& p, const int pair, const int r,
+                                              const int h, const int steps,
+                                              const int* __restrict__ hyp_s,
+                                              V* __restrict__ bufs, const int Hs) {
+    constexpr bool IS_INT = std::is_same<V, int>::value;
+    constexpr bool FLT_COST = !IS_INT && !COUNT;
+    constexpr bool RMIN = (MODE == LEV_MODE_MASK && PASS == 0);
+    constexpr bool EQ = (MODE == LEV_MODE_MASK && PASS == 1);
+    constexpr int W = 32 * C;
+    const int lane = threadIdx.x & 31;
+    const int S = (r + W) / W;  // ceil((r + 1) / W)
+    const int refcol = pair / p.ref_group;
+    const int32_t* __restrict__ rtok = p.ref_tok + (int64_t)refcol * p.Rp;
+    const V BIG = LevArith<V>::big();
+    const V insc = LevArith<V>::ins(p), delc = LevArith<V>::del(p), subc = LevArith<V>::sub(p);
+    // shared-memory columns, all indexed [32 + row]
+    V* __restrict__ bnd_v = bufs;
+    V* __restrict__ bnd_a = bufs + Hs;      // COUNT: counts ; FLT_COST: run-origin value
+    V* __restrict__ bnd_b = bufs + 2 * Hs;  // FLT_COST: fl(origin * del)
+    V* __restrict__ rowmin = bufs + (LevBufs<V, COUNT, MODE>::NB - 1) * Hs;  // MASK only
+    (void)bnd_a; (void)bnd_b; (void)rowmin;
+
+    for (int k = 0; k < S; ++k) {
+        const bool first = (k == 0), last = (k == S - 1);
+        const int jb = r - (S - k) * W;    // boundary column left of lane 0 (< 0 iff first)
+        const int j0 = jb + lane * C + 1;  // this lane's first column
+        V v[C];
+        V m[C];     // COUNT: mistake counts
+        V jd[C];    // FLT_COST: fl(j * del), SM:258-263
+        int rt[C];  // reference token of column j (ref position j-1)
+        int ud[C];  // EQ: distinct-token rank of ref position j, or -1
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int j = j0 + c;
+            v[c] = (j >= 0) ? (V)j * delc : BIG;
+            m[c] = (V)(j >= 0 ? j : 0);  // SM:260
+            jd[c] = (j >= 0) ? (V)j * delc : (V)0;
+            rt[c] = (j >= 1) ? rtok[j - 1] : 0;
+            ud[c] = -1;
+            if (EQ) ud[c] = (j >= 0 && j < r) ? p.uid[(int64_t)refcol * p.Rp + j] : -1;
+        }
+        (void)m; (void)jd; (void)ud;
+        // chain registers: what this lane publishes to lane+1 at the next step
+        V ob = BIG, oj = (V)0, rmrun = BIG;
+        (void)ob; (void)oj; (void)rmrun;
+        // previous step's hand-in (the diagonal); lane 0 starts from row 0 of the
+        // boundary column, the other lanes pick it up from the shuffle at step l
+        V pl_v = first ? BIG : (V)jb * delc;
+        V pl_m = (V)(first ? 0 : jb);
+        (void)pl_m;
+        if (steps > 0) {
+            const int nsteps = steps + 31;
+            for (int s = 1; s <= nsteps; ++s) {
+                // ---- hand-over from the left neighbour (all lanes, every step) ----
+                const V sh_v = __shfl_up_sync(LEV_FULL_MASK, v[C - 1], 1);
+                const V in_v = (lane == 0) ? (first ? BIG : bnd_v[32 + s]) : sh_v;
+                const V diag_v = pl_v;
+                pl_v = in_v;
+                V in_m = (V)0, diag_m = (V)0, in_ob = BIG, in_oj = (V)0, in_rm = BIG;
+                if (COUNT) {
+                    const V sh_m = __shfl_up_sync(LEV_FULL_MASK, m[C - 1], 1);
+                    in_m = (lane == 0) ? (first ? (V)0 : bnd_a[32 + s]) : sh_m;
+                    diag_m = pl_m;
+                    pl_m = in_m;
+                }
+                if (FLT_COST) {
+                    const V sh_ob = __shfl_up_sync(LEV_FULL_MASK, ob, 1);
+                    const V sh_oj = __shfl_up_sync(LEV_FULL_MASK, oj, 1);
+                    in_ob = (lane == 0) ? (first ? BIG : bnd_a[32 + s]) : sh_ob;
+                    in_oj = (lane == 0) ? (first ? (V)0 : bnd_b[32 + s]) : sh_oj;
+                }
+                if (RMIN) {
+                    const V sh_rm = __shfl_up_sync(LEV_FULL_MASK, rmrun, 1);
+                    in_rm = (lane == 0) ? (first ? BIG : rowmin[32 + s]) : sh_rm;
+                }
+                (void)in_m; (void)diag_m; (void)in_ob; (void)in_oj; (void)in_rm;
+                const int i = s - lane;  // the row this lane updates now
+                if (i >= 1 && i <= steps) {
+                    const int ht = hyp_s[32 + i - 1];
+                    if (COUNT) {
+                        // SM:292-314: (cost, count); ties: sub over ins over del
+                        V dc = diag_v, dm = diag_m, lc = in_v, lm = in_m;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const V uc = v[c], um = m[c];
+                            const bool neq = rt[c] != ht;
+                            const V sub_c = dc + (neq ? subc : (V)0);  // SM:293
+                            const V ins_c = uc + insc;                 // SM:292
+                            const bool ps = ins_c >= sub_c;            // SM:296
+                            V cc = ps ? sub_c : ins_c;
+                            V mm = ps ? dm + (neq ? (V)1 : (V)0) : um + (V)1;  // SM:299-301
+                            const V del_c = lc + delc;                          // SM:308
+                            const bool keep = del_c >= cc;                      // SM:309
+                            cc = keep ? cc : del_c;
+                            mm = keep ? mm : lm + (V)1;  // SM:311-313
+                            dc = uc;
+                            dm = um;
+                            lc = cc;
+                            lm = mm;
+                            v[c] = cc;
+                            m[c] = mm;
+                        }
+                    } else if (FLT_COST) {
+                        // SM:290-293,316-317 in fp32, deletion term by run origin:
+                        // new[j] = min(t[j], t[k*] + (fl(j*d) - fl(k* * d)))
+                        V dg = diag_v, obr = in_ob, ojr = in_oj;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const V up = v[c];
+                            const V a = up + insc;
+                            const V sb = dg + ((rt[c] != ht) ? subc : (V)0);
+                            const V t = a < sb ? a : sb;
+                            const V cand = obr + (jd[c] - ojr);
+                            const bool fresh = !(cand < t);
+                            v[c] = fresh ? t : cand;
+                            obr = fresh ? t : obr;
+                            ojr = fresh ? jd[c] : ojr;
+                            dg = up;
+                        }
+                        ob = obr;
+                        oj = ojr;
+                    } else {
+                        // integer costs: 4 INT32 instructions per cell
+                        int dg = (int)diag_v, lf = (int)in_v;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const int up = (int)v[c];
+                            const int sb = dg + ((rt[c] != ht) ? (int)subc : 0);
+                            const int t = __viaddmin_s32(up, (int)insc, sb);
+                            lf = __viaddmin_s32(lf, (int)delc, t);
+                            dg = up;
+                            v[c] = (V)lf;
+                        }
+                    }
+                    if (RMIN) {  // SM:332-333: running minimum of row i over columns <= mine
+                        V rm = in_rm;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) rm = v[c] < rm ? v[c] : rm;
+                        rmrun = rm;
+                    }
+                    if (EQ) {  // SM:334, 349-354
+                        const V mn = rowmin[32 + i];
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            if (ud[c] >= 0 && v[c] == mn)
+                                atomicOr(p.dbits + ((int64_t)i * p.P + pair) * p.Wd + (ud[c] >> 5),
+                                         1u << (ud[c] & 31));
+                        }
+                    }
+                    if (lane == 31) {
+                        if (!last) {
+                            bnd_v[32 + i] = v[C - 1];
+                            if (COUNT) bnd_a[32 + i] = m[C - 1];
+                            if (FLT_COST) {
+                                bnd_a[32 + i] = ob;
+                                bnd_b[32 + i] = oj;
+                            }
+                        } else if (MODE == LEV_MODE_PREFIX) {  // SM:340-346
+                            p.out[(int64_t)i * p.out_si + (int64_t)pair * p.out_sn] =
+                                lev_finalize((float)(COUNT ? m[C - 1] : v[C - 1]), p, r, true);
+                        }
+                        if (RMIN) rowmin[32 + i] = rmrun;
+                    }
+                }
+            }
+        }
+        if (MODE == LEV_MODE_FINAL && last && lane == 31)  // SM:390-405
+            p.out[pair] = lev_finalize((float)(COUNT ? m[C - 1] : v[C - 1]), p, r, h > 0);
+        __syncwarp();
+    }
+}
+
+template <typename V, bool COUNT, int MODE, int C>
+__device__ __forceinline__ void lev_warp_pair_all(const LevParams& p, int pair, int r, int h,
+                                                  int steps, const int* hyp_s, V* bufs, int Hs) {
+    lev_warp_pair<V, COUNT, MODE, C, 0>(p, pair, r, h, steps, hyp_s, bufs, Hs);
+    if (MODE == LEV_MODE_MASK) lev_warp_pair<V, COUNT, MODE, C, 1>(p, pair, r, h, steps, hyp_s, bufs, Hs);
+}
+
+// CMASK: bit c set => the kernel carries a C = 2^c variant (1, 2, 4, 8); each pair
+// takes the smallest variant whose single strip covers its r + 1 columns, the largest
+// one (multi-strip) otherwise.
+template <typename V, bool COUNT, int MODE, int CMASK>
+__global__ void __launch_bounds__(256) lev_warp_kernel(const LevParams p) {
+    LEV_DYN_SMEM(int, smem);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wpc = blockDim.x >> 5;
+    const int Hs = p.H + 64;
+    constexpr int NB = LevBufs<V, COUNT, MODE>::NB;
+    int* hyp_s = smem + (size_t)warp * (1 + NB) * Hs;
+    V* bufs = reinterpret_cast<V*>(hyp_s + Hs);
+    for (int pair = blockIdx.x * wpc + warp; pair < p.P; pair += gridDim.x * wpc) {
+        const int r = p.ref_len[pair / p.ref_group];
+        const int h = p.hyp_len[pair];
+        const int steps = p.exclude_last ? (h > 0 ? h - 1 : 0) : h;  // SM:286-288
+        if (MODE != LEV_MODE_MASK && lane == 0 && r == 0 && p.norm && p.flags != nullptr)
+            atomicOr(p.flags, B200LEV_FLAG_EMPTY_REF);  // SM:360-366, 397-404
+        const int32_t* __restrict__ htok = p.hyp_tok + (int64_t)pair * p.Hp;
+        for (int i = lane; i < steps; i += 32) hyp_s[32 + i] = htok[i];
+        __syncwarp();
+        const int cols = r + 1;
+        if ((CMASK & 1) && (cols <= 32 || !(CMASK & 14)))
+            lev_warp_pair_all<V, COUNT, MODE, 1>(p, pair, r, h, steps, hyp_s, bufs, Hs);
+        else if ((CMASK & 2) && (cols <= 64 || !(CMASK & 12)))
+            lev_warp_pair_all<V, COUNT, MODE, 2>(p, pair, r, h, steps, hyp_s, bufs, Hs);
+        else if ((CMASK & 4) && (cols <= 128 || !(CMASK & 8)))
+            lev_warp_pair_all<V, COUNT, MODE, 4>(p, pair, r, h, steps, hyp_s, bufs, Hs);
+        else if (CMASK & 8)
+            lev_warp_pair_all<V, COUNT, MODE, 8>(p, pair, r, h, steps, hyp_s, bufs, Hs);
+
+        if (MODE == LEV_MODE_PREFIX) {
+            // SM:279-285 (row 0) and SM:379-386 (tail := padding)
+            const int first_pad = h + (p.exclude_last ? 0 : 1);
+            if (lane == 0 && first_pad > 0 && p.Hout > 0) {
+                const float v0 = COUNT ? (float)r : (float)((V)r * LevArith<V>::del(p));
+                p.out[(int64_t)pair * p.out_sn] = lev_finalize(v0, p, r, false);
+            }
+            for (int i = first_pad + lane; i < p.Hout; i += 32)
+                p.out[(int64_t)i * p.out_si + (int64_t)pair * p.out_sn] = p.padding;
+        }
+        if (MODE == LEV_MODE_MASK) {
+            // SM:271-278: prefix 0 points at ref position 0 whenever the ref is non-empty
+            if (lane == 0 && r > 0 && p.Hout > 0) {
+                const int u = p.uid[(int64_t)(pair / p.ref_group) * p.Rp];
+                atomicOr(p.dbits + (int64_t)pair * p.Wd + (u >> 5), 1u << (u & 31));
+            }
+            // SM:510-511: largest target set of this pair -> global maximum U
+            __threadfence();
+            __syncwarp();
+            int mx = 0;
+            for (int i = lane; i <= steps && i < p.Hout; i += 32) {
+                const uint32_t* row = p.dbits + ((int64_t)i * p.P + pair) * p.Wd;
+                int cnt = 0;
+                for (int w = 0; w < p.Wd; ++w) cnt += __popc(__ldcg(row + w));
+                mx = cnt > mx ? cnt : mx;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int other = __shfl_xor_sync(LEV_FULL_MASK, mx, o);
+                mx = other > mx ? other : mx;
+            }
+            if (lane == 0 && mx > 0) atomicMax(p.umax, mx);
+        }
+        __syncwarp();
+    }
+}
+
+template <typename V, bool COUNT, int MODE, int CMASK>
+static int lev_launch_variant(const LevParams& p, cudaStream_t st) {
+    constexpr int NB = LevBufs<V, COUNT, MODE>::NB;
+    const size_t per_warp = (size_t)(1 + NB) * (size_t)(p.H + 64) * sizeof(int);
+    const size_t budget = 200 * 1024;
+    if (per_warp > budget) {
+        lev_set_error("hypothesis length %d needs %zu bytes of shared memory per warp (max %zu)",
+                      p.H, per_warp, budget);
+        return B200LEV_ERR_UNSUPPORTED;
+    }
+    int wpc = (int)(budget / per_warp);
+    if (wpc > 8) wpc = 8;
+    // keep at least two CTAs per SM resident when the rows are short
+    while (wpc > 1 && per_warp * wpc > 100 * 1024) --wpc;
+    const size_t smem = per_warp * wpc;
+    auto kern = lev_warp_kernel<V, COUNT, MODE, CMASK>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) {
+            lev_set_error("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+            return B200LEV_ERR_CUDA;
+        }
+    }
+    int64_t blocks = ((int64_t)p.P + wpc - 1) / wpc;
+    const int64_t cap = 148 * 64;
+    if (blocks > cap) blocks = cap;
+    lev_launch(kern, dim3((unsigned)blocks), dim3((unsigned)(32 * wpc)), smem, st, p);
+    return lev_check_cuda("lev_warp_kernel");
+}
+
+int lev_launch_dp(const LevParams& p, int mode, bool count_mode, bool float_path,
+                  cudaStream_t st) {
+    if (p.P <= 0) return B200LEV_OK;
+    if (!float_path) {
+        if (!count_mode) {
+            if (mode == LEV_MODE_FINAL) return lev_launch_variant<int, false, LEV_MODE_FINAL, 15>(p, st);
+            if (mode == LEV_MODE_PREFIX) return lev_launch_variant<int, false, LEV_MODE_PREFIX, 15>(p, st);
+            return lev_launch_variant<int, false, LEV_MODE_MASK, 14>(p, st);
+        }
+        if (mode == LEV_MODE_FINAL) return lev_launch_variant<int, true, LEV_MODE_FINAL, 10>(p, st);
+        if (mode == LEV_MODE_PREFIX) return lev_launch_variant<int, true, LEV_MODE_PREFIX, 10>(p, st);
+    } else {
+        if (!count_mode) {
+            if (mode == LEV_MODE_FINAL) return lev_launch_variant<float, false, LEV_MODE_FINAL, 4>(p, st);
+            if (mode == LEV_MODE_PREFIX) return lev_launch_variant<float, false, LEV_MODE_PREFIX, 4>(p, st);
+            return lev_launch_variant<float, false, LEV_MODE_MASK, 4>(p, st);
+        }
+        if (mode == LEV_MODE_FINAL) return lev_launch_variant<float, true, LEV_MODE_FINAL, 4>(p, st);
+        if (mode == LEV_MODE_PREFIX) return lev_launch_variant<float, true, LEV_MODE_PREFIX, 4>(p, st);
+    }
+    lev_set_error("mask mode is defined on the cost row only (SM:479-491)");
+    return B200LEV_ERR_ARG;
+}

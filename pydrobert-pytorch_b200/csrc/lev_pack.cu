@@ -1,0 +1,121 @@
+// lev_pack.cu -- K0: lengths from eos + narrow/transpose tokens into pair-major int32.
+//
+// Replaces SM:137-143 (_lens_from_eos), the include_eos adjustment of SM:195-228 and
+// the transposes of SM:181-183.  One pass over the token tensor: a CTA takes 32
+// sequences, loads 32x32 tiles with the unit-stride axis on threadIdx.x (256-byte
+// coalesced rows for a sequence-first int64 tensor), finds the first eos per
+// sequence with a shared-memory atomicMin, and writes the tile transposed so that
+// every sequence becomes one contiguous int32 row (what the DP kernels and the TMA
+// bulk copies of the long-pair kernel want).
+//
+// HBM traffic: T*N*elem_bytes read + T*N*4 written, both fully coalesced.
+#include "lev_common.cuh"
+
+template <typename TT>
+__global__ void __launch_bounds__(256)
+lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, int64_t sn,
+                int has_eos, int64_t eos, int include_eos, int32_t* __restrict__ packed,
+                int64_t Tp, int32_t* __restrict__ lens, int32_t* flags, int missing_flag,
+                int transposed) {
+    __shared__ int tile[32][33];
+    __shared__ int first[32];
+    __shared__ int blk_flags;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t n0 = (int64_t)blockIdx.x * 32;
+    if (ty == 0) first[tx] = (int)T;
+    if (tx == 0 && ty == 0) blk_flags = 0;
+    __syncthreads();
+    int wide = 0;
+    if (transposed) {
+        for (int64_t t0 = 0; t0 < T; t0 += 32) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int tl = ty + 8 * q;
+                const int64_t t = t0 + tl, n = n0 + tx;
+                if (t < T && n < N) {
+                    const int64_t v = (int64_t)tok[t * st + n * sn];
+                    tile[tl][tx] = (int)v;
+                    if (has_eos && v == eos) atomicMin(&first[tx], (int)t);
+                    if ((int64_t)(int)v != v) wide = 1;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int nl = ty + 8 * q;
+                const int64_t n = n0 + nl, t = t0 + tx;
+                if (t < T && n < N) packed[n * Tp + t] = tile[tx][nl];
+            }
+            __syncthreads();
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int nl = ty + 8 * q;
+            const int64_t n = n0 + nl;
+            if (n < N) {
+                for (int64_t t = tx; t < T; t += 32) {
+                    const int64_t v = (int64_t)tok[t * st + n * sn];
+                    packed[n * Tp + t] = (int)v;
+                    if (has_eos && v == eos) atomicMin(&first[nl], (int)t);
+                    if ((int64_t)(int)v != v) wide = 1;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (wide) atomicOr(&blk_flags, B200LEV_FLAG_WIDE_TOKENS);
+    if (ty == 0 && n0 + tx < N) {
+        int len = first[tx];
+        if (has_eos && include_eos) {  // SM:198-218
+            if (len == (int)T)
+                atomicOr(&blk_flags, missing_flag);
+            else
+                len += 1;
+        }
+        lens[n0 + tx] = len;
+    }
+    __syncthreads();
+    if (tx == 0 && ty == 0 && blk_flags != 0 && flags != nullptr) atomicOr(flags, blk_flags);
+}
+
+int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int include_eos,
+                    int32_t* packed, int64_t Tp, int32_t* lens, int32_t* flags,
+                    int missing_flag, cudaStream_t st) {
+    if (t->N <= 0) return B200LEV_OK;
+    if (t->T >= (int64_t)1 << 30) {
+        lev_set_error("sequence dimension %lld too long", (long long)t->T);
+        return B200LEV_ERR_UNSUPPORTED;
+    }
+    dim3 block(32, 8, 1);
+    dim3 grid((unsigned)((t->N + 31) / 32), 1, 1);
+    // unit stride along the batch axis => transpose through shared memory; otherwise
+    // (batch_first, or an arbitrary view) read along the sequence axis directly.
+    const int transposed = (t->stride_n == 1 && t->stride_t != 1);
+    switch (t->elem_bytes) {
+        case 8:
+            lev_launch(lev_pack_kernel<int64_t>, grid, block, 0, st, (const int64_t*)t->data, t->T,
+                       t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
+                       lens, flags, missing_flag, transposed);
+            break;
+        case 4:
+            lev_launch(lev_pack_kernel<int32_t>, grid, block, 0, st, (const int32_t*)t->data, t->T,
+                       t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
+                       lens, flags, missing_flag, transposed);
+            break;
+        case 2:
+            lev_launch(lev_pack_kernel<int16_t>, grid, block, 0, st, (const int16_t*)t->data, t->T,
+                       t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
+                       lens, flags, missing_flag, transposed);
+            break;
+        case 1:
+            lev_launch(lev_pack_kernel<int8_t>, grid, block, 0, st, (const int8_t*)t->data, t->T,
+                       t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
+                       lens, flags, missing_flag, transposed);
+            break;
+        default:
+            lev_set_error("unsupported token element size %d", (int)t->elem_bytes);
+            return B200LEV_ERR_ARG;
+    }
+    return lev_check_cuda("lev_pack_kernel");
+}

@@ -1,0 +1,29 @@
+// simt.h -- the only place that knows whether the kernels are being compiled by
+// nvcc for sm_100a (the product) or by g++ against tests/emu/emu_cuda.h (kernel-logic
+// tests on a GPU-less box; never shipped, never loaded by the product).
+#pragma once
+
+#ifdef B200LEV_EMU
+// tests/emu/emu_cuda.h was force-included by the test build and supplies the CUDA
+// vocabulary (threadIdx, __shfl_*_sync, __syncthreads, atomics, lev_launch, ...).
+#else
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+template <typename... KArgs, typename... Args>
+static inline void lev_launch(void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t st, Args... args) {
+    k<<<grid, block, smem, st>>>(KArgs(args)...);
+}
+#define LEV_DYN_SMEM(type, name)                                   \
+    extern __shared__ __align__(16) unsigned char name##_raw_[];   \
+    type* name = reinterpret_cast<type*>(name##_raw_)
+#define LEV_SPIN_YIELD() ((void)0)
+#endif
+
+#define LEV_FULL_MASK 0xffffffffu

@@ -1,0 +1,188 @@
+"""Parity checks shared by the CPU (emulated kernels) and GPU (real kernels) suites.
+
+Every check runs the PRODUCT host code (b200lev.functional / modules) and compares
+with either the committed golden fixtures (reference outputs) or the CPU oracle on the
+same seeded inputs.  Bars: bit-exact for integer/dyadic costs (distances, counts,
+prefix tables, completion targets); rtol 1e-6 for non-dyadic costs, normalised rates,
+losses and gradients (stated at each assert).
+"""
+import warnings
+
+import numpy as np
+import torch
+
+from oracle import oracle as O
+
+FLOAT_COSTS = {(0.7, 1.1, 1.3), (0.3, 0.3, 0.3), (1.1, 0.9, 1.7)}
+RTOL_FLOAT = 1e-6  # the north-star tolerance for non-integer costs / normalised values
+
+
+def kw_of(p):
+    return dict(eos=p["eos"], include_eos=p["include_eos"], batch_first=p["batch_first"],
+                ins_cost=p["ins"], del_cost=p["del"], sub_cost=p["sub"])
+
+
+def assert_same(act, exp, exact, what=""):
+    act = act.detach().cpu().numpy() if hasattr(act, "detach") else np.asarray(act)
+    assert act.shape == exp.shape, (what, act.shape, exp.shape)
+    if exact:
+        assert np.array_equal(act, exp), (what, np.abs(act.astype(np.float64) - exp).max())
+    else:
+        np.testing.assert_allclose(act, exp, rtol=RTOL_FLOAT, atol=0, err_msg=what)
+
+
+def check_golden_string_matching(F, dev, golden, names=None):
+    """error_rate / edit_distance / prefix_* / optimal_completion vs reference outputs."""
+    n_checked = 0
+    for case, p in golden.params.items():
+        if names is not None and case not in names:
+            continue
+        exact = (p["ins"], p["del"], p["sub"]) not in FLOAT_COSTS
+        ref = torch.from_numpy(golden.get(case, "ref")).to(dev)
+        hyp = torch.from_numpy(golden.get(case, "hyp")).to(dev)
+        kw = kw_of(p)
+        for func in ("error_rate", "edit_distance"):
+            if golden.has(case, func):
+                act = getattr(F, func)(ref, hyp, norm=p["norm"], warn=False, **kw)
+                assert_same(act, golden.get(case, func), exact, f"{case}.{func}")
+                n_checked += 1
+        for func in ("prefix_error_rates", "prefix_edit_distances"):
+            if golden.has(case, func):
+                act = getattr(F, func)(ref, hyp, norm=p["norm"], padding=p["padding"],
+                                       exclude_last=p["exclude_last"], warn=False, **kw)
+                assert_same(act, golden.get(case, func), exact, f"{case}.{func}")
+                n_checked += 1
+        if golden.has(case, "optimal_completion"):
+            act = F.optimal_completion(ref, hyp, padding=p["padding"],
+                                       exclude_last=p["exclude_last"], warn=False, **kw)
+            assert act.dtype == torch.long
+            assert_same(act, golden.get(case, "optimal_completion"), True, f"{case}.oc")
+            n_checked += 1
+    return n_checked
+
+
+def check_golden_losses(F, dev, golden):
+    n = 0
+    for case, p in golden.params.items():
+        g = golden
+        ref = torch.from_numpy(g.get(case, "ref")).to(dev)
+        hyp = torch.from_numpy(g.get(case, "hyp")).to(dev)
+        go = torch.from_numpy(g.get(case, "grad_output")).to(dev) if g.has(case, "grad_output") else None
+        if case.startswith("ocd"):
+            x = torch.from_numpy(g.get(case, "logits")).to(dev).requires_grad_(True)
+            w = torch.from_numpy(g.get(case, "weight")).to(dev) if p["weight"] else None
+            loss = F.hard_optimal_completion_distillation_loss(
+                x, ref, hyp, eos=p["eos"], include_eos=p["include_eos"],
+                batch_first=p["batch_first"], weight=w, reduction=p["reduction"],
+                ignore_index=p["ignore_index"], warn=False)
+        else:
+            x = torch.from_numpy(g.get(case, "log_probs")).to(dev).requires_grad_(True)
+            loss = F.minimum_error_rate_loss(
+                x, ref, hyp, eos=p["eos"], include_eos=p["include_eos"], sub_avg=p["sub_avg"],
+                batch_first=p["batch_first"], norm=p["norm"], ins_cost=p["ins"],
+                del_cost=p["del"], sub_cost=p["sub"], reduction=p["reduction"], warn=False)
+        assert loss.dtype == x.dtype
+        (grad,) = torch.autograd.grad([loss if go is None else (loss * go).sum()], [x])
+        # fp32 losses/gradients: 1e-6 relative to the scale of the result (two fp32
+        # implementations of a log-sum-exp differ by a few ulps of the largest term)
+        exp_l, exp_g = g.get(case, "loss"), g.get(case, "grad")
+        np.testing.assert_allclose(loss.detach().cpu().numpy(), exp_l, rtol=2e-6,
+                                   atol=2e-6 * max(1.0, float(np.abs(exp_l).max())), err_msg=case)
+        np.testing.assert_allclose(grad.cpu().numpy(), exp_g, rtol=2e-5,
+                                   atol=1e-6 * max(1.0, float(np.abs(exp_g).max())), err_msg=case)
+        n += 1
+    return n
+
+
+def random_tokens(rng, T, N, V, eos, pad, min_len=0, no_eos_frac=0.0):
+    tok = rng.integers(1, max(V, 2), size=(T, N), dtype=np.int64)
+    for n in range(N):
+        if T == 0 or rng.random() < no_eos_frac:
+            continue
+        pos = int(rng.integers(min(min_len, T - 1), T))
+        tok[pos, n] = eos
+        tok[pos + 1:, n] = pad
+    return tok
+
+
+def check_vs_oracle(F, dev, seed, R, H, N, V, costs, eos=0, include_eos=True, norm=False,
+                    batch_first=False, exclude_last=False, padding=-100, min_frac=0.3,
+                    no_eos_frac=0.0, do_mask=True, dtype=torch.long):
+    """All DP-backed functionals on one random batch vs the oracle."""
+    rng = np.random.default_rng(seed)
+    ref = random_tokens(rng, R, N, V, eos if eos is not None else 0, -2, int(R * min_frac), no_eos_frac)
+    hyp = random_tokens(rng, H, N, V, eos if eos is not None else 0, -3, int(H * min_frac), no_eos_frac)
+    if batch_first:
+        ref, hyp = np.ascontiguousarray(ref.T), np.ascontiguousarray(hyp.T)
+    exact = all(float(c) == round(float(c) * 8) / 8 for c in costs)  # dyadic => exact fp32 sums
+    kw = dict(eos=eos, include_eos=include_eos, batch_first=batch_first, ins_cost=costs[0],
+              del_cost=costs[1], sub_cost=costs[2])
+    tr, th = torch.from_numpy(ref).to(dev).to(dtype), torch.from_numpy(hyp).to(dev).to(dtype)
+    for func in ("error_rate", "edit_distance"):
+        exp = getattr(O, func)(ref, hyp, norm=norm, **kw)
+        act = getattr(F, func)(tr, th, norm=norm, warn=False, **kw)
+        assert_same(act, exp, exact and not norm or exact, f"{func} seed={seed}")
+    for func in ("prefix_error_rates", "prefix_edit_distances"):
+        exp = getattr(O, func)(ref, hyp, norm=norm, padding=padding, exclude_last=exclude_last, **kw)
+        act = getattr(F, func)(tr, th, norm=norm, padding=padding, exclude_last=exclude_last,
+                               warn=False, **kw)
+        assert_same(act, exp, exact, f"{func} seed={seed}")
+    if do_mask and exact:
+        exp = O.optimal_completion(ref, hyp, padding=padding, exclude_last=exclude_last, **kw)
+        act = F.optimal_completion(tr, th, padding=padding, exclude_last=exclude_last, warn=False, **kw)
+        assert_same(act, exp, True, f"optimal_completion seed={seed}")
+
+
+def check_warnings(F, dev):
+    """The three data-dependent warnings (SM:175-180, 202-217, 361-366/398-404)."""
+    ref = torch.tensor([[1, 2], [2, 0], [3, 0]], device=dev)  # column 0 has no eos(0)
+    hyp = torch.tensor([[1, 0], [0, 0]], device=dev)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        F.error_rate(ref, hyp, eos=0, include_eos=True, norm=False)
+    assert any("transcription in ref did not" in str(x.message) for x in w)
+    assert not any("transcription in hyp did not" in str(x.message) for x in w)
+    ref = torch.tensor([[0, 1], [0, 0]], device=dev)  # column 0 is an empty ref
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        er = F.error_rate(ref, hyp, eos=0, norm=True)
+        pe = F.prefix_error_rates(ref, hyp, eos=0, include_eos=False, norm=True)
+    msgs = [str(x.message) for x in w]
+    assert any("Error rates for entries will be 1 if any insertion" in m for m in msgs)
+    assert any("0 for prefixes of length 0, 1 otherwise" in m for m in msgs)
+    assert er.tolist()[0] == 1.0  # empty ref, non-empty hyp (SM:405)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        F.error_rate(ref, hyp, eos=0, norm=False, ins_cost=2.0)
+    assert any("non-uniform error rates" in str(x.message) for x in w)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        F.error_rate(ref, hyp, eos=0, norm=True, ins_cost=2.0, warn=False)
+        F.edit_distance(ref, hyp, eos=0, ins_cost=2.0)
+    assert not w
+
+
+def check_errors(F, dev):
+    import pytest
+
+    a = torch.zeros(3, 2, dtype=torch.long, device=dev)
+    with pytest.raises(RuntimeError, match="must be 2 dimensional"):
+        F.error_rate(a[0], a)
+    with pytest.raises(RuntimeError, match="ref has batch size 2, but hyp has 3"):
+        F.error_rate(a, torch.zeros(3, 3, dtype=torch.long, device=dev))
+    with pytest.raises(RuntimeError, match="logits must be 3 dimensional"):
+        F.hard_optimal_completion_distillation_loss(torch.zeros(3, 2, device=dev), a, a)
+    with pytest.raises(RuntimeError, match="first two dims of logits"):
+        F.hard_optimal_completion_distillation_loss(torch.zeros(4, 2, 5, device=dev), a, a)
+    with pytest.raises(RuntimeError, match="must be a class idx"):
+        F.hard_optimal_completion_distillation_loss(torch.zeros(3, 2, 5, device=dev), a, a, eos=7)
+    with pytest.raises(RuntimeError, match="at least two samples"):
+        F.minimum_error_rate_loss(torch.zeros(2, 1, device=dev), a,
+                                  torch.zeros(3, 2, 1, dtype=torch.long, device=dev))
+    with pytest.raises(RuntimeError, match="sample dimensions must match"):
+        F.minimum_error_rate_loss(torch.zeros(2, 3, device=dev), a,
+                                  torch.zeros(3, 2, 4, dtype=torch.long, device=dev))
+    with pytest.raises(RuntimeError, match="not a valid value for reduction"):
+        F.minimum_error_rate_loss(torch.zeros(2, 3, device=dev), a,
+                                  torch.zeros(3, 2, 3, dtype=torch.long, device=dev),
+                                  reduction="bad")

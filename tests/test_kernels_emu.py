@@ -1,0 +1,142 @@
+"""Kernel-logic + host-logic tests on a GPU-less box.
+
+The CUDA sources under pydrobert-pytorch_b200/csrc are compiled against the SIMT
+emulator of tests/emu (every CUDA thread a cooperative fiber; see emu_cuda.h) and the
+unmodified Python host layer drives them through the same C ABI.  What this pins:
+index arithmetic, wavefront skew, strip hand-off, epilogues, flags, the compaction and
+the losses -- against the reference's golden outputs and the oracle.  What it cannot
+pin (memory-model effects, real launch limits) is left to the `-m gpu` suite, which is
+the parity gate proper.
+"""
+import numpy as np
+import pytest
+import torch
+
+import parity_cases as PC
+from emu_backend import emulated_kernels
+
+
+@pytest.fixture(scope="module")
+def F():
+    with emulated_kernels():
+        import b200lev.functional as F_
+
+        yield F_
+
+
+DEV = torch.device("cpu")
+
+
+def test_golden_small_cases(F, golden_sm):
+    names = [n for n in golden_sm.params if n.startswith("s")]
+    assert PC.check_golden_string_matching(F, DEV, golden_sm, names) >= 300
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2r", "cfg3r", "cfg4r", "cfg5r", "cfg5f", "wide", "tall"])
+def test_golden_config_shaped_cases(F, golden_sm, name):
+    assert PC.check_golden_string_matching(F, DEV, golden_sm, [name]) >= 4
+
+
+def test_golden_losses(F, golden_loss):
+    assert PC.check_golden_losses(F, DEV, golden_loss) == 72
+
+
+@pytest.mark.parametrize("costs", [(1, 1, 1), (3, 3, 4), (1, 2, 3), (0.5, 1.0, 0.25), (0.7, 1.1, 1.3)])
+@pytest.mark.parametrize("shape", [(40, 45, 6), (70, 30, 5), (130, 20, 3), (300, 40, 2)])
+def test_random_vs_oracle_strips(F, costs, shape):
+    """Reference lengths on both sides of every strip-width boundary (32/64/128/256
+    columns) so the multi-strip hand-off and every C variant are exercised."""
+    R, H, N = shape
+    PC.check_vs_oracle(F, DEV, seed=R * 1000 + H, R=R, H=H, N=N, V=6, costs=costs,
+                       include_eos=True, norm=True, exclude_last=False, min_frac=0.5)
+
+
+@pytest.mark.parametrize("flags", [
+    dict(include_eos=False, norm=False, batch_first=True, exclude_last=True),
+    dict(include_eos=True, norm=True, batch_first=True, exclude_last=False, no_eos_frac=0.3),
+    dict(include_eos=False, norm=True, batch_first=False, exclude_last=True, eos=None),
+])
+def test_random_vs_oracle_flags(F, flags):
+    for seed, costs in enumerate([(1, 1, 1), (2, 1, 3), (2, 2, 2)]):
+        PC.check_vs_oracle(F, DEV, seed=seed, R=37, H=33, N=7, V=4, costs=costs, min_frac=0.0,
+                           padding=-7, **flags)
+
+
+@pytest.mark.parametrize("dtype", [torch.int32, torch.int16, torch.int8])
+def test_token_dtypes(F, dtype):
+    PC.check_vs_oracle(F, DEV, seed=5, R=20, H=22, N=5, V=9, costs=(1, 1, 1), eos=-1,
+                       include_eos=False, dtype=dtype)
+
+
+def test_n_best_shared_reference(F):
+    """MWER's 2-D ref (SM:1426/1439) is read through ref_group, never repeated."""
+    rng = np.random.default_rng(3)
+    R, H, N, M = 12, 14, 4, 3
+    ref = PC.random_tokens(rng, R, N, 7, 0, -1)
+    hyp = PC.random_tokens(rng, H, N * M, 7, 0, -1).reshape(H, N, M)
+    lp = rng.standard_normal((N, M)).astype(np.float32)
+    from oracle import oracle as O
+
+    exp_loss, exp_grad = O.minimum_error_rate_loss(lp, ref, hyp, eos=0)
+    x = torch.from_numpy(lp).requires_grad_(True)
+    loss = F.minimum_error_rate_loss(x, torch.from_numpy(ref), torch.from_numpy(hyp), eos=0,
+                                     warn=False)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), exp_loss, rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(x.grad.numpy(), exp_grad, rtol=2e-5, atol=1e-7)
+
+
+def test_warnings(F):
+    PC.check_warnings(F, DEV)
+
+
+def test_errors(F):
+    PC.check_errors(F, DEV)
+
+
+def test_sclite(F, golden_sclite):
+    z = golden_sclite
+    ers = F.error_rate(torch.from_numpy(z["ref"]), torch.from_numpy(z["hyp"]), eos=-1,
+                       include_eos=False, norm=False, ins_cost=3.0, del_cost=3.0, sub_cost=4.0,
+                       warn=False).numpy()
+    assert np.array_equal(ers, z["errs"])
+    assert f"{ers.sum() / z['ref_lens'].sum():.03f}" == f"{float(z['total']):.03f}"
+
+
+def test_fill_after_eos(F):
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(0)
+    tok = rng.integers(0, 5, (7, 6, 3))
+    for dim in (0, 1, 2, -1):
+        exp = O.fill_after_eos(tok, 2, dim=dim, fill=-9)
+        act = F.fill_after_eos(torch.from_numpy(tok), 2, dim=dim, fill=-9).numpy()
+        assert np.array_equal(act, exp)
+    val = rng.standard_normal((7, 6, 4)).astype(np.float32)
+    exp = O.fill_after_eos(tok[:, :, :1], 2, value=val)
+    act = F.fill_after_eos(torch.from_numpy(tok[:, :, :1].copy()), 2, value=torch.from_numpy(val))
+    assert np.array_equal(act.numpy(), exp)
+
+
+def test_modules_match_functionals(F):
+    import b200lev.modules as M
+
+    rng = np.random.default_rng(1)
+    ref = torch.from_numpy(PC.random_tokens(rng, 9, 4, 5, 0, -1))
+    hyp = torch.from_numpy(PC.random_tokens(rng, 8, 4, 5, 0, -1))
+    assert torch.equal(M.ErrorRate(eos=0, warn=False)(ref, hyp), F.error_rate(ref, hyp, eos=0, warn=False))
+    assert torch.equal(M.EditDistance(eos=0)(ref, hyp), F.edit_distance(ref, hyp, eos=0))
+    assert torch.equal(M.PrefixErrorRates(eos=0, warn=False)(ref, hyp),
+                       F.prefix_error_rates(ref, hyp, eos=0, warn=False))
+    assert torch.equal(M.PrefixEditDistances(eos=0, padding=-3)(ref, hyp),
+                       F.prefix_edit_distances(ref, hyp, eos=0, padding=-3))
+    assert torch.equal(M.OptimalCompletion(eos=0)(ref, hyp), F.optimal_completion(ref, hyp, eos=0))
+    assert "eos=0" in repr(M.ErrorRate(eos=0))
+    with pytest.raises(ValueError, match="eos .* is not an int"):
+        M.ErrorRate(eos="a")
+    with pytest.raises(ValueError, match="is not one of"):
+        M.MinimumErrorRateLoss(reduction="bad")
+    logits = torch.randn(8, 4, 5, requires_grad=True)
+    loss = M.HardOptimalCompletionDistillationLoss(eos=0)(logits, ref, hyp)
+    loss.backward()
+    assert torch.isfinite(loss) and logits.grad.abs().sum() > 0
