@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline metric on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): edit-distance cell-updates/s (GCUPS), cells = sum over pairs of
+ref_len * hyp_len on the valid (eos-terminated) lengths; N-best hyps/s is reported
+beside it.  Workload (BASELINE.json configs[1], "MinimumErrorRateLoss /
+prefix_error_rates: batch 64 x 8-best word hyps, T=100, vocab 10k"): the per-pair shape
+is the named one; the batch is replicated to 16384 utterances x 8-best = 131072 pairs
+per GPU so the chip is full and the inputs (212 MB int64) exceed the 126 MB L2
+(SURVEY 8d-iii).  The literal 64 x 8 batch is timed too and reported under "literal".
+
+A step = one `prefix_error_rates(ref (x) 8, hyp, eos=0)` call = 3 kernel launches
+(pack ref, pack hyp, wavefront DP with the prefix epilogue).
+
+  value     device-resident inputs, CUDA events, max over ranks (whole job, all GPUs)
+  e2e       the same public call with HOST (pinned) int64 tensors: H2D of the inputs and
+            D2H of the (H+1, N) result inside the timed region
+  roofline  the DP kernel alone (b200lev_prefix_packed) timed with CUDA events:
+            achieved = cells/s x 5 INT32 ops against the INT32 issue rate
+            measured live by the library's microbenchmark kernel
+  cpu_baseline  the oracle port (C, OpenMP) on the box's host cores, same workload
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "pydrobert-pytorch_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+T_LEN, V, NBEST = 100, 10000, 8
+OPS_PER_CELL = 5  # compare, select/add, add, add, 3-input min
+
+
+def make_batch(n_utts, seed):
+    """cfg2 synthetic batch: ref (T+1, n_utts), hyp (T+1, n_utts*8) int64; len ~ U{50..100}
+    with one eos(0) at len-1, tail = 0 (eos-padded); hyps independent of refs."""
+    rng = np.random.default_rng(seed)
+    T = T_LEN + 1
+
+    def seqs(n):
+        tok = rng.integers(1, V, size=(T, n), dtype=np.int64)
+        lens = rng.integers(50, T_LEN + 1, size=n)
+        pos = np.arange(T)[:, None]
+        tok[pos >= (lens - 1)[None, :]] = 0
+        return tok, lens
+
+    ref, rl = seqs(n_utts)
+    hyp, hl = seqs(n_utts * NBEST)
+    # include_eos=True: valid lengths include the eos token
+    cells = int((np.repeat(rl, NBEST).astype(np.int64) * hl.astype(np.int64)).sum())
+    return ref, hyp, cells
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(ref, hyp, cells, min_seconds=3.0, max_runs=5):
+    """The oracle port on the host cores (all OpenMP threads), same call, same tensors."""
+    from oracle import oracle as O
+
+    refx = np.repeat(ref, NBEST, axis=1)
+    O.prefix_error_rates(refx[:, :64], hyp[:, :64], eos=0)  # build + warm
+    best, runs, t_total = None, 0, 0.0
+    while runs < max_runs and (runs < 2 or t_total < min_seconds):
+        t0 = time.perf_counter()
+        O.prefix_error_rates(refx, hyp, eos=0)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        t_total += dt
+        runs += 1
+    return {"value": cells / best / 1e9, "unit": "GCUPS", "cores": O.num_threads(),
+            "kind": "port",
+            "sample": f"{hyp.shape[1]} pairs of the same workload, best of {runs} "
+                      f"({best * 1e3:.1f} ms); oracle/lev_oracle.c, OpenMP over pairs",
+            "pairs_per_s": hyp.shape[1] / best}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port
+    (the reference itself is pure Python on torch CPU ops and cannot travel to the box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_utts = 2048  # bounded sample: 16384 pairs of the same per-pair shape
+    ref, hyp, cells = make_batch(n_utts, seed=3)
+    from oracle import oracle as O
+
+    refx = np.repeat(ref, NBEST, axis=1)
+    O.prefix_error_rates(refx[:, :64], hyp[:, :64], eos=0)
+    for _ in range(max(args.warmup, 1)):
+        O.prefix_error_rates(refx, hyp, eos=0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.prefix_error_rates(refx, hyp, eos=0)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = cells / dt / 1e9
+    line = {
+        "impl": "reference", "metric": "edit-distance cell-updates/s", "value": val,
+        "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2 prefix_error_rates N-best: 8-best word hyps, T=100, "
+                               "vocab 10k; bounded sample of 2048 utterances x 8 = 16384 pairs",
+                   "pairs": int(hyp.shape[1]), "T": T_LEN, "nbest": NBEST, "vocab": V},
+        "hyps_per_s": hyp.shape[1] / dt,
+        "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": O.num_threads(), "kind": "port",
+                         "sample": "16384 pairs per step; oracle/lev_oracle.c, OpenMP over pairs"},
+        "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--utts", type=int, default=16384, help="utterances per GPU (x8-best)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import b200lev.functional as F
+    from b200lev import _abi, _ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _abi.lib()
+
+    ref_np, hyp_np, cells = make_batch(args.utts, seed=100 + rank)
+    refx_np = np.repeat(ref_np, NBEST, axis=1)
+    ref = torch.from_numpy(refx_np).to(dev)
+    hyp = torch.from_numpy(hyp_np).to(dev)
+    P = hyp.shape[1]
+    in_bytes = ref.numel() * 8 + hyp.numel() * 8
+
+    def step():
+        return F.prefix_error_rates(ref, hyp, eos=0, warn=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident, whole public call ------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline: the DP kernel alone, and the pack kernels alone ---------------------
+    rt, ht = _ops._tok_struct(ref, False), _ops._tok_struct(hyp, False)
+    o = _ops._opts(0, True, 1.0, 1.0, 1.0, True, False, -100, True, 1)
+    nbytes = L.b200lev_workspace_bytes(ctypes.byref(rt), ctypes.byref(ht), 0, 0)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    outp = torch.empty((T_LEN + 2, P), dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def pack_only():
+        _abi.check(L.b200lev_pack(ctypes.byref(rt), ctypes.byref(ht), ctypes.byref(o),
+                                  ws.data_ptr(), nbytes, None, st))
+
+    def dp_only():
+        _abi.check(L.b200lev_prefix_packed(ctypes.byref(rt), ctypes.byref(ht), ctypes.byref(o),
+                                           outp.data_ptr(), P, 1, ws.data_ptr(), nbytes, None, st))
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    pack_only()
+    ms_pack = timed(pack_only, args.steps)
+    ms_dp = timed(dp_only, args.steps)
+    assert torch.equal(outp, out), "packed DP path disagrees with the public call"
+
+    # INT32 issue-rate peak, measured live (variant 2 = VIADDMNMX, 0 = IADD3, 3 = DP cell mix)
+    sink = torch.zeros(4, dtype=torch.int32, device=dev)
+    peaks = {}
+    for name, var in (("iadd3", 0), ("viaddmnmx", 2), ("dp_cell_mix", 3)):
+        ops = ctypes.c_double(0)
+
+        def k(var=var):
+            _abi.check(L.b200lev_int32_peak_kernel(var, 148 * 8, 4096, sink.data_ptr(),
+                                                   ctypes.byref(ops), st))
+
+        t = timed(k, 5)
+        peaks[name] = ops.value / (t * 1e-3) / 1e12  # T int32-op/s
+    int32_peak = max(peaks["iadd3"], peaks["viaddmnmx"])
+
+    # ---- e2e: host (pinned) tensors through the public API -----------------------------
+    ref_h = torch.from_numpy(refx_np).pin_memory()
+    hyp_h = torch.from_numpy(hyp_np).pin_memory()
+    for _ in range(2):
+        F.prefix_error_rates(ref_h, hyp_h, eos=0, warn=False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(e2e_steps):
+        res = F.prefix_error_rates(ref_h, hyp_h, eos=0, warn=False)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / e2e_steps
+    assert res.device.type == "cpu"
+
+    # ---- literal BASELINE shape (64 x 8): latency of the public call --------------------
+    lref_np, lhyp_np, lcells = make_batch(64, seed=7)
+    lref = torch.from_numpy(np.repeat(lref_np, NBEST, axis=1)).to(dev)
+    lhyp = torch.from_numpy(lhyp_np).to(dev)
+    ms_lit = timed(lambda: F.prefix_error_rates(lref, lhyp, eos=0, warn=False), 50)
+
+    # ---- reduce over ranks ---------------------------------------------------------------
+    stats = torch.tensor([ms, ms_e2e, ms_dp, ms_pack], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(cells), float(P)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms, ms_e2e, ms_dp_max, ms_pack_max = stats.tolist()
+    cells_all, pairs_all = tot.tolist()
+
+    if rank == 0:
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        if os.path.exists(peaks_file):
+            hbm_peak, hbm_src = json.load(open(peaks_file))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+        achieved_ops = cells / (ms_dp * 1e-3) * OPS_PER_CELL / 1e12
+        pack_gbs = (in_bytes + in_bytes // 2) / (ms_pack * 1e-3) / 1e9
+        line = {
+            "metric": "edit-distance cell-updates/s", "value": cells_all / (ms * 1e-3) / 1e9,
+            "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "cfg2 prefix_error_rates N-best (8-best word hyps, T=100, vocab "
+                                   "10k, include_eos, norm), batch replicated to "
+                                   f"{args.utts} utts x 8 = {P} pairs per GPU",
+                       "pairs_per_gpu": P, "T": T_LEN, "nbest": NBEST, "vocab": V,
+                       "cells_per_gpu": cells,
+                       "l2": f"inputs {in_bytes / 1e6:.0f} MB per step exceed the 126 MB L2"},
+            "hyps_per_s": pairs_all / (ms * 1e-3),
+            "e2e": {"value": cells_all / (ms_e2e * 1e-3) / 1e9, "unit": "GCUPS",
+                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": int(outp.numel() * 4),
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": 3 * args.steps,
+            "roofline": {"bound": "int32_issue", "kernel": "lev_warp_kernel<int,cost,PREFIX>",
+                         "achieved": achieved_ops, "peak": int32_peak, "unit": "Tint32op/s",
+                         "frac": achieved_ops / int32_peak, "traffic": None,
+                         "ops_per_cell": OPS_PER_CELL, "kernel_ms": ms_dp,
+                         "kernel_gcups": cells / (ms_dp * 1e-3) / 1e9,
+                         "peak_source": "measured live: b200lev_int32_peak_kernel "
+                                        f"{ {k: round(v, 2) for k, v in peaks.items()} }"},
+            "roofline_pack": {"bound": "hbm", "kernel": "lev_pack_kernel<int64> x2",
+                              "achieved": pack_gbs, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": pack_gbs / hbm_peak, "kernel_ms": ms_pack,
+                              "peak_source": hbm_src},
+            "literal": {"workload": "64 utts x 8-best = 512 pairs (BASELINE configs[1] as written)",
+                        "ms_per_call": ms_lit, "gcups": lcells / (ms_lit * 1e-3) / 1e9,
+                        "hyps_per_s": 512 / (ms_lit * 1e-3)},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(ref_np, hyp_np, cells)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

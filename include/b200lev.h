@@ -104,6 +104,26 @@ int b200lev_prefix(const b200lev_tokens_t *ref, const b200lev_tokens_t *hyp,
                    int32_t *flags, void *stream);
 
 /*
+ * The two halves of b200lev_final / b200lev_prefix, exposed separately so that a caller
+ * can keep tokens packed across calls or time the DP kernel on its own (bench.py):
+ *   b200lev_pack            K0 only: lengths (SM:137-143, 195-228) + pair-major int32
+ *                           token tables into the workspace;
+ *   b200lev_prefix_packed   the DP + prefix epilogue on a workspace b200lev_pack filled
+ *                           (ref/hyp are read for their shapes only);
+ *   b200lev_final_packed    likewise for the final value.
+ */
+int b200lev_pack(const b200lev_tokens_t *ref, const b200lev_tokens_t *hyp,
+                 const b200lev_opts_t *opts, void *workspace, size_t workspace_bytes,
+                 int32_t *flags, void *stream);
+int b200lev_prefix_packed(const b200lev_tokens_t *ref, const b200lev_tokens_t *hyp,
+                          const b200lev_opts_t *opts, float *out, int64_t out_stride_i,
+                          int64_t out_stride_n, void *workspace, size_t workspace_bytes,
+                          int32_t *flags, void *stream);
+int b200lev_final_packed(const b200lev_tokens_t *ref, const b200lev_tokens_t *hyp,
+                         const b200lev_opts_t *opts, float *out, void *workspace,
+                         size_t workspace_bytes, int32_t *flags, void *stream);
+
+/*
  * optimal_completion (SM:464-517), two phases around the one host read the
  * reference also needs (SM:511: U = counts.max().item()).
  *   phase 1 runs the DP in mask mode (SM:271-278, 319-339, 347-355), leaves the

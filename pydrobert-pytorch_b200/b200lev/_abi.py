@@ -49,6 +49,10 @@ SIGNATURES = {
     "b200lev_workspace_bytes": (c_sz, [_PT, _PT, c_i32, c_i32]),
     "b200lev_final": (ctypes.c_int, [_PT, _PT, _PO, c_vp, c_vp, c_sz, c_vp, c_vp]),
     "b200lev_prefix": (ctypes.c_int, [_PT, _PT, _PO, c_vp, c_i64, c_i64, c_vp, c_sz, c_vp, c_vp]),
+    "b200lev_pack": (ctypes.c_int, [_PT, _PT, _PO, c_vp, c_sz, c_vp, c_vp]),
+    "b200lev_prefix_packed": (ctypes.c_int, [_PT, _PT, _PO, c_vp, c_i64, c_i64, c_vp, c_sz, c_vp,
+                                             c_vp]),
+    "b200lev_final_packed": (ctypes.c_int, [_PT, _PT, _PO, c_vp, c_vp, c_sz, c_vp, c_vp]),
     "b200lev_completion_count": (ctypes.c_int, [_PT, _PT, _PO, c_vp, c_sz, c_vp, c_vp, c_vp]),
     "b200lev_completion_fill": (ctypes.c_int, [_PT, _PT, _PO, c_vp, c_sz, c_i64, c_vp, c_i64,
                                                c_i64, c_vp]),

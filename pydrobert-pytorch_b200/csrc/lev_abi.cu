@@ -119,17 +119,19 @@ static void lev_classify_costs(const b200lev_opts_t* o, int64_t R, int64_t H, Le
 // pack both token tensors into the workspace and fill the common fields of `p`
 static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
                        const b200lev_opts_t* o, const LevLayout& L, char* ws, int32_t* flags,
-                       cudaStream_t st, LevParams* p) {
+                       cudaStream_t st, LevParams* p, bool do_pack = true) {
     int32_t* ref_tok = (int32_t*)(ws + L.off_ref_tok);
     int32_t* hyp_tok = (int32_t*)(ws + L.off_hyp_tok);
     int32_t* ref_len = (int32_t*)(ws + L.off_ref_len);
     int32_t* hyp_len = (int32_t*)(ws + L.off_hyp_len);
-    int rc = lev_launch_pack(ref, o->has_eos, o->eos, o->include_eos, ref_tok, L.Rp, ref_len, flags,
-                             B200LEV_FLAG_REF_NO_EOS, st);
-    if (rc) return rc;
-    rc = lev_launch_pack(hyp, o->has_eos, o->eos, o->include_eos, hyp_tok, L.Hp, hyp_len, flags,
-                         B200LEV_FLAG_HYP_NO_EOS, st);
-    if (rc) return rc;
+    if (do_pack) {
+        int rc = lev_launch_pack(ref, o->has_eos, o->eos, o->include_eos, ref_tok, L.Rp, ref_len,
+                                 flags, B200LEV_FLAG_REF_NO_EOS, st);
+        if (rc) return rc;
+        rc = lev_launch_pack(hyp, o->has_eos, o->eos, o->include_eos, hyp_tok, L.Hp, hyp_len, flags,
+                             B200LEV_FLAG_HYP_NO_EOS, st);
+        if (rc) return rc;
+    }
     memset(p, 0, sizeof(*p));
     p->ref_tok = ref_tok;
     p->hyp_tok = hyp_tok;
@@ -148,9 +150,9 @@ static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     return B200LEV_OK;
 }
 
-extern "C" int b200lev_final(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
-                             const b200lev_opts_t* opts, float* out, void* workspace,
-                             size_t workspace_bytes, int32_t* flags, void* stream) {
+static int lev_final_impl(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                          const b200lev_opts_t* opts, float* out, void* workspace,
+                          size_t workspace_bytes, int32_t* flags, void* stream, bool do_pack) {
     int rc = lev_check_tokens(ref, hyp, opts);
     if (rc) return rc;
     if (hyp->N == 0) return B200LEV_OK;
@@ -167,7 +169,7 @@ extern "C" int b200lev_final(const b200lev_tokens_t* ref, const b200lev_tokens_t
     LevParams p;
     b200lev_opts_t o = *opts;
     o.exclude_last = 0;  // SM:165
-    rc = lev_prepare(ref, hyp, &o, L, lev_ws_base(workspace), flags, st, &p);
+    rc = lev_prepare(ref, hyp, &o, L, lev_ws_base(workspace), flags, st, &p, do_pack);
     if (rc) return rc;
     bool cm, fp;
     lev_classify_costs(&o, L.R, L.H, &p, &cm, &fp);
@@ -175,10 +177,37 @@ extern "C" int b200lev_final(const b200lev_tokens_t* ref, const b200lev_tokens_t
     return lev_launch_dp(p, LEV_MODE_FINAL, cm, fp, st);
 }
 
-extern "C" int b200lev_prefix(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
-                              const b200lev_opts_t* opts, float* out, int64_t out_stride_i,
-                              int64_t out_stride_n, void* workspace, size_t workspace_bytes,
-                              int32_t* flags, void* stream) {
+extern "C" int b200lev_final(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                             const b200lev_opts_t* opts, float* out, void* workspace,
+                             size_t workspace_bytes, int32_t* flags, void* stream) {
+    return lev_final_impl(ref, hyp, opts, out, workspace, workspace_bytes, flags, stream, true);
+}
+
+extern "C" int b200lev_final_packed(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                                    const b200lev_opts_t* opts, float* out, void* workspace,
+                                    size_t workspace_bytes, int32_t* flags, void* stream) {
+    return lev_final_impl(ref, hyp, opts, out, workspace, workspace_bytes, flags, stream, false);
+}
+
+extern "C" int b200lev_pack(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                            const b200lev_opts_t* opts, void* workspace, size_t workspace_bytes,
+                            int32_t* flags, void* stream) {
+    int rc = lev_check_tokens(ref, hyp, opts);
+    if (rc) return rc;
+    if (hyp->N == 0) return B200LEV_OK;
+    const LevLayout L = lev_layout(ref, hyp, 0, 0);
+    if (!workspace || workspace_bytes < L.bytes + 128) {
+        lev_set_error("workspace too small: %zu < %zu", workspace_bytes, L.bytes + 128);
+        return B200LEV_ERR_WORKSPACE;
+    }
+    LevParams p;
+    return lev_prepare(ref, hyp, opts, L, lev_ws_base(workspace), flags, (cudaStream_t)stream, &p, true);
+}
+
+static int lev_prefix_impl(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                           const b200lev_opts_t* opts, float* out, int64_t out_stride_i,
+                           int64_t out_stride_n, void* workspace, size_t workspace_bytes,
+                           int32_t* flags, void* stream, bool do_pack) {
     int rc = lev_check_tokens(ref, hyp, opts);
     if (rc) return rc;
     const LevLayout L = lev_layout(ref, hyp, 0, opts->exclude_last);
@@ -193,7 +222,7 @@ extern "C" int b200lev_prefix(const b200lev_tokens_t* ref, const b200lev_tokens_
     }
     cudaStream_t st = (cudaStream_t)stream;
     LevParams p;
-    rc = lev_prepare(ref, hyp, opts, L, lev_ws_base(workspace), flags, st, &p);
+    rc = lev_prepare(ref, hyp, opts, L, lev_ws_base(workspace), flags, st, &p, do_pack);
     if (rc) return rc;
     bool cm, fp;
     lev_classify_costs(opts, L.R, L.H, &p, &cm, &fp);
@@ -202,6 +231,22 @@ extern "C" int b200lev_prefix(const b200lev_tokens_t* ref, const b200lev_tokens_
     p.out_sn = out_stride_n;
     p.Hout = (int)L.Hout;
     return lev_launch_dp(p, LEV_MODE_PREFIX, cm, fp, st);
+}
+
+extern "C" int b200lev_prefix(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                              const b200lev_opts_t* opts, float* out, int64_t out_stride_i,
+                              int64_t out_stride_n, void* workspace, size_t workspace_bytes,
+                              int32_t* flags, void* stream) {
+    return lev_prefix_impl(ref, hyp, opts, out, out_stride_i, out_stride_n, workspace,
+                           workspace_bytes, flags, stream, true);
+}
+
+extern "C" int b200lev_prefix_packed(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                                     const b200lev_opts_t* opts, float* out, int64_t out_stride_i,
+                                     int64_t out_stride_n, void* workspace, size_t workspace_bytes,
+                                     int32_t* flags, void* stream) {
+    return lev_prefix_impl(ref, hyp, opts, out, out_stride_i, out_stride_n, workspace,
+                           workspace_bytes, flags, stream, false);
 }
 
 extern "C" int b200lev_completion_count(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,

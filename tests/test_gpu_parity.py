@@ -1,0 +1,274 @@
+"""Parity tests proper: the sm_100a kernels, called through the C ABI by the product
+host code, against the reference's golden outputs and the CPU oracle.
+
+Bars (stated again at the asserts in parity_cases.py): bit-exact for integer / dyadic
+costs -- distances, counts, prefix tables, completion targets; rtol 1e-6 for
+non-dyadic costs; 2e-6 / 2e-5 relative (with an absolute floor of 1e-6 x scale) for
+fp32 losses / gradients.  Nothing here reads /root/reference.
+"""
+import numpy as np
+import pytest
+import torch
+
+import parity_cases as PC
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def F():
+    import b200lev.functional as F_
+    from b200lev import _abi
+
+    assert not _abi.EMULATED
+    _abi.lib()  # fail loudly if the CUDA library is missing
+    return F_
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+def test_library_is_the_cuda_build(F):
+    from b200lev import _abi
+
+    assert _abi.lib().b200lev_device_count() >= 1
+    with pytest.raises(_abi.B200LevError, match="no CPU fallback"):
+        from b200lev import _ops
+
+        _ops.string_matching(torch.zeros(2, 2, dtype=torch.long), torch.zeros(2, 2, dtype=torch.long),
+                             None, False, False, 1.0, 1.0, 1.0, False, False, False, 0, False, 1)
+
+
+def test_golden_string_matching(F, dev, golden_sm):
+    assert PC.check_golden_string_matching(F, dev, golden_sm) >= 340
+
+
+def test_golden_losses(F, dev, golden_loss):
+    assert PC.check_golden_losses(F, dev, golden_loss) == 72
+
+
+def test_sclite(F, dev, golden_sclite):
+    z = golden_sclite
+    ers = F.error_rate(torch.from_numpy(z["ref"]).to(dev), torch.from_numpy(z["hyp"]).to(dev),
+                       eos=-1, include_eos=False, norm=False, ins_cost=3.0, del_cost=3.0,
+                       sub_cost=4.0, warn=False).cpu().numpy()
+    assert np.array_equal(ers, z["errs"])
+    assert f"{ers.sum() / z['ref_lens'].sum():.03f}" == f"{float(z['total']):.03f}"
+
+
+@pytest.mark.parametrize("costs", [(1, 1, 1), (3, 3, 4), (1, 2, 3), (0.5, 1.0, 0.25), (0.7, 1.1, 1.3)])
+@pytest.mark.parametrize("shape", [(31, 33, 40), (40, 45, 33), (70, 30, 17), (130, 100, 9),
+                                   (300, 260, 5), (700, 90, 3)])
+def test_random_vs_oracle(F, dev, costs, shape):
+    R, H, N = shape
+    PC.check_vs_oracle(F, dev, seed=R * 1000 + H, R=R, H=H, N=N, V=6, costs=costs,
+                       include_eos=True, norm=True, min_frac=0.4)
+
+
+@pytest.mark.parametrize("flags", [
+    dict(include_eos=False, norm=False, batch_first=True, exclude_last=True),
+    dict(include_eos=True, norm=True, batch_first=True, exclude_last=False, no_eos_frac=0.3),
+    dict(include_eos=False, norm=True, batch_first=False, exclude_last=True, eos=None),
+    dict(include_eos=True, norm=False, batch_first=False, exclude_last=True, eos=-1),
+])
+def test_random_vs_oracle_flags(F, dev, flags):
+    for seed, costs in enumerate([(1, 1, 1), (2, 1, 3), (2, 2, 2), (0.25, 0.5, 0.5)]):
+        PC.check_vs_oracle(F, dev, seed=seed, R=37, H=33, N=65, V=4, costs=costs, min_frac=0.0,
+                           padding=-7, **flags)
+
+
+@pytest.mark.parametrize("dtype", [torch.int32, torch.int16, torch.int8])
+def test_token_dtypes(F, dev, dtype):
+    PC.check_vs_oracle(F, dev, seed=5, R=20, H=22, N=50, V=9, costs=(1, 1, 1), eos=-1,
+                       include_eos=False, dtype=dtype)
+
+
+def test_empty_and_degenerate_shapes(F, dev):
+    z = torch.zeros((0, 3), dtype=torch.long, device=dev)
+    h = torch.tensor([[1, 2, 3], [2, 2, 2]], device=dev)
+    assert F.edit_distance(z, h).tolist() == [2.0, 2.0, 2.0]       # empty ref: all insertions
+    assert F.edit_distance(h, z).tolist() == [2.0, 2.0, 2.0]       # empty hyp: all deletions
+    assert F.error_rate(z, h, warn=False).tolist() == [1.0, 1.0, 1.0]  # SM:405
+    assert F.error_rate(z, z, warn=False).tolist() == [0.0, 0.0, 0.0]
+    assert F.prefix_edit_distances(h, z).shape == (1, 3)
+    assert F.edit_distance(h[:, :0], h[:, :0]).shape == (0,)
+    oc = F.optimal_completion(h, z)
+    assert oc.shape[:2] == (1, 3) and oc[0, :, 0].tolist() == [1, 2, 3]
+
+
+def test_cfg1_error_rate(F, dev):
+    """BASELINE config 1: batch 32, T~50, vocab 30, eos-padded, unit costs."""
+    rng = np.random.default_rng(1)
+    ref = PC.random_tokens(rng, 51, 32, 30, 0, 0, min_len=24)
+    hyp = PC.random_tokens(rng, 51, 32, 30, 0, 0, min_len=24)
+    exp = O.error_rate(ref, hyp, eos=0)
+    act = F.error_rate(torch.from_numpy(ref).to(dev), torch.from_numpy(hyp).to(dev), eos=0, warn=False)
+    PC.assert_same(act, exp, True, "cfg1")
+
+
+def test_cfg2_prefix_and_mwer(F, dev):
+    """BASELINE config 2: 64 x 8-best word hyps, T=100, vocab 10k, bf16 log-probs."""
+    rng = np.random.default_rng(2)
+    N, M, T, V = 64, 8, 101, 10000
+    ref = PC.random_tokens(rng, T, N, V, 0, 0, min_len=49)
+    hyp = PC.random_tokens(rng, T, N * M, V, 0, 0, min_len=49)
+    # make the hyps noisy copies of the refs half of the time so that distances vary
+    for n in range(0, N * M, 2):
+        r = ref[:, n // M]
+        keep = rng.random(T) > 0.1
+        hyp[:, n] = np.where(keep, r, hyp[:, n])
+    refx = np.repeat(ref, M, axis=1)
+    exp = O.prefix_error_rates(refx, hyp, eos=0)
+    act = F.prefix_error_rates(torch.from_numpy(refx).to(dev), torch.from_numpy(hyp).to(dev), eos=0,
+                               warn=False)
+    PC.assert_same(act, exp, True, "cfg2 prefix_error_rates")
+    lp = rng.standard_normal((N, M)).astype(np.float32)
+    exp_loss, exp_grad = O.minimum_error_rate_loss(lp, ref, hyp.reshape(T, N, M), eos=0)
+    for dtype, rtol in ((torch.float32, 2e-6), (torch.bfloat16, 2e-2)):
+        x = torch.from_numpy(lp).to(dev).to(dtype).requires_grad_(True)
+        if dtype != torch.float32:
+            exp_loss, exp_grad = O.minimum_error_rate_loss(x.detach().float().cpu().numpy(), ref,
+                                                           hyp.reshape(T, N, M), eos=0)
+        loss = F.minimum_error_rate_loss(x, torch.from_numpy(ref).to(dev),
+                                         torch.from_numpy(hyp.reshape(T, N, M)).to(dev), eos=0,
+                                         warn=False)
+        assert loss.dtype == torch.float32  # fp32 for fp32/bf16 inputs
+        loss.backward()
+        assert x.grad.dtype == dtype
+        np.testing.assert_allclose(loss.item(), exp_loss, rtol=rtol, atol=rtol * 1e-1)
+        np.testing.assert_allclose(x.grad.float().cpu().numpy(), exp_grad, rtol=rtol * 10,
+                                   atol=rtol * float(np.abs(exp_grad).max()))
+
+
+def test_cfg3_completion_and_ocd(F, dev):
+    """BASELINE config 3: batch 128 char seqs, T=200, V=32, include_eos."""
+    rng = np.random.default_rng(3)
+    N, T, V = 128, 201, 32
+    ref = PC.random_tokens(rng, T, N, V, 0, 0, min_len=99)
+    hyp = PC.random_tokens(rng, T, N, V, 0, 0, min_len=99)
+    for n in range(0, N, 2):  # noisy copies: realistic (sparse) target sets
+        keep = rng.random(T) > 0.1
+        hyp[:, n] = np.where(keep, ref[:, n], hyp[:, n])
+    exp = O.optimal_completion(ref, hyp, eos=0)
+    tr, th = torch.from_numpy(ref).to(dev), torch.from_numpy(hyp).to(dev)
+    act = F.optimal_completion(tr, th, eos=0, warn=False)
+    PC.assert_same(act, exp, True, "cfg3 optimal_completion")
+    logits = rng.standard_normal((T, N, V)).astype(np.float32)
+    for reduction in ("mean", "none"):
+        exp_loss, exp_grad = O.hard_optimal_completion_distillation_loss(
+            logits, ref, hyp, eos=0, reduction=reduction, ignore_index=-100)
+        x = torch.from_numpy(logits).to(dev).requires_grad_(True)
+        loss = F.hard_optimal_completion_distillation_loss(x, tr, th, eos=0, reduction=reduction,
+                                                           ignore_index=-100, warn=False)
+        (g,) = torch.autograd.grad([loss.sum()], [x])
+        np.testing.assert_allclose(loss.detach().cpu().numpy(), exp_loss, rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(g.cpu().numpy(), exp_grad, rtol=2e-5,
+                                   atol=1e-6 * float(np.abs(exp_grad).max()))
+
+
+def test_cfg4_bulk_slice_and_sums(F, dev):
+    """BASELINE config 4 on a 100k-pair slice, plus the fp64 device accumulators."""
+    from b200lev import dist as D
+
+    rng = np.random.default_rng(4)
+    P, T, V = 100_000, 31, 10000
+    ref = PC.random_tokens(rng, T, P, V, -1, -2, min_len=9)
+    hyp = PC.random_tokens(rng, T, P, V, -1, -2, min_len=9)
+    exp = O.error_rate(ref, hyp, eos=-1, include_eos=False, norm=False)
+    er, acc = D.bulk_error_rate(torch.from_numpy(ref).to(dev), torch.from_numpy(hyp).to(dev), eos=-1)
+    PC.assert_same(er, exp, True, "cfg4 slice")
+    ref_lens = (ref == -1).argmax(0)
+    assert acc.tolist() == [float(exp.astype(np.float64).sum()), float(ref_lens.sum()), float(P)]
+
+
+def test_cfg5_long_nonunit_costs(F, dev):
+    """BASELINE config 5 shape (T=2000, ragged, NIST costs 3/3/4) on 24 pairs, and the
+    secondary float-cost run at 1e-6."""
+    rng = np.random.default_rng(5)
+    N, T, V = 24, 2001, 64
+    ref = PC.random_tokens(rng, T, N, V, 0, 0, min_len=199)
+    hyp = PC.random_tokens(rng, T, N, V, 0, 0, min_len=199)
+    tr, th = torch.from_numpy(ref).to(dev), torch.from_numpy(hyp).to(dev)
+    for func in ("prefix_edit_distances", "prefix_error_rates"):
+        exp = getattr(O, func)(ref, hyp, eos=0, ins_cost=3, del_cost=3, sub_cost=4)
+        act = getattr(F, func)(tr, th, eos=0, ins_cost=3, del_cost=3, sub_cost=4, warn=False)
+        PC.assert_same(act, exp, True, func)
+    exp = O.prefix_edit_distances(ref[:600, :6], hyp[:600, :6], eos=0, ins_cost=0.7, del_cost=1.1,
+                                  sub_cost=1.3)
+    act = F.prefix_edit_distances(tr[:600, :6], th[:600, :6], eos=0, ins_cost=0.7, del_cost=1.1,
+                                  sub_cost=1.3)
+    PC.assert_same(act, exp, False, "cfg5 float costs")
+
+
+def test_full_size_properties(F, dev):
+    """1M pairs (config 4 size): size-independent properties instead of the oracle."""
+    g = torch.Generator(device="cpu").manual_seed(9)
+    P, T, V = 1_000_000, 31, 10000
+    lens = torch.randint(10, 31, (P,), generator=g)
+    tok = torch.randint(1, V, (T, P), generator=g)
+    pos = torch.arange(T).unsqueeze(1)
+    ref = torch.where(pos < lens, tok, torch.where(pos == lens, -1, -2)).to(dev)
+    perm = torch.randperm(P, generator=g).to(dev)
+    hyp = ref[:, perm]
+    # identity: d(x, x) = 0
+    assert F.edit_distance(ref, ref, eos=-1).abs().sum().item() == 0
+    d_rh = F.edit_distance(ref, hyp, eos=-1, ins_cost=1, del_cost=2, sub_cost=2)
+    # duality: swapping the roles of ref and hyp swaps insertions and deletions
+    d_hr = F.edit_distance(hyp, ref, eos=-1, ins_cost=2, del_cost=1, sub_cost=2)
+    assert torch.equal(d_rh, d_hr)
+    # bounds: | |r| - |h| | * min(ins,del)  <=  d  <=  sub*min + ...; and the last valid
+    # prefix row equals the final distance
+    pe = F.prefix_edit_distances(ref, hyp, eos=-1, include_eos=False, ins_cost=1, del_cost=2,
+                                 sub_cost=2)
+    hl = (lens.to(dev))[perm]
+    last = pe.gather(0, hl.unsqueeze(0)).squeeze(0)
+    assert torch.equal(last, d_rh)
+    assert (pe[0] == 2.0 * lens.to(dev)).all()
+    # checksum against the oracle on a strided sample
+    idx = torch.arange(0, P, 997, device=dev)
+    exp = O.edit_distance(ref[:, idx].cpu().numpy(), hyp[:, idx].cpu().numpy(), eos=-1, ins_cost=1,
+                          del_cost=2, sub_cost=2)
+    assert np.array_equal(d_rh[idx].cpu().numpy(), exp)
+
+
+def test_host_tensors_and_views(F, dev):
+    rng = np.random.default_rng(7)
+    ref = PC.random_tokens(rng, 30, 64, 9, 0, -1)
+    hyp = PC.random_tokens(rng, 28, 64, 9, 0, -1)
+    exp = O.error_rate(ref, hyp, eos=0)
+    # host tensors in, host tensor out (the e2e path)
+    out = F.error_rate(torch.from_numpy(ref).pin_memory(), torch.from_numpy(hyp).pin_memory(),
+                       eos=0, warn=False)
+    assert out.device.type == "cpu" and np.array_equal(out.numpy(), exp)
+    # non-contiguous views + a side stream
+    big = torch.zeros((60, 128), dtype=torch.long, device=dev)
+    big[::2, ::2] = torch.from_numpy(ref).to(dev)
+    s = torch.cuda.Stream(dev)
+    s.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(s):
+        out = F.error_rate(big[::2, ::2], torch.from_numpy(hyp).to(dev), eos=0, warn=False)
+    s.synchronize()
+    assert np.array_equal(out.cpu().numpy(), exp)
+
+
+def test_warnings_and_errors(F, dev):
+    PC.check_warnings(F, dev)
+    PC.check_errors(F, dev)
+
+
+def test_modules_trace(F, dev):
+    """The reference's tests trace every module (conftest.py:166-174)."""
+    import b200lev.modules as M
+
+    rng = np.random.default_rng(8)
+    ref = torch.from_numpy(PC.random_tokens(rng, 9, 5, 6, 0, -1)).to(dev)
+    hyp = torch.from_numpy(PC.random_tokens(rng, 11, 5, 6, 0, -1)).to(dev)
+    m = M.ErrorRate(eos=0, warn=False)
+    tm = torch.jit.trace(m, (torch.zeros(1, 1, device=dev), torch.zeros(1, 1, device=dev)))
+    assert torch.equal(tm(ref, hyp), m(ref, hyp))
+    pm = M.PrefixErrorRates(eos=0, warn=False)
+    tpm = torch.jit.trace(pm, (torch.zeros(1, 1, dtype=torch.long, device=dev),) * 2)
+    assert torch.equal(tpm(ref, hyp), pm(ref, hyp))
