@@ -124,6 +124,13 @@ static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     int32_t* hyp_tok = (int32_t*)(ws + L.off_hyp_tok);
     int32_t* ref_len = (int32_t*)(ws + L.off_ref_len);
     int32_t* hyp_len = (int32_t*)(ws + L.off_hyp_len);
+    // K0 reports tokens that do not fit in int32 through a flag word the DP kernels
+    // read; without caller flags a workspace slot takes that role
+    if (flags == nullptr) {
+        flags = (int32_t*)(ws + L.off_flags);
+        if (do_pack && cudaMemsetAsync(flags, 0, sizeof(int32_t), st) != cudaSuccess)
+            return lev_check_cuda("memset");
+    }
     if (do_pack) {
         int rc = lev_launch_pack(ref, o->has_eos, o->eos, o->include_eos, ref_tok, L.Rp, ref_len,
                                  flags, B200LEV_FLAG_REF_NO_EOS, st);
@@ -147,6 +154,15 @@ static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     p->exclude_last = o->exclude_last;
     p->padding = (float)o->padding;
     p->flags = flags;
+    p->wide_flag = flags;
+    p->ref_raw = ref->data;
+    p->hyp_raw = hyp->data;
+    p->ref_st = ref->stride_t;
+    p->ref_sn = ref->stride_n;
+    p->hyp_st = hyp->stride_t;
+    p->hyp_sn = hyp->stride_n;
+    p->ref_eb = ref->elem_bytes;
+    p->hyp_eb = hyp->elem_bytes;
     return B200LEV_OK;
 }
 

@@ -22,7 +22,7 @@ struct LevLayout {
     int64_t Rp, Hp;  // padded row lengths of the packed int32 token tables
     int64_t Hout;    // output rows of the prefix / mask modes
     int64_t Wd;      // 32-bit words of one (prefix, pair) distinct-token bitmap
-    size_t off_ref_tok, off_hyp_tok, off_ref_len, off_hyp_len;
+    size_t off_ref_tok, off_hyp_tok, off_ref_len, off_hyp_len, off_flags;
     size_t off_uid, off_dtok, off_ndist, off_dbits;
     size_t bytes;
 };
@@ -50,6 +50,7 @@ static inline LevLayout lev_layout(const b200lev_tokens_t* ref, const b200lev_to
     L.off_hyp_tok = take(sizeof(int32_t) * (size_t)L.P * L.Hp);
     L.off_ref_len = take(sizeof(int32_t) * (size_t)L.Nref);
     L.off_hyp_len = take(sizeof(int32_t) * (size_t)L.P);
+    L.off_flags = take(sizeof(int32_t));
     L.off_uid = L.off_dtok = L.off_ndist = L.off_dbits = 0;
     if (for_completion) {
         L.off_uid = take(sizeof(int32_t) * (size_t)L.Nref * L.Rp);
@@ -84,7 +85,14 @@ struct LevParams {
     uint32_t* dbits;     // [Hout][P][Wd]
     int Wd;
     int* umax;
-    int* flags;
+    int* flags;            // caller's warning flags (may be NULL)
+    const int* wide_flag;  // never NULL: the word K0 ORs B200LEV_FLAG_WIDE_TOKENS into
+    // the caller's tensors, for the 64-bit compare path only
+    const void* ref_raw;
+    const void* hyp_raw;
+    int64_t ref_st, ref_sn, hyp_st, hyp_sn;
+    int ref_eb, hyp_eb;
+    int only_if_wide;  // lev_warp_kernel: exit unless the wide-token flag is set
 };
 
 // host-side status plumbing (lev_abi.cu)
@@ -97,6 +105,7 @@ int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int inc
                     int missing_flag, cudaStream_t st);
 int lev_launch_dp(const LevParams& p, int mode, bool count_mode, bool float_path,
                   cudaStream_t st);
+int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t st);
 int lev_launch_uid(const b200lev_tokens_t* ref, const int32_t* ref_len, int32_t* uid,
                    int64_t* dtok, int32_t* ndist, int64_t Rp, cudaStream_t st);
 int lev_launch_completion_fill(const uint32_t* dbits, const int64_t* dtok, int64_t Rp,

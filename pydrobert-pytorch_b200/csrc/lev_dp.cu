@@ -66,11 +66,24 @@ struct LevBufs {
 
 // One pair on one warp.  PASS: 0 = the only pass (FINAL/PREFIX) or the row-minimum
 // pass of MASK; 1 = the equality pass of MASK.
-template <typename V, bool COUNT, int MODE, int C, int PASS>
+// tokens that do not fit in int32 (B200LEV_FLAG_WIDE_TOKENS): read the caller's tensors
+// directly and compare in 64 bits.  Slow (strided gathers) but exact; uniform per launch.
+__device__ __forceinline__ int64_t lev_load_raw(const void* base, int elem_bytes, int64_t idx) {
+    switch (elem_bytes) {
+        case 8: return reinterpret_cast<const int64_t*>(base)[idx];
+        case 4: return reinterpret_cast<const int32_t*>(base)[idx];
+        case 2: return reinterpret_cast<const int16_t*>(base)[idx];
+        default: return reinterpret_cast<const int8_t*>(base)[idx];
+    }
+}
+
+template <typename V, bool COUNT, int MODE, int C, int PASS, bool WIDE>
 __device__ __forceinline__ void lev_warp_pair(const LevParams& p, const int pair, const int r,
                                               const int h, const int steps,
-                                              const int* __restrict__ hyp_s,
+                                              const int* __restrict__ hyp_s_,
                                               V* __restrict__ bufs, const int Hs) {
+    typedef typename std::conditional<WIDE, int64_t, int>::type Tok;
+    const Tok* __restrict__ hyp_s = reinterpret_cast<const Tok*>(hyp_s_);
     constexpr bool IS_INT = std::is_same<V, int>::value;
     constexpr bool FLT_COST = !IS_INT && !COUNT;
     constexpr bool RMIN = (MODE == LEV_MODE_MASK && PASS == 0);
@@ -96,7 +109,7 @@ __device__ __forceinline__ void lev_warp_pair(const LevParams& p, const int pair
         V v[C];
         V m[C];     // COUNT: mistake counts
         V jd[C];    // FLT_COST: fl(j * del), SM:258-263
-        int rt[C];  // reference token of column j (ref position j-1)
+        Tok rt[C];  // reference token of column j (ref position j-1)
         int ud[C];  // EQ: distinct-token rank of ref position j, or -1
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -104,7 +117,12 @@ __device__ __forceinline__ void lev_warp_pair(const LevParams& p, const int pair
             v[c] = (j >= 0) ? (V)j * delc : BIG;
             m[c] = (V)(j >= 0 ? j : 0);  // SM:260
             jd[c] = (j >= 0) ? (V)j * delc : (V)0;
-            rt[c] = (j >= 1) ? rtok[j - 1] : 0;
+            if (WIDE)
+                rt[c] = (j >= 1) ? (Tok)lev_load_raw(p.ref_raw, p.ref_eb,
+                                                      (int64_t)(j - 1) * p.ref_st + (int64_t)refcol * p.ref_sn)
+                                 : (Tok)0;
+            else
+                rt[c] = (j >= 1) ? (Tok)rtok[j - 1] : (Tok)0;
             ud[c] = -1;
             if (EQ) ud[c] = (j >= 0 && j < r) ? p.uid[(int64_t)refcol * p.Rp + j] : -1;
         }
@@ -145,7 +163,7 @@ __device__ __forceinline__ void lev_warp_pair(const LevParams& p, const int pair
                 (void)in_m; (void)diag_m; (void)in_ob; (void)in_oj; (void)in_rm;
                 const int i = s - lane;  // the row this lane updates now
                 if (i >= 1 && i <= steps) {
-                    const int ht = hyp_s[32 + i - 1];
+                    const Tok ht = hyp_s[32 + i - 1];
                     if (COUNT) {
                         // SM:292-314: (cost, count); ties: sub over ins over del
                         V dc = diag_v, dm = diag_m, lc = in_v, lm = in_m;
@@ -239,11 +257,12 @@ __device__ __forceinline__ void lev_warp_pair(const LevParams& p, const int pair
     }
 }
 
-template <typename V, bool COUNT, int MODE, int C>
+template <typename V, bool COUNT, int MODE, int C, bool WIDE = false>
 __device__ __forceinline__ void lev_warp_pair_all(const LevParams& p, int pair, int r, int h,
                                                   int steps, const int* hyp_s, V* bufs, int Hs) {
-    lev_warp_pair<V, COUNT, MODE, C, 0>(p, pair, r, h, steps, hyp_s, bufs, Hs);
-    if (MODE == LEV_MODE_MASK) lev_warp_pair<V, COUNT, MODE, C, 1>(p, pair, r, h, steps, hyp_s, bufs, Hs);
+    lev_warp_pair<V, COUNT, MODE, C, 0, WIDE>(p, pair, r, h, steps, hyp_s, bufs, Hs);
+    if (MODE == LEV_MODE_MASK)
+        lev_warp_pair<V, COUNT, MODE, C, 1, WIDE>(p, pair, r, h, steps, hyp_s, bufs, Hs);
 }
 
 // CMASK: bit c set => the kernel carries a C = 2^c variant (1, 2, 4, 8); each pair
@@ -257,8 +276,10 @@ __global__ void __launch_bounds__(256) lev_warp_kernel(const LevParams p) {
     const int wpc = blockDim.x >> 5;
     const int Hs = p.H + 64;
     constexpr int NB = LevBufs<V, COUNT, MODE>::NB;
-    int* hyp_s = smem + (size_t)warp * (1 + NB) * Hs;
-    V* bufs = reinterpret_cast<V*>(hyp_s + Hs);
+    int* hyp_s = smem + (size_t)warp * (2 + NB) * Hs;  // 2*Hs ints: room for int64 tokens
+    V* bufs = reinterpret_cast<V*>(hyp_s + 2 * Hs);
+    const bool wide = (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) != 0;
+    if (p.only_if_wide && !wide) return;  // the group kernel already did the work
     for (int pair = blockIdx.x * wpc + warp; pair < p.P; pair += gridDim.x * wpc) {
         const int r = p.ref_len[pair / p.ref_group];
         const int h = p.hyp_len[pair];
@@ -266,10 +287,19 @@ __global__ void __launch_bounds__(256) lev_warp_kernel(const LevParams p) {
         if (MODE != LEV_MODE_MASK && lane == 0 && r == 0 && p.norm && p.flags != nullptr)
             atomicOr(p.flags, B200LEV_FLAG_EMPTY_REF);  // SM:360-366, 397-404
         const int32_t* __restrict__ htok = p.hyp_tok + (int64_t)pair * p.Hp;
-        for (int i = lane; i < steps; i += 32) hyp_s[32 + i] = htok[i];
+        if (wide) {
+            int64_t* h64 = reinterpret_cast<int64_t*>(hyp_s);
+            for (int i = lane; i < steps; i += 32)
+                h64[32 + i] = lev_load_raw(p.hyp_raw, p.hyp_eb, (int64_t)i * p.hyp_st + (int64_t)pair * p.hyp_sn);
+        } else {
+            for (int i = lane; i < steps; i += 32) hyp_s[32 + i] = htok[i];
+        }
         __syncwarp();
         const int cols = r + 1;
-        if ((CMASK & 1) && (cols <= 32 || !(CMASK & 14)))
+        if (wide)
+            lev_warp_pair_all<V, COUNT, MODE, (CMASK & 8) ? 8 : ((CMASK & 4) ? 4 : ((CMASK & 2) ? 2 : 1)), true>(
+                p, pair, r, h, steps, hyp_s, bufs, Hs);
+        else if ((CMASK & 1) && (cols <= 32 || !(CMASK & 14)))
             lev_warp_pair_all<V, COUNT, MODE, 1>(p, pair, r, h, steps, hyp_s, bufs, Hs);
         else if ((CMASK & 2) && (cols <= 64 || !(CMASK & 12)))
             lev_warp_pair_all<V, COUNT, MODE, 2>(p, pair, r, h, steps, hyp_s, bufs, Hs);
@@ -318,7 +348,7 @@ __global__ void __launch_bounds__(256) lev_warp_kernel(const LevParams p) {
 template <typename V, bool COUNT, int MODE, int CMASK>
 static int lev_launch_variant(const LevParams& p, cudaStream_t st) {
     constexpr int NB = LevBufs<V, COUNT, MODE>::NB;
-    const size_t per_warp = (size_t)(1 + NB) * (size_t)(p.H + 64) * sizeof(int);
+    const size_t per_warp = (size_t)(2 + NB) * (size_t)(p.H + 64) * sizeof(int);
     const size_t budget = 200 * 1024;
     if (per_warp > budget) {
         lev_set_error("hypothesis length %d needs %zu bytes of shared memory per warp (max %zu)",
@@ -346,9 +376,18 @@ static int lev_launch_variant(const LevParams& p, cudaStream_t st) {
     return lev_check_cuda("lev_warp_kernel");
 }
 
-int lev_launch_dp(const LevParams& p, int mode, bool count_mode, bool float_path,
+int lev_launch_dp(const LevParams& p_, int mode, bool count_mode, bool float_path,
                   cudaStream_t st) {
-    if (p.P <= 0) return B200LEV_OK;
+    if (p_.P <= 0) return B200LEV_OK;
+    LevParams p = p_;
+    p.only_if_wide = 0;
+    if (!float_path) {
+        // large batches of short/mid pairs: length-bucketed group kernel (lev_group.cu);
+        // this kernel then only runs if K0 flagged tokens wider than 32 bits
+        const int took = lev_launch_group(p, mode, count_mode, st);
+        if (took < 0) return took;
+        if (took == 1) p.only_if_wide = 1;
+    }
     if (!float_path) {
         if (!count_mode) {
             if (mode == LEV_MODE_FINAL) return lev_launch_variant<int, false, LEV_MODE_FINAL, 15>(p, st);

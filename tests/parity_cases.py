@@ -186,3 +186,25 @@ def check_errors(F, dev):
         F.minimum_error_rate_loss(torch.zeros(2, 3, device=dev), a,
                                   torch.zeros(3, 2, 3, dtype=torch.long, device=dev),
                                   reduction="bad")
+
+
+def check_wide_tokens(F, dev):
+    """Tokens that differ only above bit 31 must not compare equal (64-bit path)."""
+    rng = np.random.default_rng(11)
+    R, H, N = 70, 40, 9
+    ref = random_tokens(rng, R, N, 4, 0, -1, min_len=20)
+    hyp = random_tokens(rng, H, N, 4, 0, -1, min_len=20)
+    big = np.int64(1) << 32
+    ref = np.where((ref > 0) & (rng.random(ref.shape) < 0.5), ref + big, ref)
+    hyp = np.where((hyp > 0) & (rng.random(hyp.shape) < 0.5), hyp + 3 * big, hyp)
+    tr, th = torch.from_numpy(ref).to(dev), torch.from_numpy(hyp).to(dev)
+    for costs in ((1, 1, 1), (1, 2, 3)):
+        kw = dict(eos=0, include_eos=True, ins_cost=costs[0], del_cost=costs[1], sub_cost=costs[2])
+        assert_same(F.edit_distance(tr, th, warn=False, **kw), O.edit_distance(ref, hyp, **kw), True, "wide ed")
+        assert_same(F.prefix_error_rates(tr, th, warn=False, **kw), O.prefix_error_rates(ref, hyp, **kw),
+                    True, "wide per")
+        assert_same(F.optimal_completion(tr, th, warn=False, **kw), O.optimal_completion(ref, hyp, **kw),
+                    True, "wide oc")
+    # sanity: the narrowed tokens alone would have matched
+    assert not np.array_equal(O.edit_distance(ref, hyp, eos=0),
+                              O.edit_distance(ref.astype(np.int32), hyp.astype(np.int32), eos=0))

@@ -272,3 +272,26 @@ def test_modules_trace(F, dev):
     pm = M.PrefixErrorRates(eos=0, warn=False)
     tpm = torch.jit.trace(pm, (torch.zeros(1, 1, dtype=torch.long, device=dev),) * 2)
     assert torch.equal(tpm(ref, hyp), pm(ref, hyp))
+
+
+def test_wide_tokens(F, dev):
+    PC.check_wide_tokens(F, dev)
+
+
+@pytest.mark.parametrize("shape", [(20, 25, 300), (31, 30, 500), (45, 50, 300), (101, 101, 4200),
+                                   (201, 60, 100), (420, 40, 40), (800, 30, 20)])
+@pytest.mark.parametrize("costs", [(1, 1, 1), (3, 3, 4)])
+def test_group_kernel_vs_oracle(F, dev, shape, costs, monkeypatch):
+    """lev_group.cu (length-bucketed lane groups) at every group width G = 1..32."""
+    monkeypatch.setenv("B200LEV_GROUP_MIN_PAIRS", "1")
+    R, H, N = shape
+    for flags in (dict(include_eos=True, norm=True, exclude_last=False, min_frac=0.0),
+                  dict(include_eos=False, norm=False, exclude_last=True, min_frac=0.4,
+                       batch_first=True)):
+        PC.check_vs_oracle(F, dev, seed=R + H, R=R, H=H, N=N, V=5, costs=costs, do_mask=False,
+                           padding=-3, **flags)
+
+
+def test_group_kernel_wide_tokens(F, dev, monkeypatch):
+    monkeypatch.setenv("B200LEV_GROUP_MIN_PAIRS", "1")
+    PC.check_wide_tokens(F, dev)

@@ -140,3 +140,29 @@ def test_modules_match_functionals(F):
     loss = M.HardOptimalCompletionDistillationLoss(eos=0)(logits, ref, hyp)
     loss.backward()
     assert torch.isfinite(loss) and logits.grad.abs().sum() > 0
+
+
+def test_wide_tokens(F):
+    PC.check_wide_tokens(F, DEV)
+
+
+@pytest.mark.parametrize("shape", [(20, 25, 70), (31, 30, 90), (45, 50, 40), (101, 101, 40),
+                                   (201, 60, 12), (420, 40, 6), (800, 30, 3)])
+@pytest.mark.parametrize("costs", [(1, 1, 1), (3, 3, 4)])
+def test_group_kernel_vs_oracle(F, shape, costs, monkeypatch):
+    """The length-bucketed group kernel (lev_group.cu), forced on for small batches:
+    every lane-group width G = 1..32, cost-only and (cost, count) paths, final and
+    prefix outputs, ragged lengths incl. empty sequences."""
+    monkeypatch.setenv("B200LEV_GROUP_MIN_PAIRS", "1")
+    R, H, N = shape
+    for flags in (dict(include_eos=True, norm=True, exclude_last=False, min_frac=0.0),
+                  dict(include_eos=False, norm=False, exclude_last=True, min_frac=0.4,
+                       batch_first=True)):
+        PC.check_vs_oracle(F, DEV, seed=R + H, R=R, H=H, N=N, V=5, costs=costs, do_mask=False,
+                           padding=-3, **flags)
+
+
+def test_group_kernel_n_best_and_wide(F, monkeypatch):
+    monkeypatch.setenv("B200LEV_GROUP_MIN_PAIRS", "1")
+    test_n_best_shared_reference(F)
+    PC.check_wide_tokens(F, DEV)
