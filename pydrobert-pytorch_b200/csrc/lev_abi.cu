@@ -124,19 +124,18 @@ static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     int32_t* hyp_tok = (int32_t*)(ws + L.off_hyp_tok);
     int32_t* ref_len = (int32_t*)(ws + L.off_ref_len);
     int32_t* hyp_len = (int32_t*)(ws + L.off_hyp_len);
-    // K0 reports tokens that do not fit in int32 through a flag word the DP kernels
-    // read; without caller flags a workspace slot takes that role
-    if (flags == nullptr) {
-        flags = (int32_t*)(ws + L.off_flags);
-        if (do_pack && cudaMemsetAsync(flags, 0, sizeof(int32_t), st) != cudaSuccess)
-            return lev_check_cuda("memset");
-    }
+    // K0 leaves what the DP kernels need to know about the tokens (wider than int32?
+    // value range) in 4 state words of the workspace; the caller's flags get the same
+    // warning bits
+    int32_t* state = (int32_t*)(ws + L.off_flags);
     if (do_pack) {
+        if (cudaMemsetAsync(state, 0, 4 * sizeof(int32_t), st) != cudaSuccess)
+            return lev_check_cuda("memset");
         int rc = lev_launch_pack(ref, o->has_eos, o->eos, o->include_eos, ref_tok, L.Rp, ref_len,
-                                 flags, B200LEV_FLAG_REF_NO_EOS, st);
+                                 flags, state, B200LEV_FLAG_REF_NO_EOS, st);
         if (rc) return rc;
         rc = lev_launch_pack(hyp, o->has_eos, o->eos, o->include_eos, hyp_tok, L.Hp, hyp_len, flags,
-                             B200LEV_FLAG_HYP_NO_EOS, st);
+                             state, B200LEV_FLAG_HYP_NO_EOS, st);
         if (rc) return rc;
     }
     memset(p, 0, sizeof(*p));
@@ -154,7 +153,7 @@ static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     p->exclude_last = o->exclude_last;
     p->padding = (float)o->padding;
     p->flags = flags;
-    p->wide_flag = flags;
+    p->wide_flag = state;
     p->ref_raw = ref->data;
     p->hyp_raw = hyp->data;
     p->ref_st = ref->stride_t;

@@ -50,7 +50,7 @@ static inline LevLayout lev_layout(const b200lev_tokens_t* ref, const b200lev_to
     L.off_hyp_tok = take(sizeof(int32_t) * (size_t)L.P * L.Hp);
     L.off_ref_len = take(sizeof(int32_t) * (size_t)L.Nref);
     L.off_hyp_len = take(sizeof(int32_t) * (size_t)L.P);
-    L.off_flags = take(sizeof(int32_t));
+    L.off_flags = take(4 * sizeof(int32_t));  // [flags, max(u), max(~u), -] (lev_pack.cu)
     L.off_uid = L.off_dtok = L.off_ndist = L.off_dbits = 0;
     if (for_completion) {
         L.off_uid = take(sizeof(int32_t) * (size_t)L.Nref * L.Rp);
@@ -86,7 +86,8 @@ struct LevParams {
     int Wd;
     int* umax;
     int* flags;            // caller's warning flags (may be NULL)
-    const int* wide_flag;  // never NULL: the word K0 ORs B200LEV_FLAG_WIDE_TOKENS into
+    const int* wide_flag;  // never NULL: workspace state words K0 fills: [0] flags (incl.
+                           // B200LEV_FLAG_WIDE_TOKENS), [1], [2] biased token range
     // the caller's tensors, for the 64-bit compare path only
     const void* ref_raw;
     const void* hyp_raw;
@@ -101,7 +102,7 @@ int lev_check_cuda(const char* what);
 
 // kernels' host launchers
 int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int include_eos,
-                    int32_t* packed, int64_t Tp, int32_t* lens, int32_t* flags,
+                    int32_t* packed, int64_t Tp, int32_t* lens, int32_t* flags, int32_t* state,
                     int missing_flag, cudaStream_t st);
 int lev_launch_dp(const LevParams& p, int mode, bool count_mode, bool float_path,
                   cudaStream_t st);

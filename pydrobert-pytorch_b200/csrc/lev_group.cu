@@ -31,7 +31,11 @@ struct LevGroupGeom {
     int tile;   // pairs per CTA
     int Hs;     // shared-memory row stride (ints) of the per-pair token / prefix rows
     int nbins;  // LEVG_NCLS * (H + 1)
+    int allow16;  // costs and lengths admit the packed 2 x int16 DPX path
 };
+
+// "infinity" of the packed path: BIG16 + (largest reachable value) must stay < 2^15
+#define LEVG_BIG16 16000
 
 // smallest class whose strip covers columns 0..r
 __device__ __forceinline__ int levg_class_of(int r, int G) {
@@ -125,6 +129,64 @@ __device__ __forceinline__ void levg_run(const LevParams& p, const int G, const 
     }
 }
 
+// Packed path: TWO pairs per lane group, one in each 16-bit half of every register, driven
+// by the 2-wide DPX instructions (VIADDMNMX.S16x2, VIMNMX.U16x2).  Per 2 cells: LOP3 (token
+// xor), VIMNMX.U16x2 (-> 0/1 per half), IMAD (diag + neq*sub, FMA pipe), 2 x VIADDMNMX.S16x2.
+// Needs 16-bit-injective tokens (K0 measured max - min < 65536), non-negative integer costs
+// and values below LEVG_BIG16.  Cost row only.  Both pairs run `maxsteps` rows; rows past a
+// pair's own length are never read back.
+template <int C>
+__device__ __forceinline__ void levg_run16(const LevParams& p, const int G, const int pairA,
+                                           const int rA, const int pairB, const int rB,
+                                           const int maxsteps,
+                                           const unsigned* __restrict__ hyp_row,
+                                           unsigned* __restrict__ pref_row) {
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    const int32_t* __restrict__ rtA = p.ref_tok + (int64_t)(pairA >= 0 ? pairA / p.ref_group : 0) * p.Rp;
+    const int32_t* __restrict__ rtB = p.ref_tok + (int64_t)(pairB >= 0 ? pairB / p.ref_group : 0) * p.Rp;
+    const unsigned ins2 = (unsigned)p.ins_i * 0x00010001u, del2 = (unsigned)p.del_i * 0x00010001u;
+    const unsigned subc = (unsigned)p.sub_i;
+    const unsigned BIG2 = (unsigned)LEVG_BIG16 * 0x00010001u;
+    const int j0A = rA - G * C + gl * C + 1, j0B = rB - G * C + gl * C + 1;
+    unsigned v[C], rt[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int jA = j0A + c, jB = j0B + c;
+        const unsigned vA = (jA >= 0) ? (unsigned)(jA * p.del_i) : (unsigned)LEVG_BIG16;
+        const unsigned vB = (jB >= 0) ? (unsigned)(jB * p.del_i) : (unsigned)LEVG_BIG16;
+        v[c] = vA | (vB << 16);
+        const unsigned tA = (jA >= 1 && pairA >= 0) ? ((unsigned)rtA[jA - 1] & 0xffffu) : 0u;
+        const unsigned tB = (jB >= 1 && pairB >= 0) ? ((unsigned)rtB[jB - 1] & 0xffffu) : 0u;
+        rt[c] = tA | (tB << 16);
+    }
+    unsigned pl = BIG2;
+    const bool owner = (gl == G - 1);
+    const int nsteps = maxsteps + G - 1;
+    for (int s = 1; s <= nsteps; ++s) {
+        const unsigned sh = __shfl_up_sync(LEV_FULL_MASK, v[C - 1], 1, G);
+        const unsigned in = (gl == 0) ? BIG2 : sh;
+        unsigned dg = pl;
+        pl = in;
+        const int i = s - gl;
+        if ((unsigned)(i - 1) < (unsigned)maxsteps) {
+            const unsigned ht = hyp_row[i - 1];
+            unsigned lf = in;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const unsigned up = v[c];
+                const unsigned n01 = __vminu2(rt[c] ^ ht, 0x00010001u);
+                const unsigned sb = n01 * subc + dg;
+                const unsigned t = __viaddmin_s16x2(up, ins2, sb);
+                lf = __viaddmin_s16x2(lf, del2, t);
+                dg = up;
+                v[c] = lf;
+            }
+            if (owner) pref_row[i] = v[C - 1];
+        }
+    }
+}
+
 template <bool COUNT, int MODE>
 __global__ void __launch_bounds__(256) lev_group_kernel(const LevParams p, const LevGroupGeom geo) {
     LEV_DYN_SMEM(int, smem);
@@ -134,8 +196,8 @@ __global__ void __launch_bounds__(256) lev_group_kernel(const LevParams p, const
     const int ntile = min(TILE, p.P - tile0);
     // shared-memory carve-up
     int* hist = smem;                         // [nbins + 1]
-    int* order = hist + geo.nbins + 1;        // [TILE + LEVG_NCLS * PPW]
-    short* rl_s = reinterpret_cast<short*>(order + TILE + LEVG_NCLS * PPW);  // [TILE]
+    int* order = hist + geo.nbins + 1;        // [TILE + 2 * LEVG_NCLS * PPW]
+    short* rl_s = reinterpret_cast<short*>(order + TILE + 2 * LEVG_NCLS * PPW);  // [TILE]
     short* hl_s = rl_s + TILE;                                               // [TILE]
     int* wbase = reinterpret_cast<int*>(hl_s + TILE);  // 2*TILE shorts: int-aligned
     int* hyp_w = wbase + (size_t)warp * 2 * PPW * Hs;  // [PPW][Hs]
@@ -145,9 +207,15 @@ __global__ void __launch_bounds__(256) lev_group_kernel(const LevParams p, const
     // tokens that do not fit in int32: leave the whole batch to the 64-bit compare path of
     // lev_warp_kernel, which the host enqueues right behind this kernel
     if (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) return;
+    // K0 left the (biased) token range next to the flag word: [1] = max(u), [2] = max(~u),
+    // u = token + 2^31.  All tokens inside a 65536-wide window <=> their low 16 bits are
+    // injective <=> the packed path may compare 16-bit halves.
+    const unsigned umax = (unsigned)p.wide_flag[1], umin = ~(unsigned)p.wide_flag[2];
+    const bool packed = !COUNT && geo.allow16 && (umax < umin || umax - umin < 65536u);
+    const int PPT = packed ? 2 * PPW : PPW;  // pairs per task
     // ---- 1. lengths, classes, histogram over (class desc, hyp length desc) ----
     for (int b = tid; b <= geo.nbins; b += blockDim.x) hist[b] = 0;
-    for (int q = tid; q < TILE + LEVG_NCLS * PPW; q += blockDim.x) order[q] = -1;
+    for (int q = tid; q < TILE + 2 * LEVG_NCLS * PPW; q += blockDim.x) order[q] = -1;
     if (tid == 0) next_task = 0;
     __syncthreads();
     for (int q = tid; q < ntile; q += blockDim.x) {
@@ -178,10 +246,10 @@ __global__ void __launch_bounds__(256) lev_group_kernel(const LevParams p, const
                 if (b < H1) hist[cseg * H1 + b] = carry + incl - cnt;
                 carry += __shfl_sync(LEV_FULL_MASK, incl, 31);
             }
-            carry = (carry + PPW - 1) / PPW * PPW;
+            carry = (carry + PPT - 1) / PPT * PPT;
             if (lane == 0) seg_end[cseg] = carry;
         }
-        if (lane == 0) ntasks = carry / PPW;
+        if (lane == 0) ntasks = carry / PPT;
     }
     __syncthreads();
     // ---- 3. scatter pair indices into sorted order ----
@@ -199,6 +267,76 @@ __global__ void __launch_bounds__(256) lev_group_kernel(const LevParams p, const
         if (lane == 0) t = atomicAdd(&next_task, 1);
         t = __shfl_sync(LEV_FULL_MASK, t, 0);
         if (t >= ntasks) break;
+        if (packed) {
+            // ---- packed task: 2*PPW pairs, group g runs pairs 2g (low half) and 2g+1 ----
+            const int qA = order[t * PPT + 2 * g], qB = order[t * PPT + 2 * g + 1];
+            const int rA = qA >= 0 ? rl_s[qA] : 0, rB = qB >= 0 ? rl_s[qB] : 0;
+            const int hA = qA >= 0 ? hl_s[qA] : 0, hB = qB >= 0 ? hl_s[qB] : 0;
+            const int hmax = hA > hB ? hA : hB;
+            int maxsteps = p.exclude_last ? (hmax > 0 ? hmax - 1 : 0) : hmax;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int other = __shfl_xor_sync(LEV_FULL_MASK, maxsteps, o);
+                maxsteps = other > maxsteps ? other : maxsteps;
+            }
+            int cseg = 0;
+            while (t * PPT >= seg_end[cseg]) ++cseg;
+            const int cls = LEVG_NCLS - 1 - cseg;
+            unsigned short* hyp16 = reinterpret_cast<unsigned short*>(hyp_w);
+            for (int k = 0; k < PPT; ++k) {
+                const int qk = order[t * PPT + k];
+                if (qk < 0) continue;
+                const int hk = hl_s[qk];
+                const int sk = p.exclude_last ? (hk > 0 ? hk - 1 : 0) : hk;
+                const int32_t* __restrict__ src = p.hyp_tok + (int64_t)(tile0 + qk) * p.Hp;
+                for (int i = lane; i < sk; i += 32)
+                    hyp16[(((k >> 1) * Hs + i) << 1) + (k & 1)] = (unsigned short)src[i];
+            }
+            __syncwarp();
+            const unsigned* hrow = reinterpret_cast<const unsigned*>(hyp_w) + g * Hs;
+            unsigned* prow = reinterpret_cast<unsigned*>(pref_w) + g * Hs;
+            const int pA = qA >= 0 ? tile0 + qA : -1, pB = qB >= 0 ? tile0 + qB : -1;
+            switch (cls) {
+                case 0: levg_run16<8>(p, G, pA, rA, pB, rB, maxsteps, hrow, prow); break;
+                case 1: levg_run16<12>(p, G, pA, rA, pB, rB, maxsteps, hrow, prow); break;
+                case 2: levg_run16<16>(p, G, pA, rA, pB, rB, maxsteps, hrow, prow); break;
+                case 3: levg_run16<20>(p, G, pA, rA, pB, rB, maxsteps, hrow, prow); break;
+                case 4: levg_run16<24>(p, G, pA, rA, pB, rB, maxsteps, hrow, prow); break;
+                default: levg_run16<28>(p, G, pA, rA, pB, rB, maxsteps, hrow, prow); break;
+            }
+            __syncwarp();
+            // epilogue for all 2*PPW pairs (SM:279-285, 340-346, 356-386 / 390-405)
+            for (int k = 0; k < PPT; ++k) {
+                const int qk = order[t * PPT + k];
+                if (qk < 0) continue;
+                const int rk = rl_s[qk], hk = hl_s[qk];
+                const unsigned* row = reinterpret_cast<const unsigned*>(pref_w) + (k >> 1) * Hs;
+                const int sh16 = (k & 1) * 16;
+                const float rf = (float)rk;
+                if (MODE == LEV_MODE_PREFIX) {
+                    const int first_pad = hk + (p.exclude_last ? 0 : 1);
+                    const int64_t col = (int64_t)(tile0 + qk) * p.out_sn;
+                    for (int i = lane; i < p.Hout; i += 32) {
+                        float val;
+                        if (i >= first_pad) {
+                            val = p.padding;
+                        } else {
+                            const int raw = (i == 0) ? rk * p.del_i : (int)((row[i] >> sh16) & 0xffffu);
+                            val = (float)raw * p.mult;
+                            if (p.norm) val = (rk == 0) ? (i > 0 ? 1.0f : 0.0f) : val / rf;
+                        }
+                        p.out[(int64_t)i * p.out_si + col] = val;
+                    }
+                } else if (lane == 0) {
+                    const int raw = (hk == 0) ? rk * p.del_i : (int)((row[hk] >> sh16) & 0xffffu);
+                    float val = (float)raw * p.mult;
+                    if (p.norm) val = (rk == 0) ? (hk > 0 ? 1.0f : 0.0f) : val / rf;
+                    p.out[tile0 + qk] = val;
+                }
+            }
+            __syncwarp();
+            continue;
+        }
         const int q = order[t * PPW + g];
         const int pair = q >= 0 ? tile0 + q : -1;
         const int r = q >= 0 ? rl_s[q] : 0;
@@ -278,12 +416,19 @@ int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t
     const int PPW = 32 / G;
     geo.Hs = ((p.H + 2 + 31) / 32) * 32 + G;  // stride == G (mod 32): conflict-free rows
     geo.nbins = LEVG_NCLS * (p.H + 1);
+    const int maxc = p.ins_i > p.del_i ? (p.ins_i > p.sub_i ? p.ins_i : p.sub_i)
+                                       : (p.del_i > p.sub_i ? p.del_i : p.sub_i);
+    geo.allow16 = (!count_mode && p.ins_i >= 0 && p.del_i >= 0 && p.sub_i >= 0 &&
+                   (int64_t)maxc * (p.R + p.H + 2) < LEVG_BIG16)
+                      ? 1
+                      : 0;
+    if (const char* e = getenv("B200LEV_GROUP_PACKED16")) geo.allow16 = geo.allow16 && atoi(e);
     const size_t per_warp = (size_t)2 * PPW * geo.Hs * sizeof(int);
     const int nwarps = 8;
-    int tile = 256;
-    if (tile < 8 * PPW) tile = 8 * PPW;
+    int tile = 512;
+    if (tile < 16 * PPW) tile = 16 * PPW;
     geo.tile = tile;
-    const size_t smem = sizeof(int) * (geo.nbins + 1 + tile + LEVG_NCLS * PPW) +
+    const size_t smem = sizeof(int) * (geo.nbins + 1 + tile + 2 * LEVG_NCLS * PPW) +
                         sizeof(short) * (2 * tile) + per_warp * nwarps + 16;
     if (smem > 200 * 1024) return 0;
     const int64_t blocks = ((int64_t)p.P + tile - 1) / tile;

@@ -15,17 +15,24 @@ template <typename TT>
 __global__ void __launch_bounds__(256)
 lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, int64_t sn,
                 int has_eos, int64_t eos, int include_eos, int32_t* __restrict__ packed,
-                int64_t Tp, int32_t* __restrict__ lens, int32_t* flags, int missing_flag,
-                int transposed) {
+                int64_t Tp, int32_t* __restrict__ lens, int32_t* flags, int32_t* state,
+                int missing_flag, int transposed) {
     __shared__ int tile[32][33];
     __shared__ int first[32];
     __shared__ int blk_flags;
+    __shared__ unsigned blk_umax, blk_nmax;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int64_t n0 = (int64_t)blockIdx.x * 32;
     if (ty == 0) first[tx] = (int)T;
-    if (tx == 0 && ty == 0) blk_flags = 0;
+    if (tx == 0 && ty == 0) {
+        blk_flags = 0;
+        blk_umax = 0u;
+        blk_nmax = 0u;
+    }
     __syncthreads();
     int wide = 0;
+    // biased token range for the packed 16-bit DP path: max(u) and max(~u), u = tok + 2^31
+    unsigned umax = 0u, nmax = 0u;
     if (transposed) {
         for (int64_t t0 = 0; t0 < T; t0 += 32) {
 #pragma unroll
@@ -37,6 +44,9 @@ lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, in
                     tile[tl][tx] = (int)v;
                     if (has_eos && v == eos) atomicMin(&first[tx], (int)t);
                     if ((int64_t)(int)v != v) wide = 1;
+                    const unsigned u = (unsigned)(int)v + 0x80000000u;
+                    umax = u > umax ? u : umax;
+                    nmax = ~u > nmax ? ~u : nmax;
                 }
             }
             __syncthreads();
@@ -59,12 +69,26 @@ lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, in
                     packed[n * Tp + t] = (int)v;
                     if (has_eos && v == eos) atomicMin(&first[nl], (int)t);
                     if ((int64_t)(int)v != v) wide = 1;
+                    const unsigned u = (unsigned)(int)v + 0x80000000u;
+                    umax = u > umax ? u : umax;
+                    nmax = ~u > nmax ? ~u : nmax;
                 }
             }
         }
         __syncthreads();
     }
     if (wide) atomicOr(&blk_flags, B200LEV_FLAG_WIDE_TOKENS);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned a = __shfl_xor_sync(LEV_FULL_MASK, umax, o);
+        const unsigned b = __shfl_xor_sync(LEV_FULL_MASK, nmax, o);
+        umax = a > umax ? a : umax;
+        nmax = b > nmax ? b : nmax;
+    }
+    if (tx == 0) {
+        atomicMax(&blk_umax, umax);
+        atomicMax(&blk_nmax, nmax);
+    }
     if (ty == 0 && n0 + tx < N) {
         int len = first[tx];
         if (has_eos && include_eos) {  // SM:198-218
@@ -76,11 +100,18 @@ lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, in
         lens[n0 + tx] = len;
     }
     __syncthreads();
-    if (tx == 0 && ty == 0 && blk_flags != 0 && flags != nullptr) atomicOr(flags, blk_flags);
+    if (tx == 0 && ty == 0) {
+        if (blk_flags != 0) {
+            if (flags != nullptr) atomicOr(flags, blk_flags);
+            atomicOr(state, blk_flags);
+        }
+        atomicMax(reinterpret_cast<unsigned*>(state) + 1, blk_umax);
+        atomicMax(reinterpret_cast<unsigned*>(state) + 2, blk_nmax);
+    }
 }
 
 int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int include_eos,
-                    int32_t* packed, int64_t Tp, int32_t* lens, int32_t* flags,
+                    int32_t* packed, int64_t Tp, int32_t* lens, int32_t* flags, int32_t* state,
                     int missing_flag, cudaStream_t st) {
     if (t->N <= 0) return B200LEV_OK;
     if (t->T >= (int64_t)1 << 30) {
@@ -96,22 +127,22 @@ int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int inc
         case 8:
             lev_launch(lev_pack_kernel<int64_t>, grid, block, 0, st, (const int64_t*)t->data, t->T,
                        t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
-                       lens, flags, missing_flag, transposed);
+                       lens, flags, state, missing_flag, transposed);
             break;
         case 4:
             lev_launch(lev_pack_kernel<int32_t>, grid, block, 0, st, (const int32_t*)t->data, t->T,
                        t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
-                       lens, flags, missing_flag, transposed);
+                       lens, flags, state, missing_flag, transposed);
             break;
         case 2:
             lev_launch(lev_pack_kernel<int16_t>, grid, block, 0, st, (const int16_t*)t->data, t->T,
                        t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
-                       lens, flags, missing_flag, transposed);
+                       lens, flags, state, missing_flag, transposed);
             break;
         case 1:
             lev_launch(lev_pack_kernel<int8_t>, grid, block, 0, st, (const int8_t*)t->data, t->T,
                        t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
-                       lens, flags, missing_flag, transposed);
+                       lens, flags, state, missing_flag, transposed);
             break;
         default:
             lev_set_error("unsupported token element size %d", (int)t->elem_bytes);

@@ -107,11 +107,15 @@ def random_tokens(rng, T, N, V, eos, pad, min_len=0, no_eos_frac=0.0):
 
 def check_vs_oracle(F, dev, seed, R, H, N, V, costs, eos=0, include_eos=True, norm=False,
                     batch_first=False, exclude_last=False, padding=-100, min_frac=0.3,
-                    no_eos_frac=0.0, do_mask=True, dtype=torch.long):
-    """All DP-backed functionals on one random batch vs the oracle."""
+                    no_eos_frac=0.0, do_mask=True, dtype=torch.long, spread=1):
+    """All DP-backed functionals on one random batch vs the oracle.  `spread` > 1 scales
+    the token values so that their range exceeds 16 bits (32-bit compare paths)."""
     rng = np.random.default_rng(seed)
     ref = random_tokens(rng, R, N, V, eos if eos is not None else 0, -2, int(R * min_frac), no_eos_frac)
     hyp = random_tokens(rng, H, N, V, eos if eos is not None else 0, -3, int(H * min_frac), no_eos_frac)
+    if spread != 1:
+        ref = np.where(ref > 0, ref * spread, ref)
+        hyp = np.where(hyp > 0, hyp * spread, hyp)
     if batch_first:
         ref, hyp = np.ascontiguousarray(ref.T), np.ascontiguousarray(hyp.T)
     exact = all(float(c) == round(float(c) * 8) / 8 for c in costs)  # dyadic => exact fp32 sums

@@ -158,8 +158,10 @@ def test_group_kernel_vs_oracle(F, shape, costs, monkeypatch):
     for flags in (dict(include_eos=True, norm=True, exclude_last=False, min_frac=0.0),
                   dict(include_eos=False, norm=False, exclude_last=True, min_frac=0.4,
                        batch_first=True)):
-        PC.check_vs_oracle(F, DEV, seed=R + H, R=R, H=H, N=N, V=5, costs=costs, do_mask=False,
-                           padding=-3, **flags)
+        # spread=1: tokens fit 16 bits -> packed 2 x int16 DPX path; 70001: 32-bit path
+        for spread in (1, 70001):
+            PC.check_vs_oracle(F, DEV, seed=R + H, R=R, H=H, N=N, V=5, costs=costs, do_mask=False,
+                               padding=-3, spread=spread, **flags)
 
 
 def test_group_kernel_n_best_and_wide(F, monkeypatch):
