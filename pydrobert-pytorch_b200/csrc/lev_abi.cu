@@ -131,16 +131,19 @@ static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     if (do_pack) {
         if (cudaMemsetAsync(state, 0, 4 * sizeof(int32_t), st) != cudaSuccess)
             return lev_check_cuda("memset");
-        int rc = lev_launch_pack(ref, o->has_eos, o->eos, o->include_eos, ref_tok, L.Rp, ref_len,
-                                 flags, state, B200LEV_FLAG_REF_NO_EOS, st);
+        int rc = lev_launch_pack(ref, o->has_eos, o->eos, o->include_eos, ref_tok, L.Rp, nullptr, 0,
+                                 ref_len, flags, state, B200LEV_FLAG_REF_NO_EOS, st);
         if (rc) return rc;
-        rc = lev_launch_pack(hyp, o->has_eos, o->eos, o->include_eos, hyp_tok, L.Hp, hyp_len, flags,
-                             state, B200LEV_FLAG_HYP_NO_EOS, st);
+        rc = lev_launch_pack(hyp, o->has_eos, o->eos, o->include_eos, hyp_tok, L.Hp,
+                             (uint16_t*)(ws + L.off_hyp_tok16), L.Hp16, hyp_len, flags, state,
+                             B200LEV_FLAG_HYP_NO_EOS, st);
         if (rc) return rc;
     }
     memset(p, 0, sizeof(*p));
     p->ref_tok = ref_tok;
     p->hyp_tok = hyp_tok;
+    p->hyp_tok16 = (const uint16_t*)(ws + L.off_hyp_tok16);
+    p->Hp16 = L.Hp16;
     p->ref_len = ref_len;
     p->hyp_len = hyp_len;
     p->Rp = L.Rp;

@@ -20,9 +20,10 @@ static inline int64_t lev_round_up(int64_t x, int64_t m) { return (x + m - 1) / 
 struct LevLayout {
     int64_t R, H, Nref, P;
     int64_t Rp, Hp;  // padded row lengths of the packed int32 token tables
+    int64_t Hp16;    // padded row length of the 16-bit hypothesis table (multiple of 8)
     int64_t Hout;    // output rows of the prefix / mask modes
     int64_t Wd;      // 32-bit words of one (prefix, pair) distinct-token bitmap
-    size_t off_ref_tok, off_hyp_tok, off_ref_len, off_hyp_len, off_flags;
+    size_t off_ref_tok, off_hyp_tok, off_hyp_tok16, off_ref_len, off_hyp_len, off_flags;
     size_t off_uid, off_dtok, off_ndist, off_dbits;
     size_t bytes;
 };
@@ -36,6 +37,7 @@ static inline LevLayout lev_layout(const b200lev_tokens_t* ref, const b200lev_to
     L.P = hyp->N;
     L.Rp = lev_round_up(L.R > 0 ? L.R : 1, 4);
     L.Hp = lev_round_up(L.H > 0 ? L.H : 1, 4);
+    L.Hp16 = lev_round_up(L.H > 0 ? L.H : 1, 8);
     L.Hout = L.H + (exclude_last ? 0 : 1);
     if (for_completion && L.Hout < 1) L.Hout = 1;  // SM:271-278
     L.Wd = (L.R + 31) / 32;
@@ -48,6 +50,7 @@ static inline LevLayout lev_layout(const b200lev_tokens_t* ref, const b200lev_to
     };
     L.off_ref_tok = take(sizeof(int32_t) * (size_t)L.Nref * L.Rp);
     L.off_hyp_tok = take(sizeof(int32_t) * (size_t)L.P * L.Hp);
+    L.off_hyp_tok16 = take(sizeof(uint16_t) * (size_t)L.P * L.Hp16);
     L.off_ref_len = take(sizeof(int32_t) * (size_t)L.Nref);
     L.off_hyp_len = take(sizeof(int32_t) * (size_t)L.P);
     L.off_flags = take(4 * sizeof(int32_t));  // [flags, max(u), max(~u), -] (lev_pack.cu)
@@ -66,6 +69,8 @@ static inline LevLayout lev_layout(const b200lev_tokens_t* ref, const b200lev_to
 struct LevParams {
     const int32_t* ref_tok;  // [Nref][Rp]
     const int32_t* hyp_tok;  // [P][Hp]
+    const uint16_t* hyp_tok16;  // [P][Hp16] low 16 bits of every hypothesis token
+    int64_t Hp16;
     const int32_t* ref_len;  // [Nref]
     const int32_t* hyp_len;  // [P]
     int64_t Rp, Hp;
@@ -102,8 +107,8 @@ int lev_check_cuda(const char* what);
 
 // kernels' host launchers
 int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int include_eos,
-                    int32_t* packed, int64_t Tp, int32_t* lens, int32_t* flags, int32_t* state,
-                    int missing_flag, cudaStream_t st);
+                    int32_t* packed, int64_t Tp, uint16_t* packed16, int64_t Tp16, int32_t* lens,
+                    int32_t* flags, int32_t* state, int missing_flag, cudaStream_t st);
 int lev_launch_dp(const LevParams& p, int mode, bool count_mode, bool float_path,
                   cudaStream_t st);
 int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t st);

@@ -8,14 +8,23 @@
 //     serves C cells;
 //   * the whole row fits one strip (G*C >= r+1, right-aligned, virtual +BIG columns on
 //     the left) -- no shared-memory boundary column;
-//   * a CTA takes a TILE of consecutive pairs and buckets them in shared memory by
-//     (column class C, hypothesis length) with a counting sort; a warp then runs 32/G
-//     pairs of the SAME class and near-equal length in lock step, largest first, pulled
-//     from a shared-memory work queue.  Lane utilisation is (r+1)/(G*C) instead of
-//     (r+1)/(32*C), and no step is spent on a pair that has already finished.
+//   * persistent CTAs pull TILES of consecutive pairs from a global counter and bucket
+//     each tile in shared memory by (column class C, hypothesis length) with a counting
+//     sort; a warp then runs 32/G pairs (2 x 32/G in the packed path) of the SAME class
+//     and near-equal length in lock step, largest first, from a shared-memory work queue.
+//     Lane utilisation is (r+1)/(G*C) instead of (r+1)/(32*C), and no step is spent on a
+//     pair that has already finished;
+//   * the hypothesis rows of the NEXT task are fetched with cp.async (LDGSTS) into the
+//     other half of a double buffer while the current task runs;
 //   * prefix values are parked in shared memory by the one lane that owns column r and
-//     written out after the pair by all lanes (scale, IEEE division by the reference
-//     length, padding fill: SM:356-386), so the epilogue arithmetic is off the DP loop.
+//     written out after the task by all lanes (scale, IEEE division by the reference
+//     length, padding fill: SM:356-386), off the DP loop.
+//
+// PACKED path: when K0 found all tokens inside a 65536-wide window (their low 16 bits are
+// then injective) and costs/lengths keep every value below LEVG_BIG16, TWO pairs share
+// each register, one per 16-bit half, and the 2-wide DPX instructions do the work.  Per 2
+// cells: LOP3 (token xor), VIMNMX.U16x2 (-> 0/1 per half), IMAD (diag + neq*sub, FMA
+// pipe), 2 x VIADDMNMX.S16x2.  Otherwise the 32-bit path of lev_dp.cu's cell update runs.
 //
 // Integer costs only (cost row, or (cost, count) rows for the error-rate family);
 // FINAL and PREFIX modes.  Everything else stays on lev_dp.cu.
@@ -23,32 +32,46 @@
 
 #include "lev_common.cuh"
 
-#define LEVG_NCLS 6
-__device__ __forceinline__ int levg_class_cols(int cls) { return 8 + 4 * cls; }  // 8..28
-
-struct LevGroupGeom {
-    int G;      // lanes per pair
-    int tile;   // pairs per CTA
-    int Hs;     // shared-memory row stride (ints) of the per-pair token / prefix rows
-    int nbins;  // LEVG_NCLS * (H + 1)
-    int allow16;  // costs and lengths admit the packed 2 x int16 DPX path
-};
-
+#define LEVG_NCLS 6  // column classes C = 8, 12, ..., 28
 // "infinity" of the packed path: BIG16 + (largest reachable value) must stay < 2^15
 #define LEVG_BIG16 16000
+
+struct LevGroupGeom {
+    int G;         // lanes per pair
+    int tile;      // pairs per tile
+    int ntiles;
+    int Hs;        // words per prefix row (>= H + 2)
+    int row_words; // 32-bit words per staged hypothesis row
+    int nbins;     // LEVG_NCLS * (H + 1)
+    int allow16;   // costs and lengths admit the packed 2 x int16 DPX path
+    int nwarps;
+};
 
 // smallest class whose strip covers columns 0..r
 __device__ __forceinline__ int levg_class_of(int r, int G) {
     const int need = (r + G) / G;  // ceil((r + 1) / G)
-    int cls = (need - 8 + 3) >> 2;
+    const int cls = (need - 8 + 3) >> 2;
     return cls < 0 ? 0 : cls;
 }
 
+// IEEE-754 correctly rounded a / b from the correctly rounded reciprocal y = RN(1/b)
+// (Markstein): q0 = RN(a*y), r = a - b*q0 (exact in an FMA), q = RN(q0 + r*y).  Valid for
+// the operands here (0 <= a < 2^24, 1 <= b < 2^24 - 1, no exponent corner cases) and
+// 3 instructions per element once y is hoisted out of the row loop.
+__device__ __forceinline__ float levg_div(float a, float b, float y) {
+    const float q0 = __fmul_rn(a, y);
+    const float r = __fmaf_rn(-b, q0, a);
+    return __fmaf_rn(r, y, q0);
+}
+
+// ---------------------------------------------------------------------------------------
+// 32-bit path: one pair per lane group
+// ---------------------------------------------------------------------------------------
 template <bool COUNT, int MODE, int C>
-__device__ __forceinline__ void levg_run(const LevParams& p, const int G, const int pair,
-                                         const int r, const int h, const int steps,
-                                         const int maxsteps, const int* __restrict__ hyp_row,
-                                         int* __restrict__ pref_row) {
+__device__ __forceinline__ void levg_run32(const LevParams& p, const int G, const int pair,
+                                           const int r, const int h, const int steps,
+                                           const int maxsteps, const int* __restrict__ hyp_row,
+                                           int* __restrict__ pref_row) {
     const int lane = threadIdx.x & 31;
     const int gl = lane & (G - 1);
     const int refcol = pair >= 0 ? pair / p.ref_group : 0;
@@ -129,17 +152,16 @@ __device__ __forceinline__ void levg_run(const LevParams& p, const int G, const 
     }
 }
 
-// Packed path: TWO pairs per lane group, one in each 16-bit half of every register, driven
-// by the 2-wide DPX instructions (VIADDMNMX.S16x2, VIMNMX.U16x2).  Per 2 cells: LOP3 (token
-// xor), VIMNMX.U16x2 (-> 0/1 per half), IMAD (diag + neq*sub, FMA pipe), 2 x VIADDMNMX.S16x2.
-// Needs 16-bit-injective tokens (K0 measured max - min < 65536), non-negative integer costs
-// and values below LEVG_BIG16.  Cost row only.  Both pairs run `maxsteps` rows; rows past a
-// pair's own length are never read back.
+// ---------------------------------------------------------------------------------------
+// packed path: two pairs per lane group, one per 16-bit half.  Both run `maxsteps` rows;
+// rows past a pair's own length are never read back.  Cost row only.
+// ---------------------------------------------------------------------------------------
 template <int C>
 __device__ __forceinline__ void levg_run16(const LevParams& p, const int G, const int pairA,
                                            const int rA, const int pairB, const int rB,
                                            const int maxsteps,
-                                           const unsigned* __restrict__ hyp_row,
+                                           const unsigned short* __restrict__ hypA,
+                                           const unsigned short* __restrict__ hypB,
                                            unsigned* __restrict__ pref_row) {
     const int lane = threadIdx.x & 31;
     const int gl = lane & (G - 1);
@@ -170,7 +192,7 @@ __device__ __forceinline__ void levg_run16(const LevParams& p, const int G, cons
         pl = in;
         const int i = s - gl;
         if ((unsigned)(i - 1) < (unsigned)maxsteps) {
-            const unsigned ht = hyp_row[i - 1];
+            const unsigned ht = (unsigned)hypA[i - 1] | ((unsigned)hypB[i - 1] << 16);
             unsigned lf = in;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -187,219 +209,263 @@ __device__ __forceinline__ void levg_run16(const LevParams& p, const int G, cons
     }
 }
 
-template <bool COUNT, int MODE>
-__global__ void __launch_bounds__(256) lev_group_kernel(const LevParams p, const LevGroupGeom geo) {
+template <bool COUNT, int MODE, bool PACKED>
+__global__ void __launch_bounds__(256, 2) lev_group_kernel(const LevParams p, const LevGroupGeom geo) {
     LEV_DYN_SMEM(int, smem);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int G = geo.G, PPW = 32 / G, TILE = geo.tile, Hs = geo.Hs, H1 = p.H + 1;
-    const int tile0 = blockIdx.x * TILE;
-    const int ntile = min(TILE, p.P - tile0);
-    // shared-memory carve-up
-    int* hist = smem;                         // [nbins + 1]
-    int* order = hist + geo.nbins + 1;        // [TILE + 2 * LEVG_NCLS * PPW]
-    short* rl_s = reinterpret_cast<short*>(order + TILE + 2 * LEVG_NCLS * PPW);  // [TILE]
-    short* hl_s = rl_s + TILE;                                               // [TILE]
-    int* wbase = reinterpret_cast<int*>(hl_s + TILE);  // 2*TILE shorts: int-aligned
-    int* hyp_w = wbase + (size_t)warp * 2 * PPW * Hs;  // [PPW][Hs]
-    int* pref_w = hyp_w + PPW * Hs;                     // [PPW][Hs]
-    __shared__ int next_task, ntasks, seg_end[LEVG_NCLS];
-
-    // tokens that do not fit in int32: leave the whole batch to the 64-bit compare path of
-    // lev_warp_kernel, which the host enqueues right behind this kernel
+    // Which of the two builds of this kernel runs is decided on the device from what K0
+    // found in the tokens (no host round trip): wider than int32 -> neither (the 64-bit
+    // compare path of lev_warp_kernel, enqueued right behind, takes the batch); inside a
+    // 65536-wide window and small values -> PACKED; else the 32-bit build.
     if (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) return;
-    // K0 left the (biased) token range next to the flag word: [1] = max(u), [2] = max(~u),
-    // u = token + 2^31.  All tokens inside a 65536-wide window <=> their low 16 bits are
-    // injective <=> the packed path may compare 16-bit halves.
-    const unsigned umax = (unsigned)p.wide_flag[1], umin = ~(unsigned)p.wide_flag[2];
-    const bool packed = !COUNT && geo.allow16 && (umax < umin || umax - umin < 65536u);
-    const int PPT = packed ? 2 * PPW : PPW;  // pairs per task
-    // ---- 1. lengths, classes, histogram over (class desc, hyp length desc) ----
-    for (int b = tid; b <= geo.nbins; b += blockDim.x) hist[b] = 0;
-    for (int q = tid; q < TILE + 2 * LEVG_NCLS * PPW; q += blockDim.x) order[q] = -1;
-    if (tid == 0) next_task = 0;
-    __syncthreads();
-    for (int q = tid; q < ntile; q += blockDim.x) {
-        const int pair = tile0 + q;
-        const int r = p.ref_len[pair / p.ref_group];
-        const int h = p.hyp_len[pair];
-        rl_s[q] = (short)r;
-        hl_s[q] = (short)h;
-        if (MODE != LEV_MODE_MASK && r == 0 && p.norm && p.flags != nullptr)
-            atomicOr(p.flags, B200LEV_FLAG_EMPTY_REF);  // SM:360-366, 397-404
-        const int cls = levg_class_of(r, G);
-        atomicAdd(&hist[(LEVG_NCLS - 1 - cls) * H1 + (p.H - h)], 1);
+    {
+        // [1] = max(u), [2] = max(~u), u = token + 2^31 (lev_pack.cu)
+        const unsigned umax = (unsigned)p.wide_flag[1], umin = ~(unsigned)p.wide_flag[2];
+        const bool narrow = !COUNT && geo.allow16 && (umax < umin || umax - umin < 65536u);
+        if (narrow != PACKED) return;
     }
-    __syncthreads();
-    // ---- 2. exclusive scan (one warp; bins are few), class segments padded to PPW ----
-    if (warp == 0) {
-        int carry = 0;
-        for (int cseg = 0; cseg < LEVG_NCLS; ++cseg) {
-            for (int b0 = 0; b0 < H1; b0 += 32) {
-                const int b = b0 + lane;
-                const int cnt = b < H1 ? hist[cseg * H1 + b] : 0;
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(LEV_FULL_MASK, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                if (b < H1) hist[cseg * H1 + b] = carry + incl - cnt;
-                carry += __shfl_sync(LEV_FULL_MASK, incl, 31);
-            }
-            carry = (carry + PPT - 1) / PPT * PPT;
-            if (lane == 0) seg_end[cseg] = carry;
-        }
-        if (lane == 0) ntasks = carry / PPT;
-    }
-    __syncthreads();
-    // ---- 3. scatter pair indices into sorted order ----
-    for (int q = tid; q < ntile; q += blockDim.x) {
-        const int cls = levg_class_of(rl_s[q], G);
-        const int pos = atomicAdd(&hist[(LEVG_NCLS - 1 - cls) * H1 + (p.H - hl_s[q])], 1);
-        order[pos] = q;
-    }
-    __syncthreads();
-
-    // ---- 4. work queue: a task = PPW same-class pairs, one per lane group ----
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = geo.G, PPW = 32 / G, TILE = geo.tile, Hs = geo.Hs, H1 = p.H + 1;
+    const int PPT = PACKED ? 2 * PPW : PPW;  // pairs per task
+    const int RW = geo.row_words;
+    // shared-memory carve-up
+    int* hist = smem;                                                               // [nbins + 1]
+    int* order = hist + geo.nbins + 1;                                              // [TILE + NCLS*PPT]
+    short* rl_s = reinterpret_cast<short*>(order + TILE + LEVG_NCLS * PPT);        // [TILE]
+    short* hl_s = rl_s + TILE;                                                      // [TILE]
+    int* wbase = reinterpret_cast<int*>(hl_s + TILE) + ((TILE & 1) ? 1 : 0);
+    wbase = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(wbase) + 15) & ~(uintptr_t)15);
+    const int per_warp = 2 * PPT * RW + PPW * Hs;
+    int* stage_w = wbase + (size_t)warp * per_warp;  // [2][PPT][RW]   hypothesis rows
+    int* pref_w = stage_w + 2 * PPT * RW;            // [PPW][Hs]      prefix values
+    __shared__ int next_task, ntasks, seg_end[LEVG_NCLS], cur_tile;
+    int* tile_counter = const_cast<int*>(p.wide_flag) + 3;
     const int g = lane / G;
+
     for (;;) {
-        int t = 0;
-        if (lane == 0) t = atomicAdd(&next_task, 1);
-        t = __shfl_sync(LEV_FULL_MASK, t, 0);
-        if (t >= ntasks) break;
-        if (packed) {
-            // ---- packed task: 2*PPW pairs, group g runs pairs 2g (low half) and 2g+1 ----
-            const int qA = order[t * PPT + 2 * g], qB = order[t * PPT + 2 * g + 1];
-            const int rA = qA >= 0 ? rl_s[qA] : 0, rB = qB >= 0 ? rl_s[qB] : 0;
-            const int hA = qA >= 0 ? hl_s[qA] : 0, hB = qB >= 0 ? hl_s[qB] : 0;
-            const int hmax = hA > hB ? hA : hB;
-            int maxsteps = p.exclude_last ? (hmax > 0 ? hmax - 1 : 0) : hmax;
+        // ---- 0. next tile (persistent CTAs, global counter) ----
+        __syncthreads();
+        if (tid == 0) cur_tile = atomicAdd(tile_counter, 1);
+        __syncthreads();
+        const int tile = cur_tile;
+        if (tile >= geo.ntiles) break;
+        const int tile0 = tile * TILE;
+        const int ntile = min(TILE, p.P - tile0);
+        // ---- 1. lengths, classes, histogram over (class desc, hyp length desc) ----
+        for (int b = tid; b <= geo.nbins; b += blockDim.x) hist[b] = 0;
+        for (int q = tid; q < TILE + LEVG_NCLS * PPT; q += blockDim.x) order[q] = -1;
+        if (tid == 0) next_task = 0;
+        __syncthreads();
+        for (int q = tid; q < ntile; q += blockDim.x) {
+            const int pair = tile0 + q;
+            const int r = p.ref_len[pair / p.ref_group];
+            const int h = p.hyp_len[pair];
+            rl_s[q] = (short)r;
+            hl_s[q] = (short)h;
+            if (r == 0 && p.norm && p.flags != nullptr)
+                atomicOr(p.flags, B200LEV_FLAG_EMPTY_REF);  // SM:360-366, 397-404
+            atomicAdd(&hist[(LEVG_NCLS - 1 - levg_class_of(r, G)) * H1 + (p.H - h)], 1);
+        }
+        __syncthreads();
+        // ---- 2. exclusive scan (one warp), class segments padded to whole tasks ----
+        if (warp == 0) {
+            int carry = 0;
+            for (int cseg = 0; cseg < LEVG_NCLS; ++cseg) {
+                for (int b0 = 0; b0 < H1; b0 += 32) {
+                    const int b = b0 + lane;
+                    const int cnt = b < H1 ? hist[cseg * H1 + b] : 0;
+                    int incl = cnt;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const int other = __shfl_xor_sync(LEV_FULL_MASK, maxsteps, o);
-                maxsteps = other > maxsteps ? other : maxsteps;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(LEV_FULL_MASK, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    if (b < H1) hist[cseg * H1 + b] = carry + incl - cnt;
+                    carry += __shfl_sync(LEV_FULL_MASK, incl, 31);
+                }
+                carry = (carry + PPT - 1) / PPT * PPT;
+                if (lane == 0) seg_end[cseg] = carry;
             }
-            int cseg = 0;
-            while (t * PPT >= seg_end[cseg]) ++cseg;
-            const int cls = LEVG_NCLS - 1 - cseg;
-            unsigned short* hyp16 = reinterpret_cast<unsigned short*>(hyp_w);
-            for (int k = 0; k < PPT; ++k) {
+            if (lane == 0) ntasks = carry / PPT;
+        }
+        __syncthreads();
+        // ---- 3. scatter pair indices into sorted order ----
+        for (int q = tid; q < ntile; q += blockDim.x) {
+            const int pos = atomicAdd(
+                &hist[(LEVG_NCLS - 1 - levg_class_of(rl_s[q], G)) * H1 + (p.H - hl_s[q])], 1);
+            order[pos] = q;
+        }
+        __syncthreads();
+
+        // ---- 4. work queue; hypothesis rows of the next task prefetched with cp.async ----
+        auto claim = [&]() {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&next_task, 1);
+            return __shfl_sync(LEV_FULL_MASK, t, 0);
+        };
+        auto stage = [&](int t, int buf) {
+            // 16-byte chunks of the PPT token rows (uint16 rows when PACKED, int32 otherwise)
+            const int chunks_per_row = RW / 4;
+            char* dst0 = reinterpret_cast<char*>(stage_w + buf * PPT * RW);
+            for (int c = lane; c < PPT * chunks_per_row; c += 32) {
+                const int k = c / chunks_per_row, ch = c - k * chunks_per_row;
                 const int qk = order[t * PPT + k];
                 if (qk < 0) continue;
                 const int hk = hl_s[qk];
                 const int sk = p.exclude_last ? (hk > 0 ? hk - 1 : 0) : hk;
-                const int32_t* __restrict__ src = p.hyp_tok + (int64_t)(tile0 + qk) * p.Hp;
-                for (int i = lane; i < sk; i += 32)
-                    hyp16[(((k >> 1) * Hs + i) << 1) + (k & 1)] = (unsigned short)src[i];
+                const int bytes = sk * (PACKED ? 2 : 4);
+                if (ch * 16 >= bytes) continue;
+                const char* src = PACKED
+                    ? reinterpret_cast<const char*>(p.hyp_tok16 + (int64_t)(tile0 + qk) * p.Hp16)
+                    : reinterpret_cast<const char*>(p.hyp_tok + (int64_t)(tile0 + qk) * p.Hp);
+                lev_cp_async16(dst0 + (size_t)k * RW * 4 + ch * 16, src + ch * 16);
             }
+        };
+        int cur = claim(), buf = 0;
+        if (cur < ntasks) stage(cur, buf);
+        lev_cp_async_commit();
+        while (cur < ntasks) {
+            const int nxt = claim();
+            if (nxt < ntasks) stage(nxt, buf ^ 1);
+            lev_cp_async_commit();
+            lev_cp_async_wait<1>();  // everything but the newest group: this task's rows landed
             __syncwarp();
-            const unsigned* hrow = reinterpret_cast<const unsigned*>(hyp_w) + g * Hs;
-            unsigned* prow = reinterpret_cast<unsigned*>(pref_w) + g * Hs;
-            const int pA = qA >= 0 ? tile0 + qA : -1, pB = qB >= 0 ? tile0 + qB : -1;
-            switch (cls) {
-                case 0: levg_run16<8>(p, G, pA, rA, pB, rB, maxsteps, hrow, prow); break;
-                case 1: levg_run16<12>(p, G, pA, rA, pB, rB, maxsteps, hrow, prow); break;
-                case 2: levg_run16<16>(p, G, pA, rA, pB, rB, maxsteps, hrow, prow); break;
-                case 3: levg_run16<20>(p, G, pA, rA, pB, rB, maxsteps, hrow, prow); break;
-                case 4: levg_run16<24>(p, G, pA, rA, pB, rB, maxsteps, hrow, prow); break;
-                default: levg_run16<28>(p, G, pA, rA, pB, rB, maxsteps, hrow, prow); break;
-            }
-            __syncwarp();
-            // epilogue for all 2*PPW pairs (SM:279-285, 340-346, 356-386 / 390-405)
-            for (int k = 0; k < PPT; ++k) {
-                const int qk = order[t * PPT + k];
-                if (qk < 0) continue;
-                const int rk = rl_s[qk], hk = hl_s[qk];
-                const unsigned* row = reinterpret_cast<const unsigned*>(pref_w) + (k >> 1) * Hs;
-                const int sh16 = (k & 1) * 16;
-                const float rf = (float)rk;
-                if (MODE == LEV_MODE_PREFIX) {
-                    const int first_pad = hk + (p.exclude_last ? 0 : 1);
-                    const int64_t col = (int64_t)(tile0 + qk) * p.out_sn;
-                    for (int i = lane; i < p.Hout; i += 32) {
-                        float val;
-                        if (i >= first_pad) {
-                            val = p.padding;
-                        } else {
-                            const int raw = (i == 0) ? rk * p.del_i : (int)((row[i] >> sh16) & 0xffffu);
-                            val = (float)raw * p.mult;
-                            if (p.norm) val = (rk == 0) ? (i > 0 ? 1.0f : 0.0f) : val / rf;
-                        }
-                        p.out[(int64_t)i * p.out_si + col] = val;
-                    }
-                } else if (lane == 0) {
-                    const int raw = (hk == 0) ? rk * p.del_i : (int)((row[hk] >> sh16) & 0xffffu);
-                    float val = (float)raw * p.mult;
-                    if (p.norm) val = (rk == 0) ? (hk > 0 ? 1.0f : 0.0f) : val / rf;
-                    p.out[tile0 + qk] = val;
-                }
-            }
-            __syncwarp();
-            continue;
-        }
-        const int q = order[t * PPW + g];
-        const int pair = q >= 0 ? tile0 + q : -1;
-        const int r = q >= 0 ? rl_s[q] : 0;
-        const int h = q >= 0 ? hl_s[q] : 0;
-        const int steps = p.exclude_last ? (h > 0 ? h - 1 : 0) : h;  // SM:286-288
-        int maxsteps = steps;
+            const int t = cur;
+            int cseg = 0;
+            while (t * PPT >= seg_end[cseg]) ++cseg;  // class segments are task-pure
+            const int cls = LEVG_NCLS - 1 - cseg;
+            const int* rows = stage_w + buf * PPT * RW;
+            if (PACKED) {
+                // group g runs pairs 2g (low halves) and 2g+1 (high halves) of the task
+                const int qA = order[t * PPT + 2 * g], qB = order[t * PPT + 2 * g + 1];
+                const int rA = qA >= 0 ? rl_s[qA] : 0, rB = qB >= 0 ? rl_s[qB] : 0;
+                const int hA = qA >= 0 ? hl_s[qA] : 0, hB = qB >= 0 ? hl_s[qB] : 0;
+                const int hmax = hA > hB ? hA : hB;
+                int maxsteps = p.exclude_last ? (hmax > 0 ? hmax - 1 : 0) : hmax;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const int other = __shfl_xor_sync(LEV_FULL_MASK, maxsteps, o);
-            maxsteps = other > maxsteps ? other : maxsteps;
-        }
-        // class of the task = class of its first pair (segments are class-pure)
-        int cseg = 0;
-        while (t * PPW >= seg_end[cseg]) ++cseg;
-        const int cls = LEVG_NCLS - 1 - cseg;
-        // stage the hypothesis tokens of the PPW pairs: one contiguous row each
-        for (int k = 0; k < PPW; ++k) {
-            const int qk = order[t * PPW + k];
-            if (qk < 0) continue;
-            const int hk = hl_s[qk];
-            const int sk = p.exclude_last ? (hk > 0 ? hk - 1 : 0) : hk;
-            const int32_t* __restrict__ src = p.hyp_tok + (int64_t)(tile0 + qk) * p.Hp;
-            for (int i = lane; i < sk; i += 32) hyp_w[k * Hs + i] = src[i];
-        }
-        __syncwarp();
-        const int* hyp_row = hyp_w + g * Hs;
-        int* pref_row = pref_w + g * Hs;
-        switch (cls) {
-            case 0: levg_run<COUNT, MODE, 8>(p, G, pair, r, h, steps, maxsteps, hyp_row, pref_row); break;
-            case 1: levg_run<COUNT, MODE, 12>(p, G, pair, r, h, steps, maxsteps, hyp_row, pref_row); break;
-            case 2: levg_run<COUNT, MODE, 16>(p, G, pair, r, h, steps, maxsteps, hyp_row, pref_row); break;
-            case 3: levg_run<COUNT, MODE, 20>(p, G, pair, r, h, steps, maxsteps, hyp_row, pref_row); break;
-            case 4: levg_run<COUNT, MODE, 24>(p, G, pair, r, h, steps, maxsteps, hyp_row, pref_row); break;
-            default: levg_run<COUNT, MODE, 28>(p, G, pair, r, h, steps, maxsteps, hyp_row, pref_row); break;
-        }
-        __syncwarp();
-        if (MODE == LEV_MODE_PREFIX) {
-            // SM:279-285 (row 0), 340-346 (rows 1..), 356-386 (scale, norm, tail padding)
-            for (int k = 0; k < PPW; ++k) {
-                const int qk = order[t * PPW + k];
-                if (qk < 0) continue;
-                const int rk = rl_s[qk], hk = hl_s[qk];
-                const int first_pad = hk + (p.exclude_last ? 0 : 1);
-                const int64_t col = (int64_t)(tile0 + qk) * p.out_sn;
-                const float rf = (float)rk;
-                for (int i = lane; i < p.Hout; i += 32) {
-                    float val;
-                    if (i >= first_pad) {
-                        val = p.padding;
-                    } else {
-                        const int raw = (i == 0) ? (COUNT ? rk : rk * p.del_i) : pref_w[k * Hs + i];
-                        val = (float)raw * p.mult;
-                        if (p.norm) val = (rk == 0) ? (i > 0 ? 1.0f : 0.0f) : val / rf;
-                    }
-                    p.out[(int64_t)i * p.out_si + col] = val;
+                for (int o = 16; o > 0; o >>= 1) {
+                    const int other = __shfl_xor_sync(LEV_FULL_MASK, maxsteps, o);
+                    maxsteps = other > maxsteps ? other : maxsteps;
+                }
+                const unsigned short* hA_row = reinterpret_cast<const unsigned short*>(rows + (2 * g) * RW);
+                const unsigned short* hB_row = reinterpret_cast<const unsigned short*>(rows + (2 * g + 1) * RW);
+                unsigned* prow = reinterpret_cast<unsigned*>(pref_w) + g * Hs;
+                const int pA = qA >= 0 ? tile0 + qA : -1, pB = qB >= 0 ? tile0 + qB : -1;
+                switch (cls) {
+                    case 0: levg_run16<8>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
+                    case 1: levg_run16<12>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
+                    case 2: levg_run16<16>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
+                    case 3: levg_run16<20>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
+                    case 4: levg_run16<24>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
+                    default: levg_run16<28>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
+                }
+            } else {
+                const int q = order[t * PPT + g];
+                const int pair = q >= 0 ? tile0 + q : -1;
+                const int r = q >= 0 ? rl_s[q] : 0;
+                const int h = q >= 0 ? hl_s[q] : 0;
+                const int steps = p.exclude_last ? (h > 0 ? h - 1 : 0) : h;  // SM:286-288
+                int maxsteps = steps;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const int other = __shfl_xor_sync(LEV_FULL_MASK, maxsteps, o);
+                    maxsteps = other > maxsteps ? other : maxsteps;
+                }
+                const int* hyp_row = rows + g * RW;
+                int* prow = pref_w + g * Hs;
+                switch (cls) {
+                    case 0: levg_run32<COUNT, MODE, 8>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
+                    case 1: levg_run32<COUNT, MODE, 12>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
+                    case 2: levg_run32<COUNT, MODE, 16>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
+                    case 3: levg_run32<COUNT, MODE, 20>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
+                    case 4: levg_run32<COUNT, MODE, 24>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
+                    default: levg_run32<COUNT, MODE, 28>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
                 }
             }
             __syncwarp();
+            // ---- epilogue (SM:279-285, 340-346, 356-386 / 390-405) ----
+            // 32/PPT lanes per pair, each striding over that pair's rows: the per-pair
+            // set-up (lengths, reciprocal, output column) is done once per lane
+            if (MODE == LEV_MODE_PREFIX || PACKED) {
+                const int LPP = PPT >= 32 ? 1 : 32 / PPT;  // lanes per pair
+                for (int kk = lane; kk < PPT * LPP; kk += 32) {
+                    const int k = kk / LPP, sub = kk - k * LPP;
+                    const int qk = order[t * PPT + k];
+                    if (qk < 0) continue;
+                    const int rk = rl_s[qk], hk = hl_s[qk];
+                    const unsigned* row =
+                        reinterpret_cast<const unsigned*>(pref_w) + (PACKED ? (k >> 1) : k) * Hs;
+                    const int sh16 = PACKED ? (k & 1) * 16 : 0;
+                    const unsigned msk = PACKED ? 0xffffu : 0xffffffffu;
+                    const float rf = (float)rk;
+                    const float y = rk > 0 ? __frcp_rn(rf) : 0.0f;
+                    const int row0 = COUNT ? rk : rk * p.del_i;
+                    const bool norm = p.norm != 0;
+                    if (MODE == LEV_MODE_PREFIX) {
+                        const int first_pad = hk + (p.exclude_last ? 0 : 1);
+                        float* o = p.out + (int64_t)(tile0 + qk) * p.out_sn + (int64_t)sub * p.out_si;
+                        const int64_t ostep = (int64_t)LPP * p.out_si;
+                        for (int i = sub; i < p.Hout; i += LPP, o += ostep) {
+                            float val = p.padding;
+                            if (i < first_pad) {
+                                const int raw = (i == 0) ? row0 : (int)((row[i] >> sh16) & msk);
+                                val = __fmul_rn((float)raw, p.mult);
+                                if (norm) val = (rk == 0) ? (i > 0 ? 1.0f : 0.0f) : levg_div(val, rf, y);
+                            }
+                            *o = val;
+                        }
+                    } else if (sub == 0) {  // PACKED FINAL: the value parked at row h
+                        const int raw = (hk == 0) ? row0 : (int)((row[hk] >> sh16) & msk);
+                        float val = __fmul_rn((float)raw, p.mult);
+                        if (norm) val = (rk == 0) ? (hk > 0 ? 1.0f : 0.0f) : levg_div(val, rf, y);
+                        p.out[tile0 + qk] = val;
+                    }
+                }
+            }
+            __syncwarp();
+            cur = nxt;
+            buf ^= 1;
         }
+        lev_cp_async_wait<0>();
     }
 }
 
-// Returns 1 if the group kernel took the job, 0 if it does not apply (caller falls back
+// geometry + shared-memory footprint of one build; false if it cannot keep 2 CTAs per SM
+static bool levg_geometry(const LevParams& p, bool packed, LevGroupGeom* geo, size_t* smem) {
+    const int PPW = 32 / geo->G, PPT = packed ? 2 * PPW : PPW;
+    // staged hypothesis rows: uint16 (packed) or int32; whole 16-byte chunks per row
+    geo->row_words = packed ? (int)((p.H + 7) / 8) * 4 : (int)((p.H + 3) / 4) * 4;
+    if (geo->row_words < 4) geo->row_words = 4;
+    geo->Hs = ((p.H + 2 + 3) / 4) * 4;
+    geo->tile = 512;
+    if (geo->tile < 16 * PPT) geo->tile = 16 * PPT;
+    geo->ntiles = (int)(((int64_t)p.P + geo->tile - 1) / geo->tile);
+    geo->nwarps = 8;
+    const size_t per_warp = sizeof(int) * ((size_t)2 * PPT * geo->row_words + (size_t)PPW * geo->Hs);
+    *smem = sizeof(int) * (geo->nbins + 1 + geo->tile + LEVG_NCLS * PPT) +
+            sizeof(short) * (2 * geo->tile) + per_warp * geo->nwarps + 64;
+    return *smem <= 110 * 1024;
+}
+
+template <bool COUNT, int MODE, bool PACKED>
+static int levg_launch_one(const LevParams& p, LevGroupGeom geo, cudaStream_t st) {
+    size_t smem = 0;
+    if (!levg_geometry(p, PACKED, &geo, &smem)) return 0;
+    auto kern = lev_group_kernel<COUNT, MODE, PACKED>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            lev_set_error("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+            return B200LEV_ERR_CUDA;
+        }
+    }
+    int blocks = 148 * 2;
+    if (blocks > geo.ntiles) blocks = geo.ntiles;
+    lev_launch(kern, dim3((unsigned)blocks), dim3(32 * geo.nwarps), smem, st, p, geo);
+    const int rc = lev_check_cuda("lev_group_kernel");
+    return rc ? rc : 1;
+}
+
+// Returns 1 if the group kernels took the job, 0 if they do not apply (caller falls back
 // to the warp-per-pair kernel), < 0 on error.
 int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t st) {
     if (mode == LEV_MODE_MASK) return 0;
@@ -412,9 +478,8 @@ int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t
     while (G <= 32 && G * 28 < p.R + 1) G <<= 1;
     if (G > 32 || p.H > 1000 || p.R > 30000) return 0;
     LevGroupGeom geo;
+    memset(&geo, 0, sizeof(geo));
     geo.G = G;
-    const int PPW = 32 / G;
-    geo.Hs = ((p.H + 2 + 31) / 32) * 32 + G;  // stride == G (mod 32): conflict-free rows
     geo.nbins = LEVG_NCLS * (p.H + 1);
     const int maxc = p.ins_i > p.del_i ? (p.ins_i > p.sub_i ? p.ins_i : p.sub_i)
                                        : (p.del_i > p.sub_i ? p.del_i : p.sub_i);
@@ -423,36 +488,32 @@ int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t
                       ? 1
                       : 0;
     if (const char* e = getenv("B200LEV_GROUP_PACKED16")) geo.allow16 = geo.allow16 && atoi(e);
-    const size_t per_warp = (size_t)2 * PPW * geo.Hs * sizeof(int);
-    const int nwarps = 8;
-    int tile = 512;
-    if (tile < 16 * PPW) tile = 16 * PPW;
-    geo.tile = tile;
-    const size_t smem = sizeof(int) * (geo.nbins + 1 + tile + 2 * LEVG_NCLS * PPW) +
-                        sizeof(short) * (2 * tile) + per_warp * nwarps + 16;
-    if (smem > 200 * 1024) return 0;
-    const int64_t blocks = ((int64_t)p.P + tile - 1) / tile;
-#define LEVG_LAUNCH(COUNT_, MODE_)                                                              \
-    {                                                                                           \
-        auto kern = lev_group_kernel<COUNT_, MODE_>;                                            \
-        if (smem > 48 * 1024) {                                                                 \
-            cudaError_t e = cudaFuncSetAttribute(                                               \
-                kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                  \
-            if (e != cudaSuccess) {                                                             \
-                lev_set_error("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e)); \
-                return B200LEV_ERR_CUDA;                                                        \
-            }                                                                                   \
-        }                                                                                       \
-        lev_launch(kern, dim3((unsigned)blocks), dim3(32 * nwarps), smem, st, p, geo);          \
+    // the 32-bit build must be launchable (it is the one that runs when the tokens turn
+    // out not to fit 16 bits); the packed build is optional
+    LevGroupGeom tmp = geo;
+    size_t smem = 0;
+    if (!levg_geometry(p, false, &tmp, &smem)) return 0;
+    tmp = geo;
+    if (geo.allow16 && !levg_geometry(p, true, &tmp, &smem)) geo.allow16 = 0;
+    // the persistent CTAs pull tiles from state word 3: rewind it for this launch
+    if (cudaMemsetAsync(const_cast<int*>(p.wide_flag) + 3, 0, sizeof(int), st) != cudaSuccess)
+        return lev_check_cuda("memset");
+    // both builds are enqueued; the device-side token range decides which one works
+    int rc;
+#define LEVG_BOTH(COUNT_, MODE_)                                                   \
+    rc = levg_launch_one<COUNT_, MODE_, false>(p, geo, st);                        \
+    if (rc <= 0) return rc;                                                        \
+    if (!COUNT_ && geo.allow16) {                                                  \
+        rc = levg_launch_one<COUNT_, MODE_, true>(p, geo, st);                     \
+        if (rc <= 0) return rc < 0 ? rc : B200LEV_ERR_UNSUPPORTED;                 \
     }
     if (!count_mode) {
-        if (mode == LEV_MODE_FINAL) LEVG_LAUNCH(false, LEV_MODE_FINAL)
-        else LEVG_LAUNCH(false, LEV_MODE_PREFIX)
+        if (mode == LEV_MODE_FINAL) { LEVG_BOTH(false, LEV_MODE_FINAL) }
+        else { LEVG_BOTH(false, LEV_MODE_PREFIX) }
     } else {
-        if (mode == LEV_MODE_FINAL) LEVG_LAUNCH(true, LEV_MODE_FINAL)
-        else LEVG_LAUNCH(true, LEV_MODE_PREFIX)
+        if (mode == LEV_MODE_FINAL) { LEVG_BOTH(true, LEV_MODE_FINAL) }
+        else { LEVG_BOTH(true, LEV_MODE_PREFIX) }
     }
-#undef LEVG_LAUNCH
-    const int rc = lev_check_cuda("lev_group_kernel");
-    return rc ? rc : 1;
+#undef LEVG_BOTH
+    return 1;
 }

@@ -15,7 +15,8 @@ template <typename TT>
 __global__ void __launch_bounds__(256)
 lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, int64_t sn,
                 int has_eos, int64_t eos, int include_eos, int32_t* __restrict__ packed,
-                int64_t Tp, int32_t* __restrict__ lens, int32_t* flags, int32_t* state,
+                int64_t Tp, uint16_t* __restrict__ packed16, int64_t Tp16,
+                int32_t* __restrict__ lens, int32_t* flags, int32_t* state,
                 int missing_flag, int transposed) {
     __shared__ int tile[32][33];
     __shared__ int first[32];
@@ -54,7 +55,11 @@ lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, in
             for (int q = 0; q < 4; ++q) {
                 const int nl = ty + 8 * q;
                 const int64_t n = n0 + nl, t = t0 + tx;
-                if (t < T && n < N) packed[n * Tp + t] = tile[tx][nl];
+                if (t < T && n < N) {
+                    const int v = tile[tx][nl];
+                    packed[n * Tp + t] = v;
+                    if (packed16 != nullptr) packed16[n * Tp16 + t] = (uint16_t)v;
+                }
             }
             __syncthreads();
         }
@@ -67,6 +72,7 @@ lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, in
                 for (int64_t t = tx; t < T; t += 32) {
                     const int64_t v = (int64_t)tok[t * st + n * sn];
                     packed[n * Tp + t] = (int)v;
+                    if (packed16 != nullptr) packed16[n * Tp16 + t] = (uint16_t)(int)v;
                     if (has_eos && v == eos) atomicMin(&first[nl], (int)t);
                     if ((int64_t)(int)v != v) wide = 1;
                     const unsigned u = (unsigned)(int)v + 0x80000000u;
@@ -111,8 +117,8 @@ lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, in
 }
 
 int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int include_eos,
-                    int32_t* packed, int64_t Tp, int32_t* lens, int32_t* flags, int32_t* state,
-                    int missing_flag, cudaStream_t st) {
+                    int32_t* packed, int64_t Tp, uint16_t* packed16, int64_t Tp16, int32_t* lens,
+                    int32_t* flags, int32_t* state, int missing_flag, cudaStream_t st) {
     if (t->N <= 0) return B200LEV_OK;
     if (t->T >= (int64_t)1 << 30) {
         lev_set_error("sequence dimension %lld too long", (long long)t->T);
@@ -127,22 +133,22 @@ int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int inc
         case 8:
             lev_launch(lev_pack_kernel<int64_t>, grid, block, 0, st, (const int64_t*)t->data, t->T,
                        t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
-                       lens, flags, state, missing_flag, transposed);
+                       packed16, Tp16, lens, flags, state, missing_flag, transposed);
             break;
         case 4:
             lev_launch(lev_pack_kernel<int32_t>, grid, block, 0, st, (const int32_t*)t->data, t->T,
                        t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
-                       lens, flags, state, missing_flag, transposed);
+                       packed16, Tp16, lens, flags, state, missing_flag, transposed);
             break;
         case 2:
             lev_launch(lev_pack_kernel<int16_t>, grid, block, 0, st, (const int16_t*)t->data, t->T,
                        t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
-                       lens, flags, state, missing_flag, transposed);
+                       packed16, Tp16, lens, flags, state, missing_flag, transposed);
             break;
         case 1:
             lev_launch(lev_pack_kernel<int8_t>, grid, block, 0, st, (const int8_t*)t->data, t->T,
                        t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
-                       lens, flags, state, missing_flag, transposed);
+                       packed16, Tp16, lens, flags, state, missing_flag, transposed);
             break;
         default:
             lev_set_error("unsupported token element size %d", (int)t->elem_bytes);

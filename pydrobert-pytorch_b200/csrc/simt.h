@@ -24,6 +24,19 @@ static inline void lev_launch(void (*k)(KArgs...), dim3 grid, dim3 block, size_t
     extern __shared__ __align__(16) unsigned char name##_raw_[];   \
     type* name = reinterpret_cast<type*>(name##_raw_)
 #define LEV_SPIN_YIELD() ((void)0)
+
+// Ampere-style asynchronous global->shared copies (LDGSTS), 16 bytes per call
+__device__ __forceinline__ void lev_cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void lev_cp_async_commit() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void lev_cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 #endif
 
 #define LEV_FULL_MASK 0xffffffffu

@@ -51,14 +51,14 @@ def main():
                 print(f"  {h:78s} {v:>16s} {u}")
         stalls = []
         for h in hdr:
-            if h.startswith(STALL) and h.endswith("_per_warp_active.pct"):
+            if h.startswith(STALL) and h.endswith("_per_issue_active.ratio"):
                 try:
-                    stalls.append((float(d[h]), h[len(STALL):-len("_per_warp_active.pct")]))
+                    stalls.append((float(d[h]), h[len(STALL):-len("_per_issue_active.ratio")]))
                 except ValueError:
                     pass
         stalls.sort(reverse=True)
-        print("  stall reasons (% of warp-active cycles):",
-              ", ".join(f"{n} {v:.1f}" for v, n in stalls[:8]))
+        print("  stall reasons (warps stalled per issue-active cycle):",
+              ", ".join(f"{n} {v:.2f}" for v, n in stalls[:9]))
         if "--all" not in sys.argv:
             break
 

@@ -359,3 +359,8 @@ static inline void lev_launch(void (*k)(KArgs...), dim3 grid, dim3 block, size_t
 }
 #define LEV_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::g_dyn_smem)
 #define LEV_SPIN_YIELD() emu::yield()
+static inline void lev_cp_async16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
+static inline void lev_cp_async_commit() {}
+template <int N>
+static inline void lev_cp_async_wait() {}
+static inline float __frcp_rn(float x) { return 1.0f / x; }
