@@ -129,14 +129,19 @@ static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     // warning bits
     int32_t* state = (int32_t*)(ws + L.off_flags);
     if (do_pack) {
-        if (cudaMemsetAsync(state, 0, 4 * sizeof(int32_t), st) != cudaSuccess)
-            return lev_check_cuda("memset");
+        // the group kernel's (class, length) histogram is built by the hypothesis pass
+        // whenever the shapes make that kernel eligible (lev_group.cu decides later)
+        const int G = lev_group_eligible(L.R, L.H, L.P);
+        const size_t clear = sizeof(int32_t) * (size_t)(4 + (G ? L.nbins : 0));
+        if (cudaMemsetAsync(state, 0, clear, st) != cudaSuccess) return lev_check_cuda("memset");
         int rc = lev_launch_pack(ref, o->has_eos, o->eos, o->include_eos, ref_tok, L.Rp, nullptr, 0,
-                                 ref_len, flags, state, B200LEV_FLAG_REF_NO_EOS, st);
+                                 ref_len, flags, state, B200LEV_FLAG_REF_NO_EOS, nullptr, 1, 0,
+                                 nullptr, st);
         if (rc) return rc;
         rc = lev_launch_pack(hyp, o->has_eos, o->eos, o->include_eos, hyp_tok, L.Hp,
                              (uint16_t*)(ws + L.off_hyp_tok16), L.Hp16, hyp_len, flags, state,
-                             B200LEV_FLAG_HYP_NO_EOS, st);
+                             B200LEV_FLAG_HYP_NO_EOS, ref_len, o->ref_group, G,
+                             G ? (int*)(ws + L.off_ghist) : nullptr, st);
         if (rc) return rc;
     }
     memset(p, 0, sizeof(*p));
@@ -165,6 +170,11 @@ static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     p->hyp_sn = hyp->stride_n;
     p->ref_eb = ref->elem_bytes;
     p->hyp_eb = hyp->elem_bytes;
+    p->ghist = (int*)(ws + L.off_ghist);
+    p->gcursor = (int*)(ws + L.off_gcursor);
+    p->gmeta = (int*)(ws + L.off_gmeta);
+    p->slots = (int4*)(ws + L.off_slots);
+    p->nbins = (int)L.nbins;
     return B200LEV_OK;
 }
 

@@ -15,6 +15,26 @@ enum LevMode { LEV_MODE_FINAL = 0, LEV_MODE_PREFIX = 1, LEV_MODE_MASK = 2 };
 
 static inline int64_t lev_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// ---- group kernel bucketing (lev_group.cu, histogram built by lev_pack.cu) ----
+#define LEV_GROUP_NCLS 6  // column classes C = 8, 12, ..., 28 per lane
+// lanes per pair for a padded reference length R: smallest power of two >= 2 with
+// G * 28 >= R + 1; 0 if the group kernel does not apply
+static inline int lev_group_lanes(int64_t R) {
+    int G = 2;
+    while (G <= 32 && (int64_t)G * 28 < R + 1) G <<= 1;
+    return G <= 32 ? G : 0;
+}
+// smallest class whose strip of G*C columns covers columns 0..r
+__host__ __device__ static inline int lev_group_class(int r, int G) {
+    const int need = (r + G) / G;  // ceil((r + 1) / G)
+    const int cls = (need - 8 + 3) >> 2;
+    return cls < 0 ? 0 : cls;
+}
+// histogram bin of a pair: classes descending, then hypothesis lengths descending
+__host__ __device__ static inline int lev_group_bin(int r, int h, int G, int H) {
+    return (LEV_GROUP_NCLS - 1 - lev_group_class(r, G)) * (H + 1) + (H - h);
+}
+
 // Workspace layout (device scratch supplied by the caller).  All offsets are
 // multiples of 128 bytes.
 struct LevLayout {
@@ -24,6 +44,10 @@ struct LevLayout {
     int64_t Hout;    // output rows of the prefix / mask modes
     int64_t Wd;      // 32-bit words of one (prefix, pair) distinct-token bitmap
     size_t off_ref_tok, off_hyp_tok, off_hyp_tok16, off_ref_len, off_hyp_len, off_flags;
+    // group kernel (lev_group.cu): [ghist nbins][gcursor nbins][gmeta 16] follow the 4 state
+    // words directly (one memset clears state + ghist); slots = sorted task table
+    int64_t nbins;
+    size_t off_ghist, off_gcursor, off_gmeta, off_slots;
     size_t off_uid, off_dtok, off_ndist, off_dbits;
     size_t bytes;
 };
@@ -53,7 +77,12 @@ static inline LevLayout lev_layout(const b200lev_tokens_t* ref, const b200lev_to
     L.off_hyp_tok16 = take(sizeof(uint16_t) * (size_t)L.P * L.Hp16);
     L.off_ref_len = take(sizeof(int32_t) * (size_t)L.Nref);
     L.off_hyp_len = take(sizeof(int32_t) * (size_t)L.P);
-    L.off_flags = take(4 * sizeof(int32_t));  // [flags, max(u), max(~u), -] (lev_pack.cu)
+    L.nbins = LEV_GROUP_NCLS * (L.H + 1);
+    L.off_flags = take(sizeof(int32_t) * (size_t)(4 + 2 * L.nbins + 16));  // state + group tables
+    L.off_ghist = L.off_flags + 4 * sizeof(int32_t);
+    L.off_gcursor = L.off_ghist + sizeof(int32_t) * (size_t)L.nbins;
+    L.off_gmeta = L.off_gcursor + sizeof(int32_t) * (size_t)L.nbins;
+    L.off_slots = take(16 * (size_t)(L.P + LEV_GROUP_NCLS * 32));
     L.off_uid = L.off_dtok = L.off_ndist = L.off_dbits = 0;
     if (for_completion) {
         L.off_uid = take(sizeof(int32_t) * (size_t)L.Nref * L.Rp);
@@ -99,6 +128,12 @@ struct LevParams {
     int64_t ref_st, ref_sn, hyp_st, hyp_sn;
     int ref_eb, hyp_eb;
     int only_if_wide;  // lev_warp_kernel: exit unless the wide-token flag is set
+    // group kernel tables (workspace)
+    int* ghist;
+    int* gcursor;
+    int* gmeta;   // [0] = number of tasks
+    int4* slots;  // sorted (pair, r, h, class) per task slot; pair < 0 = padding
+    int nbins;
 };
 
 // host-side status plumbing (lev_abi.cu)
@@ -108,10 +143,14 @@ int lev_check_cuda(const char* what);
 // kernels' host launchers
 int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int include_eos,
                     int32_t* packed, int64_t Tp, uint16_t* packed16, int64_t Tp16, int32_t* lens,
-                    int32_t* flags, int32_t* state, int missing_flag, cudaStream_t st);
+                    int32_t* flags, int32_t* state, int missing_flag, const int32_t* ref_len,
+                    int ref_group, int G, int* ghist, cudaStream_t st);
 int lev_launch_dp(const LevParams& p, int mode, bool count_mode, bool float_path,
                   cudaStream_t st);
 int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t st);
+// lanes per pair if the shapes admit the group kernel (its histogram is then built at
+// pack time), else 0
+int lev_group_eligible(int64_t R, int64_t H, int64_t P);
 int lev_launch_uid(const b200lev_tokens_t* ref, const int32_t* ref_len, int32_t* uid,
                    int64_t* dtok, int32_t* ndist, int64_t Rp, cudaStream_t st);
 int lev_launch_completion_fill(const uint32_t* dbits, const int64_t* dtok, int64_t Rp,

@@ -2,20 +2,21 @@
 //
 // Same anti-diagonal wavefront as lev_dp.cu, re-shaped so that warps do not idle on
 // padding (north star item 3):
-//   * a pair is handled by a GROUP of G lanes (G = 1..32, chosen from the padded
+//   * a pair is handled by a GROUP of G lanes (G = 2..32, chosen from the padded
 //     reference length), each lane owning C adjacent DP columns in registers, so the
 //     ramp of the skewed wavefront costs G-1 steps instead of 31 and one __shfl_up_sync
 //     serves C cells;
 //   * the whole row fits one strip (G*C >= r+1, right-aligned, virtual +BIG columns on
 //     the left) -- no shared-memory boundary column;
-//   * persistent CTAs pull TILES of consecutive pairs from a global counter and bucket
-//     each tile in shared memory by (column class C, hypothesis length) with a counting
-//     sort; a warp then runs 32/G pairs (2 x 32/G in the packed path) of the SAME class
-//     and near-equal length in lock step, largest first, from a shared-memory work queue.
-//     Lane utilisation is (r+1)/(G*C) instead of (r+1)/(32*C), and no step is spent on a
-//     pair that has already finished;
-//   * the hypothesis rows of the NEXT task are fetched with cp.async (LDGSTS) into the
-//     other half of a double buffer while the current task runs;
+//   * LENGTH BUCKETS: the batch is counting-sorted on the device by (column class C,
+//     hypothesis length) -- histogram built by the packing pass (lev_pack.cu), scan +
+//     scatter by lev_sort_kernel -- into a table of TASKS: 32/G pairs (2 x 32/G in the
+//     packed path) of the SAME class and near-equal length, largest first.  Warps take
+//     tasks round-robin and run their pairs in lock step: lane utilisation is
+//     (r+1)/(G*C) instead of (r+1)/(32*C) and no step is spent on a finished pair;
+//   * warps are independent (no block barrier anywhere): the task descriptors two tasks
+//     ahead and the hypothesis rows one task ahead are already in flight (cp.async /
+//     LDGSTS into the other half of a double buffer) while the current task runs;
 //   * prefix values are parked in shared memory by the one lane that owns column r and
 //     written out after the task by all lanes (scale, IEEE division by the reference
 //     length, padding fill: SM:356-386), off the DP loop.
@@ -24,7 +25,7 @@
 // then injective) and costs/lengths keep every value below LEVG_BIG16, TWO pairs share
 // each register, one per 16-bit half, and the 2-wide DPX instructions do the work.  Per 2
 // cells: LOP3 (token xor), VIMNMX.U16x2 (-> 0/1 per half), IMAD (diag + neq*sub, FMA
-// pipe), 2 x VIADDMNMX.S16x2.  Otherwise the 32-bit path of lev_dp.cu's cell update runs.
+// pipe), 2 x VIADDMNMX.S16x2.  Otherwise the 32-bit cell update of lev_dp.cu runs.
 //
 // Integer costs only (cost row, or (cost, count) rows for the error-rate family);
 // FINAL and PREFIX modes.  Everything else stays on lev_dp.cu.
@@ -32,26 +33,23 @@
 
 #include "lev_common.cuh"
 
-#define LEVG_NCLS 6  // column classes C = 8, 12, ..., 28
+#define LEVG_NCLS LEV_GROUP_NCLS
 // "infinity" of the packed path: BIG16 + (largest reachable value) must stay < 2^15
 #define LEVG_BIG16 16000
 
 struct LevGroupGeom {
-    int G;         // lanes per pair
-    int tile;      // pairs per tile
-    int ntiles;
-    int Hs;        // words per prefix row (>= H + 2)
-    int row_words; // 32-bit words per staged hypothesis row
-    int nbins;     // LEVG_NCLS * (H + 1)
-    int allow16;   // costs and lengths admit the packed 2 x int16 DPX path
-    int nwarps;
+    int G;          // lanes per pair
+    int Hs;         // words per prefix row (>= H + 2, multiple of 4)
+    int row_words;  // 32-bit words per staged hypothesis row (multiple of 4)
+    int allow16;    // costs and lengths admit the packed 2 x int16 DPX path
+    int wpc;        // warps per CTA
 };
 
-// smallest class whose strip covers columns 0..r
-__device__ __forceinline__ int levg_class_of(int r, int G) {
-    const int need = (r + G) / G;  // ceil((r + 1) / G)
-    const int cls = (need - 8 + 3) >> 2;
-    return cls < 0 ? 0 : cls;
+// device-side choice between the packed and the 32-bit build (see lev_pack.cu):
+// state[1] = max(u), state[2] = max(~u), u = token + 2^31
+__device__ __forceinline__ bool levg_tokens_narrow(const int* state) {
+    const unsigned umax = (unsigned)state[1], umin = ~(unsigned)state[2];
+    return umax < umin || umax - umin < 65536u;
 }
 
 // IEEE-754 correctly rounded a / b from the correctly rounded reciprocal y = RN(1/b)
@@ -209,247 +207,225 @@ __device__ __forceinline__ void levg_run16(const LevParams& p, const int G, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// bucketing: scan the (class, length) histogram and scatter the pairs into task slots
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lev_sort_kernel(const LevParams p, const LevGroupGeom geo, const int count_mode) {
+    LEV_DYN_SMEM(int, base);  // [nbins]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) return;
+    const bool packed = !count_mode && geo.allow16 && levg_tokens_narrow(p.wide_flag);
+    const int PPT = (32 / geo.G) * (packed ? 2 : 1);
+    const int H1 = p.H + 1;
+    if (warp == 0) {
+        // every CTA repeats the (tiny) scan; class segments are padded to whole tasks
+        int carry = 0;
+        for (int cseg = 0; cseg < LEVG_NCLS; ++cseg) {
+            for (int b0 = 0; b0 < H1; b0 += 32) {
+                const int b = b0 + lane;
+                const int cnt = b < H1 ? p.ghist[cseg * H1 + b] : 0;
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(LEV_FULL_MASK, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (b < H1) base[cseg * H1 + b] = carry + incl - cnt;
+                carry += __shfl_sync(LEV_FULL_MASK, incl, 31);
+            }
+            carry = (carry + PPT - 1) / PPT * PPT;
+        }
+        if (blockIdx.x == 0 && lane == 0) p.gmeta[0] = carry / PPT;
+    }
+    __syncthreads();
+    const int pair = blockIdx.x * blockDim.x + tid;
+    if (pair < p.P) {
+        const int r = p.ref_len[pair / p.ref_group];
+        const int h = p.hyp_len[pair];
+        if (r == 0 && p.norm && p.flags != nullptr)
+            atomicOr(p.flags, B200LEV_FLAG_EMPTY_REF);  // SM:360-366, 397-404
+        const int bin = lev_group_bin(r, h, geo.G, p.H);
+        const int pos = base[bin] + atomicAdd(&p.gcursor[bin], 1);
+        p.slots[pos] = make_int4(pair, r, h, lev_group_class(r, geo.G));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// the DP kernel: independent warps, tasks round-robin, two-deep prefetch
+// ---------------------------------------------------------------------------------------
 template <bool COUNT, int MODE, bool PACKED>
-__global__ void __launch_bounds__(256, 2) lev_group_kernel(const LevParams p, const LevGroupGeom geo) {
+__global__ void __launch_bounds__(128, 4) lev_group_kernel(const LevParams p, const LevGroupGeom geo) {
     LEV_DYN_SMEM(int, smem);
     // Which of the two builds of this kernel runs is decided on the device from what K0
     // found in the tokens (no host round trip): wider than int32 -> neither (the 64-bit
     // compare path of lev_warp_kernel, enqueued right behind, takes the batch); inside a
     // 65536-wide window and small values -> PACKED; else the 32-bit build.
     if (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) return;
-    {
-        // [1] = max(u), [2] = max(~u), u = token + 2^31 (lev_pack.cu)
-        const unsigned umax = (unsigned)p.wide_flag[1], umin = ~(unsigned)p.wide_flag[2];
-        const bool narrow = !COUNT && geo.allow16 && (umax < umin || umax - umin < 65536u);
-        if (narrow != PACKED) return;
-    }
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = geo.G, PPW = 32 / G, TILE = geo.tile, Hs = geo.Hs, H1 = p.H + 1;
-    const int PPT = PACKED ? 2 * PPW : PPW;  // pairs per task
-    const int RW = geo.row_words;
-    // shared-memory carve-up
-    int* hist = smem;                                                               // [nbins + 1]
-    int* order = hist + geo.nbins + 1;                                              // [TILE + NCLS*PPT]
-    short* rl_s = reinterpret_cast<short*>(order + TILE + LEVG_NCLS * PPT);        // [TILE]
-    short* hl_s = rl_s + TILE;                                                      // [TILE]
-    int* wbase = reinterpret_cast<int*>(hl_s + TILE) + ((TILE & 1) ? 1 : 0);
-    wbase = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(wbase) + 15) & ~(uintptr_t)15);
+    if ((!COUNT && geo.allow16 && levg_tokens_narrow(p.wide_flag)) != PACKED) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int G = geo.G, PPW = 32 / G, Hs = geo.Hs, RW = geo.row_words;
+    const int PPT = PACKED ? 2 * PPW : PPW;  // pairs per task (<= 32)
     const int per_warp = 2 * PPT * RW + PPW * Hs;
-    int* stage_w = wbase + (size_t)warp * per_warp;  // [2][PPT][RW]   hypothesis rows
-    int* pref_w = stage_w + 2 * PPT * RW;            // [PPW][Hs]      prefix values
-    __shared__ int next_task, ntasks, seg_end[LEVG_NCLS], cur_tile;
-    int* tile_counter = const_cast<int*>(p.wide_flag) + 3;
+    int* stage_w = smem + (size_t)warp * per_warp;  // [2][PPT][RW]  hypothesis rows
+    int* pref_w = stage_w + 2 * PPT * RW;           // [PPW][Hs]     prefix values
+    const int ntasks = p.gmeta[0];
+    const int nW = gridDim.x * geo.wpc;
     const int g = lane / G;
+    const int CPR = RW / 4;  // 16-byte chunks per staged row
+    const int stage_iters = (PPT * CPR + 31) / 32;
 
-    for (;;) {
-        // ---- 0. next tile (persistent CTAs, global counter) ----
-        __syncthreads();
-        if (tid == 0) cur_tile = atomicAdd(tile_counter, 1);
-        __syncthreads();
-        const int tile = cur_tile;
-        if (tile >= geo.ntiles) break;
-        const int tile0 = tile * TILE;
-        const int ntile = min(TILE, p.P - tile0);
-        // ---- 1. lengths, classes, histogram over (class desc, hyp length desc) ----
-        for (int b = tid; b <= geo.nbins; b += blockDim.x) hist[b] = 0;
-        for (int q = tid; q < TILE + LEVG_NCLS * PPT; q += blockDim.x) order[q] = -1;
-        if (tid == 0) next_task = 0;
-        __syncthreads();
-        for (int q = tid; q < ntile; q += blockDim.x) {
-            const int pair = tile0 + q;
-            const int r = p.ref_len[pair / p.ref_group];
-            const int h = p.hyp_len[pair];
-            rl_s[q] = (short)r;
-            hl_s[q] = (short)h;
-            if (r == 0 && p.norm && p.flags != nullptr)
-                atomicOr(p.flags, B200LEV_FLAG_EMPTY_REF);  // SM:360-366, 397-404
-            atomicAdd(&hist[(LEVG_NCLS - 1 - levg_class_of(r, G)) * H1 + (p.H - h)], 1);
-        }
-        __syncthreads();
-        // ---- 2. exclusive scan (one warp), class segments padded to whole tasks ----
-        if (warp == 0) {
-            int carry = 0;
-            for (int cseg = 0; cseg < LEVG_NCLS; ++cseg) {
-                for (int b0 = 0; b0 < H1; b0 += 32) {
-                    const int b = b0 + lane;
-                    const int cnt = b < H1 ? hist[cseg * H1 + b] : 0;
-                    int incl = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int t = __shfl_up_sync(LEV_FULL_MASK, incl, o);
-                        if (lane >= o) incl += t;
-                    }
-                    if (b < H1) hist[cseg * H1 + b] = carry + incl - cnt;
-                    carry += __shfl_sync(LEV_FULL_MASK, incl, 31);
-                }
-                carry = (carry + PPT - 1) / PPT * PPT;
-                if (lane == 0) seg_end[cseg] = carry;
-            }
-            if (lane == 0) ntasks = carry / PPT;
-        }
-        __syncthreads();
-        // ---- 3. scatter pair indices into sorted order ----
-        for (int q = tid; q < ntile; q += blockDim.x) {
-            const int pos = atomicAdd(
-                &hist[(LEVG_NCLS - 1 - levg_class_of(rl_s[q], G)) * H1 + (p.H - hl_s[q])], 1);
-            order[pos] = q;
-        }
-        __syncthreads();
-
-        // ---- 4. work queue; hypothesis rows of the next task prefetched with cp.async ----
-        auto claim = [&]() {
-            int t = 0;
-            if (lane == 0) t = atomicAdd(&next_task, 1);
-            return __shfl_sync(LEV_FULL_MASK, t, 0);
-        };
-        auto stage = [&](int t, int buf) {
-            // 16-byte chunks of the PPT token rows (uint16 rows when PACKED, int32 otherwise)
-            const int chunks_per_row = RW / 4;
-            char* dst0 = reinterpret_cast<char*>(stage_w + buf * PPT * RW);
-            for (int c = lane; c < PPT * chunks_per_row; c += 32) {
-                const int k = c / chunks_per_row, ch = c - k * chunks_per_row;
-                const int qk = order[t * PPT + k];
-                if (qk < 0) continue;
-                const int hk = hl_s[qk];
-                const int sk = p.exclude_last ? (hk > 0 ? hk - 1 : 0) : hk;
-                const int bytes = sk * (PACKED ? 2 : 4);
-                if (ch * 16 >= bytes) continue;
+    auto load_slot = [&](int t) {
+        int4 s = make_int4(-1, 0, 0, 0);
+        if (t < ntasks && lane < PPT) s = p.slots[(int64_t)t * PPT + lane];
+        if (s.x < 0) s = make_int4(-1, 0, 0, s.w < 0 ? 0 : s.w);
+        return s;
+    };
+    auto stage = [&](const int4& S, int buf) {
+        char* dst0 = reinterpret_cast<char*>(stage_w + buf * PPT * RW);
+        for (int it = 0; it < stage_iters; ++it) {
+            const int c = it * 32 + lane;
+            const int k = min(c / CPR, PPT - 1), ch = c - (c / CPR) * CPR;
+            const int pk = __shfl_sync(LEV_FULL_MASK, S.x, k);
+            const int hk = __shfl_sync(LEV_FULL_MASK, S.z, k);
+            const int sk = p.exclude_last ? (hk > 0 ? hk - 1 : 0) : hk;
+            if (c < PPT * CPR && pk >= 0 && ch * 16 < sk * (PACKED ? 2 : 4)) {
                 const char* src = PACKED
-                    ? reinterpret_cast<const char*>(p.hyp_tok16 + (int64_t)(tile0 + qk) * p.Hp16)
-                    : reinterpret_cast<const char*>(p.hyp_tok + (int64_t)(tile0 + qk) * p.Hp);
+                    ? reinterpret_cast<const char*>(p.hyp_tok16 + (int64_t)pk * p.Hp16)
+                    : reinterpret_cast<const char*>(p.hyp_tok + (int64_t)pk * p.Hp);
                 lev_cp_async16(dst0 + (size_t)k * RW * 4 + ch * 16, src + ch * 16);
             }
-        };
-        int cur = claim(), buf = 0;
-        if (cur < ntasks) stage(cur, buf);
+        }
+    };
+
+    int t = blockIdx.x * geo.wpc + warp;
+    int4 S_cur = load_slot(t), S_nxt = load_slot(t + nW);
+    int buf = 0;
+    if (t < ntasks) stage(S_cur, buf);
+    lev_cp_async_commit();
+    while (t < ntasks) {
+        if (t + nW < ntasks) stage(S_nxt, buf ^ 1);
         lev_cp_async_commit();
-        while (cur < ntasks) {
-            const int nxt = claim();
-            if (nxt < ntasks) stage(nxt, buf ^ 1);
-            lev_cp_async_commit();
-            lev_cp_async_wait<1>();  // everything but the newest group: this task's rows landed
-            __syncwarp();
-            const int t = cur;
-            int cseg = 0;
-            while (t * PPT >= seg_end[cseg]) ++cseg;  // class segments are task-pure
-            const int cls = LEVG_NCLS - 1 - cseg;
-            const int* rows = stage_w + buf * PPT * RW;
-            if (PACKED) {
-                // group g runs pairs 2g (low halves) and 2g+1 (high halves) of the task
-                const int qA = order[t * PPT + 2 * g], qB = order[t * PPT + 2 * g + 1];
-                const int rA = qA >= 0 ? rl_s[qA] : 0, rB = qB >= 0 ? rl_s[qB] : 0;
-                const int hA = qA >= 0 ? hl_s[qA] : 0, hB = qB >= 0 ? hl_s[qB] : 0;
-                const int hmax = hA > hB ? hA : hB;
-                int maxsteps = p.exclude_last ? (hmax > 0 ? hmax - 1 : 0) : hmax;
+        const int4 S_nn = load_slot(t + 2 * nW);
+        lev_cp_async_wait<1>();  // everything but the newest group: this task's rows landed
+        __syncwarp();
+        const int cls = __shfl_sync(LEV_FULL_MASK, S_cur.w, 0);  // tasks are class-pure
+        const int* rows = stage_w + buf * PPT * RW;
+        int maxsteps = p.exclude_last ? (S_cur.z > 0 ? S_cur.z - 1 : 0) : S_cur.z;  // SM:286-288
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const int other = __shfl_xor_sync(LEV_FULL_MASK, maxsteps, o);
-                    maxsteps = other > maxsteps ? other : maxsteps;
-                }
-                const unsigned short* hA_row = reinterpret_cast<const unsigned short*>(rows + (2 * g) * RW);
-                const unsigned short* hB_row = reinterpret_cast<const unsigned short*>(rows + (2 * g + 1) * RW);
-                unsigned* prow = reinterpret_cast<unsigned*>(pref_w) + g * Hs;
-                const int pA = qA >= 0 ? tile0 + qA : -1, pB = qB >= 0 ? tile0 + qB : -1;
-                switch (cls) {
-                    case 0: levg_run16<8>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
-                    case 1: levg_run16<12>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
-                    case 2: levg_run16<16>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
-                    case 3: levg_run16<20>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
-                    case 4: levg_run16<24>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
-                    default: levg_run16<28>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
-                }
-            } else {
-                const int q = order[t * PPT + g];
-                const int pair = q >= 0 ? tile0 + q : -1;
-                const int r = q >= 0 ? rl_s[q] : 0;
-                const int h = q >= 0 ? hl_s[q] : 0;
-                const int steps = p.exclude_last ? (h > 0 ? h - 1 : 0) : h;  // SM:286-288
-                int maxsteps = steps;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const int other = __shfl_xor_sync(LEV_FULL_MASK, maxsteps, o);
-                    maxsteps = other > maxsteps ? other : maxsteps;
-                }
-                const int* hyp_row = rows + g * RW;
-                int* prow = pref_w + g * Hs;
-                switch (cls) {
-                    case 0: levg_run32<COUNT, MODE, 8>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
-                    case 1: levg_run32<COUNT, MODE, 12>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
-                    case 2: levg_run32<COUNT, MODE, 16>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
-                    case 3: levg_run32<COUNT, MODE, 20>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
-                    case 4: levg_run32<COUNT, MODE, 24>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
-                    default: levg_run32<COUNT, MODE, 28>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
-                }
+        for (int o = 16; o > 0; o >>= 1) {
+            const int other = __shfl_xor_sync(LEV_FULL_MASK, maxsteps, o);
+            maxsteps = other > maxsteps ? other : maxsteps;
+        }
+        if (PACKED) {
+            // group g runs slots 2g (low halves) and 2g+1 (high halves) of the task
+            const int pA = __shfl_sync(LEV_FULL_MASK, S_cur.x, 2 * g);
+            const int rA = __shfl_sync(LEV_FULL_MASK, S_cur.y, 2 * g);
+            const int pB = __shfl_sync(LEV_FULL_MASK, S_cur.x, 2 * g + 1);
+            const int rB = __shfl_sync(LEV_FULL_MASK, S_cur.y, 2 * g + 1);
+            const unsigned short* hA_row = reinterpret_cast<const unsigned short*>(rows + (2 * g) * RW);
+            const unsigned short* hB_row = reinterpret_cast<const unsigned short*>(rows + (2 * g + 1) * RW);
+            unsigned* prow = reinterpret_cast<unsigned*>(pref_w) + g * Hs;
+            switch (cls) {
+                case 0: levg_run16<8>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
+                case 1: levg_run16<12>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
+                case 2: levg_run16<16>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
+                case 3: levg_run16<20>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
+                case 4: levg_run16<24>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
+                default: levg_run16<28>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
             }
-            __syncwarp();
-            // ---- epilogue (SM:279-285, 340-346, 356-386 / 390-405) ----
-            // 32/PPT lanes per pair, each striding over that pair's rows: the per-pair
-            // set-up (lengths, reciprocal, output column) is done once per lane
-            if (MODE == LEV_MODE_PREFIX || PACKED) {
-                const int LPP = PPT >= 32 ? 1 : 32 / PPT;  // lanes per pair
-                for (int kk = lane; kk < PPT * LPP; kk += 32) {
-                    const int k = kk / LPP, sub = kk - k * LPP;
-                    const int qk = order[t * PPT + k];
-                    if (qk < 0) continue;
-                    const int rk = rl_s[qk], hk = hl_s[qk];
-                    const unsigned* row =
-                        reinterpret_cast<const unsigned*>(pref_w) + (PACKED ? (k >> 1) : k) * Hs;
-                    const int sh16 = PACKED ? (k & 1) * 16 : 0;
-                    const unsigned msk = PACKED ? 0xffffu : 0xffffffffu;
-                    const float rf = (float)rk;
-                    const float y = rk > 0 ? __frcp_rn(rf) : 0.0f;
-                    const int row0 = COUNT ? rk : rk * p.del_i;
-                    const bool norm = p.norm != 0;
-                    if (MODE == LEV_MODE_PREFIX) {
-                        const int first_pad = hk + (p.exclude_last ? 0 : 1);
-                        float* o = p.out + (int64_t)(tile0 + qk) * p.out_sn + (int64_t)sub * p.out_si;
-                        const int64_t ostep = (int64_t)LPP * p.out_si;
-                        for (int i = sub; i < p.Hout; i += LPP, o += ostep) {
+        } else {
+            const int pair = __shfl_sync(LEV_FULL_MASK, S_cur.x, g);
+            const int r = __shfl_sync(LEV_FULL_MASK, S_cur.y, g);
+            const int h = __shfl_sync(LEV_FULL_MASK, S_cur.z, g);
+            const int steps = p.exclude_last ? (h > 0 ? h - 1 : 0) : h;
+            const int* hyp_row = rows + g * RW;
+            int* prow = pref_w + g * Hs;
+            switch (cls) {
+                case 0: levg_run32<COUNT, MODE, 8>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
+                case 1: levg_run32<COUNT, MODE, 12>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
+                case 2: levg_run32<COUNT, MODE, 16>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
+                case 3: levg_run32<COUNT, MODE, 20>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
+                case 4: levg_run32<COUNT, MODE, 24>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
+                default: levg_run32<COUNT, MODE, 28>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
+            }
+        }
+        __syncwarp();
+        // ---- epilogue (SM:279-285, 340-346, 356-386 / 390-405) ----
+        // pair by pair (descriptor broadcast by shuffle), lanes across rows, four rows per
+        // lane in flight so the shared-memory reads and the stores overlap
+        if (MODE == LEV_MODE_PREFIX) {
+            const bool norm = p.norm != 0;
+            for (int k = 0; k < PPT; ++k) {
+                const int pk = __shfl_sync(LEV_FULL_MASK, S_cur.x, k);
+                const int rk = __shfl_sync(LEV_FULL_MASK, S_cur.y, k);
+                const int hk = __shfl_sync(LEV_FULL_MASK, S_cur.z, k);
+                if (pk < 0) continue;
+                const unsigned* __restrict__ row =
+                    reinterpret_cast<const unsigned*>(pref_w) + (PACKED ? (k >> 1) : k) * Hs;
+                const int sh16 = PACKED ? (k & 1) * 16 : 0;
+                const unsigned msk = PACKED ? 0xffffu : 0xffffffffu;
+                const float rf = (float)rk;
+                const float y = rk > 0 ? __frcp_rn(rf) : 0.0f;
+                const int row0 = COUNT ? rk : rk * p.del_i;
+                const int first_pad = hk + (p.exclude_last ? 0 : 1);
+                float* __restrict__ o = p.out + (int64_t)pk * p.out_sn;
+                for (int i0 = lane; i0 < p.Hout; i0 += 128) {
+                    unsigned raw[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + 32 * u;
+                        raw[u] = (i > 0 && i < first_pad) ? row[i] : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + 32 * u;
+                        if (i < p.Hout) {
                             float val = p.padding;
                             if (i < first_pad) {
-                                const int raw = (i == 0) ? row0 : (int)((row[i] >> sh16) & msk);
-                                val = __fmul_rn((float)raw, p.mult);
+                                const int rv = (i == 0) ? row0 : (int)((raw[u] >> sh16) & msk);
+                                val = __fmul_rn((float)rv, p.mult);
                                 if (norm) val = (rk == 0) ? (i > 0 ? 1.0f : 0.0f) : levg_div(val, rf, y);
                             }
-                            *o = val;
+                            o[(int64_t)i * p.out_si] = val;
                         }
-                    } else if (sub == 0) {  // PACKED FINAL: the value parked at row h
-                        const int raw = (hk == 0) ? row0 : (int)((row[hk] >> sh16) & msk);
-                        float val = __fmul_rn((float)raw, p.mult);
-                        if (norm) val = (rk == 0) ? (hk > 0 ? 1.0f : 0.0f) : levg_div(val, rf, y);
-                        p.out[tile0 + qk] = val;
                     }
                 }
             }
-            __syncwarp();
-            cur = nxt;
-            buf ^= 1;
+        } else if (PACKED) {  // FINAL: the value parked at row h, one lane per pair
+            const int pk = S_cur.x, rk = S_cur.y, hk = S_cur.z;
+            if (lane < PPT && pk >= 0) {
+                const unsigned* row = reinterpret_cast<const unsigned*>(pref_w) + (lane >> 1) * Hs;
+                const int raw = (hk == 0) ? rk * p.del_i : (int)((row[hk] >> ((lane & 1) * 16)) & 0xffffu);
+                float val = __fmul_rn((float)raw, p.mult);
+                if (p.norm) val = (rk == 0) ? (hk > 0 ? 1.0f : 0.0f) : val / (float)rk;
+                p.out[pk] = val;
+            }
         }
-        lev_cp_async_wait<0>();
+        __syncwarp();
+        S_cur = S_nxt;
+        S_nxt = S_nn;
+        t += nW;
+        buf ^= 1;
     }
+    lev_cp_async_wait<0>();
 }
 
-// geometry + shared-memory footprint of one build; false if it cannot keep 2 CTAs per SM
-static bool levg_geometry(const LevParams& p, bool packed, LevGroupGeom* geo, size_t* smem) {
+// geometry + shared-memory footprint of one build
+static size_t levg_geometry(const LevParams& p, bool packed, LevGroupGeom* geo) {
     const int PPW = 32 / geo->G, PPT = packed ? 2 * PPW : PPW;
     // staged hypothesis rows: uint16 (packed) or int32; whole 16-byte chunks per row
     geo->row_words = packed ? (int)((p.H + 7) / 8) * 4 : (int)((p.H + 3) / 4) * 4;
     if (geo->row_words < 4) geo->row_words = 4;
     geo->Hs = ((p.H + 2 + 3) / 4) * 4;
-    geo->tile = 512;
-    if (geo->tile < 16 * PPT) geo->tile = 16 * PPT;
-    geo->ntiles = (int)(((int64_t)p.P + geo->tile - 1) / geo->tile);
-    geo->nwarps = 8;
+    geo->wpc = 4;
     const size_t per_warp = sizeof(int) * ((size_t)2 * PPT * geo->row_words + (size_t)PPW * geo->Hs);
-    *smem = sizeof(int) * (geo->nbins + 1 + geo->tile + LEVG_NCLS * PPT) +
-            sizeof(short) * (2 * geo->tile) + per_warp * geo->nwarps + 64;
-    return *smem <= 110 * 1024;
+    return per_warp * geo->wpc;
 }
 
 template <bool COUNT, int MODE, bool PACKED>
 static int levg_launch_one(const LevParams& p, LevGroupGeom geo, cudaStream_t st) {
-    size_t smem = 0;
-    if (!levg_geometry(p, PACKED, &geo, &smem)) return 0;
+    const size_t smem = levg_geometry(p, PACKED, &geo);
     auto kern = lev_group_kernel<COUNT, MODE, PACKED>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -458,29 +434,36 @@ static int levg_launch_one(const LevParams& p, LevGroupGeom geo, cudaStream_t st
             return B200LEV_ERR_CUDA;
         }
     }
-    int blocks = 148 * 2;
-    if (blocks > geo.ntiles) blocks = geo.ntiles;
-    lev_launch(kern, dim3((unsigned)blocks), dim3(32 * geo.nwarps), smem, st, p, geo);
+    // persistent: as many CTAs as stay resident (4 per SM by registers, fewer by smem)
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    int64_t blocks = 148 * per_sm;
+    const int PPT = (32 / geo.G) * (PACKED ? 2 : 1);
+    const int64_t max_tasks = (p.P + PPT - 1) / PPT + LEVG_NCLS;
+    if (blocks * geo.wpc > max_tasks) blocks = (max_tasks + geo.wpc - 1) / geo.wpc;
+    lev_launch(kern, dim3((unsigned)blocks), dim3(32 * geo.wpc), smem, st, p, geo);
     const int rc = lev_check_cuda("lev_group_kernel");
     return rc ? rc : 1;
+}
+
+int lev_group_eligible(int64_t R, int64_t H, int64_t P) {
+    // small batches: latency matters, one warp per pair (B200LEV_GROUP_MIN_PAIRS
+    // overrides the switch-over point; tests use it to drive both kernels)
+    int64_t min_pairs = 4096;
+    if (const char* e = getenv("B200LEV_GROUP_MIN_PAIRS")) min_pairs = atoll(e);
+    if (P < min_pairs || H > 1000 || R > 30000) return 0;
+    return lev_group_lanes(R);
 }
 
 // Returns 1 if the group kernels took the job, 0 if they do not apply (caller falls back
 // to the warp-per-pair kernel), < 0 on error.
 int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t st) {
     if (mode == LEV_MODE_MASK) return 0;
-    // small batches: latency matters, one warp per pair (B200LEV_GROUP_MIN_PAIRS
-    // overrides the switch-over point; tests use it to drive both kernels)
-    int min_pairs = 4096;
-    if (const char* e = getenv("B200LEV_GROUP_MIN_PAIRS")) min_pairs = atoi(e);
-    if (p.P < min_pairs) return 0;
-    int G = 1;
-    while (G <= 32 && G * 28 < p.R + 1) G <<= 1;
-    if (G > 32 || p.H > 1000 || p.R > 30000) return 0;
     LevGroupGeom geo;
     memset(&geo, 0, sizeof(geo));
-    geo.G = G;
-    geo.nbins = LEVG_NCLS * (p.H + 1);
+    geo.G = lev_group_eligible(p.R, p.H, p.P);
+    if (geo.G == 0) return 0;
     const int maxc = p.ins_i > p.del_i ? (p.ins_i > p.sub_i ? p.ins_i : p.sub_i)
                                        : (p.del_i > p.sub_i ? p.del_i : p.sub_i);
     geo.allow16 = (!count_mode && p.ins_i >= 0 && p.del_i >= 0 && p.sub_i >= 0 &&
@@ -488,21 +471,22 @@ int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t
                       ? 1
                       : 0;
     if (const char* e = getenv("B200LEV_GROUP_PACKED16")) geo.allow16 = geo.allow16 && atoi(e);
-    // the 32-bit build must be launchable (it is the one that runs when the tokens turn
-    // out not to fit 16 bits); the packed build is optional
     LevGroupGeom tmp = geo;
-    size_t smem = 0;
-    if (!levg_geometry(p, false, &tmp, &smem)) return 0;
+    if (levg_geometry(p, false, &tmp) > 200 * 1024) return 0;
     tmp = geo;
-    if (geo.allow16 && !levg_geometry(p, true, &tmp, &smem)) geo.allow16 = 0;
-    // the persistent CTAs pull tiles from state word 3: rewind it for this launch
-    if (cudaMemsetAsync(const_cast<int*>(p.wide_flag) + 3, 0, sizeof(int), st) != cudaSuccess)
+    if (geo.allow16 && levg_geometry(p, true, &tmp) > 200 * 1024) geo.allow16 = 0;
+    // bucketing: clear the scatter cursors + meta and the slot table, then scan + scatter
+    if (cudaMemsetAsync(p.gcursor, 0, sizeof(int) * (size_t)(p.nbins + 16), st) != cudaSuccess ||
+        cudaMemsetAsync(p.slots, 0xff, 16 * (size_t)(p.P + LEVG_NCLS * 32), st) != cudaSuccess)
         return lev_check_cuda("memset");
+    lev_launch(lev_sort_kernel, dim3((unsigned)((p.P + 255) / 256)), dim3(256),
+               sizeof(int) * (size_t)p.nbins, st, p, geo, (int)count_mode);
+    int rc = lev_check_cuda("lev_sort_kernel");
+    if (rc) return rc;
     // both builds are enqueued; the device-side token range decides which one works
-    int rc;
 #define LEVG_BOTH(COUNT_, MODE_)                                                   \
     rc = levg_launch_one<COUNT_, MODE_, false>(p, geo, st);                        \
-    if (rc <= 0) return rc;                                                        \
+    if (rc <= 0) return rc < 0 ? rc : B200LEV_ERR_UNSUPPORTED;                     \
     if (!COUNT_ && geo.allow16) {                                                  \
         rc = levg_launch_one<COUNT_, MODE_, true>(p, geo, st);                     \
         if (rc <= 0) return rc < 0 ? rc : B200LEV_ERR_UNSUPPORTED;                 \

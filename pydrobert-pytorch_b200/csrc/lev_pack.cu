@@ -17,7 +17,8 @@ lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, in
                 int has_eos, int64_t eos, int include_eos, int32_t* __restrict__ packed,
                 int64_t Tp, uint16_t* __restrict__ packed16, int64_t Tp16,
                 int32_t* __restrict__ lens, int32_t* flags, int32_t* state,
-                int missing_flag, int transposed) {
+                int missing_flag, int transposed, const int32_t* __restrict__ ref_len,
+                int ref_group, int G, int* __restrict__ ghist) {
     __shared__ int tile[32][33];
     __shared__ int first[32];
     __shared__ int blk_flags;
@@ -32,6 +33,7 @@ lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, in
     }
     __syncthreads();
     int wide = 0;
+    int my_first = (int)T;  // first eos seen by this thread (eos-padded tails hit it often)
     // biased token range for the packed 16-bit DP path: max(u) and max(~u), u = tok + 2^31
     unsigned umax = 0u, nmax = 0u;
     if (transposed) {
@@ -43,7 +45,7 @@ lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, in
                 if (t < T && n < N) {
                     const int64_t v = (int64_t)tok[t * st + n * sn];
                     tile[tl][tx] = (int)v;
-                    if (has_eos && v == eos) atomicMin(&first[tx], (int)t);
+                    if (has_eos && v == eos && (int)t < my_first) my_first = (int)t;
                     if ((int64_t)(int)v != v) wide = 1;
                     const unsigned u = (unsigned)(int)v + 0x80000000u;
                     umax = u > umax ? u : umax;
@@ -63,6 +65,8 @@ lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, in
             }
             __syncthreads();
         }
+        if (my_first < (int)T) atomicMin(&first[tx], my_first);
+        __syncthreads();
     } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -104,6 +108,10 @@ lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, in
                 len += 1;
         }
         lens[n0 + tx] = len;
+        // hypothesis side only: (class, length) histogram for the group kernel's global
+        // bucketing (the reference lengths were produced by the launch before this one)
+        if (ghist != nullptr)
+            atomicAdd(&ghist[lev_group_bin(ref_len[(n0 + tx) / ref_group], len, G, (int)T)], 1);
     }
     __syncthreads();
     if (tx == 0 && ty == 0) {
@@ -118,7 +126,8 @@ lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, in
 
 int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int include_eos,
                     int32_t* packed, int64_t Tp, uint16_t* packed16, int64_t Tp16, int32_t* lens,
-                    int32_t* flags, int32_t* state, int missing_flag, cudaStream_t st) {
+                    int32_t* flags, int32_t* state, int missing_flag, const int32_t* ref_len,
+                    int ref_group, int G, int* ghist, cudaStream_t st) {
     if (t->N <= 0) return B200LEV_OK;
     if (t->T >= (int64_t)1 << 30) {
         lev_set_error("sequence dimension %lld too long", (long long)t->T);
@@ -133,22 +142,26 @@ int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int inc
         case 8:
             lev_launch(lev_pack_kernel<int64_t>, grid, block, 0, st, (const int64_t*)t->data, t->T,
                        t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
-                       packed16, Tp16, lens, flags, state, missing_flag, transposed);
+                       packed16, Tp16, lens, flags, state, missing_flag, transposed, ref_len,
+                       ref_group, G, ghist);
             break;
         case 4:
             lev_launch(lev_pack_kernel<int32_t>, grid, block, 0, st, (const int32_t*)t->data, t->T,
                        t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
-                       packed16, Tp16, lens, flags, state, missing_flag, transposed);
+                       packed16, Tp16, lens, flags, state, missing_flag, transposed, ref_len,
+                       ref_group, G, ghist);
             break;
         case 2:
             lev_launch(lev_pack_kernel<int16_t>, grid, block, 0, st, (const int16_t*)t->data, t->T,
                        t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
-                       packed16, Tp16, lens, flags, state, missing_flag, transposed);
+                       packed16, Tp16, lens, flags, state, missing_flag, transposed, ref_len,
+                       ref_group, G, ghist);
             break;
         case 1:
             lev_launch(lev_pack_kernel<int8_t>, grid, block, 0, st, (const int8_t*)t->data, t->T,
                        t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
-                       packed16, Tp16, lens, flags, state, missing_flag, transposed);
+                       packed16, Tp16, lens, flags, state, missing_flag, transposed, ref_len,
+                       ref_group, G, ghist);
             break;
         default:
             lev_set_error("unsupported token element size %d", (int)t->elem_bytes);
