@@ -237,7 +237,7 @@ def main():
     # ---- roofline: the DP kernel alone, and the pack kernels alone ---------------------
     rt, ht = _ops._tok_struct(ref, False), _ops._tok_struct(hyp, False)
     o = _ops._opts(0, True, 1.0, 1.0, 1.0, True, False, -100, True, 1)
-    nbytes = L.b200lev_workspace_bytes(ctypes.byref(rt), ctypes.byref(ht), 0, 0)
+    nbytes = L.b200lev_workspace_bytes(ctypes.byref(rt), ctypes.byref(ht), 2, 0)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     outp = torch.empty((T_LEN + 2, P), dtype=torch.float32, device=dev)
     st = torch.cuda.current_stream(dev).cuda_stream

@@ -80,10 +80,16 @@ const char *b200lev_last_error(void);
 /* number of CUDA devices visible to the library (0 => every compute call fails) */
 int b200lev_device_count(void);
 
-/* Scratch bytes needed by the calls below for these shapes (packed int32 tokens,
- * lengths; for the completion calls also the distinct-token tables and bitmaps). */
+/* Scratch bytes needed by the calls below for these shapes (packed tokens, lengths,
+ * bucketing tables).  kind: B200LEV_WS_FINAL for b200lev_final*, B200LEV_WS_PREFIX for
+ * b200lev_prefix* (adds the raw prefix rows), B200LEV_WS_COMPLETION for the completion
+ * calls (adds the distinct-token tables and bitmaps).  b200lev_pack may be given the
+ * largest of the kinds that will follow it. */
+#define B200LEV_WS_FINAL 0
+#define B200LEV_WS_COMPLETION 1
+#define B200LEV_WS_PREFIX 2
 size_t b200lev_workspace_bytes(const b200lev_tokens_t *ref, const b200lev_tokens_t *hyp,
-                               int32_t for_completion, int32_t exclude_last);
+                               int32_t kind, int32_t exclude_last);
 
 /*
  * error_rate (SM:409-434) / edit_distance (SM:437-461): one fp32 value per pair.

@@ -117,7 +117,8 @@ def string_matching(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: b
         o = _opts(eos, include_eos, ins_cost, del_cost, sub_cost, norm, exclude_last, padding,
                   return_mistakes, ref_group)
         flags = torch.zeros(1, dtype=torch.int32, device=dev)
-        nbytes = L.b200lev_workspace_bytes(ctypes.byref(rt), ctypes.byref(ht), 0, int(exclude_last))
+        nbytes = L.b200lev_workspace_bytes(ctypes.byref(rt), ctypes.byref(ht), 2 if prefix else 0,
+                                           int(exclude_last))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         st = _stream(dev)
         if not prefix:

@@ -69,9 +69,9 @@ static int lev_check_tokens(const b200lev_tokens_t* ref, const b200lev_tokens_t*
 }
 
 extern "C" size_t b200lev_workspace_bytes(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
-                                          int32_t for_completion, int32_t exclude_last) {
+                                          int32_t kind, int32_t exclude_last) {
     if (!ref || !hyp) return 0;
-    return lev_layout(ref, hyp, for_completion, exclude_last).bytes + 128;
+    return lev_layout(ref, hyp, kind, exclude_last).bytes + 128;
 }
 
 static inline char* lev_ws_base(const void* ws) {
@@ -175,6 +175,10 @@ static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     p->gmeta = (int*)(ws + L.off_gmeta);
     p->slots = (int4*)(ws + L.off_slots);
     p->nbins = (int)L.nbins;
+    p->raw32 = L.off_raw ? (int32_t*)(ws + L.off_raw) : nullptr;
+    p->raw16 = (unsigned short*)p->raw32;
+    p->Hr = L.Hr;
+    p->Hr16 = L.Hr16;
     return B200LEV_OK;
 }
 
@@ -238,7 +242,7 @@ static int lev_prefix_impl(const b200lev_tokens_t* ref, const b200lev_tokens_t* 
                            int32_t* flags, void* stream, bool do_pack) {
     int rc = lev_check_tokens(ref, hyp, opts);
     if (rc) return rc;
-    const LevLayout L = lev_layout(ref, hyp, 0, opts->exclude_last);
+    const LevLayout L = lev_layout(ref, hyp, 2, opts->exclude_last);
     if (hyp->N == 0 || L.Hout <= 0) return B200LEV_OK;
     if (!out || !workspace) {
         lev_set_error("NULL output/workspace");

@@ -48,12 +48,17 @@ struct LevLayout {
     // words directly (one memset clears state + ghist); slots = sorted task table
     int64_t nbins;
     size_t off_ghist, off_gcursor, off_gmeta, off_slots;
+    // raw prefix rows written by the group kernel, read by lev_prefix_finalize_kernel
+    int64_t Hr, Hr16;
+    size_t off_raw;
     size_t off_uid, off_dtok, off_ndist, off_dbits;
     size_t bytes;
 };
 
+// kind: 0 = final value, 1 = completion (mask mode), 2 = prefix table
 static inline LevLayout lev_layout(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
-                                   int for_completion, int exclude_last) {
+                                   int kind, int exclude_last) {
+    const int for_completion = (kind == 1);
     LevLayout L;
     L.R = ref->T;
     L.H = hyp->T;
@@ -83,6 +88,9 @@ static inline LevLayout lev_layout(const b200lev_tokens_t* ref, const b200lev_to
     L.off_gcursor = L.off_ghist + sizeof(int32_t) * (size_t)L.nbins;
     L.off_gmeta = L.off_gcursor + sizeof(int32_t) * (size_t)L.nbins;
     L.off_slots = take(16 * (size_t)(L.P + LEV_GROUP_NCLS * 32));
+    L.Hr = lev_round_up(L.H + 1, 4);
+    L.Hr16 = lev_round_up(L.H + 1, 8);
+    L.off_raw = (kind == 2) ? take(sizeof(int32_t) * (size_t)L.P * L.Hr) : 0;
     L.off_uid = L.off_dtok = L.off_ndist = L.off_dbits = 0;
     if (for_completion) {
         L.off_uid = take(sizeof(int32_t) * (size_t)L.Nref * L.Rp);
@@ -133,6 +141,9 @@ struct LevParams {
     int* gcursor;
     int* gmeta;   // [0] = number of tasks
     int4* slots;  // sorted (pair, r, h, class) per task slot; pair < 0 = padding
+    int32_t* raw32;          // [P][Hr]   raw prefix rows (32-bit group path)
+    unsigned short* raw16;   // [P][Hr16] same storage, packed path
+    int64_t Hr, Hr16;
     int nbins;
 };
 

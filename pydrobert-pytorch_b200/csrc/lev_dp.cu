@@ -370,7 +370,9 @@ static int lev_launch_variant(const LevParams& p, cudaStream_t st) {
         }
     }
     int64_t blocks = ((int64_t)p.P + wpc - 1) / wpc;
-    const int64_t cap = 148 * 64;
+    // stand-by launch behind the group kernel (runs only for >32-bit tokens): keep the
+    // grid small so that the usual immediate exit costs next to nothing
+    const int64_t cap = p.only_if_wide ? 148 * 4 : 148 * 64;
     if (blocks > cap) blocks = cap;
     lev_launch(kern, dim3((unsigned)blocks), dim3((unsigned)(32 * wpc)), smem, st, p);
     return lev_check_cuda("lev_warp_kernel");

@@ -39,7 +39,6 @@
 
 struct LevGroupGeom {
     int G;          // lanes per pair
-    int Hs;         // words per prefix row (>= H + 2, multiple of 4)
     int row_words;  // 32-bit words per staged hypothesis row (multiple of 4)
     int allow16;    // costs and lengths admit the packed 2 x int16 DPX path
     int wpc;        // warps per CTA
@@ -68,8 +67,7 @@ __device__ __forceinline__ float levg_div(float a, float b, float y) {
 template <bool COUNT, int MODE, int C>
 __device__ __forceinline__ void levg_run32(const LevParams& p, const int G, const int pair,
                                            const int r, const int h, const int steps,
-                                           const int maxsteps, const int* __restrict__ hyp_row,
-                                           int* __restrict__ pref_row) {
+                                           const int maxsteps, const int* __restrict__ hyp_row) {
     const int lane = threadIdx.x & 31;
     const int gl = lane & (G - 1);
     const int refcol = pair >= 0 ? pair / p.ref_group : 0;
@@ -88,6 +86,9 @@ __device__ __forceinline__ void levg_run32(const LevParams& p, const int G, cons
     int pl_v = LEV_BIG_I32, pl_m = 0;
     (void)pl_m;
     const bool owner = (gl == G - 1);
+    // PREFIX: the lane that owns column r streams the raw row values to the workspace
+    // (one 4-byte store per step); lev_prefix_finalize_kernel turns them into the output
+    int* __restrict__ raw_row = p.raw32 + (int64_t)(pair >= 0 ? pair : 0) * p.Hr;
     const int nsteps = maxsteps + G - 1;
     for (int s = 1; s <= nsteps; ++s) {
         const int sh_v = __shfl_up_sync(LEV_FULL_MASK, v[C - 1], 1, G);
@@ -140,7 +141,7 @@ __device__ __forceinline__ void levg_run32(const LevParams& p, const int G, cons
                     v[c] = lf;
                 }
             }
-            if (MODE == LEV_MODE_PREFIX && owner) pref_row[i] = COUNT ? m[C - 1] : v[C - 1];
+            if (MODE == LEV_MODE_PREFIX && owner) raw_row[i] = COUNT ? m[C - 1] : v[C - 1];
         }
     }
     if (MODE == LEV_MODE_FINAL && owner && pair >= 0) {  // SM:390-405
@@ -154,13 +155,14 @@ __device__ __forceinline__ void levg_run32(const LevParams& p, const int G, cons
 // packed path: two pairs per lane group, one per 16-bit half.  Both run `maxsteps` rows;
 // rows past a pair's own length are never read back.  Cost row only.
 // ---------------------------------------------------------------------------------------
-template <int C>
+template <int MODE, int C>
 __device__ __forceinline__ void levg_run16(const LevParams& p, const int G, const int pairA,
                                            const int rA, const int pairB, const int rB,
                                            const int maxsteps,
                                            const unsigned short* __restrict__ hypA,
                                            const unsigned short* __restrict__ hypB,
-                                           unsigned* __restrict__ pref_row) {
+                                           const int stepsA, const int stepsB,
+                                           const int hA, const int hB) {
     const int lane = threadIdx.x & 31;
     const int gl = lane & (G - 1);
     const int32_t* __restrict__ rtA = p.ref_tok + (int64_t)(pairA >= 0 ? pairA / p.ref_group : 0) * p.Rp;
@@ -182,6 +184,8 @@ __device__ __forceinline__ void levg_run16(const LevParams& p, const int G, cons
     }
     unsigned pl = BIG2;
     const bool owner = (gl == G - 1);
+    unsigned short* __restrict__ rawA = p.raw16 + (int64_t)(pairA >= 0 ? pairA : 0) * p.Hr16;
+    unsigned short* __restrict__ rawB = p.raw16 + (int64_t)(pairB >= 0 ? pairB : 0) * p.Hr16;
     const int nsteps = maxsteps + G - 1;
     for (int s = 1; s <= nsteps; ++s) {
         const unsigned sh = __shfl_up_sync(LEV_FULL_MASK, v[C - 1], 1, G);
@@ -202,7 +206,39 @@ __device__ __forceinline__ void levg_run16(const LevParams& p, const int G, cons
                 dg = up;
                 v[c] = lf;
             }
-            if (owner) pref_row[i] = v[C - 1];
+            if (owner) {
+                const unsigned last = v[C - 1];
+                if (MODE == LEV_MODE_PREFIX) {
+                    // raw row values of both pairs to the workspace (rows past a pair's own
+                    // length are never read by the finalize kernel)
+                    if (i <= stepsA) rawA[i] = (unsigned short)(last & 0xffffu);
+                    if (i <= stepsB) rawB[i] = (unsigned short)(last >> 16);
+                } else {
+                    // FINAL (SM:390-405): each pair's value is complete at its own last row
+                    if (i == stepsA && pairA >= 0) {
+                        float val = __fmul_rn((float)(last & 0xffffu), p.mult);
+                        if (p.norm) val = (rA == 0) ? (hA > 0 ? 1.0f : 0.0f) : val / (float)rA;
+                        p.out[pairA] = val;
+                    }
+                    if (i == stepsB && pairB >= 0) {
+                        float val = __fmul_rn((float)(last >> 16), p.mult);
+                        if (p.norm) val = (rB == 0) ? (hB > 0 ? 1.0f : 0.0f) : val / (float)rB;
+                        p.out[pairB] = val;
+                    }
+                }
+            }
+        }
+    }
+    if (MODE == LEV_MODE_FINAL && owner) {  // pairs with no hypothesis rows at all
+        if (stepsA == 0 && pairA >= 0) {
+            float val = __fmul_rn((float)(rA * p.del_i), p.mult);
+            if (p.norm) val = (rA == 0) ? (hA > 0 ? 1.0f : 0.0f) : val / (float)rA;
+            p.out[pairA] = val;
+        }
+        if (stepsB == 0 && pairB >= 0) {
+            float val = __fmul_rn((float)(rB * p.del_i), p.mult);
+            if (p.norm) val = (rB == 0) ? (hB > 0 ? 1.0f : 0.0f) : val / (float)rB;
+            p.out[pairB] = val;
         }
     }
 }
@@ -218,13 +254,16 @@ lev_sort_kernel(const LevParams p, const LevGroupGeom geo, const int count_mode)
     const bool packed = !count_mode && geo.allow16 && levg_tokens_narrow(p.wide_flag);
     const int PPT = (32 / geo.G) * (packed ? 2 : 1);
     const int H1 = p.H + 1;
+    // every CTA repeats the (tiny) scan: histogram -> shared memory (all threads), then one
+    // warp turns it into exclusive offsets with class segments padded to whole tasks
+    for (int b = tid; b < p.nbins; b += blockDim.x) base[b] = p.ghist[b];
+    __syncthreads();
     if (warp == 0) {
-        // every CTA repeats the (tiny) scan; class segments are padded to whole tasks
         int carry = 0;
         for (int cseg = 0; cseg < LEVG_NCLS; ++cseg) {
             for (int b0 = 0; b0 < H1; b0 += 32) {
                 const int b = b0 + lane;
-                const int cnt = b < H1 ? p.ghist[cseg * H1 + b] : 0;
+                const int cnt = b < H1 ? base[cseg * H1 + b] : 0;
                 int incl = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -264,11 +303,9 @@ __global__ void __launch_bounds__(128, 4) lev_group_kernel(const LevParams p, co
     if (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) return;
     if ((!COUNT && geo.allow16 && levg_tokens_narrow(p.wide_flag)) != PACKED) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int G = geo.G, PPW = 32 / G, Hs = geo.Hs, RW = geo.row_words;
+    const int G = geo.G, PPW = 32 / G, RW = geo.row_words;
     const int PPT = PACKED ? 2 * PPW : PPW;  // pairs per task (<= 32)
-    const int per_warp = 2 * PPT * RW + PPW * Hs;
-    int* stage_w = smem + (size_t)warp * per_warp;  // [2][PPT][RW]  hypothesis rows
-    int* pref_w = stage_w + 2 * PPT * RW;           // [PPW][Hs]     prefix values
+    int* stage_w = smem + (size_t)warp * (2 * PPT * RW);  // [2][PPT][RW]  hypothesis rows
     const int ntasks = p.gmeta[0];
     const int nW = gridDim.x * geo.wpc;
     const int g = lane / G;
@@ -321,86 +358,40 @@ __global__ void __launch_bounds__(128, 4) lev_group_kernel(const LevParams p, co
             // group g runs slots 2g (low halves) and 2g+1 (high halves) of the task
             const int pA = __shfl_sync(LEV_FULL_MASK, S_cur.x, 2 * g);
             const int rA = __shfl_sync(LEV_FULL_MASK, S_cur.y, 2 * g);
+            const int hA = __shfl_sync(LEV_FULL_MASK, S_cur.z, 2 * g);
             const int pB = __shfl_sync(LEV_FULL_MASK, S_cur.x, 2 * g + 1);
             const int rB = __shfl_sync(LEV_FULL_MASK, S_cur.y, 2 * g + 1);
+            const int hB = __shfl_sync(LEV_FULL_MASK, S_cur.z, 2 * g + 1);
+            const int sA = p.exclude_last ? (hA > 0 ? hA - 1 : 0) : hA;
+            const int sB = p.exclude_last ? (hB > 0 ? hB - 1 : 0) : hB;
             const unsigned short* hA_row = reinterpret_cast<const unsigned short*>(rows + (2 * g) * RW);
             const unsigned short* hB_row = reinterpret_cast<const unsigned short*>(rows + (2 * g + 1) * RW);
-            unsigned* prow = reinterpret_cast<unsigned*>(pref_w) + g * Hs;
+#define LEVG_R16(C_) levg_run16<MODE, C_>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, sA, sB, hA, hB)
             switch (cls) {
-                case 0: levg_run16<8>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
-                case 1: levg_run16<12>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
-                case 2: levg_run16<16>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
-                case 3: levg_run16<20>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
-                case 4: levg_run16<24>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
-                default: levg_run16<28>(p, G, pA, rA, pB, rB, maxsteps, hA_row, hB_row, prow); break;
+                case 0: LEVG_R16(8); break;
+                case 1: LEVG_R16(12); break;
+                case 2: LEVG_R16(16); break;
+                case 3: LEVG_R16(20); break;
+                case 4: LEVG_R16(24); break;
+                default: LEVG_R16(28); break;
             }
+#undef LEVG_R16
         } else {
             const int pair = __shfl_sync(LEV_FULL_MASK, S_cur.x, g);
             const int r = __shfl_sync(LEV_FULL_MASK, S_cur.y, g);
             const int h = __shfl_sync(LEV_FULL_MASK, S_cur.z, g);
             const int steps = p.exclude_last ? (h > 0 ? h - 1 : 0) : h;
             const int* hyp_row = rows + g * RW;
-            int* prow = pref_w + g * Hs;
+#define LEVG_R32(C_) levg_run32<COUNT, MODE, C_>(p, G, pair, r, h, steps, maxsteps, hyp_row)
             switch (cls) {
-                case 0: levg_run32<COUNT, MODE, 8>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
-                case 1: levg_run32<COUNT, MODE, 12>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
-                case 2: levg_run32<COUNT, MODE, 16>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
-                case 3: levg_run32<COUNT, MODE, 20>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
-                case 4: levg_run32<COUNT, MODE, 24>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
-                default: levg_run32<COUNT, MODE, 28>(p, G, pair, r, h, steps, maxsteps, hyp_row, prow); break;
+                case 0: LEVG_R32(8); break;
+                case 1: LEVG_R32(12); break;
+                case 2: LEVG_R32(16); break;
+                case 3: LEVG_R32(20); break;
+                case 4: LEVG_R32(24); break;
+                default: LEVG_R32(28); break;
             }
-        }
-        __syncwarp();
-        // ---- epilogue (SM:279-285, 340-346, 356-386 / 390-405) ----
-        // pair by pair (descriptor broadcast by shuffle), lanes across rows, four rows per
-        // lane in flight so the shared-memory reads and the stores overlap
-        if (MODE == LEV_MODE_PREFIX) {
-            const bool norm = p.norm != 0;
-            for (int k = 0; k < PPT; ++k) {
-                const int pk = __shfl_sync(LEV_FULL_MASK, S_cur.x, k);
-                const int rk = __shfl_sync(LEV_FULL_MASK, S_cur.y, k);
-                const int hk = __shfl_sync(LEV_FULL_MASK, S_cur.z, k);
-                if (pk < 0) continue;
-                const unsigned* __restrict__ row =
-                    reinterpret_cast<const unsigned*>(pref_w) + (PACKED ? (k >> 1) : k) * Hs;
-                const int sh16 = PACKED ? (k & 1) * 16 : 0;
-                const unsigned msk = PACKED ? 0xffffu : 0xffffffffu;
-                const float rf = (float)rk;
-                const float y = rk > 0 ? __frcp_rn(rf) : 0.0f;
-                const int row0 = COUNT ? rk : rk * p.del_i;
-                const int first_pad = hk + (p.exclude_last ? 0 : 1);
-                float* __restrict__ o = p.out + (int64_t)pk * p.out_sn;
-                for (int i0 = lane; i0 < p.Hout; i0 += 128) {
-                    unsigned raw[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = i0 + 32 * u;
-                        raw[u] = (i > 0 && i < first_pad) ? row[i] : 0u;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = i0 + 32 * u;
-                        if (i < p.Hout) {
-                            float val = p.padding;
-                            if (i < first_pad) {
-                                const int rv = (i == 0) ? row0 : (int)((raw[u] >> sh16) & msk);
-                                val = __fmul_rn((float)rv, p.mult);
-                                if (norm) val = (rk == 0) ? (i > 0 ? 1.0f : 0.0f) : levg_div(val, rf, y);
-                            }
-                            o[(int64_t)i * p.out_si] = val;
-                        }
-                    }
-                }
-            }
-        } else if (PACKED) {  // FINAL: the value parked at row h, one lane per pair
-            const int pk = S_cur.x, rk = S_cur.y, hk = S_cur.z;
-            if (lane < PPT && pk >= 0) {
-                const unsigned* row = reinterpret_cast<const unsigned*>(pref_w) + (lane >> 1) * Hs;
-                const int raw = (hk == 0) ? rk * p.del_i : (int)((row[hk] >> ((lane & 1) * 16)) & 0xffffu);
-                float val = __fmul_rn((float)raw, p.mult);
-                if (p.norm) val = (rk == 0) ? (hk > 0 ? 1.0f : 0.0f) : val / (float)rk;
-                p.out[pk] = val;
-            }
+#undef LEVG_R32
         }
         __syncwarp();
         S_cur = S_nxt;
@@ -411,15 +402,119 @@ __global__ void __launch_bounds__(128, 4) lev_group_kernel(const LevParams p, co
     lev_cp_async_wait<0>();
 }
 
+// ---------------------------------------------------------------------------------------
+// PREFIX epilogue: raw row values -> the caller's (H', N) / (N, H') fp32 tensor.
+//   row 0 = r * (1 | del) (SM:279-285); rows 1..steps = raw (SM:340-346); x mult, / r with
+//   the empty-reference rule (SM:356-378); rows >= h + (0|1) = padding (SM:379-386).
+// Sequence-first output (unit stride along n): 32 rows x 128 pairs tiles are transposed
+// through shared memory so that both the raw reads (along rows) and the output writes
+// (along pairs, one float4 = 128 bits per thread) are coalesced.
+// ---------------------------------------------------------------------------------------
+template <bool COUNT>
+__device__ __forceinline__ float levg_finalize_one(const LevParams& p, bool packed, int n, int i,
+                                                   int r, int h, float y) {
+    const int first_pad = h + (p.exclude_last ? 0 : 1);
+    if (i >= first_pad) return p.padding;
+    int raw;
+    if (i == 0)
+        raw = COUNT ? r : r * p.del_i;
+    else
+        raw = packed ? (int)p.raw16[(int64_t)n * p.Hr16 + i] : p.raw32[(int64_t)n * p.Hr + i];
+    float val = __fmul_rn((float)raw, p.mult);
+    if (p.norm) val = (r == 0) ? (i > 0 ? 1.0f : 0.0f) : levg_div(val, (float)r, y);
+    return val;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256)
+lev_prefix_finalize_kernel(const LevParams p, const LevGroupGeom geo) {
+    if (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) return;  // lev_warp_kernel wrote `out` itself
+    const bool packed = !COUNT && geo.allow16 && levg_tokens_narrow(p.wide_flag);
+    const int tid = threadIdx.x;
+    if (p.out_sn == 1) {
+        __shared__ float tile[32][129];
+        const int n0 = blockIdx.x * 128, i0 = blockIdx.y * 32;
+        {
+            // thread = (pair, half of the 32 rows): 16 consecutive raw values of one pair
+            // fetched with 128-bit loads; lengths and reciprocal fetched once
+            const int nl = tid & 127, half = tid >> 7;
+            const int n = n0 + nl;
+            if (n < p.P) {
+                const int r = p.ref_len[n / p.ref_group], h = p.hyp_len[n];
+                const float rf = (float)r;
+                const float y = r > 0 ? __frcp_rn(rf) : 0.0f;
+                const int first_pad = h + (p.exclude_last ? 0 : 1);
+                const int ib = i0 + half * 16;
+                int raw[16];
+                if (packed) {
+                    const uint4* src = reinterpret_cast<const uint4*>(p.raw16 + (int64_t)n * p.Hr16 + ib);
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+                        if (ib + 8 * c < p.Hr16) w = src[c];
+                        raw[8 * c + 0] = (int)(w.x & 0xffffu); raw[8 * c + 1] = (int)(w.x >> 16);
+                        raw[8 * c + 2] = (int)(w.y & 0xffffu); raw[8 * c + 3] = (int)(w.y >> 16);
+                        raw[8 * c + 4] = (int)(w.z & 0xffffu); raw[8 * c + 5] = (int)(w.z >> 16);
+                        raw[8 * c + 6] = (int)(w.w & 0xffffu); raw[8 * c + 7] = (int)(w.w >> 16);
+                    }
+                } else {
+                    const int4* src = reinterpret_cast<const int4*>(p.raw32 + (int64_t)n * p.Hr + ib);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        int4 w = make_int4(0, 0, 0, 0);
+                        if (ib + 4 * c < p.Hr) w = src[c];
+                        raw[4 * c + 0] = w.x; raw[4 * c + 1] = w.y;
+                        raw[4 * c + 2] = w.z; raw[4 * c + 3] = w.w;
+                    }
+                }
+                const bool norm = p.norm != 0;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int i = ib + u;
+                    const int rv = (i == 0) ? (COUNT ? r : r * p.del_i) : raw[u];
+                    float val = __fmul_rn((float)rv, p.mult);
+                    if (norm) val = (r == 0) ? (i > 0 ? 1.0f : 0.0f) : levg_div(val, rf, y);
+                    tile[half * 16 + u][nl] = (i < first_pad) ? val : p.padding;
+                }
+            }
+        }
+        __syncthreads();
+        // 32 rows x 32 float4 columns; a warp writes 512 contiguous bytes of one row
+        const int cx = tid & 31, ry = tid >> 5;
+        for (int q = 0; q < 4; ++q) {
+            const int il = ry + 8 * q, i = i0 + il, n = n0 + 4 * cx;
+            if (i >= p.Hout || n >= p.P) continue;
+            float* dst = p.out + (int64_t)i * p.out_si + n;
+            if (n + 3 < p.P && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                *reinterpret_cast<float4*>(dst) =
+                    make_float4(tile[il][4 * cx], tile[il][4 * cx + 1], tile[il][4 * cx + 2],
+                                tile[il][4 * cx + 3]);
+            } else {
+                for (int u = 0; u < 4 && n + u < p.P; ++u) dst[u] = tile[il][4 * cx + u];
+            }
+        }
+    } else {
+        // batch-first (or arbitrary strides): rows of one pair are adjacent in the output
+        const int64_t total = (int64_t)p.P * p.Hout;
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + tid; e < total;
+             e += (int64_t)gridDim.x * blockDim.x) {
+            const int n = (int)(e / p.Hout), i = (int)(e - (int64_t)n * p.Hout);
+            const int r = p.ref_len[n / p.ref_group], h = p.hyp_len[n];
+            const float y = r > 0 ? __frcp_rn((float)r) : 0.0f;
+            p.out[(int64_t)i * p.out_si + (int64_t)n * p.out_sn] =
+                levg_finalize_one<COUNT>(p, packed, n, i, r, h, y);
+        }
+    }
+}
+
 // geometry + shared-memory footprint of one build
 static size_t levg_geometry(const LevParams& p, bool packed, LevGroupGeom* geo) {
     const int PPW = 32 / geo->G, PPT = packed ? 2 * PPW : PPW;
     // staged hypothesis rows: uint16 (packed) or int32; whole 16-byte chunks per row
     geo->row_words = packed ? (int)((p.H + 7) / 8) * 4 : (int)((p.H + 3) / 4) * 4;
     if (geo->row_words < 4) geo->row_words = 4;
-    geo->Hs = ((p.H + 2 + 3) / 4) * 4;
     geo->wpc = 4;
-    const size_t per_warp = sizeof(int) * ((size_t)2 * PPT * geo->row_words + (size_t)PPW * geo->Hs);
+    const size_t per_warp = sizeof(int) * ((size_t)2 * PPT * geo->row_words);
     return per_warp * geo->wpc;
 }
 
@@ -499,5 +594,18 @@ int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t
         else { LEVG_BOTH(true, LEV_MODE_PREFIX) }
     }
 #undef LEVG_BOTH
+    if (mode == LEV_MODE_PREFIX && p.Hout > 0) {
+        dim3 grid, block(256);
+        if (p.out_sn == 1)
+            grid = dim3((unsigned)((p.P + 127) / 128), (unsigned)((p.Hout + 31) / 32));
+        else
+            grid = dim3((unsigned)min((int64_t)148 * 16, ((int64_t)p.P * p.Hout + 255) / 256));
+        if (count_mode)
+            lev_launch(lev_prefix_finalize_kernel<true>, grid, block, 0, st, p, geo);
+        else
+            lev_launch(lev_prefix_finalize_kernel<false>, grid, block, 0, st, p, geo);
+        rc = lev_check_cuda("lev_prefix_finalize_kernel");
+        if (rc) return rc;
+    }
     return 1;
 }

@@ -12,7 +12,7 @@
 #include "lev_common.cuh"
 
 template <typename TT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, int64_t sn,
                 int has_eos, int64_t eos, int include_eos, int32_t* __restrict__ packed,
                 int64_t Tp, uint16_t* __restrict__ packed16, int64_t Tp16,
@@ -34,38 +34,64 @@ lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, in
     __syncthreads();
     int wide = 0;
     int my_first = (int)T;  // first eos seen by this thread (eos-padded tails hit it often)
-    // biased token range for the packed 16-bit DP path: max(u) and max(~u), u = tok + 2^31
-    unsigned umax = 0u, nmax = 0u;
+    // int32 range of the (truncated) tokens this thread saw; turned into the biased
+    // max(u) / max(~u), u = tok + 2^31, that the packed 16-bit DP path tests
+    int lo = 0x7fffffff, hi = (int)0x80000000;
+    const int Ti = (int)T;
     if (transposed) {
-        for (int64_t t0 = 0; t0 < T; t0 += 32) {
+        // software pipeline: the loads of tile k+1 are issued before the stores of tile k,
+        // so the two directions of HBM traffic overlap inside one CTA; addresses advance
+        // by pointer increments only
+        const bool n_ok = (n0 + tx) < N;
+        const TT* __restrict__ src = tok + (n0 + tx) * sn + (int64_t)ty * st;
+        const int64_t st8 = 8 * st, st32 = 32 * st;
+        TT regs[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) regs[q] = (n_ok && ty + 8 * q < Ti) ? src[q * st8] : (TT)0;
+        int32_t* dst32[4];
+        uint16_t* dst16[4];
+        bool row_ok[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t n = n0 + ty + 8 * q;
+            row_ok[q] = n < N;
+            dst32[q] = packed + n * Tp + tx;
+            dst16[q] = packed16 != nullptr ? packed16 + n * Tp16 + tx : nullptr;
+        }
+        for (int t0 = 0; t0 < Ti; t0 += 32) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int tl = ty + 8 * q;
-                const int64_t t = t0 + tl, n = n0 + tx;
-                if (t < T && n < N) {
-                    const int64_t v = (int64_t)tok[t * st + n * sn];
-                    tile[tl][tx] = (int)v;
-                    if (has_eos && v == eos && (int)t < my_first) my_first = (int)t;
-                    if ((int64_t)(int)v != v) wide = 1;
-                    const unsigned u = (unsigned)(int)v + 0x80000000u;
-                    umax = u > umax ? u : umax;
-                    nmax = ~u > nmax ? ~u : nmax;
+                const int tl = ty + 8 * q, t = t0 + tl;
+                if (n_ok && t < Ti) {
+                    const int64_t v = (int64_t)regs[q];
+                    const int v32 = (int)v;
+                    tile[tl][tx] = v32;
+                    if (has_eos && v == eos && t < my_first) my_first = t;
+                    if (sizeof(TT) == 8 && (int64_t)v32 != v) wide = 1;
+                    lo = v32 < lo ? v32 : lo;
+                    hi = v32 > hi ? v32 : hi;
                 }
             }
             __syncthreads();
+            if (t0 + 32 < Ti) {
+                src += st32;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int nl = ty + 8 * q;
-                const int64_t n = n0 + nl, t = t0 + tx;
-                if (t < T && n < N) {
-                    const int v = tile[tx][nl];
-                    packed[n * Tp + t] = v;
-                    if (packed16 != nullptr) packed16[n * Tp16 + t] = (uint16_t)v;
+                for (int q = 0; q < 4; ++q)
+                    regs[q] = (n_ok && t0 + 32 + ty + 8 * q < Ti) ? src[q * st8] : (TT)0;
+            }
+            if (t0 + tx < Ti) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (row_ok[q]) {
+                        const int v = tile[tx][ty + 8 * q];
+                        dst32[q][t0] = v;
+                        if (dst16[q] != nullptr) dst16[q][t0] = (uint16_t)v;
+                    }
                 }
             }
             __syncthreads();
         }
-        if (my_first < (int)T) atomicMin(&first[tx], my_first);
+        if (my_first < Ti) atomicMin(&first[tx], my_first);
         __syncthreads();
     } else {
 #pragma unroll
@@ -79,15 +105,15 @@ lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, in
                     if (packed16 != nullptr) packed16[n * Tp16 + t] = (uint16_t)(int)v;
                     if (has_eos && v == eos) atomicMin(&first[nl], (int)t);
                     if ((int64_t)(int)v != v) wide = 1;
-                    const unsigned u = (unsigned)(int)v + 0x80000000u;
-                    umax = u > umax ? u : umax;
-                    nmax = ~u > nmax ? ~u : nmax;
+                    lo = (int)v < lo ? (int)v : lo;
+                    hi = (int)v > hi ? (int)v : hi;
                 }
             }
         }
         __syncthreads();
     }
     if (wide) atomicOr(&blk_flags, B200LEV_FLAG_WIDE_TOKENS);
+    unsigned umax = (unsigned)hi + 0x80000000u, nmax = ~((unsigned)lo + 0x80000000u);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const unsigned a = __shfl_xor_sync(LEV_FULL_MASK, umax, o);
