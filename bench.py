@@ -12,13 +12,16 @@ is the named one; the batch is replicated to 16384 utterances x 8-best = 131072 
 per GPU so the chip is full and the inputs (212 MB int64) exceed the 126 MB L2
 (SURVEY 8d-iii).  The literal 64 x 8 batch is timed too and reported under "literal".
 
-A step = one `prefix_error_rates(ref (x) 8, hyp, eos=0)` call = 3 kernel launches
-(pack ref, pack hyp, wavefront DP with the prefix epilogue).
+A step = one `prefix_error_rates(ref (x) 8, hyp, eos=0)` call = 7 kernel launches: pack ref,
+pack hyp (+ length histogram), bucketing (scan + scatter), the wavefront DP kernel in its
+two builds (32-bit / packed 16x2; the device-side token range picks one, the other exits at
+once), the prefix finalize (normalise + transpose, 128-bit stores) and the stand-by 64-bit
+token kernel (exits at once).
 
   value     device-resident inputs, CUDA events, max over ranks (whole job, all GPUs)
   e2e       the same public call with HOST (pinned) int64 tensors: H2D of the inputs and
             D2H of the (H+1, N) result inside the timed region
-  roofline  the DP kernel alone (b200lev_prefix_packed) timed with CUDA events:
+  roofline  the DP kernel alone, timed with CUDA events on the launch stream (b200lev_profile):
             achieved = cells/s x 5 INT32 ops against the INT32 issue rate
             measured live by the library's microbenchmark kernel
   cpu_baseline  the oracle port (C, OpenMP) on the box's host cores, same workload
@@ -234,21 +237,24 @@ def main():
     ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- roofline: the DP kernel alone, and the pack kernels alone ---------------------
-    rt, ht = _ops._tok_struct(ref, False), _ops._tok_struct(hyp, False)
-    o = _ops._opts(0, True, 1.0, 1.0, 1.0, True, False, -100, True, 1)
-    nbytes = L.b200lev_workspace_bytes(ctypes.byref(rt), ctypes.byref(ht), 2, 0)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    outp = torch.empty((T_LEN + 2, P), dtype=torch.float32, device=dev)
-    st = torch.cuda.current_stream(dev).cuda_stream
-
-    def pack_only():
-        _abi.check(L.b200lev_pack(ctypes.byref(rt), ctypes.byref(ht), ctypes.byref(o),
-                                  ws.data_ptr(), nbytes, None, st))
-
-    def dp_only():
-        _abi.check(L.b200lev_prefix_packed(ctypes.byref(rt), ctypes.byref(ht), ctypes.byref(o),
-                                           outp.data_ptr(), P, 1, ws.data_ptr(), nbytes, None, st))
+    # ---- roofline: per-kernel CUDA-event times of the same public call --------------------
+    # (b200lev_profile brackets every phase with events on the launch stream)
+    prof = np.zeros(6, dtype=np.float64)
+    buf = (ctypes.c_float * 6)()
+    _abi.check(L.b200lev_profile(1))
+    for _ in range(3):
+        step()
+    nprof = max(5, min(args.steps, 20))
+    for _ in range(nprof):
+        out = step()
+        _abi.check(L.b200lev_profile_read(buf, 6))
+        prof += np.array([max(x, 0.0) for x in buf])
+    _abi.check(L.b200lev_profile(0))
+    prof /= nprof
+    ms_pack = float(prof[0] + prof[1])
+    ms_dp = float(prof[3])
+    phases = {"pack_ref": prof[0], "pack_hyp": prof[1], "bucketing": prof[2], "dp": prof[3],
+              "prefix_finalize": prof[4], "standby_wide": prof[5]}
 
     def timed(fn, reps):
         for _ in range(3):
@@ -262,10 +268,8 @@ def main():
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
-    pack_only()
-    ms_pack = timed(pack_only, args.steps)
-    ms_dp = timed(dp_only, args.steps)
-    assert torch.equal(outp, out), "packed DP path disagrees with the public call"
+    st = torch.cuda.current_stream(dev).cuda_stream
+    outp = out
 
     # INT32 issue-rate peak, measured live (variant 2 = VIADDMNMX, 0 = IADD3, 3 = DP cell mix)
     sink = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -279,7 +283,9 @@ def main():
 
         t = timed(k, 5)
         peaks[name] = ops.value / (t * 1e-3) / 1e12  # T int32-op/s
-    int32_peak = max(peaks["iadd3"], peaks["viaddmnmx"])
+    # denominator = the ALU-pipe rate (VIADDMNMX / VIMNMX / ISETP live there): SURVEY 8(d)'s
+    # "64 lanes/clk/SM".  Plain IADD3 also dual-issues on the FMA pipe (the iadd3 figure).
+    int32_peak = peaks["viaddmnmx"]
 
     # ---- e2e: host (pinned) tensors through the public API -----------------------------
     ref_h = torch.from_numpy(refx_np).pin_memory()
@@ -318,6 +324,10 @@ def main():
         if os.path.exists(peaks_file):
             hbm_peak, hbm_src = json.load(open(peaks_file))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
         achieved_ops = cells / (ms_dp * 1e-3) * OPS_PER_CELL / 1e12
+        traffic = None
+        tf = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tf):  # dram bytes per launch from the last `ncu --set full` capture
+            traffic = json.load(open(tf)).get("lev_group_kernel")
         pack_gbs = (in_bytes + in_bytes // 2) / (ms_pack * 1e-3) / 1e9
         line = {
             "metric": "edit-distance cell-updates/s", "value": cells_all / (ms * 1e-3) / 1e9,
@@ -334,14 +344,23 @@ def main():
             "e2e": {"value": cells_all / (ms_e2e * 1e-3) / 1e9, "unit": "GCUPS",
                     "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": int(outp.numel() * 4),
                     "ms_per_step": ms_e2e},
-            "gpu_launches": 3 * args.steps,
-            "roofline": {"bound": "int32_issue", "kernel": "lev_warp_kernel<int,cost,PREFIX>",
+            # per step: 2 pack, 1 bucketing, 2 DP builds (one exits at once), 1 prefix
+            # finalize, 1 stand-by 64-bit-token kernel
+            "gpu_launches": 7 * args.steps,
+            "roofline": {"bound": "int32_issue",
+                         "kernel": "lev_group_kernel<cost,PREFIX,packed16> (+ its 32-bit twin's "
+                                   "immediate exit)",
                          "achieved": achieved_ops, "peak": int32_peak, "unit": "Tint32op/s",
-                         "frac": achieved_ops / int32_peak, "traffic": None,
+                         "frac": achieved_ops / int32_peak, "traffic": traffic,
                          "ops_per_cell": OPS_PER_CELL, "kernel_ms": ms_dp,
                          "kernel_gcups": cells / (ms_dp * 1e-3) / 1e9,
-                         "peak_source": "measured live: b200lev_int32_peak_kernel "
-                                        f"{ {k: round(v, 2) for k, v in peaks.items()} }"},
+                         "peak_source": "measured live (b200lev_int32_peak_kernel), ALU pipe = "
+                                        "viaddmnmx; T int32-op/s: "
+                                        f"{ {k: round(v, 2) for k, v in peaks.items()} }",
+                         "note": "algorithmic 5 INT32 ops/cell (SURVEY 8d); the kernel issues 2.5 "
+                                 "instructions per cell (2 cells per 16x2 DPX instruction), so "
+                                 "frac can exceed 1"},
+            "phases_ms": {k: round(float(v), 5) for k, v in phases.items()},
             "roofline_pack": {"bound": "hbm", "kernel": "lev_pack_kernel<int64> x2",
                               "achieved": pack_gbs, "peak": hbm_peak, "unit": "GB/s",
                               "frac": pack_gbs / hbm_peak, "kernel_ms": ms_pack,

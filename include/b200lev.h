@@ -217,6 +217,14 @@ const int32_t *b200lev_workspace_hyp_lens(const b200lev_tokens_t *ref,
 int b200lev_after_eos_mask(const int64_t *tokens, int64_t outer, int64_t T, int64_t inner,
                            int64_t eos, unsigned char *mask, void *stream);
 
+/* Optional per-kernel timing for bench.py: when enabled, every phase of the calls above is
+ * bracketed by CUDA events on the launch stream.  b200lev_profile_read waits for the last
+ * recorded events and returns milliseconds (or -1) for the slots
+ *   0 pack(ref)  1 pack(hyp)  2 bucketing (sort)  3 DP kernel(s)  4 prefix finalize
+ *   5 stand-by 64-bit-token kernel. */
+int b200lev_profile(int enable);
+int b200lev_profile_read(float *ms, int n);
+
 /* INT32 issue-rate microbenchmark used for the roofline denominator (bench.py):
  * runs `iters` dependent-free VIADDMNMX/IADD3 per thread on `blocks` x 256 threads and
  * returns the op count through *ops (host).  Timed by the caller with CUDA events. */

@@ -42,7 +42,16 @@ def _offload(*tensors):
             "b200lev needs a CUDA device: the string-matching kernels have no CPU fallback")
     dev = torch.device("cuda", torch.cuda.current_device())
     moved = tuple(None if t is None else t.to(dev, non_blocking=True) for t in tensors)
-    return moved, (lambda x: x.to(first.device))
+
+    def back(x):
+        # D2H into page-locked memory (torch's caching host allocator recycles the block):
+        # one DMA, no staging copy through a pageable buffer
+        host = torch.empty(x.shape, dtype=x.dtype, device="cpu", pin_memory=True)
+        host.copy_(x, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return host
+
+    return moved, back
 
 
 def _warn_flags(flags: torch.Tensor, eos: Optional[int], include_eos: bool, norm: bool,

@@ -32,6 +32,7 @@ def _deps():
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ_DIR, exist_ok=True)
+    extra = os.environ.get("B200LEV_NVCC_EXTRA", "").split()  # tuning experiments only
     hdr_m = max(os.path.getmtime(h) for h in _deps())
     jobs = []
     objs = []
@@ -40,7 +41,7 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_m):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):

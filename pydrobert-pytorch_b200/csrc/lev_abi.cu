@@ -25,6 +25,52 @@ int lev_check_cuda(const char* what) {
     return B200LEV_OK;
 }
 
+// ---- optional per-kernel timing ----------------------------------------------------------
+#ifndef B200LEV_EMU
+static bool g_prof_on = false;
+static cudaEvent_t g_prof_ev[LEV_PROF_NSLOTS][2];
+static bool g_prof_used[LEV_PROF_NSLOTS];
+static bool g_prof_init = false;
+void lev_prof_begin(int slot, cudaStream_t st) {
+    if (g_prof_on) cudaEventRecord(g_prof_ev[slot][0], st);
+}
+void lev_prof_end(int slot, cudaStream_t st) {
+    if (g_prof_on) {
+        cudaEventRecord(g_prof_ev[slot][1], st);
+        g_prof_used[slot] = true;
+    }
+}
+extern "C" int b200lev_profile(int enable) {
+    if (enable && !g_prof_init) {
+        for (int s = 0; s < LEV_PROF_NSLOTS; ++s)
+            for (int k = 0; k < 2; ++k)
+                if (cudaEventCreate(&g_prof_ev[s][k]) != cudaSuccess) return lev_check_cuda("cudaEventCreate");
+        g_prof_init = true;
+    }
+    for (int s = 0; s < LEV_PROF_NSLOTS; ++s) g_prof_used[s] = false;
+    g_prof_on = enable != 0;
+    return B200LEV_OK;
+}
+extern "C" int b200lev_profile_read(float* ms, int n) {
+    for (int s = 0; s < n && s < LEV_PROF_NSLOTS; ++s) {
+        ms[s] = -1.0f;
+        if (g_prof_init && g_prof_used[s]) {
+            if (cudaEventSynchronize(g_prof_ev[s][1]) != cudaSuccess) return lev_check_cuda("cudaEventSynchronize");
+            cudaEventElapsedTime(&ms[s], g_prof_ev[s][0], g_prof_ev[s][1]);
+        }
+    }
+    return B200LEV_OK;
+}
+#else
+void lev_prof_begin(int, cudaStream_t) {}
+void lev_prof_end(int, cudaStream_t) {}
+extern "C" int b200lev_profile(int) { return B200LEV_OK; }
+extern "C" int b200lev_profile_read(float* ms, int n) {
+    for (int s = 0; s < n; ++s) ms[s] = -1.0f;
+    return B200LEV_OK;
+}
+#endif
+
 extern "C" int b200lev_abi_version(void) { return B200LEV_ABI_VERSION; }
 extern "C" const char* b200lev_last_error(void) { return g_err; }
 
@@ -134,14 +180,18 @@ static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
         const int G = lev_group_eligible(L.R, L.H, L.P);
         const size_t clear = sizeof(int32_t) * (size_t)(4 + (G ? L.nbins : 0));
         if (cudaMemsetAsync(state, 0, clear, st) != cudaSuccess) return lev_check_cuda("memset");
+        lev_prof_begin(LEV_PROF_PACK_REF, st);
         int rc = lev_launch_pack(ref, o->has_eos, o->eos, o->include_eos, ref_tok, L.Rp, nullptr, 0,
                                  ref_len, flags, state, B200LEV_FLAG_REF_NO_EOS, nullptr, 1, 0,
                                  nullptr, st);
+        lev_prof_end(LEV_PROF_PACK_REF, st);
         if (rc) return rc;
+        lev_prof_begin(LEV_PROF_PACK_HYP, st);
         rc = lev_launch_pack(hyp, o->has_eos, o->eos, o->include_eos, hyp_tok, L.Hp,
                              (uint16_t*)(ws + L.off_hyp_tok16), L.Hp16, hyp_len, flags, state,
                              B200LEV_FLAG_HYP_NO_EOS, ref_len, o->ref_group, G,
                              G ? (int*)(ws + L.off_ghist) : nullptr, st);
+        lev_prof_end(LEV_PROF_PACK_HYP, st);
         if (rc) return rc;
     }
     memset(p, 0, sizeof(*p));

@@ -147,6 +147,13 @@ struct LevParams {
     int nbins;
 };
 
+// optional per-kernel timing (b200lev_profile): CUDA events recorded on the launch stream
+// around each phase; slots of b200lev_profile_read()
+enum LevProfSlot { LEV_PROF_PACK_REF = 0, LEV_PROF_PACK_HYP, LEV_PROF_SORT, LEV_PROF_DP,
+                   LEV_PROF_FINALIZE, LEV_PROF_STANDBY, LEV_PROF_NSLOTS };
+void lev_prof_begin(int slot, cudaStream_t st);
+void lev_prof_end(int slot, cudaStream_t st);
+
 // host-side status plumbing (lev_abi.cu)
 void lev_set_error(const char* fmt, ...);
 int lev_check_cuda(const char* what);

@@ -374,7 +374,10 @@ static int lev_launch_variant(const LevParams& p, cudaStream_t st) {
     // grid small so that the usual immediate exit costs next to nothing
     const int64_t cap = p.only_if_wide ? 148 * 4 : 148 * 64;
     if (blocks > cap) blocks = cap;
+    const int slot = p.only_if_wide ? LEV_PROF_STANDBY : LEV_PROF_DP;
+    lev_prof_begin(slot, st);
     lev_launch(kern, dim3((unsigned)blocks), dim3((unsigned)(32 * wpc)), smem, st, p);
+    lev_prof_end(slot, st);
     return lev_check_cuda("lev_warp_kernel");
 }
 

@@ -36,6 +36,9 @@
 #define LEVG_NCLS LEV_GROUP_NCLS
 // "infinity" of the packed path: BIG16 + (largest reachable value) must stay < 2^15
 #define LEVG_BIG16 16000
+#ifndef LEVG_MIN_CTAS
+#define LEVG_MIN_CTAS 4
+#endif
 
 struct LevGroupGeom {
     int G;          // lanes per pair
@@ -246,9 +249,12 @@ __device__ __forceinline__ void levg_run16(const LevParams& p, const int G, cons
 // ---------------------------------------------------------------------------------------
 // bucketing: scan the (class, length) histogram and scatter the pairs into task slots
 // ---------------------------------------------------------------------------------------
+#define LEVG_SORT_PER_THREAD 8
 __global__ void __launch_bounds__(256)
 lev_sort_kernel(const LevParams p, const LevGroupGeom geo, const int count_mode) {
-    LEV_DYN_SMEM(int, base);  // [nbins]
+    LEV_DYN_SMEM(int, base);          // [nbins] exclusive offsets of the bins (global)
+    int* lhist = base + p.nbins;      // [nbins] this CTA's pairs per bin
+    int* goff = lhist + p.nbins;      // [nbins] this CTA's reserved offset inside each bin
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) return;
     const bool packed = !count_mode && geo.allow16 && levg_tokens_narrow(p.wide_flag);
@@ -256,7 +262,10 @@ lev_sort_kernel(const LevParams p, const LevGroupGeom geo, const int count_mode)
     const int H1 = p.H + 1;
     // every CTA repeats the (tiny) scan: histogram -> shared memory (all threads), then one
     // warp turns it into exclusive offsets with class segments padded to whole tasks
-    for (int b = tid; b < p.nbins; b += blockDim.x) base[b] = p.ghist[b];
+    for (int b = tid; b < p.nbins; b += blockDim.x) {
+        base[b] = p.ghist[b];
+        lhist[b] = 0;
+    }
     __syncthreads();
     if (warp == 0) {
         int carry = 0;
@@ -277,16 +286,39 @@ lev_sort_kernel(const LevParams p, const LevGroupGeom geo, const int count_mode)
         }
         if (blockIdx.x == 0 && lane == 0) p.gmeta[0] = carry / PPT;
     }
+    // two-level scatter: rank inside the CTA with shared-memory atomics, then ONE global
+    // atomic per (CTA, non-empty bin) reserves the CTA's range -- same-address global
+    // atomics serialise in L2, and a bin holds hundreds of pairs
+    const int pair0 = blockIdx.x * (256 * LEVG_SORT_PER_THREAD);
+    int bin[LEVG_SORT_PER_THREAD], rank[LEVG_SORT_PER_THREAD], rr[LEVG_SORT_PER_THREAD],
+        hh[LEVG_SORT_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < LEVG_SORT_PER_THREAD; ++u) {
+        const int pair = pair0 + u * 256 + tid;
+        bin[u] = -1;
+        rank[u] = rr[u] = hh[u] = 0;
+        if (pair < p.P) {
+            rr[u] = p.ref_len[pair / p.ref_group];
+            hh[u] = p.hyp_len[pair];
+            if (rr[u] == 0 && p.norm && p.flags != nullptr)
+                atomicOr(p.flags, B200LEV_FLAG_EMPTY_REF);  // SM:360-366, 397-404
+            bin[u] = lev_group_bin(rr[u], hh[u], geo.G, p.H);
+        }
+    }
+    // (the histogram copy above is complete: the scan warp and these atomics touch
+    // different arrays, the barrier below orders both against their readers)
+#pragma unroll
+    for (int u = 0; u < LEVG_SORT_PER_THREAD; ++u)
+        if (bin[u] >= 0) rank[u] = atomicAdd(&lhist[bin[u]], 1);
     __syncthreads();
-    const int pair = blockIdx.x * blockDim.x + tid;
-    if (pair < p.P) {
-        const int r = p.ref_len[pair / p.ref_group];
-        const int h = p.hyp_len[pair];
-        if (r == 0 && p.norm && p.flags != nullptr)
-            atomicOr(p.flags, B200LEV_FLAG_EMPTY_REF);  // SM:360-366, 397-404
-        const int bin = lev_group_bin(r, h, geo.G, p.H);
-        const int pos = base[bin] + atomicAdd(&p.gcursor[bin], 1);
-        p.slots[pos] = make_int4(pair, r, h, lev_group_class(r, geo.G));
+    for (int b = tid; b < p.nbins; b += blockDim.x)
+        if (lhist[b] > 0) goff[b] = atomicAdd(&p.gcursor[b], lhist[b]);
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < LEVG_SORT_PER_THREAD; ++u) {
+        if (bin[u] < 0) continue;
+        const int pos = base[bin[u]] + goff[bin[u]] + rank[u];
+        p.slots[pos] = make_int4(pair0 + u * 256 + tid, rr[u], hh[u], lev_group_class(rr[u], geo.G));
     }
 }
 
@@ -294,7 +326,7 @@ lev_sort_kernel(const LevParams p, const LevGroupGeom geo, const int count_mode)
 // the DP kernel: independent warps, tasks round-robin, two-deep prefetch
 // ---------------------------------------------------------------------------------------
 template <bool COUNT, int MODE, bool PACKED>
-__global__ void __launch_bounds__(128, 4) lev_group_kernel(const LevParams p, const LevGroupGeom geo) {
+__global__ void __launch_bounds__(128, LEVG_MIN_CTAS) lev_group_kernel(const LevParams p, const LevGroupGeom geo) {
     LEV_DYN_SMEM(int, smem);
     // Which of the two builds of this kernel runs is decided on the device from what K0
     // found in the tokens (no host round trip): wider than int32 -> neither (the 64-bit
@@ -529,9 +561,9 @@ static int levg_launch_one(const LevParams& p, LevGroupGeom geo, cudaStream_t st
             return B200LEV_ERR_CUDA;
         }
     }
-    // persistent: as many CTAs as stay resident (4 per SM by registers, fewer by smem)
+    // persistent: as many CTAs as stay resident (LEVG_MIN_CTAS per SM by registers, fewer by smem)
     int per_sm = (int)((220 * 1024) / (smem + 1024));
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > LEVG_MIN_CTAS) per_sm = LEVG_MIN_CTAS;
     if (per_sm < 1) per_sm = 1;
     int64_t blocks = 148 * per_sm;
     const int PPT = (32 / geo.G) * (PACKED ? 2 : 1);
@@ -574,10 +606,20 @@ int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t
     if (cudaMemsetAsync(p.gcursor, 0, sizeof(int) * (size_t)(p.nbins + 16), st) != cudaSuccess ||
         cudaMemsetAsync(p.slots, 0xff, 16 * (size_t)(p.P + LEVG_NCLS * 32), st) != cudaSuccess)
         return lev_check_cuda("memset");
-    lev_launch(lev_sort_kernel, dim3((unsigned)((p.P + 255) / 256)), dim3(256),
-               sizeof(int) * (size_t)p.nbins, st, p, geo, (int)count_mode);
+    lev_prof_begin(LEV_PROF_SORT, st);
+    {
+        const int per_cta = 256 * LEVG_SORT_PER_THREAD;
+        const size_t sort_smem = 3 * sizeof(int) * (size_t)p.nbins;
+        if (sort_smem > 48 * 1024)
+            cudaFuncSetAttribute(lev_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sort_smem);
+        lev_launch(lev_sort_kernel, dim3((unsigned)((p.P + per_cta - 1) / per_cta)), dim3(256),
+                   sort_smem, st, p, geo, (int)count_mode);
+    }
+    lev_prof_end(LEV_PROF_SORT, st);
     int rc = lev_check_cuda("lev_sort_kernel");
     if (rc) return rc;
+    lev_prof_begin(LEV_PROF_DP, st);
     // both builds are enqueued; the device-side token range decides which one works
 #define LEVG_BOTH(COUNT_, MODE_)                                                   \
     rc = levg_launch_one<COUNT_, MODE_, false>(p, geo, st);                        \
@@ -594,7 +636,9 @@ int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t
         else { LEVG_BOTH(true, LEV_MODE_PREFIX) }
     }
 #undef LEVG_BOTH
+    lev_prof_end(LEV_PROF_DP, st);
     if (mode == LEV_MODE_PREFIX && p.Hout > 0) {
+        lev_prof_begin(LEV_PROF_FINALIZE, st);
         dim3 grid, block(256);
         if (p.out_sn == 1)
             grid = dim3((unsigned)((p.P + 127) / 128), (unsigned)((p.Hout + 31) / 32));
@@ -604,6 +648,7 @@ int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t
             lev_launch(lev_prefix_finalize_kernel<true>, grid, block, 0, st, p, geo);
         else
             lev_launch(lev_prefix_finalize_kernel<false>, grid, block, 0, st, p, geo);
+        lev_prof_end(LEV_PROF_FINALIZE, st);
         rc = lev_check_cuda("lev_prefix_finalize_kernel");
         if (rc) return rc;
     }
