@@ -166,6 +166,7 @@ int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int inc
 int lev_launch_dp(const LevParams& p, int mode, bool count_mode, bool float_path,
                   cudaStream_t st);
 int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t st);
+int lev_launch_cta(const LevParams& p, int mode, bool count_mode, bool float_path, cudaStream_t st);
 // lanes per pair if the shapes admit the group kernel (its histogram is then built at
 // pack time), else 0
 int lev_group_eligible(int64_t R, int64_t H, int64_t P);

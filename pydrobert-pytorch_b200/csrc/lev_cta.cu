@@ -1,0 +1,318 @@
+// lev_cta.cu -- K2: one CTA per pair, strips pipelined across warps.  For long pairs and
+// for batches too small to fill the chip with one warp per pair (north-star item 1b).
+//
+// Same cell update, right-aligned strips and lane skew as lev_dp.cu, but the strips of ONE
+// pair run CONCURRENTLY: warp w owns strips w, w+NW, ...; strip k consumes the boundary
+// column (row i, last column of strip k-1) that strip k-1's lane 31 publishes to shared
+// memory, a progress counter per boundary (release/acquire through __threadfence_block +
+// volatile shared accesses) keeping the consumer at most ~40 rows behind.  All live
+// diagonals stay in registers; shared memory holds only the boundary columns and the
+// pair's tokens, which are staged with TMA bulk copies (cp.async.bulk -> SASS UBLKCP)
+// completing on an mbarrier: two descriptors-free 1-D copies per pair, issued by one thread.
+//
+// Pairs are pulled from a global counter (ragged lengths -> dynamic balance).  FINAL and
+// PREFIX modes; integer costs (cost row or (cost, count) rows) and fp32 costs.
+#include <cstdlib>
+
+#include "lev_arith.cuh"
+
+struct LevCtaGeom {
+    int NW;    // warps per CTA
+    int Smax;  // boundary columns provisioned
+    int Hs;    // words per boundary column (H + 64)
+    int Rs;    // words reserved for the reference tokens (multiple of 4)
+    int Hts;   // words reserved for the hypothesis tokens (multiple of 4)
+};
+
+template <typename V, bool COUNT>
+struct LevCtaChan {
+    static constexpr bool FLT_COST = !std::is_same<V, int>::value && !COUNT;
+    static constexpr int NCH = COUNT ? 2 : (FLT_COST ? 3 : 1);
+};
+
+template <typename V, bool COUNT, int MODE, int C>
+__device__ __forceinline__ void lev_cta_strip(const LevParams& p, const int pair, const int r,
+                                              const int h, const int steps, const int k,
+                                              const int S, const int* __restrict__ ref_s,
+                                              const int* __restrict__ hyp_s, V* __restrict__ bnd,
+                                              int* __restrict__ done, const int Hs, const float rcp) {
+    constexpr bool IS_INT = std::is_same<V, int>::value;
+    constexpr bool FLT_COST = !IS_INT && !COUNT;
+    constexpr int NCH = LevCtaChan<V, COUNT>::NCH;
+    constexpr int W = 32 * C;
+    const int lane = threadIdx.x & 31;
+    const V BIG = LevArith<V>::big();
+    const V insc = LevArith<V>::ins(p), delc = LevArith<V>::del(p), subc = LevArith<V>::sub(p);
+    const bool first = (k == 0), last = (k == S - 1);
+    const int jb = r - (S - k) * W;    // boundary column left of lane 0 (< 0 iff first)
+    const int j0 = jb + lane * C + 1;  // this lane's first column
+    // boundary k-1 is read, boundary k written; channels: value | count or (origin, fl(k*d))
+    const V* __restrict__ in_v = bnd + (size_t)(k > 0 ? k - 1 : 0) * NCH * Hs;
+    const V* __restrict__ in_a = in_v + Hs;
+    const V* __restrict__ in_b = in_v + 2 * Hs;
+    V* __restrict__ out_v = bnd + (size_t)k * NCH * Hs;
+    V* __restrict__ out_a = out_v + Hs;
+    V* __restrict__ out_b = out_v + 2 * Hs;
+    (void)in_a; (void)in_b; (void)out_a; (void)out_b;
+    V v[C], m[C], jd[C];
+    int rt[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int j = j0 + c;
+        v[c] = (j >= 0) ? (V)j * delc : BIG;     // SM:258-263
+        m[c] = (V)(j >= 0 ? j : 0);              // SM:260
+        jd[c] = (j >= 0) ? (V)j * delc : (V)0;
+        rt[c] = (j >= 1) ? ref_s[j - 1] : 0;
+    }
+    (void)m; (void)jd;
+    V ob = BIG, oj = (V)0;
+    (void)ob; (void)oj;
+    V pl_v = first ? BIG : (V)jb * delc;
+    V pl_m = (V)(first ? 0 : jb);
+    (void)pl_m;
+    if (steps <= 0) {
+        if (MODE == LEV_MODE_FINAL && last && lane == 31)
+            p.out[pair] = lev_finalize((float)(COUNT ? m[C - 1] : v[C - 1]), p, r, h > 0);
+        return;
+    }
+    const int nsteps = steps + 31;
+    for (int s = 1; s <= nsteps; ++s) {
+        // ---- flow control: rows s .. s+7 of the left boundary must have been published ----
+        if (!first && (s & 7) == 1 && s <= steps) {
+            const int need = min(s + 7, steps);
+            while (lev_ld_volatile_shared(done + (k - 1)) < need) LEV_SPIN_YIELD();
+            __threadfence_block();
+        }
+        const V sh_v = __shfl_up_sync(LEV_FULL_MASK, v[C - 1], 1);
+        const V hand_v = (lane == 0) ? (first || s > steps ? BIG : in_v[32 + s]) : sh_v;
+        const V diag_v = pl_v;
+        pl_v = hand_v;
+        V hand_m = (V)0, diag_m = (V)0, hand_ob = BIG, hand_oj = (V)0;
+        if (COUNT) {
+            const V sh_m = __shfl_up_sync(LEV_FULL_MASK, m[C - 1], 1);
+            hand_m = (lane == 0) ? (first || s > steps ? (V)0 : in_a[32 + s]) : sh_m;
+            diag_m = pl_m;
+            pl_m = hand_m;
+        }
+        if (FLT_COST) {
+            const V sh_ob = __shfl_up_sync(LEV_FULL_MASK, ob, 1);
+            const V sh_oj = __shfl_up_sync(LEV_FULL_MASK, oj, 1);
+            hand_ob = (lane == 0) ? (first || s > steps ? BIG : in_a[32 + s]) : sh_ob;
+            hand_oj = (lane == 0) ? (first || s > steps ? (V)0 : in_b[32 + s]) : sh_oj;
+        }
+        (void)hand_m; (void)diag_m; (void)hand_ob; (void)hand_oj;
+        const int i = s - lane;
+        if (i >= 1 && i <= steps) {
+            const int ht = hyp_s[i - 1];
+            if (COUNT) {  // SM:292-314
+                V dc = diag_v, dm = diag_m, lc = hand_v, lm = hand_m;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const V uc = v[c], um = m[c];
+                    const bool neq = rt[c] != ht;
+                    const V sub_c = dc + (neq ? subc : (V)0);
+                    const V ins_c = uc + insc;
+                    const bool ps = ins_c >= sub_c;
+                    V cc = ps ? sub_c : ins_c;
+                    V mm = ps ? dm + (neq ? (V)1 : (V)0) : um + (V)1;
+                    const V del_c = lc + delc;
+                    const bool keep = del_c >= cc;
+                    cc = keep ? cc : del_c;
+                    mm = keep ? mm : lm + (V)1;
+                    dc = uc;
+                    dm = um;
+                    lc = cc;
+                    lm = mm;
+                    v[c] = cc;
+                    m[c] = mm;
+                }
+            } else if (FLT_COST) {  // SM:290-293, 316-317; deletion run tracked by origin
+                V dg = diag_v, obr = hand_ob, ojr = hand_oj;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const V up = v[c];
+                    const V a = up + insc;
+                    const V sb = dg + ((rt[c] != ht) ? subc : (V)0);
+                    const V t = a < sb ? a : sb;
+                    const V cand = obr + (jd[c] - ojr);
+                    const bool fresh = !(cand < t);
+                    v[c] = fresh ? t : cand;
+                    obr = fresh ? t : obr;
+                    ojr = fresh ? jd[c] : ojr;
+                    dg = up;
+                }
+                ob = obr;
+                oj = ojr;
+            } else {
+                int dg = (int)diag_v, lf = (int)hand_v;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int up = (int)v[c];
+                    int sb = dg;
+                    if (rt[c] != ht) sb += (int)subc;
+                    const int t = __viaddmin_s32(up, (int)insc, sb);
+                    lf = __viaddmin_s32(lf, (int)delc, t);
+                    dg = up;
+                    v[c] = (V)lf;
+                }
+            }
+            if (lane == 31) {
+                if (!last) {
+                    out_v[32 + i] = v[C - 1];
+                    if (COUNT) out_a[32 + i] = m[C - 1];
+                    if (FLT_COST) {
+                        out_a[32 + i] = ob;
+                        out_b[32 + i] = oj;
+                    }
+                    if ((i & 7) == 0 || i == steps) {  // publish rows <= i
+                        __threadfence_block();
+                        lev_st_volatile_shared(done + k, i);
+                    }
+                } else if (MODE == LEV_MODE_PREFIX) {  // SM:340-346, 356-378
+                    float val = (float)(COUNT ? m[C - 1] : v[C - 1]) * p.mult;
+                    if (p.norm) {
+                        if (r == 0) {
+                            val = 1.0f;
+                        } else {
+                            const float rf = (float)r;
+                            const float q0 = __fmul_rn(val, rcp);
+                            val = __fmaf_rn(__fmaf_rn(-rf, q0, val), rcp, q0);  // == val / rf
+                        }
+                    }
+                    p.out[(int64_t)i * p.out_si + (int64_t)pair * p.out_sn] = val;
+                }
+            }
+        }
+    }
+    if (MODE == LEV_MODE_FINAL && last && lane == 31)  // SM:390-405
+        p.out[pair] = lev_finalize((float)(COUNT ? m[C - 1] : v[C - 1]), p, r, h > 0);
+}
+
+template <typename V, bool COUNT, int MODE>
+__global__ void __launch_bounds__(256) lev_cta_kernel(const LevParams p, const LevCtaGeom geo) {
+    LEV_DYN_SMEM(int, smem);
+    if (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) return;  // stand-by lev_warp_kernel takes over
+    constexpr int NCH = LevCtaChan<V, COUNT>::NCH;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = geo.NW;
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem);  // 16 bytes reserved
+    int* ref_s = smem + 4;
+    int* hyp_s = ref_s + geo.Rs;
+    int* done = hyp_s + geo.Hts;
+    V* bnd = reinterpret_cast<V*>(done + ((geo.Smax + 3) & ~3));
+    __shared__ int cur_pair;
+    int* counter = const_cast<int*>(p.wide_flag) + 3;
+    if (tid == 0) lev_mbar_init(mbar, 1);
+    unsigned parity = 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) cur_pair = atomicAdd(counter, 1);
+        __syncthreads();
+        const int pair = cur_pair;
+        if (pair >= p.P) break;
+        const int refcol = pair / p.ref_group;
+        const int r = p.ref_len[refcol], h = p.hyp_len[pair];
+        const int steps = p.exclude_last ? (h > 0 ? h - 1 : 0) : h;  // SM:286-288
+        if (tid == 0 && r == 0 && p.norm && p.flags != nullptr)
+            atomicOr(p.flags, B200LEV_FLAG_EMPTY_REF);  // SM:360-366, 397-404
+        // ---- stage the pair's tokens: two TMA bulk copies completing on the mbarrier ----
+        const unsigned rbytes = (unsigned)((r * 4 + 15) & ~15), hbytes = (unsigned)((steps * 4 + 15) & ~15);
+        if (tid == 0 && rbytes + hbytes > 0) {
+            lev_mbar_expect_tx(mbar, rbytes + hbytes);
+            if (rbytes) lev_bulk_g2s(ref_s, p.ref_tok + (int64_t)refcol * p.Rp, rbytes, mbar);
+            if (hbytes) lev_bulk_g2s(hyp_s, p.hyp_tok + (int64_t)pair * p.Hp, hbytes, mbar);
+        }
+        for (int q = tid; q < geo.Smax; q += blockDim.x) done[q] = 0;
+        // PREFIX: row 0 and the padded tail do not depend on the DP (SM:279-285, 379-386)
+        if (MODE == LEV_MODE_PREFIX) {
+            const int first_pad = h + (p.exclude_last ? 0 : 1);
+            if (tid == 0 && first_pad > 0 && p.Hout > 0) {
+                const float v0 = COUNT ? (float)r : (float)((V)r * LevArith<V>::del(p));
+                p.out[(int64_t)pair * p.out_sn] = lev_finalize(v0, p, r, false);
+            }
+            for (int i = first_pad + tid; i < p.Hout; i += blockDim.x)
+                p.out[(int64_t)i * p.out_si + (int64_t)pair * p.out_sn] = p.padding;
+        }
+        __syncthreads();
+        if (rbytes + hbytes > 0) {
+            lev_mbar_wait(mbar, parity);
+            parity ^= 1;
+        }
+        const float rcp = r > 0 ? __frcp_rn((float)r) : 0.0f;
+        // smallest C whose NW concurrent strips cover the row; C = 8 beyond (several rounds)
+        const int cols = r + 1;
+        int S;
+#define LEV_CTA_RUN(C_)                                                                          \
+    S = (cols + 32 * C_ - 1) / (32 * C_);                                                        \
+    for (int k = warp; k < S; k += NW)                                                           \
+        lev_cta_strip<V, COUNT, MODE, C_>(p, pair, r, h, steps, k, S, ref_s, hyp_s, bnd, done,   \
+                                          geo.Hs, rcp);
+        if (cols <= 32 * NW) { LEV_CTA_RUN(1) }
+        else if (cols <= 64 * NW) { LEV_CTA_RUN(2) }
+        else if (cols <= 128 * NW) { LEV_CTA_RUN(4) }
+        else { LEV_CTA_RUN(8) }
+#undef LEV_CTA_RUN
+        (void)lane;
+    }
+}
+
+template <typename V, bool COUNT, int MODE>
+static int lev_cta_launch_one(const LevParams& p, cudaStream_t st) {
+    constexpr int NCH = LevCtaChan<V, COUNT>::NCH;
+    LevCtaGeom geo;
+    // enough warps to cover a row with C = 1 strips, at most 8
+    int NW = (p.R + 1 + 31) / 32;
+    geo.NW = NW < 2 ? 2 : (NW > 8 ? 8 : NW);
+    geo.Smax = (p.R + 1 + 255) / 256;
+    if (geo.Smax < geo.NW) geo.Smax = geo.NW;
+    geo.Hs = p.H + 64;
+    geo.Rs = (int)p.Rp + 4;
+    geo.Hts = (int)p.Hp + 4;
+    const size_t smem = sizeof(int) * ((size_t)4 + geo.Rs + geo.Hts + ((geo.Smax + 3) & ~3) +
+                                       (size_t)geo.Smax * NCH * geo.Hs);
+    if (smem > 200 * 1024) return 0;
+    auto kern = lev_cta_kernel<V, COUNT, MODE>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            lev_set_error("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+            return B200LEV_ERR_CUDA;
+        }
+    }
+    if (cudaMemsetAsync(const_cast<int*>(p.wide_flag) + 3, 0, sizeof(int), st) != cudaSuccess)
+        return lev_check_cuda("memset");
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    const int by_threads = 2048 / (32 * geo.NW);
+    if (per_sm > by_threads) per_sm = by_threads;
+    if (per_sm < 1) per_sm = 1;
+    int64_t blocks = (int64_t)148 * per_sm;
+    if (blocks > p.P) blocks = p.P;
+    lev_prof_begin(LEV_PROF_DP, st);
+    lev_launch(kern, dim3((unsigned)blocks), dim3(32 * geo.NW), smem, st, p, geo);
+    lev_prof_end(LEV_PROF_DP, st);
+    const int rc = lev_check_cuda("lev_cta_kernel");
+    return rc ? rc : 1;
+}
+
+// Returns 1 if the CTA-per-pair kernel took the job, 0 if it does not apply, < 0 on error.
+int lev_launch_cta(const LevParams& p, int mode, bool count_mode, bool float_path, cudaStream_t st) {
+    if (mode == LEV_MODE_MASK) return 0;
+    // worth it when one warp per pair cannot fill the chip (few pairs) or rows are long;
+    // B200LEV_CTA_KERNEL=0/1 forces the choice (tests)
+    bool use = (p.R >= 48) && ((int64_t)p.P < 148 * 16 || p.R > 512);
+    if (const char* e = getenv("B200LEV_CTA_KERNEL")) use = atoi(e) != 0;
+    if (!use) return 0;
+    if (!float_path) {
+        if (!count_mode) {
+            if (mode == LEV_MODE_FINAL) return lev_cta_launch_one<int, false, LEV_MODE_FINAL>(p, st);
+            return lev_cta_launch_one<int, false, LEV_MODE_PREFIX>(p, st);
+        }
+        if (mode == LEV_MODE_FINAL) return lev_cta_launch_one<int, true, LEV_MODE_FINAL>(p, st);
+        return lev_cta_launch_one<int, true, LEV_MODE_PREFIX>(p, st);
+    }
+    if (!count_mode) {
+        if (mode == LEV_MODE_FINAL) return lev_cta_launch_one<float, false, LEV_MODE_FINAL>(p, st);
+        return lev_cta_launch_one<float, false, LEV_MODE_PREFIX>(p, st);
+    }
+    if (mode == LEV_MODE_FINAL) return lev_cta_launch_one<float, true, LEV_MODE_FINAL>(p, st);
+    return lev_cta_launch_one<float, true, LEV_MODE_PREFIX>(p, st);
+}

@@ -27,35 +27,7 @@
 // Arithmetic: int32 for integer costs (exact; converted to fp32 on store), fp32 for
 // the rest, in the reference's operation order (including its deletion term
 // min_k v[k] + (fl(j*d) - fl(k*d)), SM:263-266,317, tracked by run origin).
-#include <type_traits>
-
-#include "lev_common.cuh"
-
-template <typename V>
-struct LevArith;
-template <>
-struct LevArith<int> {
-    static __device__ __forceinline__ int big() { return LEV_BIG_I32; }
-    static __device__ __forceinline__ int ins(const LevParams& p) { return p.ins_i; }
-    static __device__ __forceinline__ int del(const LevParams& p) { return p.del_i; }
-    static __device__ __forceinline__ int sub(const LevParams& p) { return p.sub_i; }
-};
-template <>
-struct LevArith<float> {
-    static __device__ __forceinline__ float big() { return __int_as_float(0x7f800000); }
-    static __device__ __forceinline__ float ins(const LevParams& p) { return p.ins_f; }
-    static __device__ __forceinline__ float del(const LevParams& p) { return p.del_f; }
-    static __device__ __forceinline__ float sub(const LevParams& p) { return p.sub_f; }
-};
-
-// SM:390-405 (final) and SM:356-378 (prefix row i): scale, normalise, empty-ref rule.
-// `positive` is (hyp_len > 0) for the final value and (i > 0) for prefix row i.
-__device__ __forceinline__ float lev_finalize(float val, const LevParams& p, int r,
-                                              bool positive) {
-    float v = val * p.mult;
-    if (p.norm) v = (r == 0) ? (positive ? 1.0f : 0.0f) : v / (float)r;
-    return v;
-}
+#include "lev_arith.cuh"
 
 // number of per-warp shared-memory columns (boundary channels + row minima)
 template <typename V, bool COUNT, int MODE>
@@ -390,6 +362,12 @@ int lev_launch_dp(const LevParams& p_, int mode, bool count_mode, bool float_pat
         // large batches of short/mid pairs: length-bucketed group kernel (lev_group.cu);
         // this kernel then only runs if K0 flagged tokens wider than 32 bits
         const int took = lev_launch_group(p, mode, count_mode, st);
+        if (took < 0) return took;
+        if (took == 1) p.only_if_wide = 1;
+    }
+    if (!p.only_if_wide) {
+        // few pairs or long rows: one CTA per pair, strips pipelined across warps (lev_cta.cu)
+        const int took = lev_launch_cta(p, mode, count_mode, float_path, st);
         if (took < 0) return took;
         if (took == 1) p.only_if_wide = 1;
     }

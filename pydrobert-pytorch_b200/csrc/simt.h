@@ -37,6 +37,48 @@ template <int N>
 __device__ __forceinline__ void lev_cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+
+// TMA bulk copy (cp.async.bulk, SASS UBLKCP) global -> shared, completion on an mbarrier
+__device__ __forceinline__ void lev_mbar_init(unsigned long long* bar, unsigned count) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void lev_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes)
+                 : "memory");
+}
+// bytes must be a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void lev_bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes,
+                                             unsigned long long* bar) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+        "l"(gsrc), "r"(bytes), "r"(b)
+        : "memory");
+}
+__device__ __forceinline__ void lev_mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LEV_MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LEV_MBAR_DONE_%=;\n"
+        "bra LEV_MBAR_WAIT_%=;\n"
+        "LEV_MBAR_DONE_%=:\n"
+        "}" ::"r"(a),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ int lev_ld_volatile_shared(const int* p) {
+    return *reinterpret_cast<const volatile int*>(p);
+}
+__device__ __forceinline__ void lev_st_volatile_shared(int* p, int v) {
+    *reinterpret_cast<volatile int*>(p) = v;
+}
 #endif
 
 #define LEV_FULL_MASK 0xffffffffu

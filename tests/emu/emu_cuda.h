@@ -364,3 +364,20 @@ static inline void lev_cp_async_commit() {}
 template <int N>
 static inline void lev_cp_async_wait() {}
 static inline float __frcp_rn(float x) { return 1.0f / x; }
+// mbarrier + bulk copy.  Barrier word: low 32 bits = completed phases, high 32 bits =
+// bytes still expected in the current phase.  The copy itself happens at issue.
+static inline void lev_mbar_init(unsigned long long* bar, unsigned) { *bar = 0; }
+static inline void lev_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    *bar += (unsigned long long)bytes << 32;
+}
+static inline void lev_bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes,
+                                unsigned long long* bar) {
+    memcpy(smem_dst, gsrc, bytes);
+    *bar -= (unsigned long long)bytes << 32;
+    if ((*bar >> 32) == 0) *bar += 1;  // all expected bytes landed: the phase completes
+}
+static inline void lev_mbar_wait(unsigned long long* bar, unsigned parity) {
+    while (((*bar) & 1ull) == parity) emu::yield();
+}
+static inline int lev_ld_volatile_shared(const int* p) { return *(const volatile int*)p; }
+static inline void lev_st_volatile_shared(int* p, int v) { *(volatile int*)p = v; }

@@ -62,7 +62,11 @@ def test_sclite(F, dev, golden_sclite):
 @pytest.mark.parametrize("costs", [(1, 1, 1), (3, 3, 4), (1, 2, 3), (0.5, 1.0, 0.25), (0.7, 1.1, 1.3)])
 @pytest.mark.parametrize("shape", [(31, 33, 40), (40, 45, 33), (70, 30, 17), (130, 100, 9),
                                    (300, 260, 5), (700, 90, 3)])
-def test_random_vs_oracle(F, dev, costs, shape):
+@pytest.mark.parametrize("cta", ["0", "1"], ids=["warp_kernel", "cta_kernel"])
+def test_random_vs_oracle(F, dev, costs, shape, cta, monkeypatch):
+    """Both the warp-per-pair kernel (lev_dp.cu) and the CTA-per-pair kernel with TMA-staged
+    tokens (lev_cta.cu), forced through B200LEV_CTA_KERNEL."""
+    monkeypatch.setenv("B200LEV_CTA_KERNEL", cta)
     R, H, N = shape
     PC.check_vs_oracle(F, dev, seed=R * 1000 + H, R=R, H=H, N=N, V=6, costs=costs,
                        include_eos=True, norm=True, min_frac=0.4)
@@ -297,3 +301,24 @@ def test_group_kernel_vs_oracle(F, dev, shape, costs, monkeypatch):
 def test_group_kernel_wide_tokens(F, dev, monkeypatch):
     monkeypatch.setenv("B200LEV_GROUP_MIN_PAIRS", "1")
     PC.check_wide_tokens(F, dev)
+
+
+def test_cfg5_full_batch_properties(F, dev):
+    """BASELINE config 5 at full size (256 pairs, T=2000, NIST costs) on the CTA-per-pair
+    kernel: the last valid prefix row equals the final distance; identical pairs cost 0;
+    a strided sample is checked against the oracle."""
+    rng = np.random.default_rng(55)
+    N, T, V = 256, 2001, 64
+    ref = PC.random_tokens(rng, T, N, V, 0, 0, min_len=199)
+    hyp = PC.random_tokens(rng, T, N, V, 0, 0, min_len=199)
+    tr, th = torch.from_numpy(ref).to(dev), torch.from_numpy(hyp).to(dev)
+    kw = dict(eos=0, ins_cost=3, del_cost=3, sub_cost=4)
+    pe = F.prefix_edit_distances(tr, th, **kw)
+    ed = F.edit_distance(tr, th, include_eos=True, **kw)
+    hl = torch.from_numpy((hyp == 0).argmax(0) + 1).to(dev)
+    assert torch.equal(pe.gather(0, hl.unsqueeze(0)).squeeze(0), ed)
+    assert F.edit_distance(tr, tr, include_eos=True, **kw).abs().sum().item() == 0
+    idx = np.arange(0, N, 37)
+    exp = O.prefix_error_rates(ref[:, idx], hyp[:, idx], **kw)
+    act = F.prefix_error_rates(tr[:, idx], th[:, idx], warn=False, **kw)
+    PC.assert_same(act, exp, True, "cfg5 sample")

@@ -43,9 +43,12 @@ def test_golden_losses(F, golden_loss):
 
 @pytest.mark.parametrize("costs", [(1, 1, 1), (3, 3, 4), (1, 2, 3), (0.5, 1.0, 0.25), (0.7, 1.1, 1.3)])
 @pytest.mark.parametrize("shape", [(40, 45, 6), (70, 30, 5), (130, 20, 3), (300, 40, 2)])
-def test_random_vs_oracle_strips(F, costs, shape):
+@pytest.mark.parametrize("cta", ["0", "1"], ids=["warp_kernel", "cta_kernel"])
+def test_random_vs_oracle_strips(F, costs, shape, cta, monkeypatch):
     """Reference lengths on both sides of every strip-width boundary (32/64/128/256
-    columns) so the multi-strip hand-off and every C variant are exercised."""
+    columns) so the multi-strip hand-off and every C variant are exercised, on both the
+    warp-per-pair kernel (lev_dp.cu) and the CTA-per-pair kernel (lev_cta.cu)."""
+    monkeypatch.setenv("B200LEV_CTA_KERNEL", cta)
     R, H, N = shape
     PC.check_vs_oracle(F, DEV, seed=R * 1000 + H, R=R, H=H, N=N, V=6, costs=costs,
                        include_eos=True, norm=True, exclude_last=False, min_frac=0.5)
@@ -168,3 +171,22 @@ def test_group_kernel_n_best_and_wide(F, monkeypatch):
     monkeypatch.setenv("B200LEV_GROUP_MIN_PAIRS", "1")
     test_n_best_shared_reference(F)
     PC.check_wide_tokens(F, DEV)
+
+
+@pytest.mark.parametrize("shape", [(60, 70, 5), (130, 40, 4), (300, 90, 3), (700, 45, 2)])
+@pytest.mark.parametrize("costs", [(1, 1, 1), (3, 3, 4), (0.5, 1.0, 0.25), (0.7, 1.1, 1.3)])
+def test_cta_kernel_vs_oracle(F, shape, costs, monkeypatch):
+    """lev_cta.cu: one CTA per pair, strips pipelined across warps, tokens staged by (emulated)
+    TMA bulk copies; every C variant, cost / count / float channels, final + prefix."""
+    monkeypatch.setenv("B200LEV_CTA_KERNEL", "1")
+    R, H, N = shape
+    for flags in (dict(include_eos=True, norm=True, exclude_last=False, min_frac=0.0),
+                  dict(include_eos=False, norm=False, exclude_last=True, min_frac=0.5,
+                       batch_first=True)):
+        PC.check_vs_oracle(F, DEV, seed=R * 7 + H, R=R, H=H, N=N, V=5, costs=costs, do_mask=False,
+                           padding=-3, **flags)
+
+
+def test_warp_kernel_when_cta_disabled(F, monkeypatch):
+    monkeypatch.setenv("B200LEV_CTA_KERNEL", "0")
+    PC.check_vs_oracle(F, DEV, seed=3, R=130, H=40, N=4, V=5, costs=(1, 2, 3), do_mask=False)
