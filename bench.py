@@ -125,6 +125,7 @@ def cpu_baseline(ref, hyp, cells, min_seconds=3.0, max_runs=5):
     """The oracle port on the host cores (all OpenMP threads), same call, same tensors."""
     from oracle import oracle as O
 
+    O.use_all_cores()
     refx = np.repeat(ref, NBEST, axis=1)
     O.prefix_error_rates(refx[:, :64], hyp[:, :64], eos=0)  # build + warm
     best, runs, t_total = None, 0, 0.0
@@ -152,6 +153,7 @@ def run_reference(args):
     ref, hyp, cells = make_batch(n_utts, seed=3)
     from oracle import oracle as O
 
+    O.use_all_cores()
     refx = np.repeat(ref, NBEST, axis=1)
     O.prefix_error_rates(refx[:, :64], hyp[:, :64], eos=0)
     for _ in range(max(args.warmup, 1)):

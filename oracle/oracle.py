@@ -86,6 +86,13 @@ def num_threads() -> int:
     return int(lib().lev_oracle_num_threads())
 
 
+def use_all_cores() -> int:
+    """Ask OpenMP for every core this process may run on (torchrun pins OMP_NUM_THREADS=1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().lev_oracle_set_threads(ctypes.c_int(n))
+    return num_threads()
+
+
 def _np_tokens(x) -> np.ndarray:
     if hasattr(x, "detach"):
         x = x.detach().cpu().numpy()

@@ -433,3 +433,25 @@ def _(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost, sub_cost, nor
     n = hyp.shape[0] if batch_first else hyp.shape[1]
     return (ref.new_empty((n,), dtype=torch.float32), ref.new_empty((3,), dtype=torch.float64),
             ref.new_empty((1,), dtype=torch.int32))
+
+
+# ---------------------------------------------------------------------------------------
+# eager fast path
+# ---------------------------------------------------------------------------------------
+def _needs_dispatcher() -> bool:
+    """The registered ops exist so that tracing / torch.compile see ONE opaque op per public
+    call.  In plain eager mode the dispatcher round trip (~20-30 us) is pure overhead next to
+    kernels that take a few microseconds, so the op bodies are called directly."""
+    return torch.jit.is_tracing() or torch.compiler.is_compiling()
+
+
+def string_matching_fast(*args):
+    if _needs_dispatcher():
+        return string_matching(*args)
+    return string_matching._init_fn(*args)
+
+
+def optimal_completion_fast(*args):
+    if _needs_dispatcher():
+        return optimal_completion(*args)
+    return optimal_completion._init_fn(*args)

@@ -98,7 +98,7 @@ def _string_matching(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost
             "warn=False to suppress this warning"
         )
     (ref_d, hyp_d), back = _offload(ref, hyp)
-    out, flags = _ops.string_matching(ref_d, hyp_d, eos, include_eos, batch_first, float(ins_cost),
+    out, flags = _ops.string_matching_fast(ref_d, hyp_d, eos, include_eos, batch_first, float(ins_cost),
                                       float(del_cost), float(sub_cost), norm, return_prf_dsts,
                                       exclude_last, int(padding), return_mistakes, ref_group)
     if warn:
@@ -197,9 +197,9 @@ def optimal_completion(
     if ref.dim() != 2 or hyp.dim() != 2:
         raise RuntimeError("ref and hyp must be 2 dimensional")
     (ref_d, hyp_d), back = _offload(ref, hyp)
-    out, flags = _ops.optimal_completion(ref_d, hyp_d, eos, include_eos, batch_first,
-                                         float(ins_cost), float(del_cost), float(sub_cost),
-                                         int(padding), exclude_last)
+    out, flags = _ops.optimal_completion_fast(ref_d, hyp_d, eos, include_eos, batch_first,
+                                              float(ins_cost), float(del_cost), float(sub_cost),
+                                              int(padding), exclude_last)
     if warn:
         _warn_flags(flags, eos, include_eos, False, False)
     return back(out)
@@ -233,9 +233,10 @@ def hard_optimal_completion_distillation_loss(
     if reduction not in _abi.REDUCE:
         raise RuntimeError(f"'{reduction}' is not a valid value for reduction")
     (logits_d, ref_d, hyp_d, weight_d), back = _offload(logits, ref, hyp, weight)
-    optimals, flags = _ops.optimal_completion(ref_d, hyp_d, eos, include_eos, batch_first,
-                                              float(ins_cost), float(del_cost), float(sub_cost),
-                                              int(ignore_index), True)  # SM:1216-1228
+    optimals, flags = _ops.optimal_completion_fast(ref_d, hyp_d, eos, include_eos, batch_first,
+                                                   float(ins_cost), float(del_cost),
+                                                   float(sub_cost), int(ignore_index),
+                                                   True)  # SM:1216-1228
     if warn:
         _warn_flags(flags, eos, include_eos, False, False)
     loss, _, _ = _ops.ocd_loss(logits_d, optimals, weight_d, int(ignore_index),
@@ -295,9 +296,9 @@ def minimum_error_rate_loss(
             "Please switch to edit_distance functions for old behaviour. Set "
             "warn=False to suppress this warning"
         )
-    er, flags = _ops.string_matching(ref_d, hyp_d, eos, include_eos, batch_first,
-                                     float(ins_cost), float(del_cost), float(sub_cost), norm,
-                                     False, False, 0, True, group)  # SM:1451-1462
+    er, flags = _ops.string_matching_fast(ref_d, hyp_d, eos, include_eos, batch_first,
+                                          float(ins_cost), float(del_cost), float(sub_cost), norm,
+                                          False, False, 0, True, group)  # SM:1451-1462
     if warn:
         _warn_flags(flags, eos, include_eos, norm, False)
     loss = _ops.mwer_loss(er, lp_d, sub_avg, _abi.REDUCE[reduction])

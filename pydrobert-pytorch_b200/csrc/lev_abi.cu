@@ -224,6 +224,7 @@ static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     p->gcursor = (int*)(ws + L.off_gcursor);
     p->gmeta = (int*)(ws + L.off_gmeta);
     p->slots = (int4*)(ws + L.off_slots);
+    p->gmeta_order = (int*)(ws + L.off_slots);
     p->nbins = (int)L.nbins;
     p->raw32 = L.off_raw ? (int32_t*)(ws + L.off_raw) : nullptr;
     p->raw16 = (unsigned short*)p->raw32;

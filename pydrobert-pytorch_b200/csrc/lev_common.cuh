@@ -141,6 +141,7 @@ struct LevParams {
     int* gcursor;
     int* gmeta;   // [0] = number of tasks
     int4* slots;  // sorted (pair, r, h, class) per task slot; pair < 0 = padding
+    int* gmeta_order;  // same storage viewed as int[P]: pair order of the CTA kernel
     int32_t* raw32;          // [P][Hr]   raw prefix rows (32-bit group path)
     unsigned short* raw16;   // [P][Hr16] same storage, packed path
     int64_t Hr, Hr16;

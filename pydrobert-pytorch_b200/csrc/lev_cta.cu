@@ -16,13 +16,67 @@
 
 #include "lev_arith.cuh"
 
+// rows between two publications of a strip's boundary progress (power of two)
+#ifndef LEV_CTA_PUB
+#define LEV_CTA_PUB 8
+#endif
+#ifdef LEV_CTA_NOFENCE  // timing experiments only
+#define LEV_CTA_FENCE() ((void)0)
+#else
+#define LEV_CTA_FENCE() __threadfence_block()
+#endif
+
 struct LevCtaGeom {
     int NW;    // warps per CTA
     int Smax;  // boundary columns provisioned
     int Hs;    // words per boundary column (H + 64)
     int Rs;    // words reserved for the reference tokens (multiple of 4)
     int Hts;   // words reserved for the hypothesis tokens (multiple of 4)
+    int ordered;  // pairs are taken in the order lev_cta_order_kernel wrote (largest first)
+    int shift;    // order key = (r * h) >> shift, < 1024
 };
+
+// Largest-first order of the pairs (LPT): a counting sort on the cell count r*h quantised
+// to 1024 levels.  One CTA; the order lands in the (otherwise unused) slot table.
+__global__ void __launch_bounds__(1024) lev_cta_order_kernel(const LevParams p, const LevCtaGeom geo) {
+    __shared__ int hist[1024];
+    const int tid = threadIdx.x;
+    hist[tid] = 0;
+    __syncthreads();
+    for (int q = tid; q < p.P; q += 1024) {
+        const long long key = ((long long)p.ref_len[q / p.ref_group] * p.hyp_len[q]) >> geo.shift;
+        atomicAdd(&hist[1023 - (int)(key > 1023 ? 1023 : key)], 1);
+    }
+    __syncthreads();
+    // exclusive scan of 1024 bins: warp scans + one pass over the 32 warp totals
+    const int lane = tid & 31, warp = tid >> 5;
+    __shared__ int wsum[32];
+    const int cnt = hist[tid];
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(LEV_FULL_MASK, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(LEV_FULL_MASK, w, o);
+            if (lane >= o) w += t;
+        }
+        wsum[lane] = w - wsum[lane];
+    }
+    __syncthreads();
+    hist[tid] = wsum[warp] + incl - cnt;
+    __syncthreads();
+    for (int q = tid; q < p.P; q += 1024) {
+        const long long key = ((long long)p.ref_len[q / p.ref_group] * p.hyp_len[q]) >> geo.shift;
+        p.gmeta_order[atomicAdd(&hist[1023 - (int)(key > 1023 ? 1023 : key)], 1)] = q;
+    }
+}
 
 template <typename V, bool COUNT>
 struct LevCtaChan {
@@ -75,35 +129,62 @@ __device__ __forceinline__ void lev_cta_strip(const LevParams& p, const int pair
             p.out[pair] = lev_finalize((float)(COUNT ? m[C - 1] : v[C - 1]), p, r, h > 0);
         return;
     }
+    // Shared memory is addressed through 32-bit shared-space addresses computed once, so
+    // that the step loop carries no generic->shared conversions:
+    //   row of this lane at step s is i = s - lane; its hypothesis token sits at hyp_a + 4*s;
+    //   lane 0 reads row s of the left boundary at in_*_a + 4*s; lane 31 writes row s - 31.
+    const lev_saddr hyp_a = lev_saddr_of(hyp_s) - 4u * (unsigned)(1 + lane);
+    const lev_saddr in_v_a = lev_saddr_of(in_v + 32), in_a_a = lev_saddr_of(in_a + 32),
+                    in_b_a = lev_saddr_of(in_b + 32);
+    const lev_saddr out_v_a = lev_saddr_of(out_v + 1), out_a_a = lev_saddr_of(out_a + 1),
+                    out_b_a = lev_saddr_of(out_b + 1);
+    (void)in_a_a; (void)in_b_a; (void)out_a_a; (void)out_b_a;
+    float* __restrict__ orow = p.out + (int64_t)pair * p.out_sn - (int64_t)31 * p.out_si;
+    const float rf = (float)r, mult = p.mult;
+    const bool norm = p.norm != 0;
+    const bool is0 = (lane == 0), is31 = (lane == 31);
+    const int* done_in = done + (k > 0 ? k - 1 : 0);
     const int nsteps = steps + 31;
-    for (int s = 1; s <= nsteps; ++s) {
-        // ---- flow control: rows s .. s+7 of the left boundary must have been published ----
-        if (!first && (s & 7) == 1 && s <= steps) {
-            const int need = min(s + 7, steps);
-            while (lev_ld_volatile_shared(done + (k - 1)) < need) LEV_SPIN_YIELD();
-            __threadfence_block();
+    auto as_v = [](int bits) -> V { return IS_INT ? (V)bits : (V)__int_as_float(bits); };
+    auto as_bits = [](V x) -> int { return IS_INT ? (int)x : __float_as_int((float)x); };
+    int ht_next = lev_lds32(hyp_a + 4u);  // token of step 1 (software-pipelined one step ahead)
+
+    // one wavefront step; ALL = every lane has a row to update (32 <= s <= steps), which
+    // removes the divergent branch from the steady state
+    auto step = [&](auto ALL, const int s) {
+        constexpr bool all_active = decltype(ALL)::value;
+        // ---- flow control (warp-uniform): next LEV_CTA_PUB rows of the left boundary ----
+        if (!first && (s & (LEV_CTA_PUB - 1)) == 1 && s <= steps) {
+            const int need = min(s + LEV_CTA_PUB - 1, steps);
+            while (lev_ld_volatile_shared(done_in) < need) __nanosleep(32);
+            LEV_CTA_FENCE();
         }
         const V sh_v = __shfl_up_sync(LEV_FULL_MASK, v[C - 1], 1);
-        const V hand_v = (lane == 0) ? (first || s > steps ? BIG : in_v[32 + s]) : sh_v;
+        // past the last row lane 0 is idle; whatever it reads there is never used
+        V hand_v = sh_v;
+        if (is0) hand_v = first ? BIG : as_v(lev_lds32_sync(in_v_a + 4u * (unsigned)s));
         const V diag_v = pl_v;
         pl_v = hand_v;
         V hand_m = (V)0, diag_m = (V)0, hand_ob = BIG, hand_oj = (V)0;
         if (COUNT) {
-            const V sh_m = __shfl_up_sync(LEV_FULL_MASK, m[C - 1], 1);
-            hand_m = (lane == 0) ? (first || s > steps ? (V)0 : in_a[32 + s]) : sh_m;
+            hand_m = __shfl_up_sync(LEV_FULL_MASK, m[C - 1], 1);
+            if (is0) hand_m = first ? (V)0 : as_v(lev_lds32_sync(in_a_a + 4u * (unsigned)s));
             diag_m = pl_m;
             pl_m = hand_m;
         }
         if (FLT_COST) {
-            const V sh_ob = __shfl_up_sync(LEV_FULL_MASK, ob, 1);
-            const V sh_oj = __shfl_up_sync(LEV_FULL_MASK, oj, 1);
-            hand_ob = (lane == 0) ? (first || s > steps ? BIG : in_a[32 + s]) : sh_ob;
-            hand_oj = (lane == 0) ? (first || s > steps ? (V)0 : in_b[32 + s]) : sh_oj;
+            hand_ob = __shfl_up_sync(LEV_FULL_MASK, ob, 1);
+            hand_oj = __shfl_up_sync(LEV_FULL_MASK, oj, 1);
+            if (is0) {
+                hand_ob = first ? BIG : as_v(lev_lds32_sync(in_a_a + 4u * (unsigned)s));
+                hand_oj = first ? (V)0 : as_v(lev_lds32_sync(in_b_a + 4u * (unsigned)s));
+            }
         }
         (void)hand_m; (void)diag_m; (void)hand_ob; (void)hand_oj;
-        const int i = s - lane;
-        if (i >= 1 && i <= steps) {
-            const int ht = hyp_s[i - 1];
+        const int ht = ht_next;
+        ht_next = lev_lds32(hyp_a + 4u * (unsigned)(s + 1));
+        const bool active = all_active || (unsigned)(s - lane - 1) < (unsigned)steps;
+        if (active) {
             if (COUNT) {  // SM:292-314
                 V dc = diag_v, dm = diag_m, lc = hand_v, lm = hand_m;
 #pragma unroll
@@ -156,40 +237,50 @@ __device__ __forceinline__ void lev_cta_strip(const LevParams& p, const int pair
                     v[c] = (V)lf;
                 }
             }
-            if (lane == 31) {
-                if (!last) {
-                    out_v[32 + i] = v[C - 1];
-                    if (COUNT) out_a[32 + i] = m[C - 1];
-                    if (FLT_COST) {
-                        out_a[32 + i] = ob;
-                        out_b[32 + i] = oj;
+        }
+        if (is31 && active) {
+            if (!last) {
+                lev_sts32(out_v_a + 4u * (unsigned)s, as_bits(v[C - 1]));
+                if (COUNT) lev_sts32(out_a_a + 4u * (unsigned)s, as_bits(m[C - 1]));
+                if (FLT_COST) {
+                    lev_sts32(out_a_a + 4u * (unsigned)s, as_bits(ob));
+                    lev_sts32(out_b_a + 4u * (unsigned)s, as_bits(oj));
+                }
+            } else if (MODE == LEV_MODE_PREFIX) {  // SM:340-346, 356-378
+                float val = (float)(COUNT ? m[C - 1] : v[C - 1]) * mult;
+                if (norm) {
+                    if (r == 0) {
+                        val = 1.0f;
+                    } else {
+                        const float q0 = __fmul_rn(val, rcp);
+                        val = __fmaf_rn(__fmaf_rn(-rf, q0, val), rcp, q0);  // == val / rf
                     }
-                    if ((i & 7) == 0 || i == steps) {  // publish rows <= i
-                        __threadfence_block();
-                        lev_st_volatile_shared(done + k, i);
-                    }
-                } else if (MODE == LEV_MODE_PREFIX) {  // SM:340-346, 356-378
-                    float val = (float)(COUNT ? m[C - 1] : v[C - 1]) * p.mult;
-                    if (p.norm) {
-                        if (r == 0) {
-                            val = 1.0f;
-                        } else {
-                            const float rf = (float)r;
-                            const float q0 = __fmul_rn(val, rcp);
-                            val = __fmaf_rn(__fmaf_rn(-rf, q0, val), rcp, q0);  // == val / rf
-                        }
-                    }
-                    p.out[(int64_t)i * p.out_si + (int64_t)pair * p.out_sn] = val;
+                }
+                orow[(int64_t)s * p.out_si] = val;
+            }
+        }
+        // ---- publish (warp-uniform test on s): rows <= s - 31 of this strip's boundary ----
+        if (!last) {
+            const int i31 = s - 31;
+            if (i31 >= 1 && ((i31 & (LEV_CTA_PUB - 1)) == 0 || i31 == steps)) {
+                __syncwarp();
+                if (is31) {
+                    LEV_CTA_FENCE();
+                    lev_st_volatile_shared(done + k, i31);
                 }
             }
         }
-    }
+    };
+    int s = 1;
+    for (; s <= 31 && s <= nsteps; ++s) step(std::false_type(), s);   // ramp-up
+    for (; s <= steps; ++s) step(std::true_type(), s);                // steady state
+    for (; s <= nsteps; ++s) step(std::false_type(), s);              // ramp-down
     if (MODE == LEV_MODE_FINAL && last && lane == 31)  // SM:390-405
         p.out[pair] = lev_finalize((float)(COUNT ? m[C - 1] : v[C - 1]), p, r, h > 0);
 }
 
 template <typename V, bool COUNT, int MODE>
-__global__ void __launch_bounds__(256) lev_cta_kernel(const LevParams p, const LevCtaGeom geo) {
+__global__ void __launch_bounds__(128) lev_cta_kernel(const LevParams p, const LevCtaGeom geo) {
     LEV_DYN_SMEM(int, smem);
     if (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) return;  // stand-by lev_warp_kernel takes over
     constexpr int NCH = LevCtaChan<V, COUNT>::NCH;
@@ -207,8 +298,8 @@ __global__ void __launch_bounds__(256) lev_cta_kernel(const LevParams p, const L
         __syncthreads();
         if (tid == 0) cur_pair = atomicAdd(counter, 1);
         __syncthreads();
-        const int pair = cur_pair;
-        if (pair >= p.P) break;
+        if (cur_pair >= p.P) break;
+        const int pair = geo.ordered ? p.gmeta_order[cur_pair] : cur_pair;  // longest first
         const int refcol = pair / p.ref_group;
         const int r = p.ref_len[refcol], h = p.hyp_len[pair];
         const int steps = p.exclude_last ? (h > 0 ? h - 1 : 0) : h;  // SM:286-288
@@ -249,7 +340,8 @@ __global__ void __launch_bounds__(256) lev_cta_kernel(const LevParams p, const L
         if (cols <= 32 * NW) { LEV_CTA_RUN(1) }
         else if (cols <= 64 * NW) { LEV_CTA_RUN(2) }
         else if (cols <= 128 * NW) { LEV_CTA_RUN(4) }
-        else { LEV_CTA_RUN(8) }
+        else if (cols <= 256 * NW) { LEV_CTA_RUN(8) }
+        else { LEV_CTA_RUN(16) }
 #undef LEV_CTA_RUN
         (void)lane;
     }
@@ -259,11 +351,16 @@ template <typename V, bool COUNT, int MODE>
 static int lev_cta_launch_one(const LevParams& p, cudaStream_t st) {
     constexpr int NCH = LevCtaChan<V, COUNT>::NCH;
     LevCtaGeom geo;
-    // enough warps to cover a row with C = 1 strips, at most 8
+    // enough warps to cover a row with C = 1 strips, at most 4: with C up to 16 columns per
+    // lane four concurrent strips span 2048 columns, and 2-3 CTAs share an SM
     int NW = (p.R + 1 + 31) / 32;
-    geo.NW = NW < 2 ? 2 : (NW > 8 ? 8 : NW);
-    geo.Smax = (p.R + 1 + 255) / 256;
+    geo.NW = NW < 2 ? 2 : (NW > 4 ? 4 : NW);
+    geo.Smax = (p.R + 1 + 511) / 512;
     if (geo.Smax < geo.NW) geo.Smax = geo.NW;
+    // largest-first order when the batch is ragged enough to matter
+    geo.ordered = p.P > 1 ? 1 : 0;
+    geo.shift = 0;
+    while ((((long long)p.R * p.H) >> geo.shift) > 1023) ++geo.shift;
     geo.Hs = p.H + 64;
     geo.Rs = (int)p.Rp + 4;
     geo.Hts = (int)p.Hp + 4;
@@ -280,6 +377,7 @@ static int lev_cta_launch_one(const LevParams& p, cudaStream_t st) {
     }
     if (cudaMemsetAsync(const_cast<int*>(p.wide_flag) + 3, 0, sizeof(int), st) != cudaSuccess)
         return lev_check_cuda("memset");
+    if (geo.ordered) lev_launch(lev_cta_order_kernel, dim3(1), dim3(1024), 0, st, p, geo);
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     const int by_threads = 2048 / (32 * geo.NW);
     if (per_sm > by_threads) per_sm = by_threads;

@@ -73,6 +73,29 @@ __device__ __forceinline__ void lev_mbar_wait(unsigned long long* bar, unsigned 
         "r"(parity)
         : "memory");
 }
+// Shared-memory accesses through a 32-bit shared-space address computed ONCE: inside the
+// DP step loops this keeps the generic->shared conversion (S2UR SR_CgaCtaId + ULEA on
+// sm_100) off the per-step critical path.
+typedef unsigned lev_saddr;
+__device__ __forceinline__ lev_saddr lev_saddr_of(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ int lev_lds32(lev_saddr a) {
+    // volatile + memory clobber: the same shared address holds different data for every
+    // pair a CTA processes, so the load must never be commoned or hoisted across the
+    // staging barrier
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lev_lds32_sync(lev_saddr a) {  // data another warp produces
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lev_sts32(lev_saddr a, int v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ int lev_ld_volatile_shared(const int* p) {
     return *reinterpret_cast<const volatile int*>(p);
 }

@@ -379,5 +379,10 @@ static inline void lev_bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes
 static inline void lev_mbar_wait(unsigned long long* bar, unsigned parity) {
     while (((*bar) & 1ull) == parity) emu::yield();
 }
+typedef uintptr_t lev_saddr;
+static inline lev_saddr lev_saddr_of(const void* p) { return (lev_saddr)p; }
+static inline int lev_lds32(lev_saddr a) { return *(const int*)a; }
+static inline int lev_lds32_sync(lev_saddr a) { return *(const volatile int*)a; }
+static inline void lev_sts32(lev_saddr a, int v) { *(volatile int*)a = v; }
 static inline int lev_ld_volatile_shared(const int* p) { return *(const volatile int*)p; }
 static inline void lev_st_volatile_shared(int* p, int v) { *(volatile int*)p = v; }
