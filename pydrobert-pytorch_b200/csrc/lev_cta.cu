@@ -271,16 +271,25 @@ __device__ __forceinline__ void lev_cta_strip(const LevParams& p, const int pair
             }
         }
     };
+#ifdef LEV_CTA_CLOCK
+    const long long clk0 = clock64();
+#endif
     int s = 1;
     for (; s <= 31 && s <= nsteps; ++s) step(std::false_type(), s);   // ramp-up
     for (; s <= steps; ++s) step(std::true_type(), s);                // steady state
     for (; s <= nsteps; ++s) step(std::false_type(), s);              // ramp-down
+#ifdef LEV_CTA_CLOCK
+    if (lane == 0 && pair == 0) {  // debug: cycles of this strip's step loop
+        p.gmeta[2 + 2 * k] = (int)(clock64() - clk0);
+        p.gmeta[3 + 2 * k] = nsteps;
+    }
+#endif
     if (MODE == LEV_MODE_FINAL && last && lane == 31)  // SM:390-405
         p.out[pair] = lev_finalize((float)(COUNT ? m[C - 1] : v[C - 1]), p, r, h > 0);
 }
 
 template <typename V, bool COUNT, int MODE>
-__global__ void __launch_bounds__(128) lev_cta_kernel(const LevParams p, const LevCtaGeom geo) {
+__global__ void __launch_bounds__(512) lev_cta_kernel(const LevParams p, const LevCtaGeom geo) {
     LEV_DYN_SMEM(int, smem);
     if (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) return;  // stand-by lev_warp_kernel takes over
     constexpr int NCH = LevCtaChan<V, COUNT>::NCH;
@@ -354,7 +363,9 @@ static int lev_cta_launch_one(const LevParams& p, cudaStream_t st) {
     // enough warps to cover a row with C = 1 strips, at most 4: with C up to 16 columns per
     // lane four concurrent strips span 2048 columns, and 2-3 CTAs share an SM
     int NW = (p.R + 1 + 31) / 32;
-    geo.NW = NW < 2 ? 2 : (NW > 4 ? 4 : NW);
+    int maxw = 4;
+    if (const char* e = getenv("B200LEV_CTA_WARPS")) maxw = atoi(e);  // tuning experiments
+    geo.NW = NW < 2 ? 2 : (NW > maxw ? maxw : NW);
     geo.Smax = (p.R + 1 + 511) / 512;
     if (geo.Smax < geo.NW) geo.Smax = geo.NW;
     // largest-first order when the batch is ragged enough to matter
