@@ -1,153 +1,293 @@
-// lev_pack.cu -- K0: lengths from eos + narrow/transpose tokens into pair-major int32.
+// lev_pack.cu -- K0: lengths from eos + narrow/transpose tokens into pair-major tables.
 //
 // Replaces SM:137-143 (_lens_from_eos), the include_eos adjustment of SM:195-228 and
-// the transposes of SM:181-183.  One pass over the token tensor: a CTA takes 32
-// sequences, loads 32x32 tiles with the unit-stride axis on threadIdx.x (256-byte
-// coalesced rows for a sequence-first int64 tensor), finds the first eos per
-// sequence with a shared-memory atomicMin, and writes the tile transposed so that
-// every sequence becomes one contiguous int32 row (what the DP kernels and the TMA
-// bulk copies of the long-pair kernel want).
+// the transposes of SM:181-183.  One pass over the token tensor, HBM-bound:
+//   read  T*N*elem_bytes            (coalesced: 32 lanes x 8 B per load instruction)
+//   write T*N*4  [+ T*N*2]          (int32 rows [+ uint16 rows for the packed DP path])
 //
-// HBM traffic: T*N*elem_bytes read + T*N*4 written, both fully coalesced.
+// Sequence-first tensors (unit stride along the batch axis): a CTA owns 32 sequences; lane l
+// of every warp loads tok[t][n0 + l] -- each load instruction is one coalesced 256-byte row,
+// 16 of them in flight per lane -- so a lane holds consecutive tokens of ITS OWN sequence in
+// registers and the transpose is free.  The four warps take four 32-position slices of a
+// 128-position chunk, stage them in a shared [32][132] tile and write whole rows back as
+// 128-bit vectors: the 32 rows of a CTA are one contiguous block of each pair-major table
+// (scripts/micro/pack.cu: per-lane row stores reach 66 us on the cfg2 hypothesis tensor,
+// this layout 40 us, a plain streaming copy of the same bytes 35 us).  First-eos position,
+// the "fits in int32" flag and the token range stay per-lane scalars: no atomics in the loop.
+//
+// Other layouts (batch-first, arbitrary views): one warp per sequence, lanes along the
+// sequence axis (coalesced when that axis has unit stride).
+//
+// Side products: warning / width flags (B200LEV_FLAG_*), the biased token range
+// [max(u), max(~u)], u = tok + 2^31, that lets the DP kernels pick the packed 16-bit path
+// on the device, and -- on the hypothesis side -- the (column class, length) histogram of
+// the group kernel's bucketing.
 #include "lev_common.cuh"
 
-template <typename TT>
-__global__ void __launch_bounds__(256, 6)
-lev_pack_kernel(const TT* __restrict__ tok, int64_t T, int64_t N, int64_t st, int64_t sn,
-                int has_eos, int64_t eos, int include_eos, int32_t* __restrict__ packed,
-                int64_t Tp, uint16_t* __restrict__ packed16, int64_t Tp16,
-                int32_t* __restrict__ lens, int32_t* flags, int32_t* state,
-                int missing_flag, int transposed, const int32_t* __restrict__ ref_len,
-                int ref_group, int G, int* __restrict__ ghist) {
-    __shared__ int tile[32][33];
-    __shared__ int first[32];
-    __shared__ int blk_flags;
-    __shared__ unsigned blk_umax, blk_nmax;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int64_t n0 = (int64_t)blockIdx.x * 32;
-    if (ty == 0) first[tx] = (int)T;
-    if (tx == 0 && ty == 0) {
-        blk_flags = 0;
-        blk_umax = 0u;
-        blk_nmax = 0u;
+struct LevPackArgs {
+    const void* tok;
+    int64_t T, N, st, sn;
+    int has_eos;
+    int64_t eos;
+    int include_eos;
+    int32_t* packed;
+    int64_t Tp;
+    uint16_t* packed16;  // may be NULL
+    int64_t Tp16;
+    int32_t* lens;
+    int32_t* flags;  // caller's warning flags, may be NULL
+    int32_t* state;  // workspace state words: [0] flags, [1] max(u), [2] max(~u)
+    int missing_flag;
+    const int32_t* ref_len;  // histogram side product (hypothesis pass only)
+    int ref_group, G;
+    int* ghist;
+};
+
+// ---- epilogue pieces shared by both layouts ----------------------------------------------
+// owner lane of a sequence: length rule (SM:198-218) and, on the hypothesis side, the
+// (class, length) histogram for the group kernel's global bucketing (the reference lengths
+// were produced by the launch before this one).  Returns the warning flags it raises.
+__device__ __forceinline__ int lev_pack_owner(const LevPackArgs& a, int ref_len, int64_t n,
+                                              int first) {
+    int len = first, flags = 0;
+    if (a.has_eos && a.include_eos) {
+        if (len == (int)a.T)
+            flags = a.missing_flag;
+        else
+            len += 1;
     }
-    __syncthreads();
-    int wide = 0;
-    int my_first = (int)T;  // first eos seen by this thread (eos-padded tails hit it often)
-    // int32 range of the (truncated) tokens this thread saw; turned into the biased
-    // max(u) / max(~u), u = tok + 2^31, that the packed 16-bit DP path tests
-    int lo = 0x7fffffff, hi = (int)0x80000000;
-    const int Ti = (int)T;
-    if (transposed) {
-        // software pipeline: the loads of tile k+1 are issued before the stores of tile k,
-        // so the two directions of HBM traffic overlap inside one CTA; addresses advance
-        // by pointer increments only
-        const bool n_ok = (n0 + tx) < N;
-        const TT* __restrict__ src = tok + (n0 + tx) * sn + (int64_t)ty * st;
-        const int64_t st8 = 8 * st, st32 = 32 * st;
-        TT regs[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) regs[q] = (n_ok && ty + 8 * q < Ti) ? src[q * st8] : (TT)0;
-        int32_t* dst32[4];
-        uint16_t* dst16[4];
-        bool row_ok[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int64_t n = n0 + ty + 8 * q;
-            row_ok[q] = n < N;
-            dst32[q] = packed + n * Tp + tx;
-            dst16[q] = packed16 != nullptr ? packed16 + n * Tp16 + tx : nullptr;
-        }
-        for (int t0 = 0; t0 < Ti; t0 += 32) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int tl = ty + 8 * q, t = t0 + tl;
-                if (n_ok && t < Ti) {
-                    const int64_t v = (int64_t)regs[q];
-                    const int v32 = (int)v;
-                    tile[tl][tx] = v32;
-                    if (has_eos && v == eos && t < my_first) my_first = t;
-                    if (sizeof(TT) == 8 && (int64_t)v32 != v) wide = 1;
-                    lo = v32 < lo ? v32 : lo;
-                    hi = v32 > hi ? v32 : hi;
-                }
-            }
-            __syncthreads();
-            if (t0 + 32 < Ti) {
-                src += st32;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    regs[q] = (n_ok && t0 + 32 + ty + 8 * q < Ti) ? src[q * st8] : (TT)0;
-            }
-            if (t0 + tx < Ti) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (row_ok[q]) {
-                        const int v = tile[tx][ty + 8 * q];
-                        dst32[q][t0] = v;
-                        if (dst16[q] != nullptr) dst16[q][t0] = (uint16_t)v;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        if (my_first < Ti) atomicMin(&first[tx], my_first);
-        __syncthreads();
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int nl = ty + 8 * q;
-            const int64_t n = n0 + nl;
-            if (n < N) {
-                for (int64_t t = tx; t < T; t += 32) {
-                    const int64_t v = (int64_t)tok[t * st + n * sn];
-                    packed[n * Tp + t] = (int)v;
-                    if (packed16 != nullptr) packed16[n * Tp16 + t] = (uint16_t)(int)v;
-                    if (has_eos && v == eos) atomicMin(&first[nl], (int)t);
-                    if ((int64_t)(int)v != v) wide = 1;
-                    lo = (int)v < lo ? (int)v : lo;
-                    hi = (int)v > hi ? (int)v : hi;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (wide) atomicOr(&blk_flags, B200LEV_FLAG_WIDE_TOKENS);
-    unsigned umax = (unsigned)hi + 0x80000000u, nmax = ~((unsigned)lo + 0x80000000u);
+    a.lens[n] = len;
+    if (a.ghist != nullptr) atomicAdd(&a.ghist[lev_group_bin(ref_len, len, a.G, (int)a.T)], 1);
+    return flags;
+}
+
+// (flags, max(u), max(~u)) over the warp, valid in every lane
+__device__ __forceinline__ void lev_pack_warp_reduce(int& flags, unsigned& umax, unsigned& nmax) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const unsigned a = __shfl_xor_sync(LEV_FULL_MASK, umax, o);
-        const unsigned b = __shfl_xor_sync(LEV_FULL_MASK, nmax, o);
-        umax = a > umax ? a : umax;
-        nmax = b > nmax ? b : nmax;
+        const unsigned x = __shfl_xor_sync(LEV_FULL_MASK, umax, o);
+        const unsigned y = __shfl_xor_sync(LEV_FULL_MASK, nmax, o);
+        const int f = __shfl_xor_sync(LEV_FULL_MASK, flags, o);
+        umax = x > umax ? x : umax;
+        nmax = y > nmax ? y : nmax;
+        flags |= f;
     }
-    if (tx == 0) {
-        atomicMax(&blk_umax, umax);
-        atomicMax(&blk_nmax, nmax);
+}
+
+// One thread publishes.  The range words only grow, so a recent copy (cur_u, cur_n) tells
+// whether the reduction can be skipped: thousands of reductions on one address would
+// otherwise queue behind each other at the end of the kernel.
+__device__ __forceinline__ void lev_pack_publish(const LevPackArgs& a, int flags, unsigned umax,
+                                                 unsigned nmax, unsigned cur_u, unsigned cur_n) {
+    if (flags != 0) {
+        if (a.flags != nullptr) atomicOr(a.flags, flags);
+        atomicOr(a.state, flags);
     }
-    if (ty == 0 && n0 + tx < N) {
-        int len = first[tx];
-        if (has_eos && include_eos) {  // SM:198-218
-            if (len == (int)T)
-                atomicOr(&blk_flags, missing_flag);
-            else
-                len += 1;
+    if (umax > cur_u) atomicMax(reinterpret_cast<unsigned*>(a.state) + 1, umax);
+    if (nmax > cur_n) atomicMax(reinterpret_cast<unsigned*>(a.state) + 2, nmax);
+}
+
+#define LEV_PACK_OBSERVE(x, t)                                       \
+    {                                                                \
+        const int v32_ = (int)(x);                                   \
+        if (sizeof(TT) == 8 && (int64_t)v32_ != (x)) wide = 1;       \
+        if (a.has_eos && (x) == a.eos && (t) < first) first = (t);   \
+        lo = v32_ < lo ? v32_ : lo;                                  \
+        hi = v32_ > hi ? v32_ : hi;                                  \
+    }
+
+// ---- sequence-first: a CTA owns 32 sequences, chunks of 128 positions -------------------
+// Warp w loads positions [tb + 32w, tb + 32w + 32) of the chunk, lane l the sequence n0 + l:
+// every load instruction is one coalesced row of 32 tokens, NB of them in flight per lane.
+// The lane's consecutive positions go into its row of the shared tile as 128-bit stores (row
+// stride 132 words: conflict-free); after the barrier whole rows leave as contiguous 16-byte
+// vectors -- the CTA's 32 output rows are one contiguous block of each table.
+constexpr int LEV_PACK_CHUNK = 128;
+constexpr int LEV_PACK_STRIDE = LEV_PACK_CHUNK + 4;
+constexpr int LEV_PACK_NB = 16;  // loads in flight per lane
+
+// What a lane learns from the tokens it moves, at ~5 instructions per token:
+//   first  first position whose LOW word equals eos32 (exact unless the lane saw a token that
+//          does not fit in int32, or eos itself does not fit: the caller rescans then)
+//   wacc   nonzero iff some token does not fit in int32
+//   lo/hi  range of the low words
+struct LevPackSeen {
+    int first, wacc, lo, hi;
+};
+
+// One 32-position slice of one sequence: 2 batches of NB coalesced loads, tokens narrowed
+// into the lane's row of the shared tile.  GUARD adds the t < T predicate (last slice only).
+template <typename TT, bool GUARD>
+__device__ __forceinline__ void lev_pack_slice(const TT* __restrict__ src, int st, int t0,
+                                               int Ti, bool eos_fast, int eos32, int* trow,
+                                               LevPackSeen& seen) {
+    constexpr int NB = LEV_PACK_NB;
+    LEV_OPAQUE_PTR(src);
+#pragma unroll
+    for (int h = 0; h < 32 / NB; ++h) {
+        TT raw[NB];
+#pragma unroll
+        for (int u = 0; u < NB; ++u)
+            raw[u] = (!GUARD || t0 + h * NB + u < Ti)
+                         ? lev_ldg_stream(src + (int64_t)(h * NB + u) * (int64_t)st)
+                         : (TT)0;
+        int v[NB];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int64_t x = (int64_t)raw[u];
+            v[u] = (int)x;
+            if (sizeof(TT) == 8) seen.wacc |= (int)(x >> 32) ^ (v[u] >> 31);
+            const int t = t0 + h * NB + u;
+            if (GUARD) {
+                if (t < Ti) {
+                    if (eos_fast && v[u] == eos32) seen.first = t < seen.first ? t : seen.first;
+                    seen.lo = v[u] < seen.lo ? v[u] : seen.lo;
+                    seen.hi = v[u] > seen.hi ? v[u] : seen.hi;
+                }
+            } else {
+                if (eos_fast && v[u] == eos32) seen.first = t < seen.first ? t : seen.first;
+            }
         }
-        lens[n0 + tx] = len;
-        // hypothesis side only: (class, length) histogram for the group kernel's global
-        // bucketing (the reference lengths were produced by the launch before this one)
-        if (ghist != nullptr)
-            atomicAdd(&ghist[lev_group_bin(ref_len[(n0 + tx) / ref_group], len, G, (int)T)], 1);
+        if (!GUARD) {
+#pragma unroll
+            for (int u = 0; u < NB; u += 2) {
+                seen.lo = __vimin3_s32(seen.lo, v[u], v[u + 1]);
+                seen.hi = __vimax3_s32(seen.hi, v[u], v[u + 1]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NB / 4; ++c)
+            *reinterpret_cast<int4*>(trow + h * NB + 4 * c) =
+                make_int4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    }
+}
+
+template <typename TT>
+__global__ void __launch_bounds__(128, 8) lev_pack_seqfirst_kernel(const LevPackArgs a) {
+    __shared__ __align__(16) int tile[32][LEV_PACK_STRIDE];
+    __shared__ int first_s[32];
+    __shared__ unsigned blk_u, blk_n;
+    __shared__ int blk_flags;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t n0 = (int64_t)blockIdx.x * 32;
+    const int64_t n = n0 + lane;
+    const bool valid_seq = n < a.N;
+    const int rows = (int)(a.N - n0 < 32 ? a.N - n0 : 32);
+    const int Ti = (int)a.T, Tp = (int)a.Tp, Tp16 = (int)a.Tp16;
+    const int st = (int)a.st;  // the launcher routes strides beyond int32 to the rows kernel
+    // lanes past the batch re-read sequence 0: its tokens are legitimate members of the
+    // tensor's range, and such a lane owns no output
+    const TT* __restrict__ seq = reinterpret_cast<const TT*>(a.tok) + (valid_seq ? n : 0);
+    const int eos32 = (int)a.eos;
+    const bool eos_fast = a.has_eos && (int64_t)eos32 == a.eos;
+    LevPackSeen seen = {Ti, 0, 0x7fffffff, (int)0x80000000};
+    // fetched before the token stream so that the latency hides under it
+    const int ref_len = (w == 0 && valid_seq && a.ghist != nullptr) ? a.ref_len[n / a.ref_group] : 0;
+    unsigned cur_u = 0u, cur_n = 0u;
+    if (w == 0) first_s[lane] = Ti;
+    if (threadIdx.x == 0) {
+        blk_u = 0u;
+        blk_n = 0u;
+        blk_flags = 0;
     }
     __syncthreads();
-    if (tx == 0 && ty == 0) {
-        if (blk_flags != 0) {
-            if (flags != nullptr) atomicOr(flags, blk_flags);
-            atomicOr(state, blk_flags);
+    for (int tb = 0; tb < Ti; tb += LEV_PACK_CHUNK) {
+        const int t0 = tb + 32 * w;
+        if (t0 + 32 <= Ti)
+            lev_pack_slice<TT, false>(seq + (int64_t)t0 * st, st, t0, Ti, eos_fast, eos32, &tile[lane][32 * w], seen);
+        else
+            lev_pack_slice<TT, true>(seq + (int64_t)t0 * st, st, t0, Ti, eos_fast, eos32, &tile[lane][32 * w], seen);
+        __syncthreads();
+        if (threadIdx.x == 0 && tb + LEV_PACK_CHUNK >= Ti) {
+            // a recent copy of the range words; the load completes under the row stores
+            cur_u = lev_ldg_l2(reinterpret_cast<const unsigned*>(a.state) + 1);
+            cur_n = lev_ldg_l2(reinterpret_cast<const unsigned*>(a.state) + 2);
         }
-        atomicMax(reinterpret_cast<unsigned*>(state) + 1, blk_umax);
-        atomicMax(reinterpret_cast<unsigned*>(state) + 2, blk_nmax);
+        // rows are 16-byte aligned and padded to a multiple of 4 (8 for the 16-bit table);
+        // positions T..Tp-1 receive zeros
+        const int width = Tp - tb < LEV_PACK_CHUNK ? Tp - tb : LEV_PACK_CHUNK;
+        const int width16 = Tp16 - tb < LEV_PACK_CHUNK ? Tp16 - tb : LEV_PACK_CHUNK;
+        for (int r = w; r < rows; r += 4) {
+            int32_t* __restrict__ row32 = a.packed + (n0 + r) * a.Tp + tb;
+            for (int c = lane; 4 * c < width; c += 32)
+                *reinterpret_cast<int4*>(row32 + 4 * c) = *reinterpret_cast<const int4*>(&tile[r][4 * c]);
+            if (a.packed16 != nullptr) {
+                uint16_t* __restrict__ row16 = a.packed16 + (n0 + r) * a.Tp16 + tb;
+                for (int c = lane; 8 * c < width16; c += 32) {
+                    const int4 x = *reinterpret_cast<const int4*>(&tile[r][8 * c]);
+                    const int4 y = *reinterpret_cast<const int4*>(&tile[r][8 * c + 4]);
+                    *reinterpret_cast<uint4*>(row16 + 8 * c) =
+                        make_uint4(__byte_perm(x.x, x.y, 0x5410), __byte_perm(x.z, x.w, 0x5410),
+                                   __byte_perm(y.x, y.y, 0x5410), __byte_perm(y.z, y.w, 0x5410));
+                }
+            }
+        }
+        __syncthreads();
     }
+    if (a.has_eos && (!eos_fast || (sizeof(TT) == 8 && seen.wacc != 0))) {
+        // rare: a low-word match may be a wide token (or eos itself is wide) -- rescan this
+        // lane's slices with the exact comparison
+        seen.first = Ti;
+        for (int tb = 0; tb < Ti; tb += LEV_PACK_CHUNK)
+            for (int t = tb + 32 * w; t < Ti && t < tb + 32 * w + 32; ++t)
+                if ((int64_t)seq[(int64_t)t * st] == a.eos) {
+                    seen.first = t < seen.first ? t : seen.first;
+                    break;
+                }
+    }
+    if (seen.first < Ti) atomicMin(&first_s[lane], seen.first);
+    {
+        int flags = seen.wacc != 0 ? B200LEV_FLAG_WIDE_TOKENS : 0;
+        unsigned umax = (unsigned)seen.hi + 0x80000000u, nmax = ~((unsigned)seen.lo + 0x80000000u);
+        lev_pack_warp_reduce(flags, umax, nmax);
+        if (lane == 0) {
+            atomicMax(&blk_u, umax);
+            atomicMax(&blk_n, nmax);
+            if (flags != 0) atomicOr(&blk_flags, flags);
+        }
+    }
+    __syncthreads();
+    if (w == 0) {
+        int flags = valid_seq ? lev_pack_owner(a, ref_len, n, first_s[lane]) : 0;
+        unsigned umax = blk_u, nmax = blk_n;
+        lev_pack_warp_reduce(flags, umax, nmax);
+        if (lane == 0) lev_pack_publish(a, flags | blk_flags, umax, nmax, cur_u, cur_n);
+    }
+}
+
+// ---- any other layout: one warp per sequence, lanes along the sequence axis -------------
+template <typename TT>
+__global__ void __launch_bounds__(128) lev_pack_rows_kernel(const LevPackArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const bool valid_seq = n < a.N;  // warp-uniform
+    const int Ti = (int)a.T;
+    int first = Ti, wide = 0, lo = 0x7fffffff, hi = (int)0x80000000;
+    const int ref_len = (valid_seq && lane == 0 && a.ghist != nullptr) ? a.ref_len[n / a.ref_group] : 0;
+    if (valid_seq) {
+        const TT* __restrict__ src = reinterpret_cast<const TT*>(a.tok) + n * a.sn;
+        int32_t* __restrict__ row32 = a.packed + n * a.Tp;
+        uint16_t* __restrict__ row16 = a.packed16 ? a.packed16 + n * a.Tp16 : nullptr;
+        for (int t = lane; t < Ti; t += 32) {
+            const int64_t x = (int64_t)src[(int64_t)t * a.st];
+            row32[t] = (int)x;
+            if (row16 != nullptr) row16[t] = (uint16_t)(int)x;
+            LEV_PACK_OBSERVE(x, t)
+        }
+    }
+    // first eos of the sequence = minimum over the lanes
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int f = __shfl_xor_sync(LEV_FULL_MASK, first, o);
+        first = f < first ? f : first;
+    }
+    int flags = wide ? B200LEV_FLAG_WIDE_TOKENS : 0;
+    if (valid_seq && lane == 0) flags |= lev_pack_owner(a, ref_len, n, first);
+    unsigned umax = (unsigned)hi + 0x80000000u, nmax = ~((unsigned)lo + 0x80000000u);
+    lev_pack_warp_reduce(flags, umax, nmax);
+    if (lane == 0)
+        lev_pack_publish(a, flags, umax, nmax, lev_ldg_l2(reinterpret_cast<const unsigned*>(a.state) + 1),
+                         lev_ldg_l2(reinterpret_cast<const unsigned*>(a.state) + 2));
 }
 
 int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int include_eos,
@@ -159,39 +299,47 @@ int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int inc
         lev_set_error("sequence dimension %lld too long", (long long)t->T);
         return B200LEV_ERR_UNSUPPORTED;
     }
-    dim3 block(32, 8, 1);
-    dim3 grid((unsigned)((t->N + 31) / 32), 1, 1);
-    // unit stride along the batch axis => transpose through shared memory; otherwise
-    // (batch_first, or an arbitrary view) read along the sequence axis directly.
-    const int transposed = (t->stride_n == 1 && t->stride_t != 1);
+    LevPackArgs a;
+    a.tok = t->data;
+    a.T = t->T;
+    a.N = t->N;
+    a.st = t->stride_t;
+    a.sn = t->stride_n;
+    a.has_eos = has_eos;
+    a.eos = eos;
+    a.include_eos = include_eos;
+    a.packed = packed;
+    a.Tp = Tp;
+    a.packed16 = packed16;
+    a.Tp16 = Tp16;
+    a.lens = lens;
+    a.flags = flags;
+    a.state = state;
+    a.missing_flag = missing_flag;
+    a.ref_len = ref_len;
+    a.ref_group = ref_group < 1 ? 1 : ref_group;
+    a.G = G;
+    a.ghist = ghist;
+    // unit stride along the batch axis => register-tile transpose; otherwise (batch_first,
+    // or an arbitrary view) one warp per sequence.
+    const bool seqfirst = (t->stride_n == 1 && t->stride_t != 1 && t->stride_t > -((int64_t)1 << 31) &&
+                           t->stride_t < ((int64_t)1 << 31));
+    const dim3 block(128, 1, 1);
+    const dim3 grid((unsigned)(seqfirst ? (t->N + 31) / 32 : (t->N + 3) / 4), 1, 1);
+#define LEV_PACK_CASE(TT)                                                \
+    if (seqfirst)                                                        \
+        lev_launch(lev_pack_seqfirst_kernel<TT>, grid, block, 0, st, a); \
+    else                                                                 \
+        lev_launch(lev_pack_rows_kernel<TT>, grid, block, 0, st, a);
     switch (t->elem_bytes) {
-        case 8:
-            lev_launch(lev_pack_kernel<int64_t>, grid, block, 0, st, (const int64_t*)t->data, t->T,
-                       t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
-                       packed16, Tp16, lens, flags, state, missing_flag, transposed, ref_len,
-                       ref_group, G, ghist);
-            break;
-        case 4:
-            lev_launch(lev_pack_kernel<int32_t>, grid, block, 0, st, (const int32_t*)t->data, t->T,
-                       t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
-                       packed16, Tp16, lens, flags, state, missing_flag, transposed, ref_len,
-                       ref_group, G, ghist);
-            break;
-        case 2:
-            lev_launch(lev_pack_kernel<int16_t>, grid, block, 0, st, (const int16_t*)t->data, t->T,
-                       t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
-                       packed16, Tp16, lens, flags, state, missing_flag, transposed, ref_len,
-                       ref_group, G, ghist);
-            break;
-        case 1:
-            lev_launch(lev_pack_kernel<int8_t>, grid, block, 0, st, (const int8_t*)t->data, t->T,
-                       t->N, t->stride_t, t->stride_n, has_eos, eos, include_eos, packed, Tp,
-                       packed16, Tp16, lens, flags, state, missing_flag, transposed, ref_len,
-                       ref_group, G, ghist);
-            break;
+        case 8: LEV_PACK_CASE(int64_t) break;
+        case 4: LEV_PACK_CASE(int32_t) break;
+        case 2: LEV_PACK_CASE(int16_t) break;
+        case 1: LEV_PACK_CASE(int8_t) break;
         default:
             lev_set_error("unsupported token element size %d", (int)t->elem_bytes);
             return B200LEV_ERR_ARG;
     }
+#undef LEV_PACK_CASE
     return lev_check_cuda("lev_pack_kernel");
 }

@@ -96,6 +96,24 @@ __device__ __forceinline__ int lev_lds32_sync(lev_saddr a) {  // data another wa
 __device__ __forceinline__ void lev_sts32(lev_saddr a, int v) {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+// hide a pointer's derivation from the optimiser, so that the addresses built from it stay
+// "pointer + small constant x stride" (one IMAD.WIDE each) instead of being re-derived
+#define LEV_OPAQUE_PTR(p) asm volatile("" : "+l"(p))
+// a value other CTAs may be raising concurrently: read it at L2, never from a stale L1 line
+__device__ __forceinline__ unsigned lev_ldg_l2(const unsigned* p) { return __ldcg(p); }
+// read-once global data: evict-first so it does not displace what the next kernel re-reads
+template <typename T>
+__device__ __forceinline__ T lev_ldg_stream(const T* p) {
+    return __ldcs(p);
+}
+template <>
+__device__ __forceinline__ int64_t lev_ldg_stream<int64_t>(const int64_t* p) {
+    return (int64_t)__ldcs(reinterpret_cast<const long long*>(p));
+}
+template <>
+__device__ __forceinline__ int8_t lev_ldg_stream<int8_t>(const int8_t* p) {
+    return (int8_t)__ldcs(reinterpret_cast<const signed char*>(p));
+}
 __device__ __forceinline__ int lev_ld_volatile_shared(const int* p) {
     return *reinterpret_cast<const volatile int*>(p);
 }

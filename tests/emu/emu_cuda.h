@@ -38,6 +38,7 @@ struct float4 { float x, y, z, w; };
 struct longlong2 { long long x, y; };
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
@@ -69,7 +70,7 @@ static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
 #define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __shared__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __constant__ static
 
 namespace emu {
@@ -233,6 +234,17 @@ static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 static inline int __viaddmin_s32(int a, int b, int c) { return std::min(a + b, c); }
 static inline int __viaddmax_s32(int a, int b, int c) { return std::max(a + b, c); }
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {
+    const unsigned long long src = ((unsigned long long)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const unsigned s = (sel >> (4 * i)) & 0xf;
+        unsigned b = (unsigned)(src >> (8 * (s & 7))) & 0xff;
+        if (s & 8) b = (b & 0x80) ? 0xff : 0;
+        r |= b << (8 * i);
+    }
+    return r;
+}
 static inline int __vimin3_s32(int a, int b, int c) { return std::min(std::min(a, b), c); }
 static inline int __vimax3_s32(int a, int b, int c) { return std::max(std::max(a, b), c); }
 static inline unsigned __emu_pack16(int lo, int hi) {
@@ -359,6 +371,10 @@ static inline void lev_launch(void (*k)(KArgs...), dim3 grid, dim3 block, size_t
 }
 #define LEV_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::g_dyn_smem)
 #define LEV_SPIN_YIELD() emu::yield()
+#define LEV_OPAQUE_PTR(p) asm volatile("" : "+r"(p))
+static inline unsigned lev_ldg_l2(const unsigned* p) { return *p; }
+template <typename T>
+static inline T lev_ldg_stream(const T* p) { return *p; }
 static inline void lev_cp_async16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
 static inline void lev_cp_async_commit() {}
 template <int N>
