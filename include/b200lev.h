@@ -217,6 +217,16 @@ const int32_t *b200lev_workspace_hyp_lens(const b200lev_tokens_t *ref,
 int b200lev_after_eos_mask(const int64_t *tokens, int64_t outer, int64_t T, int64_t inner,
                            int64_t eos, unsigned char *mask, void *stream);
 
+/* Host-side plumbing for callers whose tensors live in HOST memory (the reference API accepts
+ * CPU tensors: SM:146 has no device requirement): one strided 2-D copy between host and
+ * device on `stream`, so that a caller can move a COLUMN block of a (T, N) tensor -- all
+ * positions of a slice of the batch -- with one DMA and overlap the copies of block k+1,
+ * the kernels of block k and the read-back of block k-1 on three streams.  Pitches and
+ * width in bytes; to_device != 0: host -> device, else device -> host.  The copy is
+ * asynchronous when the host side is page-locked. */
+int b200lev_copy2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_pitch,
+                         size_t width_bytes, size_t height, int32_t to_device, void *stream);
+
 /* Optional per-kernel timing for bench.py: when enabled, every phase of the calls above is
  * bracketed by CUDA events on the launch stream.  b200lev_profile_read waits for the last
  * recorded events and returns milliseconds (or -1) for the slots

@@ -7,8 +7,11 @@ the reference's; the numbers come from the sm_100a kernels behind ``torch.ops.b2
 
 Host tensors: the reference runs wherever its inputs live.  Here a CPU tensor is
 copied to the current CUDA device (asynchronously when it is pinned), the kernels run
-there and the result is copied back -- the ``e2e`` path of ``bench.py``.  Without a
-CUDA device the call raises; there is no CPU implementation.
+there and the result is copied back -- the ``e2e`` path of ``bench.py``.  Large host
+batches of the final / prefix modes are cut into blocks of the batch axis that flow
+through three streams (copy in, kernels, copy out), so that the PCIe transfers of both
+directions and the kernels overlap.  Without a CUDA device the call raises; there is
+no CPU implementation.
 """
 from __future__ import annotations
 
@@ -54,6 +57,106 @@ def _offload(*tensors):
     return moved, back
 
 
+# ---- host tensors, large batches: three-stream pipeline over blocks of the batch ----------
+_PIPE_MIN_BYTES = 16 << 20  # below this one copy each way is as fast
+_PIPE_BLOCKS = 8
+_pipe_streams = {}
+
+
+def _pipe_streams_for(dev: torch.device):
+    if dev.index not in _pipe_streams:
+        _pipe_streams[dev.index] = tuple(torch.cuda.Stream(dev) for _ in range(3))
+    return _pipe_streams[dev.index]
+
+
+def _pipe_plan(ref, hyp, batch_first, ref_group):
+    """Block boundaries (in reference sequences) or None when the single-copy path is the
+    right one (small batch, odd shapes that the op itself must reject, emulation)."""
+    if _abi.EMULATED or ref.device.type != "cpu" or hyp.device.type != "cpu":
+        return None
+    if not torch.cuda.is_available() or ref.dim() != 2 or hyp.dim() != 2:
+        return None
+    bdim = 0 if batch_first else 1
+    nr, n = ref.shape[bdim], hyp.shape[bdim]
+    if nr * ref_group != n or ref.shape[1 - bdim] == 0 or hyp.shape[1 - bdim] == 0:
+        return None
+    if ref.dtype not in _ops._INT_DTYPES or hyp.dtype not in _ops._INT_DTYPES:
+        return None
+    nbytes = ref.numel() * ref.element_size() + hyp.numel() * hyp.element_size()
+    if nbytes < _PIPE_MIN_BYTES or nr < 2 * 256:
+        return None
+    blocks = min(_PIPE_BLOCKS, nr // 256)
+    step = -(-nr // blocks)
+    step = -(-step // 32) * 32
+    return [(a, min(a + step, nr)) for a in range(0, nr, step)]
+
+
+def _copy_block(lib, dev_t, host_t, batch_first, a, b, to_device, stream):
+    """One DMA between rows/columns [a, b) of the batch axis of a host matrix (inner stride
+    1) and the contiguous device matrix of that block."""
+    es = host_t.element_size()
+    if host_t.dim() == 1:
+        base, pitch, width, height = a * es, (b - a) * es, (b - a) * es, 1
+    elif batch_first:
+        base, pitch, width, height = a * host_t.stride(0) * es, host_t.stride(0) * es, \
+            host_t.shape[1] * es, b - a
+    else:
+        base, pitch, width, height = a * es, host_t.stride(0) * es, (b - a) * es, host_t.shape[0]
+    hp, dp = host_t.data_ptr() + base, dev_t.data_ptr()
+    if to_device:
+        _abi.check(lib.b200lev_copy2d_async(dp, width, hp, pitch, width, height, 1, stream))
+    else:
+        _abi.check(lib.b200lev_copy2d_async(hp, pitch, dp, width, width, height, 0, stream))
+
+
+def _string_matching_pipelined(plan, ref, hyp, op_args, batch_first, prefix, exclude_last,
+                               ref_group):
+    """Blocks of the batch through (H2D, kernels, D2H) on three streams; same numbers as one
+    call on the whole batch (pairs are independent).  Returns (host result, flags)."""
+    lib = _abi.lib()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    s_in, s_run, s_out = _pipe_streams_for(dev)
+    if ref.dim() == 2 and ref.stride(1) != 1:
+        ref = ref.contiguous()
+    if hyp.stride(1) != 1:
+        hyp = hyp.contiguous()
+    bdim = 0 if batch_first else 1
+    n = hyp.shape[bdim]
+    hout = hyp.shape[1 - bdim] + (0 if exclude_last else 1)
+    if not prefix:
+        shape = (n,)
+    else:
+        shape = (n, hout) if batch_first else (hout, n)
+    host_out = torch.empty(shape, dtype=torch.float32, device="cpu", pin_memory=True)
+    flags = None
+    keep = []  # blocks stay referenced until the last stream drains
+    here = torch.cuda.current_stream(dev)
+    s_in.wait_stream(here)
+    for (a, b) in plan:
+        ha, hb = a * ref_group, b * ref_group
+        with torch.cuda.stream(s_in):
+            rshape = (b - a, ref.shape[1]) if batch_first else (ref.shape[0], b - a)
+            hshape = (hb - ha, hyp.shape[1]) if batch_first else (hyp.shape[0], hb - ha)
+            ref_d = torch.empty(rshape, dtype=ref.dtype, device=dev)
+            hyp_d = torch.empty(hshape, dtype=hyp.dtype, device=dev)
+            _copy_block(lib, ref_d, ref, batch_first, a, b, True, s_in.cuda_stream)
+            _copy_block(lib, hyp_d, hyp, batch_first, ha, hb, True, s_in.cuda_stream)
+            arrived = s_in.record_event()
+        with torch.cuda.stream(s_run):
+            s_run.wait_event(arrived)
+            out_d, f = _ops.string_matching_fast(ref_d, hyp_d, *op_args)
+            flags = f if flags is None else flags.bitwise_or_(f)
+            done = s_run.record_event()
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(done)
+            _copy_block(lib, out_d, host_out, batch_first, ha, hb, False, s_out.cuda_stream)
+        keep.append((ref_d, hyp_d, out_d, f))
+    s_out.synchronize()
+    s_run.synchronize()
+    del keep
+    return host_out, flags
+
+
 def _warn_flags(flags: torch.Tensor, eos: Optional[int], include_eos: bool, norm: bool,
                 prefix: bool) -> None:
     """The data-dependent warnings of SM:202-217, 361-366, 398-404 (one 4-byte D2H)."""
@@ -97,10 +200,17 @@ def _string_matching(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost
             "Please switch to edit_distance functions for old behaviour. Set "
             "warn=False to suppress this warning"
         )
+    op_args = (eos, include_eos, batch_first, float(ins_cost), float(del_cost), float(sub_cost),
+               norm, return_prf_dsts, exclude_last, int(padding), return_mistakes, ref_group)
+    plan = _pipe_plan(ref, hyp, batch_first, ref_group)
+    if plan is not None:
+        out, flags = _string_matching_pipelined(plan, ref, hyp, op_args, batch_first,
+                                                return_prf_dsts, exclude_last, ref_group)
+        if warn:
+            _warn_flags(flags, eos, include_eos, norm, return_prf_dsts)
+        return out
     (ref_d, hyp_d), back = _offload(ref, hyp)
-    out, flags = _ops.string_matching_fast(ref_d, hyp_d, eos, include_eos, batch_first, float(ins_cost),
-                                      float(del_cost), float(sub_cost), norm, return_prf_dsts,
-                                      exclude_last, int(padding), return_mistakes, ref_group)
+    out, flags = _ops.string_matching_fast(ref_d, hyp_d, *op_args)
     if warn:
         _warn_flags(flags, eos, include_eos, norm, return_prf_dsts)
     return back(out)

@@ -74,6 +74,28 @@ extern "C" int b200lev_profile_read(float* ms, int n) {
 extern "C" int b200lev_abi_version(void) { return B200LEV_ABI_VERSION; }
 extern "C" const char* b200lev_last_error(void) { return g_err; }
 
+extern "C" int b200lev_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
+                                    size_t width_bytes, size_t height, int32_t to_device,
+                                    void* stream) {
+    if (width_bytes == 0 || height == 0) return B200LEV_OK;
+    if (dst == nullptr || src == nullptr || dst_pitch < width_bytes || src_pitch < width_bytes) {
+        lev_set_error("b200lev_copy2d_async: bad pointers or pitches");
+        return B200LEV_ERR_ARG;
+    }
+#ifdef B200LEV_EMU
+    (void)to_device;
+    (void)stream;
+    for (size_t r = 0; r < height; ++r)
+        memcpy((char*)dst + r * dst_pitch, (const char*)src + r * src_pitch, width_bytes);
+    return B200LEV_OK;
+#else
+    cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, height,
+                      to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                      (cudaStream_t)stream);
+    return lev_check_cuda("cudaMemcpy2DAsync");
+#endif
+}
+
 extern "C" int b200lev_device_count(void) {
 #ifdef B200LEV_EMU
     return 1;

@@ -258,6 +258,42 @@ def test_host_tensors_and_views(F, dev):
     assert np.array_equal(out.cpu().numpy(), exp)
 
 
+@pytest.mark.parametrize("batch_first", [False, True], ids=["seq_first", "batch_first"])
+@pytest.mark.parametrize("pinned", [True, False], ids=["pinned", "pageable"])
+def test_host_pipeline_matches_single_call(F, dev, batch_first, pinned, monkeypatch):
+    """Large host batches flow through the three-stream block pipeline (functional.py); the
+    numbers, the host-side result layout and the warnings are those of one call."""
+    import b200lev.functional as Fm
+    monkeypatch.setattr(Fm, "_PIPE_MIN_BYTES", 1 << 16)
+    rng = np.random.default_rng(11)
+    n = 2000 + 37  # not a multiple of the block size
+    ref = PC.random_tokens(rng, 40, n, 50, 0, -1)
+    hyp = PC.random_tokens(rng, 45, n, 50, 0, -1)
+    ref[:, 5] = 3  # a reference without eos: the warning must survive the blocks
+    assert Fm._pipe_plan(torch.from_numpy(ref), torch.from_numpy(hyp), False, 1) is not None
+    rt, ht = torch.from_numpy(ref), torch.from_numpy(hyp)
+    if batch_first:
+        rt, ht = rt.t().contiguous(), ht.t().contiguous()
+    if pinned:
+        rt, ht = rt.pin_memory(), ht.pin_memory()
+    for fn, kw in ((F.prefix_error_rates, dict(eos=0, include_eos=True)),
+                   (F.prefix_edit_distances, dict(eos=0, include_eos=False, exclude_last=True)),
+                   (F.error_rate, dict(eos=0, include_eos=True)),
+                   (F.edit_distance, dict(eos=0, ins_cost=1.0, del_cost=2.0, sub_cost=3.0))):
+        want = fn(rt.to(dev), ht.to(dev), batch_first=batch_first, warn=False, **kw).cpu()
+        got = fn(rt, ht, batch_first=batch_first, warn=False, **kw)
+        assert got.device.type == "cpu" and got.shape == want.shape
+        assert torch.equal(got, want), fn.__name__
+    with pytest.warns(UserWarning, match="transcription in ref did not"):
+        F.error_rate(rt, ht, eos=0, include_eos=True, batch_first=batch_first)
+    # column views of a wider host matrix (pitch != width)
+    if not batch_first:
+        wide = torch.zeros((40, n + 100), dtype=torch.long)
+        wide[:, 50:50 + n] = torch.from_numpy(ref)
+        got = F.error_rate(wide[:, 50:50 + n], ht, eos=0, warn=False)
+        assert torch.equal(got, F.error_rate(rt.to(dev), ht.to(dev), eos=0, warn=False).cpu())
+
+
 def test_warnings_and_errors(F, dev):
     PC.check_warnings(F, dev)
     PC.check_errors(F, dev)
