@@ -255,6 +255,25 @@ static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     return B200LEV_OK;
 }
 
+// Unit costs, short references, sequence-first tensors: the bit-vector path (lev_bitvec.cu)
+// takes the whole call -- lengths, warnings and DP -- straight from the raw tokens.
+// Returns 0 if it does not apply, 1 if it ran, < 0 on error.
+static int lev_try_bitvec(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                          const b200lev_opts_t* o, const LevLayout& L, char* ws, int32_t* flags,
+                          cudaStream_t st, int mode, float* out, int64_t out_si, int64_t out_sn,
+                          int Hout) {
+    if (!L.off_bv_ref) return 0;
+    LevParams tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    bool cm, fp;
+    lev_classify_costs(o, L.R, L.H, &tmp, &cm, &fp);
+    if (!lev_bitvec_eligible(ref, hyp, mode, cm, fp, tmp.ins_i, tmp.del_i, tmp.sub_i, out_sn)) return 0;
+    const int rc = lev_bitvec_launch(ref, hyp, o, mode, tmp.mult, (int32_t*)(ws + L.off_ref_len),
+                                     (int32_t*)(ws + L.off_hyp_len), ws + L.off_bv_ref,
+                                     ws + L.off_hyp_tok, flags, out, out_si, Hout, st);
+    return rc ? rc : 1;
+}
+
 static int lev_final_impl(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
                           const b200lev_opts_t* opts, float* out, void* workspace,
                           size_t workspace_bytes, int32_t* flags, void* stream, bool do_pack) {
@@ -274,6 +293,11 @@ static int lev_final_impl(const b200lev_tokens_t* ref, const b200lev_tokens_t* h
     LevParams p;
     b200lev_opts_t o = *opts;
     o.exclude_last = 0;  // SM:165
+    if (do_pack) {
+        const int took = lev_try_bitvec(ref, hyp, &o, L, lev_ws_base(workspace), flags, st,
+                                        LEV_MODE_FINAL, out, 0, 1, 0);
+        if (took) return took < 0 ? took : B200LEV_OK;
+    }
     rc = lev_prepare(ref, hyp, &o, L, lev_ws_base(workspace), flags, st, &p, do_pack);
     if (rc) return rc;
     bool cm, fp;
@@ -327,6 +351,12 @@ static int lev_prefix_impl(const b200lev_tokens_t* ref, const b200lev_tokens_t* 
     }
     cudaStream_t st = (cudaStream_t)stream;
     LevParams p;
+    if (do_pack) {
+        const int took = lev_try_bitvec(ref, hyp, opts, L, lev_ws_base(workspace), flags, st,
+                                        LEV_MODE_PREFIX, out, out_stride_i, out_stride_n,
+                                        (int)L.Hout);
+        if (took) return took < 0 ? took : B200LEV_OK;
+    }
     rc = lev_prepare(ref, hyp, opts, L, lev_ws_base(workspace), flags, st, &p, do_pack);
     if (rc) return rc;
     bool cm, fp;

@@ -52,6 +52,9 @@ struct LevLayout {
     int64_t Hr, Hr16;
     size_t off_raw;
     size_t off_uid, off_dtok, off_ndist, off_dbits;
+    // bit-vector path (lev_bitvec.cu): 16-byte uid chunks [ceil(R/16)][P]; the hypothesis
+    // chunks [ceil(H/16)][P] reuse the packed-hypothesis region, which that path leaves idle
+    size_t off_bv_ref;
     size_t bytes;
 };
 
@@ -91,6 +94,7 @@ static inline LevLayout lev_layout(const b200lev_tokens_t* ref, const b200lev_to
     L.Hr = lev_round_up(L.H + 1, 4);
     L.Hr16 = lev_round_up(L.H + 1, 8);
     L.off_raw = (kind == 2) ? take(sizeof(int32_t) * (size_t)L.P * L.Hr) : 0;
+    L.off_bv_ref = (kind != 1 && L.R <= 128) ? take((size_t)L.P * (size_t)lev_round_up(L.R > 0 ? L.R : 1, 16)) : 0;
     L.off_uid = L.off_dtok = L.off_ndist = L.off_dbits = 0;
     if (for_completion) {
         L.off_uid = take(sizeof(int32_t) * (size_t)L.Nref * L.Rp);
@@ -171,6 +175,14 @@ int lev_launch_cta(const LevParams& p, int mode, bool count_mode, bool float_pat
 // lanes per pair if the shapes admit the group kernel (its histogram is then built at
 // pack time), else 0
 int lev_group_eligible(int64_t R, int64_t H, int64_t P);
+// unit-cost bit-vector path (lev_bitvec.cu)
+bool lev_bitvec_eligible(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp, int mode,
+                         bool count_mode, bool float_path, int ins_i, int del_i, int sub_i,
+                         int64_t out_sn);
+int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                      const b200lev_opts_t* o, int mode, float mult, int32_t* ref_len,
+                      int32_t* hyp_len, void* uid_ref, void* uid_hyp, int32_t* flags, float* out,
+                      int64_t out_si, int Hout, cudaStream_t st);
 int lev_launch_uid(const b200lev_tokens_t* ref, const int32_t* ref_len, int32_t* uid,
                    int64_t* dtok, int32_t* ndist, int64_t Rp, cudaStream_t st);
 int lev_launch_completion_fill(const uint32_t* dbits, const int64_t* dtok, int64_t Rp,

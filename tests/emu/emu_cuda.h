@@ -234,6 +234,10 @@ static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 static inline int __viaddmin_s32(int a, int b, int c) { return std::min(a + b, c); }
 static inline int __viaddmax_s32(int a, int b, int c) { return std::max(a + b, c); }
+static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift) {
+    shift &= 31;
+    return shift ? (hi << shift) | (lo >> (32 - shift)) : hi;
+}
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {
     const unsigned long long src = ((unsigned long long)y << 32) | x;
     unsigned r = 0;

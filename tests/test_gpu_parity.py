@@ -334,6 +334,23 @@ def test_group_kernel_vs_oracle(F, dev, shape, costs, monkeypatch):
                                padding=-3, spread=spread, **flags)
 
 
+@pytest.mark.parametrize("shape", [(20, 25, 300), (33, 30, 500), (64, 50, 300), (101, 101, 4200),
+                                   (128, 60, 700)])
+def test_bitvec_path_vs_oracle(F, dev, shape, monkeypatch):
+    """The experimental unit-cost bit-vector path (lev_bitvec.cu, B200LEV_BITVEC=1): every word
+    count, final + prefix, ragged lengths, narrow and wide token ranges, uniform multiplier."""
+    monkeypatch.setenv("B200LEV_BITVEC", "1")
+    monkeypatch.setenv("B200LEV_BITVEC_MIN_PAIRS", "1")
+    R, H, N = shape
+    for costs in ((1, 1, 1), (0.5, 0.5, 0.5)):
+        for flags in (dict(include_eos=True, norm=True, exclude_last=False, min_frac=0.0),
+                      dict(include_eos=False, norm=False, exclude_last=True, min_frac=0.4, no_eos_frac=0.2)):
+            for spread in (1, 70001):
+                PC.check_vs_oracle(F, dev, seed=R + H, R=R, H=H, N=N, V=50, costs=costs, do_mask=False,
+                                   padding=-3, spread=spread, **flags)
+    PC.check_wide_tokens(F, dev)
+
+
 def test_group_kernel_wide_tokens(F, dev, monkeypatch):
     monkeypatch.setenv("B200LEV_GROUP_MIN_PAIRS", "1")
     PC.check_wide_tokens(F, dev)

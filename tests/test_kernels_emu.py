@@ -167,6 +167,44 @@ def test_group_kernel_vs_oracle(F, shape, costs, monkeypatch):
                                padding=-3, spread=spread, **flags)
 
 
+@pytest.mark.parametrize("shape", [(1, 9, 33), (20, 25, 70), (32, 40, 64), (33, 30, 31), (64, 70, 40),
+                                   (65, 20, 45), (96, 101, 35), (101, 101, 40), (128, 60, 34)])
+@pytest.mark.parametrize("costs", [(1, 1, 1), (3, 3, 3), (0.5, 0.5, 0.5)])
+def test_bitvec_kernels_vs_oracle(F, shape, costs, monkeypatch):
+    """The unit-cost bit-vector path (lev_bitvec.cu), forced on for small batches: every
+    word count W = 1..4 with reference lengths on both sides of the word boundaries,
+    final and prefix outputs, ragged lengths incl. empty sequences, missing eos, the uniform
+    cost multiplier, narrow and >16-bit token ranges."""
+    monkeypatch.setenv("B200LEV_BITVEC", "1")
+    monkeypatch.setenv("B200LEV_BITVEC_MIN_PAIRS", "1")
+    R, H, N = shape
+    for flags in (dict(include_eos=True, norm=True, exclude_last=False, min_frac=0.0),
+                  dict(include_eos=False, norm=False, exclude_last=True, min_frac=0.4),
+                  dict(include_eos=True, norm=True, exclude_last=True, min_frac=0.2, no_eos_frac=0.3),
+                  dict(include_eos=False, norm=True, exclude_last=False, min_frac=0.0, eos=None)):
+        for spread, V in ((1, 5), (70001, 40)):
+            PC.check_vs_oracle(F, DEV, seed=R + H, R=R, H=H, N=N, V=V, costs=costs, do_mask=False,
+                               padding=-3, spread=spread, **flags)
+
+
+@pytest.mark.parametrize("dtype", [torch.int32, torch.int16, torch.int8])
+def test_bitvec_token_dtypes_nbest_and_wide(F, dtype, monkeypatch):
+    monkeypatch.setenv("B200LEV_BITVEC", "1")
+    monkeypatch.setenv("B200LEV_BITVEC_MIN_PAIRS", "1")
+    PC.check_vs_oracle(F, DEV, seed=5, R=40, H=45, N=37, V=9, costs=(1, 1, 1), do_mask=False,
+                       dtype=dtype, norm=True)
+    test_n_best_shared_reference(F)
+    PC.check_wide_tokens(F, DEV)
+    PC.check_warnings(F, DEV)
+
+
+def test_bitvec_golden(F, golden_sm, monkeypatch):
+    monkeypatch.setenv("B200LEV_BITVEC", "1")
+    monkeypatch.setenv("B200LEV_BITVEC_MIN_PAIRS", "1")
+    names = [n for n in golden_sm.params if n.startswith("s")] + ["cfg1", "cfg2r", "cfg4r", "wide"]
+    assert PC.check_golden_string_matching(F, DEV, golden_sm, names) >= 300
+
+
 def test_group_kernel_n_best_and_wide(F, monkeypatch):
     monkeypatch.setenv("B200LEV_GROUP_MIN_PAIRS", "1")
     test_n_best_shared_reference(F)
