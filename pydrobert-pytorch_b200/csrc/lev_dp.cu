@@ -371,6 +371,8 @@ int lev_launch_dp(const LevParams& p_, int mode, bool count_mode, bool float_pat
         if (took < 0) return took;
         if (took == 1) p.only_if_wide = 1;
     }
+    // the stand-by launch exists for tokens wider than int32: impossible below 8-byte elements
+    if (p.only_if_wide && p.ref_eb < 8 && p.hyp_eb < 8) return B200LEV_OK;
     if (!float_path) {
         if (!count_mode) {
             if (mode == LEV_MODE_FINAL) return lev_launch_variant<int, false, LEV_MODE_FINAL, 15>(p, st);

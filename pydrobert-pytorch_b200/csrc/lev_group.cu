@@ -249,7 +249,7 @@ __device__ __forceinline__ void levg_run16(const LevParams& p, const int G, cons
 // ---------------------------------------------------------------------------------------
 // bucketing: scan the (class, length) histogram and scatter the pairs into task slots
 // ---------------------------------------------------------------------------------------
-#define LEVG_SORT_PER_THREAD 8
+#define LEVG_SORT_PER_THREAD 2
 __global__ void __launch_bounds__(256)
 lev_sort_kernel(const LevParams p, const LevGroupGeom geo, const int count_mode) {
     LEV_DYN_SMEM(int, base);          // [nbins] exclusive offsets of the bins (global)
@@ -261,30 +261,31 @@ lev_sort_kernel(const LevParams p, const LevGroupGeom geo, const int count_mode)
     const int PPT = (32 / geo.G) * (packed ? 2 : 1);
     const int H1 = p.H + 1;
     // every CTA repeats the (tiny) scan: histogram -> shared memory (all threads), then one
-    // warp turns it into exclusive offsets with class segments padded to whole tasks
+    // warp per class turns it into exclusive offsets, class segments padded to whole tasks
     for (int b = tid; b < p.nbins; b += blockDim.x) {
         base[b] = p.ghist[b];
         lhist[b] = 0;
     }
     __syncthreads();
-    if (warp == 0) {
+    // one warp per class segment: exclusive offsets relative to the segment's start; the
+    // segment starts (each rounded up to whole tasks) are combined after the barrier
+    __shared__ int segtot[LEVG_NCLS];
+    if (warp < LEVG_NCLS) {
+        const int cseg = warp;
         int carry = 0;
-        for (int cseg = 0; cseg < LEVG_NCLS; ++cseg) {
-            for (int b0 = 0; b0 < H1; b0 += 32) {
-                const int b = b0 + lane;
-                const int cnt = b < H1 ? base[cseg * H1 + b] : 0;
-                int incl = cnt;
+        for (int b0 = 0; b0 < H1; b0 += 32) {
+            const int b = b0 + lane;
+            const int cnt = b < H1 ? base[cseg * H1 + b] : 0;
+            int incl = cnt;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(LEV_FULL_MASK, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                if (b < H1) base[cseg * H1 + b] = carry + incl - cnt;
-                carry += __shfl_sync(LEV_FULL_MASK, incl, 31);
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(LEV_FULL_MASK, incl, o);
+                if (lane >= o) incl += t;
             }
-            carry = (carry + PPT - 1) / PPT * PPT;
+            if (b < H1) base[cseg * H1 + b] = carry + incl - cnt;
+            carry += __shfl_sync(LEV_FULL_MASK, incl, 31);
         }
-        if (blockIdx.x == 0 && lane == 0) p.gmeta[0] = carry / PPT;
+        if (lane == 0) segtot[cseg] = carry;
     }
     // two-level scatter: rank inside the CTA with shared-memory atomics, then ONE global
     // atomic per (CTA, non-empty bin) reserves the CTA's range -- same-address global
@@ -311,14 +312,43 @@ lev_sort_kernel(const LevParams p, const LevGroupGeom geo, const int count_mode)
     for (int u = 0; u < LEVG_SORT_PER_THREAD; ++u)
         if (bin[u] >= 0) rank[u] = atomicAdd(&lhist[bin[u]], 1);
     __syncthreads();
-    for (int b = tid; b < p.nbins; b += blockDim.x)
-        if (lhist[b] > 0) goff[b] = atomicAdd(&p.gcursor[b], lhist[b]);
+    // all reservations of a thread are issued before the first result is needed
+    {
+        int got[4], bb[4];
+        for (int b0 = tid; b0 < p.nbins; b0 += 4 * blockDim.x) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int b = b0 + k * blockDim.x;
+                bb[k] = b;
+                got[k] = 0;
+                if (b < p.nbins && lhist[b] > 0) got[k] = atomicAdd(&p.gcursor[b], lhist[b]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (bb[k] < p.nbins) goff[bb[k]] = got[k];
+        }
+    }
+    int segstart[LEVG_NCLS];
+    {
+        int start = 0;
+#pragma unroll
+        for (int c = 0; c < LEVG_NCLS; ++c) {
+            segstart[c] = start;
+            start = (start + segtot[c] + PPT - 1) / PPT * PPT;
+        }
+        if (blockIdx.x == 0 && tid == 0) p.gmeta[0] = start / PPT;
+    }
     __syncthreads();
 #pragma unroll
     for (int u = 0; u < LEVG_SORT_PER_THREAD; ++u) {
         if (bin[u] < 0) continue;
-        const int pos = base[bin[u]] + goff[bin[u]] + rank[u];
-        p.slots[pos] = make_int4(pair0 + u * 256 + tid, rr[u], hh[u], lev_group_class(rr[u], geo.G));
+        const int cls = lev_group_class(rr[u], geo.G);
+        int sstart = 0;
+#pragma unroll
+        for (int c = 0; c < LEVG_NCLS; ++c)
+            if (c == LEVG_NCLS - 1 - cls) sstart = segstart[c];
+        const int pos = sstart + base[bin[u]] + goff[bin[u]] + rank[u];
+        p.slots[pos] = make_int4(pair0 + u * 256 + tid, rr[u], hh[u], cls);
     }
 }
 
@@ -464,65 +494,55 @@ lev_prefix_finalize_kernel(const LevParams p, const LevGroupGeom geo) {
     const bool packed = !COUNT && geo.allow16 && levg_tokens_narrow(p.wide_flag);
     const int tid = threadIdx.x;
     if (p.out_sn == 1) {
-        __shared__ float tile[32][129];
-        const int n0 = blockIdx.x * 128, i0 = blockIdx.y * 32;
-        {
-            // thread = (pair, half of the 32 rows): 16 consecutive raw values of one pair
-            // fetched with 128-bit loads; lengths and reciprocal fetched once
-            const int nl = tid & 127, half = tid >> 7;
-            const int n = n0 + nl;
-            if (n < p.P) {
-                const int r = p.ref_len[n / p.ref_group], h = p.hyp_len[n];
-                const float rf = (float)r;
-                const float y = r > 0 ? __frcp_rn(rf) : 0.0f;
-                const int first_pad = h + (p.exclude_last ? 0 : 1);
-                const int ib = i0 + half * 16;
-                int raw[16];
-                if (packed) {
-                    const uint4* src = reinterpret_cast<const uint4*>(p.raw16 + (int64_t)n * p.Hr16 + ib);
+        // lane = pair: a lane walks 32 rows of ITS pair's raw values (128-bit loads, the row's
+        // line stays in L1) and every store instruction writes 32 neighbouring pairs of one
+        // output row -- 128 contiguous bytes -- so nothing has to be transposed
+        const int n = blockIdx.x * blockDim.x + tid;
+        const int i0 = blockIdx.y * 32;
+        if (n >= p.P) return;
+        const int i1 = i0 + 32 < p.Hout ? i0 + 32 : p.Hout;
+        const int r = p.ref_len[n / p.ref_group], h = p.hyp_len[n];
+        const float rf = (float)r;
+        const float y = r > 0 ? __frcp_rn(rf) : 0.0f;
+        const int first_pad = h + (p.exclude_last ? 0 : 1);
+        const bool norm = p.norm != 0;
+        float* __restrict__ o = p.out + (int64_t)i0 * p.out_si + n;
+        // all four 128-bit loads of the packed rows are issued before the first value is used
+        uint4 w16[4];
+        if (packed) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.raw16 + (int64_t)n * p.Hr16 + i0);
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint4 w = make_uint4(0u, 0u, 0u, 0u);
-                        if (ib + 8 * c < p.Hr16) w = src[c];
-                        raw[8 * c + 0] = (int)(w.x & 0xffffu); raw[8 * c + 1] = (int)(w.x >> 16);
-                        raw[8 * c + 2] = (int)(w.y & 0xffffu); raw[8 * c + 3] = (int)(w.y >> 16);
-                        raw[8 * c + 4] = (int)(w.z & 0xffffu); raw[8 * c + 5] = (int)(w.z >> 16);
-                        raw[8 * c + 6] = (int)(w.w & 0xffffu); raw[8 * c + 7] = (int)(w.w >> 16);
-                    }
-                } else {
-                    const int4* src = reinterpret_cast<const int4*>(p.raw32 + (int64_t)n * p.Hr + ib);
+            for (int k = 0; k < 4; ++k)
+                w16[k] = (i0 + 8 * k < i1) ? src[k] : make_uint4(0u, 0u, 0u, 0u);
+        }
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        int4 w = make_int4(0, 0, 0, 0);
-                        if (ib + 4 * c < p.Hr) w = src[c];
-                        raw[4 * c + 0] = w.x; raw[4 * c + 1] = w.y;
-                        raw[4 * c + 2] = w.z; raw[4 * c + 3] = w.w;
-                    }
-                }
-                const bool norm = p.norm != 0;
+        for (int k = 0; k < 4; ++k) {
+            const int ib = i0 + 8 * k;
+            if (ib >= i1) break;
+            int raw[8];
+            if (packed) {
+                const uint4 w = w16[k];
+                raw[0] = (int)(w.x & 0xffffu); raw[1] = (int)(w.x >> 16);
+                raw[2] = (int)(w.y & 0xffffu); raw[3] = (int)(w.y >> 16);
+                raw[4] = (int)(w.z & 0xffffu); raw[5] = (int)(w.z >> 16);
+                raw[6] = (int)(w.w & 0xffffu); raw[7] = (int)(w.w >> 16);
+            } else {
+                const int4* src = reinterpret_cast<const int4*>(p.raw32 + (int64_t)n * p.Hr + ib);
+                const int4 w0 = src[0];
+                const int4 w1 = ib + 4 < p.Hr ? src[1] : make_int4(0, 0, 0, 0);
+                raw[0] = w0.x; raw[1] = w0.y; raw[2] = w0.z; raw[3] = w0.w;
+                raw[4] = w1.x; raw[5] = w1.y; raw[6] = w1.z; raw[7] = w1.w;
+            }
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const int i = ib + u;
+            for (int u = 0; u < 8; ++u) {
+                const int i = ib + u;
+                if (i < i1) {
                     const int rv = (i == 0) ? (COUNT ? r : r * p.del_i) : raw[u];
                     float val = __fmul_rn((float)rv, p.mult);
                     if (norm) val = (r == 0) ? (i > 0 ? 1.0f : 0.0f) : levg_div(val, rf, y);
-                    tile[half * 16 + u][nl] = (i < first_pad) ? val : p.padding;
+                    *o = (i < first_pad) ? val : p.padding;
+                    o += p.out_si;
                 }
-            }
-        }
-        __syncthreads();
-        // 32 rows x 32 float4 columns; a warp writes 512 contiguous bytes of one row
-        const int cx = tid & 31, ry = tid >> 5;
-        for (int q = 0; q < 4; ++q) {
-            const int il = ry + 8 * q, i = i0 + il, n = n0 + 4 * cx;
-            if (i >= p.Hout || n >= p.P) continue;
-            float* dst = p.out + (int64_t)i * p.out_si + n;
-            if (n + 3 < p.P && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                *reinterpret_cast<float4*>(dst) =
-                    make_float4(tile[il][4 * cx], tile[il][4 * cx + 1], tile[il][4 * cx + 2],
-                                tile[il][4 * cx + 3]);
-            } else {
-                for (int u = 0; u < 4 && n + u < p.P; ++u) dst[u] = tile[il][4 * cx + u];
             }
         }
     } else {
@@ -641,7 +661,7 @@ int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t
         lev_prof_begin(LEV_PROF_FINALIZE, st);
         dim3 grid, block(256);
         if (p.out_sn == 1)
-            grid = dim3((unsigned)((p.P + 127) / 128), (unsigned)((p.Hout + 31) / 32));
+            grid = dim3((unsigned)((p.P + 255) / 256), (unsigned)((p.Hout + 31) / 32));
         else
             grid = dim3((unsigned)min((int64_t)148 * 16, ((int64_t)p.P * p.Hout + 255) / 256));
         if (count_mode)
