@@ -203,8 +203,12 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # one process per GPU: keep this rank's host buffers on its GPU's NUMA node
+        from b200lev.dist import bind_host_to_gpu
+        numa_node = bind_host_to_gpu(local)
     L = _abi.lib()
 
     ref_np, hyp_np, cells = make_batch(args.utts, seed=100 + rank)
@@ -353,7 +357,7 @@ def main():
                                    "10k, include_eos, norm), batch replicated to "
                                    f"{args.utts} utts x 8 = {P} pairs per GPU",
                        "pairs_per_gpu": P, "T": T_LEN, "nbest": NBEST, "vocab": V,
-                       "cells_per_gpu": cells,
+                       "cells_per_gpu": cells, "host_numa_node": numa_node,
                        "l2": f"inputs {in_bytes / 1e6:.0f} MB per step exceed the 126 MB L2"},
             "hyps_per_s": pairs_all / (ms * 1e-3),
             "e2e": {"value": cells_all / (ms_e2e * 1e-3) / 1e9, "unit": "GCUPS",
