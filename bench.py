@@ -254,22 +254,24 @@ def main():
 
     # ---- roofline: per-kernel CUDA-event times of the same public call --------------------
     # (b200lev_profile brackets every phase with events on the launch stream)
-    prof = np.zeros(6, dtype=np.float64)
-    buf = (ctypes.c_float * 6)()
+    prof = np.zeros(8, dtype=np.float64)
+    buf = (ctypes.c_float * 8)()
     _abi.check(L.b200lev_profile(1))
     for _ in range(3):
         step()
     nprof = max(5, min(args.steps, 20))
     for _ in range(nprof):
         out = step()
-        _abi.check(L.b200lev_profile_read(buf, 6))
+        _abi.check(L.b200lev_profile_read(buf, 8))
         prof += np.array([max(x, 0.0) for x in buf])
     _abi.check(L.b200lev_profile(0))
     prof /= nprof
-    ms_pack = float(prof[0] + prof[1])
-    ms_dp = float(prof[3])
+    ms_pack = max(float(prof[0] + prof[1]), 1e-6)
+    bitvec = prof[7] > prof[3]  # which DP ran: the bit-vector kernels or the wavefront kernels
+    ms_dp = float(prof[7] if bitvec else prof[3])
     phases = {"pack_ref": prof[0], "pack_hyp": prof[1], "bucketing": prof[2], "dp": prof[3],
-              "prefix_finalize": prof[4], "standby_wide": prof[5]}
+              "prefix_finalize": prof[4], "standby_wide": prof[5], "bitvec_uid": prof[6],
+              "bitvec_dp": prof[7]}
 
     def timed(fn, reps):
         for _ in range(3):

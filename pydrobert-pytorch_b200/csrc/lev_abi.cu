@@ -187,7 +187,7 @@ static void lev_classify_costs(const b200lev_opts_t* o, int64_t R, int64_t H, Le
 // pack both token tensors into the workspace and fill the common fields of `p`
 static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
                        const b200lev_opts_t* o, const LevLayout& L, char* ws, int32_t* flags,
-                       cudaStream_t st, LevParams* p, bool do_pack = true) {
+                       cudaStream_t st, LevParams* p, bool do_pack = true, int bv_check = 0) {
     int32_t* ref_tok = (int32_t*)(ws + L.off_ref_tok);
     int32_t* hyp_tok = (int32_t*)(ws + L.off_hyp_tok);
     int32_t* ref_len = (int32_t*)(ws + L.off_ref_len);
@@ -201,18 +201,19 @@ static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
         // whenever the shapes make that kernel eligible (lev_group.cu decides later)
         const int G = lev_group_eligible(L.R, L.H, L.P);
         const size_t clear = sizeof(int32_t) * (size_t)(4 + (G ? L.nbins : 0));
-        if (cudaMemsetAsync(state, 0, clear, st) != cudaSuccess) return lev_check_cuda("memset");
+        // (with bv_check the bit-vector launcher cleared them before its kernels ran)
+        if (!bv_check && cudaMemsetAsync(state, 0, clear, st) != cudaSuccess) return lev_check_cuda("memset");
         lev_prof_begin(LEV_PROF_PACK_REF, st);
         int rc = lev_launch_pack(ref, o->has_eos, o->eos, o->include_eos, ref_tok, L.Rp, nullptr, 0,
                                  ref_len, flags, state, B200LEV_FLAG_REF_NO_EOS, nullptr, 1, 0,
-                                 nullptr, st);
+                                 nullptr, bv_check, st);
         lev_prof_end(LEV_PROF_PACK_REF, st);
         if (rc) return rc;
         lev_prof_begin(LEV_PROF_PACK_HYP, st);
         rc = lev_launch_pack(hyp, o->has_eos, o->eos, o->include_eos, hyp_tok, L.Hp,
                              (uint16_t*)(ws + L.off_hyp_tok16), L.Hp16, hyp_len, flags, state,
                              B200LEV_FLAG_HYP_NO_EOS, ref_len, o->ref_group, G,
-                             G ? (int*)(ws + L.off_ghist) : nullptr, st);
+                             G ? (int*)(ws + L.off_ghist) : nullptr, bv_check, st);
         lev_prof_end(LEV_PROF_PACK_HYP, st);
         if (rc) return rc;
     }
@@ -234,6 +235,7 @@ static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     p->padding = (float)o->padding;
     p->flags = flags;
     p->wide_flag = state;
+    p->bv_check = bv_check;
     p->ref_raw = ref->data;
     p->hyp_raw = hyp->data;
     p->ref_st = ref->stride_t;
@@ -257,7 +259,10 @@ static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
 
 // Unit costs, short references, sequence-first tensors: the bit-vector path (lev_bitvec.cu)
 // takes the whole call -- lengths, warnings and DP -- straight from the raw tokens.
-// Returns 0 if it does not apply, 1 if it ran, < 0 on error.
+// Returns 0 if it does not apply, 1 if it ran unconditionally (forced mode: the call is
+// done), 2 if its kernels were enqueued in device-selected mode (the caller goes on to
+// enqueue the wavefront path with bv_check set; the state words are already cleared),
+// < 0 on error.
 static int lev_try_bitvec(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
                           const b200lev_opts_t* o, const LevLayout& L, char* ws, int32_t* flags,
                           cudaStream_t st, int mode, float* out, int64_t out_si, int64_t out_sn,
@@ -268,10 +273,22 @@ static int lev_try_bitvec(const b200lev_tokens_t* ref, const b200lev_tokens_t* h
     bool cm, fp;
     lev_classify_costs(o, L.R, L.H, &tmp, &cm, &fp);
     if (!lev_bitvec_eligible(ref, hyp, mode, cm, fp, tmp.ins_i, tmp.del_i, tmp.sub_i, out_sn)) return 0;
+    const bool forced = lev_bitvec_mode() == 1;
+    int32_t* state = (int32_t*)(ws + L.off_flags);
+    if (!forced) {
+        // device-selected: only where the wavefront fallback is the group path, whose kernels
+        // know how to stand by; the state words are cleared here, once, for both paths
+        const int G = lev_group_eligible(L.R, L.H, L.P);
+        if (G == 0) return 0;
+        const size_t clear = sizeof(int32_t) * (size_t)(4 + L.nbins);
+        if (cudaMemsetAsync(state, 0, clear, st) != cudaSuccess) return lev_check_cuda("memset");
+    }
     const int rc = lev_bitvec_launch(ref, hyp, o, mode, tmp.mult, (int32_t*)(ws + L.off_ref_len),
                                      (int32_t*)(ws + L.off_hyp_len), ws + L.off_bv_ref,
-                                     ws + L.off_hyp_tok, flags, out, out_si, Hout, st);
-    return rc ? rc : 1;
+                                     ws + L.off_hyp_tok, ws + L.off_slots, forced ? nullptr : state,
+                                     flags, out, out_si, Hout, st);
+    if (rc) return rc;
+    return forced ? 1 : 2;
 }
 
 static int lev_final_impl(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
@@ -293,12 +310,14 @@ static int lev_final_impl(const b200lev_tokens_t* ref, const b200lev_tokens_t* h
     LevParams p;
     b200lev_opts_t o = *opts;
     o.exclude_last = 0;  // SM:165
+    int bv = 0;
     if (do_pack) {
-        const int took = lev_try_bitvec(ref, hyp, &o, L, lev_ws_base(workspace), flags, st,
-                                        LEV_MODE_FINAL, out, 0, 1, 0);
-        if (took) return took < 0 ? took : B200LEV_OK;
+        bv = lev_try_bitvec(ref, hyp, &o, L, lev_ws_base(workspace), flags, st, LEV_MODE_FINAL, out,
+                            0, 1, 0);
+        if (bv < 0) return bv;
+        if (bv == 1) return B200LEV_OK;
     }
-    rc = lev_prepare(ref, hyp, &o, L, lev_ws_base(workspace), flags, st, &p, do_pack);
+    rc = lev_prepare(ref, hyp, &o, L, lev_ws_base(workspace), flags, st, &p, do_pack, bv == 2);
     if (rc) return rc;
     bool cm, fp;
     lev_classify_costs(&o, L.R, L.H, &p, &cm, &fp);
@@ -351,13 +370,14 @@ static int lev_prefix_impl(const b200lev_tokens_t* ref, const b200lev_tokens_t* 
     }
     cudaStream_t st = (cudaStream_t)stream;
     LevParams p;
+    int bv = 0;
     if (do_pack) {
-        const int took = lev_try_bitvec(ref, hyp, opts, L, lev_ws_base(workspace), flags, st,
-                                        LEV_MODE_PREFIX, out, out_stride_i, out_stride_n,
-                                        (int)L.Hout);
-        if (took) return took < 0 ? took : B200LEV_OK;
+        bv = lev_try_bitvec(ref, hyp, opts, L, lev_ws_base(workspace), flags, st, LEV_MODE_PREFIX,
+                            out, out_stride_i, out_stride_n, (int)L.Hout);
+        if (bv < 0) return bv;
+        if (bv == 1) return B200LEV_OK;
     }
-    rc = lev_prepare(ref, hyp, opts, L, lev_ws_base(workspace), flags, st, &p, do_pack);
+    rc = lev_prepare(ref, hyp, opts, L, lev_ws_base(workspace), flags, st, &p, do_pack, bv == 2);
     if (rc) return rc;
     bool cm, fp;
     lev_classify_costs(opts, L.R, L.H, &p, &cm, &fp);

@@ -33,6 +33,9 @@
 #include "lev_common.cuh"
 
 #define LEV_BV_NOMATCH 0xffu
+#define LEV_BV_EMPTY ((int)0x80000000)  // key of a free way (a token with this value: exact path)
+constexpr int LEV_BV_NT = 4;     // tables per warp = runs of identical references per pass
+constexpr int LEV_BV_WARPS = 4;  // warps per CTA (independent: no block barrier anywhere)
 
 struct LevBvArgs {
     const void* ref;  // raw token tensors, stride 1 along the batch axis
@@ -44,166 +47,353 @@ struct LevBvArgs {
     int include_eos;
     int32_t* ref_len;  // [Nref]  (same workspace slots K0 fills on the other paths)
     int32_t* hyp_len;  // [P]
-    uint4* ref_uid;    // [ceil(R/16)][P]  16 uid bytes per (chunk, pair)
+    uint4* ref_uid;    // [ceil(R/16)][P]  16 uid bytes per (chunk, pair); run leaders only
     uint4* hyp_uid;    // [ceil(H/16)][P]
+    unsigned char* lead;  // [P] lane (0..31) of the leader of the pair's run in its 32-block
     int32_t* flags;    // caller's warning flags, may be NULL
-    int slots_log2;    // hash slots per pair (power of two >= 2 R)
+    int32_t* state;  // workspace state words; [3] != 0 = "not for this path" (lev_bv_took)
+    int check_state;   // device-selected mode: veto through state[3] instead of multi-pass
+    int slots_log2;    // hash buckets per table (power of two >= R), 4 ways each
     int mode, norm, exclude_last, Hout;
     float mult, padding;
     float* out;
     int64_t out_si;  // prefix: elements between output rows (pairs are adjacent)
 };
 
-__device__ __forceinline__ unsigned lev_bv_hash(int v, int slots_log2) {
-    return ((unsigned)v * 0x9E3779B1u) >> (32 - slots_log2);
+// Bucketed hash: 4 ways per bucket, one 128-bit read of the keys and one 32-bit read of the
+// position bytes settle a probe -- no loop, so 32 lanes with 32 different tokens cost the same
+// as one.  A run leader builds its table with the first of a few multipliers under which no
+// bucket overflows (load <= 1 token per bucket on average: a couple of tries at most).
+constexpr int LEV_BV_TRIES = 6;
+__device__ __forceinline__ unsigned lev_bv_mult(int seed) {
+    switch (seed) {
+        case 0: return 0x9E3779B1u;
+        case 1: return 0x85EBCA6Bu;
+        case 2: return 0xC2B2AE35u;
+        case 3: return 0x27D4EB2Fu;
+        case 4: return 0x165667B1u;
+        default: return 0xD3A2646Du;
+    }
+}
+__device__ __forceinline__ unsigned lev_bv_hash(int v, unsigned mult, int buckets_log2) {
+    return ((unsigned)v * mult) >> (32 - buckets_log2);
+}
+
+// Runs of identical references inside a block of 32 consecutive pairs, from each lane's
+// "same as the lane before" bit: leader lane of the run, its index, number of runs.
+struct LevBvRuns {
+    int lead, index, count, len;
+    unsigned mask;  // the lanes of my run
+};
+__device__ __forceinline__ LevBvRuns lev_bv_runs(bool same, int lane) {
+    const unsigned starts = ~__ballot_sync(LEV_FULL_MASK, same && lane > 0);
+    const unsigned upto = starts & (0xffffffffu >> (31 - lane));
+    LevBvRuns r;
+    r.lead = 31 - __clz((int)upto);
+    r.index = __popc(upto) - 1;
+    r.count = __popc(starts);
+    const unsigned higher = r.lead == 31 ? 0u : (starts & ~(0xffffffffu >> (31 - r.lead)));
+    const int next = higher ? __ffs((int)higher) - 1 : 32;
+    r.len = next - r.lead;
+    r.mask = (r.len == 32 ? 0xffffffffu : ((1u << r.len) - 1u)) << r.lead;
+    return r;
+}
+
+__device__ __forceinline__ unsigned lev_bv_set_byte(unsigned word, unsigned byte, int k) {
+    return (word & ~(0xffu << (8 * k))) | (byte << (8 * k));
 }
 
 // ---------------------------------------------------------------------------------------
 // uid pre-pass
 // ---------------------------------------------------------------------------------------
 template <typename TT>
-__global__ void __launch_bounds__(32) lev_bv_uid_kernel(const LevBvArgs a) {
+__global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_uid_kernel(const LevBvArgs a) {
+    if (a.check_state && !lev_bv_took(a.state)) return;  // another warp has vetoed already
     LEV_DYN_SMEM(int, smem);
-    const int lane = threadIdx.x;
-    const int nslots = 1 << a.slots_log2, smask = nslots - 1;
-    int* keys = smem;                                                        // [nslots][32]
-    unsigned char* pos = reinterpret_cast<unsigned char*>(smem + nslots * 32);  // [nslots][32]
-    const int64_t pair = (int64_t)blockIdx.x * 32 + lane;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nb = 1 << a.slots_log2;  // buckets per table
+    constexpr int NT = LEV_BV_NT;
+    // per warp: keys [nb][NT] int4 (4 ways), then posw [nb][NT] words (4 position bytes)
+    int4* keys4 = reinterpret_cast<int4*>(smem + (size_t)warp * (nb * NT * 5));
+    unsigned* posw = reinterpret_cast<unsigned*>(keys4 + nb * NT);
+    const int64_t pair = ((int64_t)blockIdx.x * LEV_BV_WARPS + warp) * 32 + lane;
+    if (pair - lane >= a.P) return;  // whole warp past the batch
     const bool valid = pair < a.P;
     const int64_t pc = valid ? pair : (int64_t)a.P - 1;  // lanes past the batch shadow the last pair
-    {
-        uint4* pz = reinterpret_cast<uint4*>(pos);
-        for (int i = lane; i < nslots * 2; i += 32) pz[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
-    }
-    __syncwarp();
-    const TT* __restrict__ rsrc = reinterpret_cast<const TT*>(a.ref) + pc / a.ref_group;
+    const int64_t rcol = pc / a.ref_group;
+    const TT* __restrict__ rsrc = reinterpret_cast<const TT*>(a.ref) + rcol;
     const TT* __restrict__ hsrc = reinterpret_cast<const TT*>(a.hyp) + pc;
-    int myflags = 0, wide = 0;
+    const int rst = (int)a.ref_st, hst = (int)a.hyp_st;  // (lev_bitvec_eligible: strides fit int32)
 
-    // ---- reference: insert, ref_uid[j] = first position of the token at j ---------------
-    int rlen = a.R;
-    bool open = true;  // no eos seen yet
-    for (int c = 0; c * 16 < a.R; ++c) {
-        TT buf[16];
+    // ---- one coalesced pass over my reference column: is it the same as my left neighbour's
+    // (runs), where is its first eos (SM:137-143, 198-218), does it hold a token the 32-bit
+    // keys cannot represent -----------------------------------------------------------------
+    for (int k = 0; k < 48 && k < a.H; ++k) lev_prefetch_l2(hsrc + (int64_t)k * hst);
+    // Both streaming passes work on 16 positions as two halves of 8 whose loads ping-pong:
+    // one half's 8 loads are in flight while the other half is processed.
+    int first_eos = a.R, exact0 = 0;
+    bool diff;
+    {
+        const int prev_col = __shfl_up_sync(LEV_FULL_MASK, (int)rcol, 1);
+        const bool other = prev_col != (int)rcol;
+        const int eos_lo = (int)a.eos, eos_hi = (int)(a.eos >> 32);
+        int dacc = 0, wacc = 0;  // differences to the left neighbour / to a sign extension
+        auto observe = [&](const TT (&buf)[8], int t0) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-            buf[k] = (c * 16 + k < a.R) ? rsrc[(int64_t)(c * 16 + k) * a.ref_st] : (TT)0;
-        unsigned q[4] = {~0u, ~0u, ~0u, ~0u};
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int t = c * 16 + k;
-            const int64_t x = (int64_t)buf[k];
-            const int v = (int)x;
-            bool take = open && t < a.R;
-            if (take && a.has_eos && x == a.eos) {  // SM:137-143, 198-218
-                open = false;
-                rlen = t + (a.include_eos ? 1 : 0);
-                take = a.include_eos != 0;
-            }
-            if (take) {
-                if (sizeof(TT) == 8 && (int64_t)v != x) wide = 1;
-                unsigned slot = lev_bv_hash(v, a.slots_log2), u;
-                while (true) {
-                    const unsigned p = pos[slot * 32 + lane];
-                    const int key = keys[slot * 32 + lane];
-                    if (p == LEV_BV_NOMATCH) {
-                        pos[slot * 32 + lane] = (unsigned char)t;
-                        keys[slot * 32 + lane] = v;
-                        u = (unsigned)t;
-                        break;
-                    }
-                    if (key == v) {
-                        u = p;
-                        break;
-                    }
-                    slot = (slot + 1) & smask;
+            for (int k = 0; k < 8; ++k) {
+                const int64_t x = (int64_t)buf[k];
+                const int lo = (int)x, hi = (int)(x >> 32);
+                dacc |= lo ^ __shfl_up_sync(LEV_FULL_MASK, lo, 1);
+                if (sizeof(TT) == 8) {
+                    dacc |= hi ^ __shfl_up_sync(LEV_FULL_MASK, hi, 1);
+                    wacc |= hi ^ (lo >> 31);
                 }
-                q[k >> 2] = (q[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (u << (8 * (k & 3)));
-            }
-        }
-        if (valid) a.ref_uid[(int64_t)c * a.P + pair] = make_uint4(q[0], q[1], q[2], q[3]);
-    }
-    if (open && a.has_eos && a.include_eos) myflags |= B200LEV_FLAG_REF_NO_EOS;
-
-    // ---- hypothesis: look up, hyp_uid[i] = first reference position with hyp[i]'s token ---
-    int hlen = a.H;
-    open = true;
-    for (int c = 0; c * 16 < a.H; ++c) {
-        TT buf[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            buf[k] = (c * 16 + k < a.H) ? lev_ldg_stream(hsrc + (int64_t)(c * 16 + k) * a.hyp_st) : (TT)0;
-        unsigned q[4] = {~0u, ~0u, ~0u, ~0u};
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int t = c * 16 + k;
-            const int64_t x = (int64_t)buf[k];
-            const int v = (int)x;
-            bool take = open && t < a.H;
-            if (take && a.has_eos && x == a.eos) {
-                open = false;
-                hlen = t + (a.include_eos ? 1 : 0);
-                take = a.include_eos != 0;
-            }
-            if (take) {
-                if (sizeof(TT) == 8 && (int64_t)v != x) wide = 1;
-                unsigned slot = lev_bv_hash(v, a.slots_log2), u;
-                while (true) {
-                    const unsigned p = pos[slot * 32 + lane];
-                    const int key = keys[slot * 32 + lane];
-                    if (p == LEV_BV_NOMATCH || key == v) {
-                        u = p;
-                        break;
-                    }
-                    slot = (slot + 1) & smask;
+                // positions past R were loaded as 0 = what the neighbour loaded
+                if (t0 + k < a.R) {
+                    if (a.has_eos && lo == eos_lo && hi == eos_hi) first_eos = min(first_eos, t0 + k);
+                    if (lo == LEV_BV_EMPTY) exact0 = 1;
                 }
-                q[k >> 2] = (q[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (u << (8 * (k & 3)));
+            }
+        };
+        const TT* rp = rsrc;
+        TT bufA[8], bufB[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bufA[k] = (k < a.R) ? rp[(int64_t)k * rst] : (TT)0;
+        for (int t0 = 0; t0 < a.R; t0 += 16) {
+            LEV_OPAQUE_PTR(rp);
+            // 8 loads per lane in flight do not cover DRAM latency at 20 warps per SM: ask L2
+            // for the rows three groups ahead (a hint: no register, nothing to wait for)
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (t0 + 48 + k < a.R) lev_prefetch_l2(rp + (int64_t)(48 + k) * rst);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bufB[k] = (t0 + 8 + k < a.R) ? rp[(int64_t)(8 + k) * rst] : (TT)0;
+            observe(bufA, t0);
+            rp += 16 * (int64_t)rst;
+            LEV_OPAQUE_PTR(rp);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bufA[k] = (t0 + 16 + k < a.R) ? rp[(int64_t)k * rst] : (TT)0;
+            observe(bufB, t0 + 8);
+            if (a.check_state && t0 == 0) {
+                // unrelated references differ within their first tokens: such a batch is
+                // handed back to the wavefront path after one group of loads per warp
+                const unsigned same = __ballot_sync(LEV_FULL_MASK, lane > 0 && !(dacc != 0 && other));
+                if (32 - __popc(same) > LEV_BV_NT) {
+                    if (lane == 0) atomicExch(a.state + 3, 1);
+                    return;
+                }
             }
         }
-        if (valid) a.hyp_uid[(int64_t)c * a.P + pair] = make_uint4(q[0], q[1], q[2], q[3]);
+        diff = dacc != 0 && other;
+        if (wacc != 0) exact0 = 1;
     }
-    if (open && a.has_eos && a.include_eos) myflags |= B200LEV_FLAG_HYP_NO_EOS;
+    const LevBvRuns runs = lev_bv_runs(!diff, lane);
+    if (a.check_state && runs.count > LEV_BV_NT) {
+        if (lane == 0) atomicExch(a.state + 3, 1);
+        return;
+    }
+    if (valid) a.lead[pair] = (unsigned char)runs.lead;
 
-    if (sizeof(TT) == 8 && wide && valid) {
-        // rare: some token of this pair does not fit in int32, so equal low words prove
-        // nothing -- redo this lane's uids by exact comparison (O(r (r + h)) cached loads)
-        for (int c = 0; c * 16 < a.R; ++c) {
-            unsigned q[4] = {~0u, ~0u, ~0u, ~0u};
-            for (int k = 0; k < 16; ++k) {
-                const int j = c * 16 + k;
-                if (j >= rlen) break;
-                const TT x = rsrc[(int64_t)j * a.ref_st];
-                int u = j;
-                for (int e = 0; e < j; ++e)
-                    if (rsrc[(int64_t)e * a.ref_st] == x) {
-                        u = e;
-                        break;
+    int myflags = 0;
+    int rlen = a.R, hlen = a.H;
+    for (int base = 0; base < runs.count; base += NT) {
+        const bool active = runs.index >= base && runs.index < base + NT;
+        const int tb = active ? runs.index - base : 0;
+        const bool leader = active && runs.lead == lane;
+        // ---- reference: the lanes of a run build its table together ------------------------
+        // Lane i of a run of n lanes takes positions i, i + n, ...: it claims a free way of the
+        // token's bucket with a CAS on the key word (an equal key already there = duplicate),
+        // then writes its position byte.  Which occurrence ends up representing a token is a
+        // race, and does not matter: a uid only has to be the SAME row for every occurrence
+        // and for the hypothesis look-ups, which all read the finished table.  Positions past
+        // the eos may get in too: their rows receive no bits, so matching them is no match.
+        const int run_pos = lane - runs.lead;
+        int seed = 0;
+        int exact = exact0;  // no usable table: compare tokens one by one (rare)
+        bool need = active && !exact;
+        for (int attempt = 0; attempt < LEV_BV_TRIES; ++attempt) {
+            unsigned clear = 0;  // tables (of this pass) being (re)built
+#pragma unroll
+            for (int t = 0; t < NT; ++t)
+                if (__any_sync(LEV_FULL_MASK, need && tb == t)) clear |= 1u << t;
+            if (clear == 0) break;
+            __syncwarp();
+            for (int i = lane; i < nb * NT; i += 32)
+                if ((clear >> (i % NT)) & 1u) {
+                    keys4[i] = make_int4(LEV_BV_EMPTY, LEV_BV_EMPTY, LEV_BV_EMPTY, LEV_BV_EMPTY);
+                    posw[i] = ~0u;
+                }
+            __syncwarp();
+            bool overflow = false;
+            if (need) {
+                seed = attempt;
+                const unsigned hmul = lev_bv_mult(seed);
+                for (int t0 = run_pos; t0 < a.R; t0 += 8 * runs.len) {
+                    int vv[8];  // 8 of my positions at a time: the loads overlap
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        vv[k] = (t0 + k * runs.len < a.R) ? (int)rsrc[(int64_t)(t0 + k * runs.len) * rst] : 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int t = t0 + k * runs.len;
+                        if (t >= a.R) break;
+                        const int v = vv[k];
+                        const int idx = (int)lev_bv_hash(v, hmul, a.slots_log2) * NT + tb;
+                        int* kk = reinterpret_cast<int*>(&keys4[idx]);
+                        int w = 0;
+                        for (; w < 4; ++w) {
+                            const int old = atomicCAS(&kk[w], LEV_BV_EMPTY, v);
+                            if (old == LEV_BV_EMPTY) {
+                                reinterpret_cast<unsigned char*>(&posw[idx])[w] = (unsigned char)t;
+                                break;
+                            }
+                            if (old == v) break;
+                        }
+                        overflow |= w == 4;
                     }
-                q[k >> 2] = (q[k >> 2] & ~(0xffu << (8 * (k & 3)))) | ((unsigned)u << (8 * (k & 3)));
+                }
             }
-            a.ref_uid[(int64_t)c * a.P + pair] = make_uint4(q[0], q[1], q[2], q[3]);
+            // the run retries (next multiplier) if any of its lanes met a full bucket
+            const bool run_bad = (__ballot_sync(LEV_FULL_MASK, overflow) & runs.mask) != 0;
+            need = need && run_bad;
+            if (need && attempt == LEV_BV_TRIES - 1) {
+                need = false;
+                exact = 1;
+            }
         }
-        for (int c = 0; c * 16 < a.H; ++c) {
-            unsigned q[4] = {~0u, ~0u, ~0u, ~0u};
-            for (int k = 0; k < 16; ++k) {
-                const int i = c * 16 + k;
-                if (i >= hlen) break;
-                const TT x = hsrc[(int64_t)i * a.hyp_st];
-                unsigned u = LEV_BV_NOMATCH;
-                for (int e = 0; e < rlen; ++e)
-                    if (rsrc[(int64_t)e * a.ref_st] == x) {
-                        u = (unsigned)e;
-                        break;
-                    }
-                q[k >> 2] = (q[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (u << (8 * (k & 3)));
+        __syncwarp();
+        if (active) {
+            rlen = a.R;
+            if (a.has_eos && first_eos < a.R) rlen = first_eos + (a.include_eos ? 1 : 0);
+            if (a.has_eos && a.include_eos && first_eos == a.R) myflags |= B200LEV_FLAG_REF_NO_EOS;
+        }
+        if (active && !exact) {
+            // each lane looks its own positions up and drops the byte into the leader's chunks
+            const unsigned hmul = lev_bv_mult(seed);
+            unsigned char* bytes = reinterpret_cast<unsigned char*>(a.ref_uid);
+            const int64_t lead_pair = pair - run_pos;  // (the leader of a run is always inside the batch)
+            for (int t0 = run_pos; t0 < rlen; t0 += 8 * runs.len) {
+                int vv[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    vv[k] = (t0 + k * runs.len < rlen) ? (int)rsrc[(int64_t)(t0 + k * runs.len) * rst] : 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int t = t0 + k * runs.len;
+                    if (t >= rlen) break;
+                    const int v = vv[k];
+                    const int idx = (int)lev_bv_hash(v, hmul, a.slots_log2) * NT + tb;
+                    const int4 kk = keys4[idx];
+                    const unsigned pw = posw[idx];
+                    int way = 4;  // first matching way, the rule the hypothesis look-ups use too
+                    if (kk.w == v) way = 3;
+                    if (kk.z == v) way = 2;
+                    if (kk.y == v) way = 1;
+                    if (kk.x == v) way = 0;
+                    bytes[((int64_t)(t >> 4) * a.P + lead_pair) * 16 + (t & 15)] =
+                        (unsigned char)__byte_perm(pw, LEV_BV_NOMATCH, way);
+                }
             }
-            a.hyp_uid[(int64_t)c * a.P + pair] = make_uint4(q[0], q[1], q[2], q[3]);
+        }
+        if (leader && exact && valid) {
+            // rare: a reference token outside int32 (equal low words prove nothing) or no
+            // overflow-free table -- this run's uids by exact comparison, O(r^2) cached loads
+            for (int c = 0; c * 16 < a.R; ++c) {
+                unsigned q[4] = {~0u, ~0u, ~0u, ~0u};
+                for (int k = 0; k < 16; ++k) {
+                    const int j = c * 16 + k;
+                    if (j >= rlen) break;
+                    const TT x = rsrc[(int64_t)j * rst];
+                    int u = j;
+                    for (int e = 0; e < j; ++e)
+                        if (rsrc[(int64_t)e * rst] == x) {
+                            u = e;
+                            break;
+                        }
+                    q[k >> 2] = lev_bv_set_byte(q[k >> 2], (unsigned)u, k & 3);
+                }
+                a.ref_uid[(int64_t)c * a.P + pair] = make_uint4(q[0], q[1], q[2], q[3]);
+            }
+        }
+        __syncwarp();
+        // ---- hypothesis: hyp_uid[i] = the row of hyp[i]'s token (0xff: not in the reference).
+        // Every position is looked up, also those past the eos: the DP never reads their bytes,
+        // and the loop stays free of control flow.
+        if (active) {
+            const unsigned hmul = lev_bv_mult(seed);
+            const int eos_lo = (int)a.eos, eos_hi = (int)(a.eos >> 32);
+            int h_eos = a.H;
+            unsigned q[4];
+            // (kept free of branches: the 8 table reads of a half are independent and overlap)
+            auto lookup = [&](const TT (&buf)[8], int t0, int qbase) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int64_t x = (int64_t)buf[k];
+                    const int v = (int)x, hi = (int)(x >> 32);
+                    const bool is_eos = a.has_eos && v == eos_lo && hi == eos_hi && t0 + k < a.H;
+                    h_eos = is_eos ? min(h_eos, t0 + k) : h_eos;
+                    const int idx = (int)lev_bv_hash(v, hmul, a.slots_log2) * NT + tb;
+                    const int4 kk = keys4[idx];
+                    const unsigned pw = posw[idx];
+                    // first matching way; a token outside int32 cannot equal an int32 key
+                    int way = 4;
+                    way = kk.w == v ? 3 : way;
+                    way = kk.z == v ? 2 : way;
+                    way = kk.y == v ? 1 : way;
+                    way = kk.x == v ? 0 : way;
+                    if (sizeof(TT) == 8) way = hi != (v >> 31) ? 4 : way;
+                    const unsigned u = __byte_perm(pw, LEV_BV_NOMATCH, way);
+                    q[qbase + (k >> 2)] = lev_bv_set_byte(q[qbase + (k >> 2)], u, k & 3);
+                }
+            };
+            const TT* hp = hsrc;
+            TT bufA[8], bufB[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bufA[k] = (k < a.H) ? lev_ldg_stream(hp + (int64_t)k * hst) : (TT)0;
+            for (int t0 = 0; t0 < a.H; t0 += 16) {
+                LEV_OPAQUE_PTR(hp);
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (t0 + 48 + k < a.H) lev_prefetch_l2(hp + (int64_t)(48 + k) * hst);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    bufB[k] = (t0 + 8 + k < a.H) ? lev_ldg_stream(hp + (int64_t)(8 + k) * hst) : (TT)0;
+                q[0] = q[1] = q[2] = q[3] = ~0u;
+                lookup(bufA, t0, 0);
+                hp += 16 * (int64_t)hst;
+                LEV_OPAQUE_PTR(hp);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    bufA[k] = (t0 + 16 + k < a.H) ? lev_ldg_stream(hp + (int64_t)k * hst) : (TT)0;
+                lookup(bufB, t0 + 8, 2);
+                if (valid) a.hyp_uid[(int64_t)(t0 >> 4) * a.P + pair] = make_uint4(q[0], q[1], q[2], q[3]);
+            }
+            hlen = a.H;
+            if (a.has_eos && h_eos < a.H) hlen = h_eos + (a.include_eos ? 1 : 0);
+            if (a.has_eos && a.include_eos && h_eos == a.H) myflags |= B200LEV_FLAG_HYP_NO_EOS;
+            if (exact && valid) {
+                // rare (see above): the table of this run is unusable, so what the stream just
+                // wrote for this pair is too -- redo it by exact comparison
+                for (int c = 0; c * 16 < hlen; ++c) {
+                    unsigned qq[4] = {~0u, ~0u, ~0u, ~0u};
+                    for (int k = 0; k < 16 && c * 16 + k < hlen; ++k) {
+                        const int64_t x = (int64_t)hsrc[(int64_t)(c * 16 + k) * hst];
+                        unsigned u = LEV_BV_NOMATCH;
+                        for (int e = 0; e < rlen; ++e)
+                            if ((int64_t)rsrc[(int64_t)e * rst] == x) {
+                                u = (unsigned)e;
+                                break;
+                            }
+                        qq[k >> 2] = lev_bv_set_byte(qq[k >> 2], u, k & 3);
+                    }
+                    a.hyp_uid[(int64_t)c * a.P + pair] = make_uint4(qq[0], qq[1], qq[2], qq[3]);
+                }
+            }
         }
     }
-
     if (valid) {
         a.hyp_len[pair] = hlen;
-        if (pair % a.ref_group == 0) a.ref_len[pair / a.ref_group] = rlen;
+        if (pair % a.ref_group == 0) a.ref_len[rcol] = rlen;
         if (a.norm && rlen == 0) myflags |= B200LEV_FLAG_EMPTY_REF;  // SM:360-366, 397-404
     } else {
         myflags = 0;
@@ -277,121 +467,130 @@ __device__ __forceinline__ int lev_bv_step(const unsigned (&eq)[W], unsigned (&p
 }
 
 template <int W, int MODE>
-__global__ void __launch_bounds__(32) lev_bv_dp_kernel(const LevBvArgs a) {
-    LEV_DYN_SMEM(unsigned, M);  // Peq[(R + 1)][W][32 lanes]; row R stays zero (no match)
-    const int lane = threadIdx.x;
-    const int64_t pair = (int64_t)blockIdx.x * 32 + lane;
+__global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_dp_kernel(const LevBvArgs a) {
+    if (a.check_state && !lev_bv_took(a.state)) return;
+    LEV_DYN_SMEM(unsigned, smem);
+    constexpr int NT = LEV_BV_NT;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // per warp: Peq[(R + 1)][W][NT tables]; row R stays zero (no match)
+    const int tab_words = (a.R + 1) * W * NT;
+    unsigned* M = smem + (size_t)warp * tab_words;
+    const int64_t pair = ((int64_t)blockIdx.x * LEV_BV_WARPS + warp) * 32 + lane;
+    if (pair - lane >= a.P) return;  // whole warp past the batch
     const bool valid = pair < a.P;
     const int64_t pc = valid ? pair : (int64_t)a.P - 1;
     const int r = a.ref_len[pc / a.ref_group], h = a.hyp_len[pc];
     const int Z = a.R;
-    {
-        uint4* mz = reinterpret_cast<uint4*>(M);
-        const int n16 = (a.R + 1) * W * 8;
-        for (int i = lane; i < n16; i += 32) mz[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    __syncwarp();
+    const LevBvRuns runs = lev_bv_runs(lane > 0 && (int)a.lead[pc] != lane, lane);
     // the reference occupies bits [o, 32 W)
     const int o = 32 * W - r;
-    int rmax = r;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        const int other = __shfl_xor_sync(LEV_FULL_MASK, rmax, d);
-        rmax = other > rmax ? other : rmax;
-    }
-    for (int c = 0; c * 16 < rmax; ++c) {
-        const uint4 q4 = a.ref_uid[(int64_t)c * a.P + pc];
-        const unsigned q[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int j = c * 16 + k;
-            if (j < r) {
-                const unsigned u = (q[k >> 2] >> (8 * (k & 3))) & 0xffu;
-                const int b = j + o;
-                M[(u * W + (b >> 5)) * 32 + lane] |= 1u << (b & 31);
-            }
-        }
-    }
-    unsigned pv[W], mv[W];
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-        const int lo = 32 * w;
-        pv[w] = o <= lo ? ~0u : (o >= lo + 32 ? 0u : (~0u << (o - lo)));
-        mv[w] = 0u;
-    }
-    int score = r;
-    // rows this warp has to run: the longest hypothesis among its pairs
     const int mysteps = a.exclude_last ? (h > 0 ? h - 1 : 0) : h;  // SM:286-288
-    int steps = mysteps;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        const int other = __shfl_xor_sync(LEV_FULL_MASK, steps, d);
-        steps = other > steps ? other : steps;
-    }
     const float rf = (float)r;
     const float y = r > 0 ? __frcp_rn(rf) : 0.0f;
     const int first_pad = h + (a.exclude_last ? 0 : 1);
-    float* __restrict__ orow = a.out + pair;  // prefix: row 0 of this pair
-    auto emit = [&](int i, int rv) {          // SM:352-388: one output row
-        float val = __fmul_rn((float)rv, a.mult);
-        if (a.norm) {
-            if (r == 0) {
-                val = i > 0 ? 1.0f : 0.0f;
-            } else {  // correctly rounded val / r (Markstein, see lev_group.cu)
-                const float q0 = __fmul_rn(val, y);
-                val = __fmaf_rn(__fmaf_rn(-rf, q0, val), y, q0);
+
+    for (int base = 0; base < runs.count; base += NT) {
+        const bool active = runs.index >= base && runs.index < base + NT;
+        const int tb = active ? runs.index - base : 0;
+        const bool leader = active && runs.lead == lane;
+        __syncwarp();
+        {
+            uint4* mz = reinterpret_cast<uint4*>(M);
+            for (int i = lane; i < tab_words / 4; i += 32) mz[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncwarp();
+        if (leader) {  // the run's match masks, from its leader's uid bytes
+            for (int c = 0; c * 16 < r; ++c) {
+                const uint4 q4 = a.ref_uid[(int64_t)c * a.P + pc];
+                const unsigned q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int j = c * 16 + k;
+                    if (j < r) {
+                        const unsigned u = (q[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                        const int b = j + o;
+                        M[(u * W + (b >> 5)) * NT + tb] |= 1u << (b & 31);
+                    }
+                }
             }
         }
-        if (valid) *orow = i < first_pad ? val : a.padding;
-        orow += a.out_si;
-    };
-    int fin = r;  // FINAL: hypotheses without rows keep D[r][0] = r
-    if (MODE == LEV_MODE_PREFIX && a.Hout > 0) emit(0, r);
-    int i = 1;
-    for (int c = 0; c * 16 < steps; ++c) {
-        const uint4 q4 = a.hyp_uid[(int64_t)c * a.P + pc];
-        const unsigned q[4] = {q4.x, q4.y, q4.z, q4.w};
+        __syncwarp();
+        // rows this pass has to run: the longest hypothesis among its pairs
+        int steps = active ? mysteps : 0;
 #pragma unroll
-        for (int k = 0; k < 16; ++k, ++i) {
-            if (i > steps) break;
-            unsigned u = (q[k >> 2] >> (8 * (k & 3))) & 0xffu;
-            u = u < (unsigned)Z ? u : (unsigned)Z;
-            unsigned eq[W];
-#pragma unroll
-            for (int w = 0; w < W; ++w) eq[w] = M[(u * W + w) * 32 + lane];
-            score += lev_bv_step<W>(eq, pv, mv);
-            if (MODE == LEV_MODE_PREFIX) {
-                emit(i, score);
-            } else if (i == h) {
-                fin = score;
-            }
+        for (int d = 16; d > 0; d >>= 1) {
+            const int other = __shfl_xor_sync(LEV_FULL_MASK, steps, d);
+            steps = other > steps ? other : steps;
         }
-    }
-    if (MODE == LEV_MODE_PREFIX) {
-        for (; i < a.Hout; ++i) {  // rows past every hypothesis of this warp
-            if (valid) *orow = a.padding;
+        if (!active) continue;  // (no warp-wide operation below this line in the pass)
+        unsigned pv[W], mv[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int lo = 32 * w;
+            pv[w] = o <= lo ? ~0u : (o >= lo + 32 ? 0u : (~0u << (o - lo)));
+            mv[w] = 0u;
+        }
+        int score = r;
+        float* __restrict__ orow = a.out + pair;  // prefix: row 0 of this pair
+        auto emit = [&](int i, int rv) {          // SM:352-388: one output row
+            float val = __fmul_rn((float)rv, a.mult);
+            if (a.norm) {
+                if (r == 0) {
+                    val = i > 0 ? 1.0f : 0.0f;
+                } else {  // correctly rounded val / r (Markstein, see lev_group.cu)
+                    const float q0 = __fmul_rn(val, y);
+                    val = __fmaf_rn(__fmaf_rn(-rf, q0, val), y, q0);
+                }
+            }
+            if (valid) *orow = i < first_pad ? val : a.padding;
             orow += a.out_si;
+        };
+        int fin = r;  // FINAL: hypotheses without rows keep D[r][0] = r
+        if (MODE == LEV_MODE_PREFIX && a.Hout > 0) emit(0, r);
+        int i = 1;
+        uint4 q4 = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (steps > 0) q4 = a.hyp_uid[pc];
+        for (int c = 0; c * 16 < steps; ++c) {
+            const unsigned q[4] = {q4.x, q4.y, q4.z, q4.w};
+            if ((c + 1) * 16 < steps) q4 = a.hyp_uid[(int64_t)(c + 1) * a.P + pc];  // next chunk
+#pragma unroll
+            for (int k = 0; k < 16; ++k, ++i) {
+                if (i > steps) break;
+                unsigned u = (q[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                u = u < (unsigned)Z ? u : (unsigned)Z;
+                unsigned eq[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w) eq[w] = M[(u * W + w) * NT + tb];
+                score += lev_bv_step<W>(eq, pv, mv);
+                if (MODE == LEV_MODE_PREFIX) {
+                    emit(i, score);
+                } else if (i == h) {
+                    fin = score;
+                }
+            }
         }
-    } else if (valid) {  // SM:390-405
-        float val = __fmul_rn((float)fin, a.mult);
-        if (a.norm) val = (r == 0) ? (h > 0 ? 1.0f : 0.0f) : val / rf;
-        a.out[pair] = val;
+        if (MODE == LEV_MODE_PREFIX) {
+            for (; i < a.Hout; ++i) {  // rows past every hypothesis of this pass
+                if (valid) *orow = a.padding;
+                orow += a.out_si;
+            }
+        } else if (valid) {  // SM:390-405
+            float val = __fmul_rn((float)fin, a.mult);
+            if (a.norm) val = (r == 0) ? (h > 0 ? 1.0f : 0.0f) : val / rf;
+            a.out[pair] = val;
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-// EXPERIMENTAL, off unless B200LEV_BITVEC=1.  Parity-green on the GPU and in the emulator, but
-// on cfg2 (131072 pairs, R = H = 101, W = 4) the two kernels take 390 + 165 us against 314 us
-// for the whole wavefront path: per-lane tables cost 40 KB (hash) and 52 KB (Peq) of shared
-// memory per WARP, i.e. one warp per scheduler, and both kernels are serial dependency
-// chains (ncu: 0.2 IPC, "wait"/scoreboard stalls).  What it needs to win -- tables shared
-// by the lanes of an n-best group, or 2-4 lanes per pair, and a probe loop that does not
-// run at the pace of the slowest of 32 lanes -- is listed in DESIGN.md.
-static bool lev_bv_enabled() {
+// B200LEV_BITVEC: 0 = never, 1 = forced (tests: whatever the references look like, multi-pass
+// where a block of 32 pairs holds more than 4 distinct references), default 2 = enqueued ahead
+// of the wavefront path, which it pre-empts on the device when the batch is n-best shaped.
+int lev_bitvec_mode() {
     const char* e = getenv("B200LEV_BITVEC");
-    return e != nullptr && atoi(e) != 0;
+    return e != nullptr ? atoi(e) : 2;
 }
 static int64_t lev_bv_min_pairs() {
     int64_t v = 1024;  // below this the warp-per-pair kernels have the lower latency
@@ -402,12 +601,15 @@ static int64_t lev_bv_min_pairs() {
 bool lev_bitvec_eligible(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp, int mode,
                          bool count_mode, bool float_path, int ins_i, int del_i, int sub_i,
                          int64_t out_sn) {
-    if (!lev_bv_enabled()) return false;
+    if (lev_bitvec_mode() == 0) return false;
     if (mode != LEV_MODE_FINAL && mode != LEV_MODE_PREFIX) return false;
     if (count_mode || float_path || ins_i != 1 || del_i != 1 || sub_i != 1) return false;
     if (ref->T > 128 || ref->T < 1 || hyp->T >= (1 << 20)) return false;
     if (hyp->N < lev_bv_min_pairs()) return false;
     if (ref->elem_bytes != hyp->elem_bytes) return false;
+    if (ref->stride_t >= ((int64_t)1 << 31) || hyp->stride_t >= ((int64_t)1 << 31) ||
+        ref->stride_t < 0 || hyp->stride_t < 0)
+        return false;
     if ((ref->N > 1 && ref->stride_n != 1) || (hyp->N > 1 && hyp->stride_n != 1)) return false;
     if (mode == LEV_MODE_PREFIX && out_sn != 1) return false;
     return true;
@@ -417,13 +619,14 @@ template <typename TT>
 static void lev_bv_launch_uid(const LevBvArgs& a, size_t smem, cudaStream_t st) {
     auto kern = lev_bv_uid_kernel<TT>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    lev_launch(kern, dim3((unsigned)((a.P + 31) / 32)), dim3(32), smem, st, a);
+    lev_launch(kern, dim3((unsigned)((a.P + 32 * LEV_BV_WARPS - 1) / (32 * LEV_BV_WARPS))),
+               dim3(32 * LEV_BV_WARPS), smem, st, a);
 }
 
 template <int W>
 static void lev_bv_launch_dp(const LevBvArgs& a, cudaStream_t st) {
-    const size_t smem = sizeof(unsigned) * (size_t)(a.R + 1) * W * 32;
-    const dim3 grid((unsigned)((a.P + 31) / 32)), block(32);
+    const size_t smem = sizeof(unsigned) * (size_t)(a.R + 1) * W * LEV_BV_NT * LEV_BV_WARPS;
+    const dim3 grid((unsigned)((a.P + 32 * LEV_BV_WARPS - 1) / (32 * LEV_BV_WARPS))), block(32 * LEV_BV_WARPS);
     if (a.mode == LEV_MODE_PREFIX) {
         auto kern = lev_bv_dp_kernel<W, LEV_MODE_PREFIX>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -436,11 +639,13 @@ static void lev_bv_launch_dp(const LevBvArgs& a, cudaStream_t st) {
 }
 
 // The caller has checked lev_bitvec_eligible.  `uid_ref` / `uid_hyp` are workspace regions of
-// P * round_up(R, 16) and P * round_up(H, 16) bytes.
+// P * round_up(R, 16) and P * round_up(H, 16) bytes, `lead` of P bytes.  `state` non-NULL:
+// the kernels run only if K0's state words select this path (lev_bv_selected).
 int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
                       const b200lev_opts_t* o, int mode, float mult, int32_t* ref_len,
-                      int32_t* hyp_len, void* uid_ref, void* uid_hyp, int32_t* flags, float* out,
-                      int64_t out_si, int Hout, cudaStream_t st) {
+                      int32_t* hyp_len, void* uid_ref, void* uid_hyp, void* lead,
+                      int32_t* state, int32_t* flags, float* out, int64_t out_si, int Hout,
+                      cudaStream_t st) {
     LevBvArgs a;
     memset(&a, 0, sizeof(a));
     a.ref = ref->data;
@@ -458,9 +663,12 @@ int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     a.hyp_len = hyp_len;
     a.ref_uid = (uint4*)uid_ref;
     a.hyp_uid = (uint4*)uid_hyp;
+    a.lead = (unsigned char*)lead;
+    a.state = state;
+    a.check_state = state != nullptr;
     a.flags = flags;
-    a.slots_log2 = 5;
-    while ((1 << a.slots_log2) < 2 * a.R) ++a.slots_log2;
+    a.slots_log2 = 4;  // buckets of 4 ways: on average at most one token per bucket
+    while ((1 << a.slots_log2) < a.R) ++a.slots_log2;
     a.mode = mode;
     a.norm = o->norm;
     a.exclude_last = mode == LEV_MODE_PREFIX ? o->exclude_last : 0;
@@ -469,11 +677,11 @@ int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     a.padding = (float)o->padding;
     a.out = out;
     a.out_si = out_si;
-    const size_t smem_uid = (size_t)(1 << a.slots_log2) * 32 * (sizeof(int) + 1);
+    const size_t smem_uid = (size_t)(1 << a.slots_log2) * LEV_BV_NT * 20 * LEV_BV_WARPS;
     if (getenv("B200LEV_TRACE"))
-        fprintf(stderr, "b200lev: bit-vector path, mode %d, R=%d H=%d P=%d W=%d\n", mode, a.R, a.H,
-                a.P, (a.R + 31) / 32);
-    lev_prof_begin(LEV_PROF_PACK_HYP, st);
+        fprintf(stderr, "b200lev: bit-vector path, mode %d, R=%d H=%d P=%d W=%d device-selected=%d\n",
+                mode, a.R, a.H, a.P, (a.R + 31) / 32, a.check_state);
+    lev_prof_begin(LEV_PROF_BV_UID, st);
     switch (ref->elem_bytes) {
         case 8: lev_bv_launch_uid<int64_t>(a, smem_uid, st); break;
         case 4: lev_bv_launch_uid<int32_t>(a, smem_uid, st); break;
@@ -483,10 +691,10 @@ int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
             lev_set_error("unsupported token element size %d", (int)ref->elem_bytes);
             return B200LEV_ERR_ARG;
     }
-    lev_prof_end(LEV_PROF_PACK_HYP, st);
+    lev_prof_end(LEV_PROF_BV_UID, st);
     int rc = lev_check_cuda("lev_bv_uid_kernel");
     if (rc) return rc;
-    lev_prof_begin(LEV_PROF_DP, st);
+    lev_prof_begin(LEV_PROF_BV_DP, st);
     const int W = (a.R + 31) / 32;
     switch (W) {
         case 1: lev_bv_launch_dp<1>(a, st); break;
@@ -494,6 +702,6 @@ int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
         case 3: lev_bv_launch_dp<3>(a, st); break;
         default: lev_bv_launch_dp<4>(a, st); break;
     }
-    lev_prof_end(LEV_PROF_DP, st);
+    lev_prof_end(LEV_PROF_BV_DP, st);
     return lev_check_cuda("lev_bv_dp_kernel");
 }

@@ -140,6 +140,7 @@ struct LevParams {
     int64_t ref_st, ref_sn, hyp_st, hyp_sn;
     int ref_eb, hyp_eb;
     int only_if_wide;  // lev_warp_kernel: exit unless the wide-token flag is set
+    int bv_check;      // the bit-vector kernels ran first: exit if they took the batch
     // group kernel tables (workspace)
     int* ghist;
     int* gcursor;
@@ -155,7 +156,8 @@ struct LevParams {
 // optional per-kernel timing (b200lev_profile): CUDA events recorded on the launch stream
 // around each phase; slots of b200lev_profile_read()
 enum LevProfSlot { LEV_PROF_PACK_REF = 0, LEV_PROF_PACK_HYP, LEV_PROF_SORT, LEV_PROF_DP,
-                   LEV_PROF_FINALIZE, LEV_PROF_STANDBY, LEV_PROF_NSLOTS };
+                   LEV_PROF_FINALIZE, LEV_PROF_STANDBY, LEV_PROF_BV_UID, LEV_PROF_BV_DP,
+                   LEV_PROF_NSLOTS };
 void lev_prof_begin(int slot, cudaStream_t st);
 void lev_prof_end(int slot, cudaStream_t st);
 
@@ -167,7 +169,7 @@ int lev_check_cuda(const char* what);
 int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int include_eos,
                     int32_t* packed, int64_t Tp, uint16_t* packed16, int64_t Tp16, int32_t* lens,
                     int32_t* flags, int32_t* state, int missing_flag, const int32_t* ref_len,
-                    int ref_group, int G, int* ghist, cudaStream_t st);
+                    int ref_group, int G, int* ghist, int bv_check, cudaStream_t st);
 int lev_launch_dp(const LevParams& p, int mode, bool count_mode, bool float_path,
                   cudaStream_t st);
 int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t st);
@@ -175,14 +177,26 @@ int lev_launch_cta(const LevParams& p, int mode, bool count_mode, bool float_pat
 // lanes per pair if the shapes admit the group kernel (its histogram is then built at
 // pack time), else 0
 int lev_group_eligible(int64_t R, int64_t H, int64_t P);
+// Device-side choice between the bit-vector path and the wavefront path (no host round trip).
+// When the shapes and costs admit the bit-vector kernels they are enqueued FIRST: the uid
+// kernel finds out whether every block of 32 consecutive pairs holds at most 4 runs of
+// identical references (n-best batches do) and vetoes through state[3] otherwise; every
+// kernel of the wavefront path, enqueued behind, then starts with lev_bv_took() and exits at
+// once if the work is already done (and the bit-vector DP kernel with the opposite test).
+__device__ __forceinline__ bool lev_bv_took(const int* state) {
+    return *reinterpret_cast<const volatile int*>(state + 3) == 0;
+}
 // unit-cost bit-vector path (lev_bitvec.cu)
 bool lev_bitvec_eligible(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp, int mode,
                          bool count_mode, bool float_path, int ins_i, int del_i, int sub_i,
                          int64_t out_sn);
 int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
                       const b200lev_opts_t* o, int mode, float mult, int32_t* ref_len,
-                      int32_t* hyp_len, void* uid_ref, void* uid_hyp, int32_t* flags, float* out,
-                      int64_t out_si, int Hout, cudaStream_t st);
+                      int32_t* hyp_len, void* uid_ref, void* uid_hyp, void* lead,
+                      int32_t* state, int32_t* flags, float* out, int64_t out_si, int Hout,
+                      cudaStream_t st);
+// 0: off, 1: forced (tests; runs whatever the references look like), 2: device-selected
+int lev_bitvec_mode();
 int lev_launch_uid(const b200lev_tokens_t* ref, const int32_t* ref_len, int32_t* uid,
                    int64_t* dtok, int32_t* ndist, int64_t Rp, cudaStream_t st);
 int lev_launch_completion_fill(const uint32_t* dbits, const int64_t* dtok, int64_t Rp,

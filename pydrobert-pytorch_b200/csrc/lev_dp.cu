@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(256) lev_warp_kernel(const LevParams p) {
     V* bufs = reinterpret_cast<V*>(hyp_s + 2 * Hs);
     const bool wide = (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) != 0;
     if (p.only_if_wide && !wide) return;  // the group kernel already did the work
+    if (p.bv_check && lev_bv_took(p.wide_flag)) return;
     for (int pair = blockIdx.x * wpc + warp; pair < p.P; pair += gridDim.x * wpc) {
         const int r = p.ref_len[pair / p.ref_group];
         const int h = p.hyp_len[pair];

@@ -256,6 +256,7 @@ lev_sort_kernel(const LevParams p, const LevGroupGeom geo, const int count_mode)
     int* lhist = base + p.nbins;      // [nbins] this CTA's pairs per bin
     int* goff = lhist + p.nbins;      // [nbins] this CTA's reserved offset inside each bin
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (p.bv_check && lev_bv_took(p.wide_flag)) return;
     if (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) return;
     const bool packed = !count_mode && geo.allow16 && levg_tokens_narrow(p.wide_flag);
     const int PPT = (32 / geo.G) * (packed ? 2 : 1);
@@ -362,6 +363,7 @@ __global__ void __launch_bounds__(128, LEVG_MIN_CTAS) lev_group_kernel(const Lev
     // found in the tokens (no host round trip): wider than int32 -> neither (the 64-bit
     // compare path of lev_warp_kernel, enqueued right behind, takes the batch); inside a
     // 65536-wide window and small values -> PACKED; else the 32-bit build.
+    if (p.bv_check && lev_bv_took(p.wide_flag)) return;
     if (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) return;
     if ((!COUNT && geo.allow16 && levg_tokens_narrow(p.wide_flag)) != PACKED) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -490,6 +492,7 @@ __device__ __forceinline__ float levg_finalize_one(const LevParams& p, bool pack
 template <bool COUNT>
 __global__ void __launch_bounds__(256)
 lev_prefix_finalize_kernel(const LevParams p, const LevGroupGeom geo) {
+    if (p.bv_check && lev_bv_took(p.wide_flag)) return;
     if (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) return;  // lev_warp_kernel wrote `out` itself
     const bool packed = !COUNT && geo.allow16 && levg_tokens_narrow(p.wide_flag);
     const int tid = threadIdx.x;

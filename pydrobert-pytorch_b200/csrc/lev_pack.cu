@@ -41,6 +41,7 @@ struct LevPackArgs {
     const int32_t* ref_len;  // histogram side product (hypothesis pass only)
     int ref_group, G;
     int* ghist;
+    int bv_check;  // exit if the bit-vector kernels, enqueued first, took the batch
 };
 
 // ---- epilogue pieces shared by both layouts ----------------------------------------------
@@ -164,6 +165,7 @@ __device__ __forceinline__ void lev_pack_slice(const TT* __restrict__ src, int s
 
 template <typename TT>
 __global__ void __launch_bounds__(128, 8) lev_pack_seqfirst_kernel(const LevPackArgs a) {
+    if (a.bv_check && lev_bv_took(a.state)) return;
     __shared__ __align__(16) int tile[32][LEV_PACK_STRIDE];
     __shared__ int first_s[32];
     __shared__ unsigned blk_u, blk_n;
@@ -258,6 +260,7 @@ __global__ void __launch_bounds__(128, 8) lev_pack_seqfirst_kernel(const LevPack
 // ---- any other layout: one warp per sequence, lanes along the sequence axis -------------
 template <typename TT>
 __global__ void __launch_bounds__(128) lev_pack_rows_kernel(const LevPackArgs a) {
+    if (a.bv_check && lev_bv_took(a.state)) return;
     const int lane = threadIdx.x & 31;
     const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const bool valid_seq = n < a.N;  // warp-uniform
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(128) lev_pack_rows_kernel(const LevPackArgs a)
 int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int include_eos,
                     int32_t* packed, int64_t Tp, uint16_t* packed16, int64_t Tp16, int32_t* lens,
                     int32_t* flags, int32_t* state, int missing_flag, const int32_t* ref_len,
-                    int ref_group, int G, int* ghist, cudaStream_t st) {
+                    int ref_group, int G, int* ghist, int bv_check, cudaStream_t st) {
     if (t->N <= 0) return B200LEV_OK;
     if (t->T >= (int64_t)1 << 30) {
         lev_set_error("sequence dimension %lld too long", (long long)t->T);
@@ -320,6 +323,7 @@ int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int inc
     a.ref_group = ref_group < 1 ? 1 : ref_group;
     a.G = G;
     a.ghist = ghist;
+    a.bv_check = bv_check;
     // unit stride along the batch axis => register-tile transpose; otherwise (batch_first,
     // or an arbitrary view) one warp per sequence.
     const bool seqfirst = (t->stride_n == 1 && t->stride_t != 1 && t->stride_t > -((int64_t)1 << 31) &&

@@ -96,6 +96,10 @@ __device__ __forceinline__ int lev_lds32_sync(lev_saddr a) {  // data another wa
 __device__ __forceinline__ void lev_sts32(lev_saddr a, int v) {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+// ask L2 for a line a later load will want (no register, no scoreboard)
+__device__ __forceinline__ void lev_prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 // hide a pointer's derivation from the optimiser, so that the addresses built from it stay
 // "pointer + small constant x stride" (one IMAD.WIDE each) instead of being re-derived
 #define LEV_OPAQUE_PTR(p) asm volatile("" : "+l"(p))

@@ -376,6 +376,7 @@ static inline void lev_launch(void (*k)(KArgs...), dim3 grid, dim3 block, size_t
 #define LEV_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::g_dyn_smem)
 #define LEV_SPIN_YIELD() emu::yield()
 #define LEV_OPAQUE_PTR(p) asm volatile("" : "+r"(p))
+static inline void lev_prefetch_l2(const void*) {}
 static inline unsigned lev_ldg_l2(const unsigned* p) { return *p; }
 template <typename T>
 static inline T lev_ldg_stream(const T* p) { return *p; }

@@ -212,3 +212,23 @@ def check_wide_tokens(F, dev):
     # sanity: the narrowed tokens alone would have matched
     assert not np.array_equal(O.edit_distance(ref, hyp, eos=0),
                               O.edit_distance(ref.astype(np.int32), hyp.astype(np.int32), eos=0))
+
+
+def check_nbest_batch(F, dev, seed, R, H, n_utts, nbest, V=30, shared=True, **kw):
+    """prefix_error_rates / error_rate on an n-best shaped batch: every reference repeated
+    `nbest` times along the batch axis (`shared`), or a batch of unrelated references -- the two
+    shapes between which the device-side path selection of lev_bitvec.cu decides."""
+    rng = np.random.default_rng(seed)
+    ref = random_tokens(rng, R, n_utts, V, 0, -2, 0, 0.1)
+    hyp = random_tokens(rng, H, n_utts * nbest, V, 0, -3, 0, 0.1)
+    if shared:
+        ref = np.repeat(ref, nbest, axis=1)
+    else:
+        ref = random_tokens(rng, R, n_utts * nbest, V, 0, -2, 0, 0.1)
+    tr, th = torch.from_numpy(ref).to(dev), torch.from_numpy(hyp).to(dev)
+    for func, okw in (("prefix_error_rates", dict(padding=-7)), ("error_rate", {}),
+                      ("prefix_edit_distances", dict(padding=-7, exclude_last=True)),
+                      ("edit_distance", {})):
+        exp = getattr(O, func)(ref, hyp, eos=0, include_eos=True, **okw, **kw)
+        act = getattr(F, func)(tr, th, eos=0, include_eos=True, warn=False, **okw, **kw)
+        assert_same(act, exp, True, f"{func} nbest seed={seed} shared={shared}")

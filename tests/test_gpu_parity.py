@@ -345,8 +345,8 @@ def test_bitvec_path_vs_oracle(F, dev, shape, monkeypatch):
     for costs in ((1, 1, 1), (0.5, 0.5, 0.5)):
         for flags in (dict(include_eos=True, norm=True, exclude_last=False, min_frac=0.0),
                       dict(include_eos=False, norm=False, exclude_last=True, min_frac=0.4, no_eos_frac=0.2)):
-            for spread in (1, 70001):
-                PC.check_vs_oracle(F, dev, seed=R + H, R=R, H=H, N=N, V=50, costs=costs, do_mask=False,
+            for spread, V in ((1, 50), (70001, 50), (1, 3000)):
+                PC.check_vs_oracle(F, dev, seed=R + H, R=R, H=H, N=N, V=V, costs=costs, do_mask=False,
                                    padding=-3, spread=spread, **flags)
     PC.check_wide_tokens(F, dev)
 

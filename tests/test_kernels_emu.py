@@ -182,7 +182,8 @@ def test_bitvec_kernels_vs_oracle(F, shape, costs, monkeypatch):
                   dict(include_eos=False, norm=False, exclude_last=True, min_frac=0.4),
                   dict(include_eos=True, norm=True, exclude_last=True, min_frac=0.2, no_eos_frac=0.3),
                   dict(include_eos=False, norm=True, exclude_last=False, min_frac=0.0, eos=None)):
-        for spread, V in ((1, 5), (70001, 40)):
+        # V=3000: mostly distinct tokens, so hash buckets fill up and builds are retried
+        for spread, V in ((1, 5), (70001, 40), (1, 3000)):
             PC.check_vs_oracle(F, DEV, seed=R + H, R=R, H=H, N=N, V=V, costs=costs, do_mask=False,
                                padding=-3, spread=spread, **flags)
 
@@ -196,6 +197,19 @@ def test_bitvec_token_dtypes_nbest_and_wide(F, dtype, monkeypatch):
     test_n_best_shared_reference(F)
     PC.check_wide_tokens(F, DEV)
     PC.check_warnings(F, DEV)
+
+
+@pytest.mark.parametrize("shared", [True, False], ids=["nbest", "unrelated_refs"])
+@pytest.mark.parametrize("shape", [(30, 33, 12, 8), (101, 101, 9, 8), (64, 40, 5, 16), (90, 70, 20, 4)])
+def test_bitvec_device_selected(F, shape, shared, monkeypatch):
+    """Default mode: the bit-vector kernels are enqueued ahead of the wavefront path and decide
+    on the device -- they take n-best shaped batches (<= 4 distinct references per 32 pairs)
+    and veto the others, whose work the group kernels then do.  Same numbers either way."""
+    monkeypatch.delenv("B200LEV_BITVEC", raising=False)
+    monkeypatch.setenv("B200LEV_BITVEC_MIN_PAIRS", "1")
+    monkeypatch.setenv("B200LEV_GROUP_MIN_PAIRS", "1")
+    R, H, n_utts, nbest = shape
+    PC.check_nbest_batch(F, DEV, seed=R + H, R=R, H=H, n_utts=n_utts, nbest=nbest, shared=shared)
 
 
 def test_bitvec_golden(F, golden_sm, monkeypatch):
