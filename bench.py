@@ -345,11 +345,53 @@ def main():
         if os.path.exists(peaks_file):
             hbm_peak, hbm_src = json.load(open(peaks_file))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
         achieved_ops = cells / (ms_dp * 1e-3) * OPS_PER_CELL / 1e12
-        traffic = None
+        traffic_all = {}
         tf = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tf):  # dram bytes per launch from the last `ncu --set full` capture
-            traffic = json.load(open(tf)).get("lev_group_kernel")
+        if os.path.exists(tf):  # dram bytes per launch from the last `ncu --set full` captures
+            traffic_all = json.load(open(tf))
         pack_gbs = (in_bytes + in_bytes // 2) / (ms_pack * 1e-3) / 1e9
+        peak_note = ("measured live (b200lev_int32_peak_kernel), ALU pipe = viaddmnmx; T int32-op/s: "
+                     f"{ {k: round(v, 2) for k, v in peaks.items()} }")
+        if bitvec:
+            # n-best shaped batch: the bit-vector kernels took the call on the device.  The
+            # dominant kernel is the uid pre-pass (it reads the raw tokens once: HBM-bound);
+            # the DP kernel is reported next to it against the INT32 issue rate.
+            ms_uid = float(prof[6])
+            R1 = T_LEN + 1
+            uid_bytes = in_bytes + 2 * P * ((R1 + 15) // 16) * 16 + 2 * 4 * P + P
+            roofline = {"bound": "hbm", "kernel": "lev_bv_uid_kernel<int64>",
+                        "achieved": uid_bytes / (ms_uid * 1e-3) / 1e9, "peak": hbm_peak,
+                        "unit": "GB/s", "frac": uid_bytes / (ms_uid * 1e-3) / 1e9 / hbm_peak,
+                        "traffic": traffic_all.get("lev_bv_uid_kernel"), "kernel_ms": ms_uid,
+                        "algorithmic_bytes": uid_bytes, "peak_source": hbm_src,
+                        "note": "reads both raw int64 token tensors once, writes 1 uid byte per "
+                                "token + lengths; share of the step = kernel_ms / ms_per_step"}
+            roofline_dp = {"bound": "int32_issue", "kernel": "lev_bv_dp_kernel<W=4,PREFIX>",
+                           "achieved": achieved_ops, "peak": int32_peak, "unit": "Tint32op/s",
+                           "frac": achieved_ops / int32_peak,
+                           "traffic": traffic_all.get("lev_bv_dp_kernel"),
+                           "ops_per_cell": OPS_PER_CELL, "kernel_ms": ms_dp,
+                           "kernel_gcups": cells / (ms_dp * 1e-3) / 1e9, "peak_source": peak_note,
+                           "note": "algorithmic 5 INT32 ops/cell (SURVEY 8d); Myers' bit-vector "
+                                   "recurrence advances 32 cells with ~17 instructions, so frac "
+                                   "exceeds 1; ncu: ALU pipe 78 % busy"}
+            launches = 9  # 2 bit-vector kernels + 7 wavefront kernels standing by (exit at once)
+        else:
+            roofline = {"bound": "int32_issue",
+                        "kernel": "lev_group_kernel<cost,PREFIX,packed16> (+ its 32-bit twin's "
+                                  "immediate exit)",
+                        "achieved": achieved_ops, "peak": int32_peak, "unit": "Tint32op/s",
+                        "frac": achieved_ops / int32_peak,
+                        "traffic": traffic_all.get("lev_group_kernel"),
+                        "ops_per_cell": OPS_PER_CELL, "kernel_ms": ms_dp,
+                        "kernel_gcups": cells / (ms_dp * 1e-3) / 1e9, "peak_source": peak_note,
+                        "note": "algorithmic 5 INT32 ops/cell (SURVEY 8d); the kernel issues 2.5 "
+                                "instructions per cell (2 cells per 16x2 DPX instruction), so "
+                                "frac can exceed 1"}
+            roofline_dp = None
+            # 2 pack, 1 bucketing, 2 DP builds (one exits at once), 1 prefix finalize, 1 stand-by
+            # 64-bit-token kernel (+ 2 bit-vector kernels that vetoed, when they were eligible)
+            launches = 7 + (2 if prof[6] > 0 else 0)
         line = {
             "metric": "edit-distance cell-updates/s", "value": cells_all / (ms * 1e-3) / 1e9,
             "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -365,32 +407,22 @@ def main():
             "e2e": {"value": cells_all / (ms_e2e * 1e-3) / 1e9, "unit": "GCUPS",
                     "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": int(outp.numel() * 4),
                     "ms_per_step": ms_e2e},
-            # per step: 2 pack, 1 bucketing, 2 DP builds (one exits at once), 1 prefix
-            # finalize, 1 stand-by 64-bit-token kernel
-            "gpu_launches": 7 * args.steps,
-            "roofline": {"bound": "int32_issue",
-                         "kernel": "lev_group_kernel<cost,PREFIX,packed16> (+ its 32-bit twin's "
-                                   "immediate exit)",
-                         "achieved": achieved_ops, "peak": int32_peak, "unit": "Tint32op/s",
-                         "frac": achieved_ops / int32_peak, "traffic": traffic,
-                         "ops_per_cell": OPS_PER_CELL, "kernel_ms": ms_dp,
-                         "kernel_gcups": cells / (ms_dp * 1e-3) / 1e9,
-                         "peak_source": "measured live (b200lev_int32_peak_kernel), ALU pipe = "
-                                        "viaddmnmx; T int32-op/s: "
-                                        f"{ {k: round(v, 2) for k, v in peaks.items()} }",
-                         "note": "algorithmic 5 INT32 ops/cell (SURVEY 8d); the kernel issues 2.5 "
-                                 "instructions per cell (2 cells per 16x2 DPX instruction), so "
-                                 "frac can exceed 1"},
+            "gpu_launches": launches * args.steps,
+            "roofline": roofline,
             "phases_ms": {k: round(float(v), 5) for k, v in phases.items()},
-            "roofline_pack": {"bound": "hbm", "kernel": "lev_pack_seqfirst_kernel<int64> x2 (ref, hyp)",
-                              "achieved": pack_gbs, "peak": hbm_peak, "unit": "GB/s",
-                              "frac": pack_gbs / hbm_peak, "kernel_ms": ms_pack,
-                              "peak_source": hbm_src},
             "literal": {"workload": "64 utts x 8-best = 512 pairs (BASELINE configs[1] as written)",
                         "ms_per_call": ms_lit, "gcups": lcells / (ms_lit * 1e-3) / 1e9,
                         "hyps_per_s": 512 / (ms_lit * 1e-3)},
             "clocks": clocks,
         }
+        if roofline_dp is not None:
+            line["roofline_dp"] = roofline_dp
+        else:
+            line["roofline_pack"] = {"bound": "hbm",
+                                     "kernel": "lev_pack_seqfirst_kernel<int64> x2 (ref, hyp)",
+                                     "achieved": pack_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": pack_gbs / hbm_peak, "kernel_ms": ms_pack,
+                                     "peak_source": hbm_src}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(ref_np, hyp_np, cells)
         print(json.dumps(line))
