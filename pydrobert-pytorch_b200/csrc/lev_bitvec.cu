@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_uid_kernel(const Lev
         const int eos_lo = (int)a.eos, eos_hi = (int)(a.eos >> 32);
         int dacc = 0, wacc = 0;  // differences to the left neighbour / to a sign extension
         auto observe = [&](const TT (&buf)[8], int t0) {
+            unsigned eos_bits = 0, empty_bits = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int64_t x = (int64_t)buf[k];
@@ -148,17 +149,20 @@ __global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_uid_kernel(const Lev
                     dacc |= hi ^ __shfl_up_sync(LEV_FULL_MASK, hi, 1);
                     wacc |= hi ^ (lo >> 31);
                 }
-                // positions past R were loaded as 0 = what the neighbour loaded
-                if (t0 + k < a.R) {
-                    if (a.has_eos && lo == eos_lo && hi == eos_hi) first_eos = min(first_eos, t0 + k);
-                    if (lo == LEV_BV_EMPTY) exact0 = 1;
-                }
+                eos_bits |= (lo == eos_lo && hi == eos_hi) ? (1u << k) : 0u;
+                empty_bits |= lo == LEV_BV_EMPTY ? 1u : 0u;
             }
+            // positions past R were loaded as 0 (= what the neighbour loaded): mask them out
+            const int live = a.R - t0;
+            if (live < 8) eos_bits &= live > 0 ? (1u << live) - 1u : 0u;
+            if (a.has_eos && eos_bits != 0 && first_eos == a.R) first_eos = t0 + __ffs((int)eos_bits) - 1;
+            if (empty_bits) exact0 = 1;
         };
         const TT* rp = rsrc;
         TT bufA[8], bufB[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) bufA[k] = (k < a.R) ? rp[(int64_t)k * rst] : (TT)0;
+#pragma unroll 1
         for (int t0 = 0; t0 < a.R; t0 += 16) {
             LEV_OPAQUE_PTR(rp);
             // 8 loads per lane in flight do not cover DRAM latency at 20 warps per SM: ask L2
@@ -196,6 +200,7 @@ __global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_uid_kernel(const Lev
 
     int myflags = 0;
     int rlen = a.R, hlen = a.H;
+#pragma unroll 1
     for (int base = 0; base < runs.count; base += NT) {
         const bool active = runs.index >= base && runs.index < base + NT;
         const int tb = active ? runs.index - base : 0;
@@ -211,6 +216,7 @@ __global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_uid_kernel(const Lev
         int seed = 0;
         int exact = exact0;  // no usable table: compare tokens one by one (rare)
         bool need = active && !exact;
+#pragma unroll 1
         for (int attempt = 0; attempt < LEV_BV_TRIES; ++attempt) {
             unsigned clear = 0;  // tables (of this pass) being (re)built
 #pragma unroll
@@ -326,12 +332,12 @@ __global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_uid_kernel(const Lev
             unsigned q[4];
             // (kept free of branches: the 8 table reads of a half are independent and overlap)
             auto lookup = [&](const TT (&buf)[8], int t0, int qbase) {
+                unsigned eos_bits = 0;  // bit k: position t0 + k holds the eos
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int64_t x = (int64_t)buf[k];
                     const int v = (int)x, hi = (int)(x >> 32);
-                    const bool is_eos = a.has_eos && v == eos_lo && hi == eos_hi && t0 + k < a.H;
-                    h_eos = is_eos ? min(h_eos, t0 + k) : h_eos;
+                    eos_bits |= (v == eos_lo && hi == eos_hi) ? (1u << k) : 0u;
                     const int idx = (int)lev_bv_hash(v, hmul, a.slots_log2) * NT + tb;
                     const int4 kk = keys4[idx];
                     const unsigned pw = posw[idx];
@@ -345,11 +351,16 @@ __global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_uid_kernel(const Lev
                     const unsigned u = __byte_perm(pw, LEV_BV_NOMATCH, way);
                     q[qbase + (k >> 2)] = lev_bv_set_byte(q[qbase + (k >> 2)], u, k & 3);
                 }
+                // positions past H were loaded as 0, which may be the eos: mask them out
+                const int live = a.H - t0;
+                if (live < 8) eos_bits &= live > 0 ? (1u << live) - 1u : 0u;
+                if (a.has_eos && eos_bits != 0 && h_eos == a.H) h_eos = t0 + __ffs((int)eos_bits) - 1;
             };
             const TT* hp = hsrc;
             TT bufA[8], bufB[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) bufA[k] = (k < a.H) ? lev_ldg_stream(hp + (int64_t)k * hst) : (TT)0;
+#pragma unroll 1
             for (int t0 = 0; t0 < a.H; t0 += 16) {
                 LEV_OPAQUE_PTR(hp);
 #pragma unroll

@@ -500,9 +500,14 @@ lev_prefix_finalize_kernel(const LevParams p, const LevGroupGeom geo) {
         // lane = pair: a lane walks 32 rows of ITS pair's raw values (128-bit loads, the row's
         // line stays in L1) and every store instruction writes 32 neighbouring pairs of one
         // output row -- 128 contiguous bytes -- so nothing has to be transposed
-        const int n = blockIdx.x * blockDim.x + tid;
-        const int i0 = blockIdx.y * 32;
-        if (n >= p.P) return;
+        // (work item = 256 pairs x 32 rows; a CTA takes several, which keeps the grid -- and the
+        // cost of standing by for the bit-vector path -- small)
+        const int segs = (p.Hout + 31) / 32;
+        const int64_t items = (int64_t)((p.P + 255) / 256) * segs;
+        for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const int n = (int)(item / segs) * 256 + tid;
+        const int i0 = (int)(item % segs) * 32;
+        if (n >= p.P) continue;
         const int i1 = i0 + 32 < p.Hout ? i0 + 32 : p.Hout;
         const int r = p.ref_len[n / p.ref_group], h = p.hyp_len[n];
         const float rf = (float)r;
@@ -547,6 +552,7 @@ lev_prefix_finalize_kernel(const LevParams p, const LevGroupGeom geo) {
                     o += p.out_si;
                 }
             }
+        }
         }
     } else {
         // batch-first (or arbitrary strides): rows of one pair are adjacent in the output
@@ -663,8 +669,14 @@ int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t
     if (mode == LEV_MODE_PREFIX && p.Hout > 0) {
         lev_prof_begin(LEV_PROF_FINALIZE, st);
         dim3 grid, block(256);
-        if (p.out_sn == 1)
-            grid = dim3((unsigned)((p.P + 255) / 256), (unsigned)((p.Hout + 31) / 32));
+        if (p.out_sn == 1) {
+            int64_t items = (int64_t)((p.P + 255) / 256) * ((p.Hout + 31) / 32);
+            if (p.bv_check && items > 148 * 4) {  // stand-by duty: a small grid exits faster
+                const int64_t per_cta = (items + 148 * 4 - 1) / (148 * 4);
+                items = (items + per_cta - 1) / per_cta;
+            }
+            grid = dim3((unsigned)items);
+        }
         else
             grid = dim3((unsigned)min((int64_t)148 * 16, ((int64_t)p.P * p.Hout + 255) / 256));
         if (count_mode)

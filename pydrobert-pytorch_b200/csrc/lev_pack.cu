@@ -171,7 +171,9 @@ __global__ void __launch_bounds__(128, 8) lev_pack_seqfirst_kernel(const LevPack
     __shared__ unsigned blk_u, blk_n;
     __shared__ int blk_flags;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t n0 = (int64_t)blockIdx.x * 32;
+    // a CTA walks blocks of 32 sequences (a few each: the grid stays small, so that standing by
+    // for the bit-vector path costs a 1000-CTA launch and not one of N / 32 CTAs)
+    for (int64_t n0 = (int64_t)blockIdx.x * 32; n0 < a.N; n0 += (int64_t)gridDim.x * 32) {
     const int64_t n = n0 + lane;
     const bool valid_seq = n < a.N;
     const int rows = (int)(a.N - n0 < 32 ? a.N - n0 : 32);
@@ -255,6 +257,8 @@ __global__ void __launch_bounds__(128, 8) lev_pack_seqfirst_kernel(const LevPack
         lev_pack_warp_reduce(flags, umax, nmax);
         if (lane == 0) lev_pack_publish(a, flags | blk_flags, umax, nmax, cur_u, cur_n);
     }
+    __syncthreads();  // the next block re-initialises the shared scalars
+    }
 }
 
 // ---- any other layout: one warp per sequence, lanes along the sequence axis -------------
@@ -329,7 +333,12 @@ int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int inc
     const bool seqfirst = (t->stride_n == 1 && t->stride_t != 1 && t->stride_t > -((int64_t)1 << 31) &&
                            t->stride_t < ((int64_t)1 << 31));
     const dim3 block(128, 1, 1);
-    const dim3 grid((unsigned)(seqfirst ? (t->N + 31) / 32 : (t->N + 3) / 4), 1, 1);
+    int64_t nblk = seqfirst ? (t->N + 31) / 32 : (t->N + 3) / 4;
+    if (seqfirst && bv_check && nblk > 148 * 8) {  // stand-by duty: equal shares, 8 CTAs per SM
+        const int64_t per_cta = (nblk + 148 * 8 - 1) / (148 * 8);
+        nblk = (nblk + per_cta - 1) / per_cta;
+    }
+    const dim3 grid((unsigned)nblk, 1, 1);
 #define LEV_PACK_CASE(TT)                                                \
     if (seqfirst)                                                        \
         lev_launch(lev_pack_seqfirst_kernel<TT>, grid, block, 0, st, a); \
