@@ -106,18 +106,13 @@ __device__ __forceinline__ unsigned lev_bv_set_byte(unsigned word, unsigned byte
 // ---------------------------------------------------------------------------------------
 // uid pre-pass
 // ---------------------------------------------------------------------------------------
+// One block of 32 consecutive pairs, one warp.  Returns false if the warp should stop (it
+// vetoed the path for the whole batch).
 template <typename TT>
-__global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_uid_kernel(const LevBvArgs a) {
-    if (a.check_state && !lev_bv_took(a.state)) return;  // another warp has vetoed already
-    LEV_DYN_SMEM(int, smem);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nb = 1 << a.slots_log2;  // buckets per table
+__device__ __forceinline__ bool lev_bv_uid_block(const LevBvArgs& a, int4* keys4, unsigned* posw,
+                                                 const int nb, const int64_t block, const int lane) {
     constexpr int NT = LEV_BV_NT;
-    // per warp: keys [nb][NT] int4 (4 ways), then posw [nb][NT] words (4 position bytes)
-    int4* keys4 = reinterpret_cast<int4*>(smem + (size_t)warp * (nb * NT * 5));
-    unsigned* posw = reinterpret_cast<unsigned*>(keys4 + nb * NT);
-    const int64_t pair = ((int64_t)blockIdx.x * LEV_BV_WARPS + warp) * 32 + lane;
-    if (pair - lane >= a.P) return;  // whole warp past the batch
+    const int64_t pair = block * 32 + lane;
     const bool valid = pair < a.P;
     const int64_t pc = valid ? pair : (int64_t)a.P - 1;  // lanes past the batch shadow the last pair
     const int64_t rcol = pc / a.ref_group;
@@ -184,7 +179,7 @@ __global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_uid_kernel(const Lev
                 const unsigned same = __ballot_sync(LEV_FULL_MASK, lane > 0 && !(dacc != 0 && other));
                 if (32 - __popc(same) > LEV_BV_NT) {
                     if (lane == 0) atomicExch(a.state + 3, 1);
-                    return;
+                    return false;
                 }
             }
         }
@@ -194,7 +189,7 @@ __global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_uid_kernel(const Lev
     const LevBvRuns runs = lev_bv_runs(!diff, lane);
     if (a.check_state && runs.count > LEV_BV_NT) {
         if (lane == 0) atomicExch(a.state + 3, 1);
-        return;
+        return false;
     }
     if (valid) a.lead[pair] = (unsigned char)runs.lead;
 
@@ -412,6 +407,26 @@ __global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_uid_kernel(const Lev
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) myflags |= __shfl_xor_sync(LEV_FULL_MASK, myflags, o);
     if (lane == 0 && myflags != 0 && a.flags != nullptr) atomicOr(a.flags, myflags);
+    __syncwarp();  // the next block of this warp reuses the tables
+    return true;
+}
+
+// Warps are independent and walk the blocks of 32 pairs with a grid stride: the grid stays
+// small (a vetoed launch, or this kernel standing by, drains in a few microseconds).
+template <typename TT>
+__global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_uid_kernel(const LevBvArgs a) {
+    LEV_DYN_SMEM(int, smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nb = 1 << a.slots_log2;  // buckets per table
+    // per warp: keys [nb][NT] int4 (4 ways), then posw [nb][NT] words (4 position bytes)
+    int4* keys4 = reinterpret_cast<int4*>(smem + (size_t)warp * (nb * LEV_BV_NT * 5));
+    unsigned* posw = reinterpret_cast<unsigned*>(keys4 + nb * LEV_BV_NT);
+    const int64_t nblocks = ((int64_t)a.P + 31) / 32;
+    for (int64_t block = (int64_t)blockIdx.x * LEV_BV_WARPS + warp; block < nblocks;
+         block += (int64_t)gridDim.x * LEV_BV_WARPS) {
+        if (a.check_state && !lev_bv_took(a.state)) return;  // some warp has vetoed
+        if (!lev_bv_uid_block<TT>(a, keys4, posw, nb, block, lane)) return;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -478,16 +493,10 @@ __device__ __forceinline__ int lev_bv_step(const unsigned (&eq)[W], unsigned (&p
 }
 
 template <int W, int MODE>
-__global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_dp_kernel(const LevBvArgs a) {
-    if (a.check_state && !lev_bv_took(a.state)) return;
-    LEV_DYN_SMEM(unsigned, smem);
+__device__ __forceinline__ void lev_bv_dp_block(const LevBvArgs& a, unsigned* M, const int tab_words,
+                                                const int64_t block, const int lane) {
     constexpr int NT = LEV_BV_NT;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // per warp: Peq[(R + 1)][W][NT tables]; row R stays zero (no match)
-    const int tab_words = (a.R + 1) * W * NT;
-    unsigned* M = smem + (size_t)warp * tab_words;
-    const int64_t pair = ((int64_t)blockIdx.x * LEV_BV_WARPS + warp) * 32 + lane;
-    if (pair - lane >= a.P) return;  // whole warp past the batch
+    const int64_t pair = block * 32 + lane;
     const bool valid = pair < a.P;
     const int64_t pc = valid ? pair : (int64_t)a.P - 1;
     const int r = a.ref_len[pc / a.ref_group], h = a.hyp_len[pc];
@@ -591,6 +600,21 @@ __global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_dp_kernel(const LevB
             a.out[pair] = val;
         }
     }
+    __syncwarp();  // the next block of this warp reuses the tables
+}
+
+template <int W, int MODE>
+__global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_dp_kernel(const LevBvArgs a) {
+    if (a.check_state && !lev_bv_took(a.state)) return;
+    LEV_DYN_SMEM(unsigned, smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // per warp: Peq[(R + 1)][W][NT tables]; row R stays zero (no match)
+    const int tab_words = (a.R + 1) * W * LEV_BV_NT;
+    unsigned* M = smem + (size_t)warp * tab_words;
+    const int64_t nblocks = ((int64_t)a.P + 31) / 32;
+    for (int64_t block = (int64_t)blockIdx.x * LEV_BV_WARPS + warp; block < nblocks;
+         block += (int64_t)gridDim.x * LEV_BV_WARPS)
+        lev_bv_dp_block<W, MODE>(a, M, tab_words, block, lane);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -626,18 +650,28 @@ bool lev_bitvec_eligible(const b200lev_tokens_t* ref, const b200lev_tokens_t* hy
     return true;
 }
 
+// CTAs for P pairs: every CTA an equal number of 128-pair blocks, at most `per_sm` x 148 CTAs
+static unsigned lev_bv_grid(int64_t P, int per_sm) {
+    int64_t n = (P + 32 * LEV_BV_WARPS - 1) / (32 * LEV_BV_WARPS);
+    const int64_t cap = (int64_t)148 * per_sm;
+    if (n > cap) {
+        const int64_t each = (n + cap - 1) / cap;
+        n = (n + each - 1) / each;
+    }
+    return (unsigned)n;
+}
+
 template <typename TT>
 static void lev_bv_launch_uid(const LevBvArgs& a, size_t smem, cudaStream_t st) {
     auto kern = lev_bv_uid_kernel<TT>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    lev_launch(kern, dim3((unsigned)((a.P + 32 * LEV_BV_WARPS - 1) / (32 * LEV_BV_WARPS))),
-               dim3(32 * LEV_BV_WARPS), smem, st, a);
+    lev_launch(kern, dim3(lev_bv_grid(a.P, 10)), dim3(32 * LEV_BV_WARPS), smem, st, a);
 }
 
 template <int W>
 static void lev_bv_launch_dp(const LevBvArgs& a, cudaStream_t st) {
     const size_t smem = sizeof(unsigned) * (size_t)(a.R + 1) * W * LEV_BV_NT * LEV_BV_WARPS;
-    const dim3 grid((unsigned)((a.P + 32 * LEV_BV_WARPS - 1) / (32 * LEV_BV_WARPS))), block(32 * LEV_BV_WARPS);
+    const dim3 grid(lev_bv_grid(a.P, 16)), block(32 * LEV_BV_WARPS);
     if (a.mode == LEV_MODE_PREFIX) {
         auto kern = lev_bv_dp_kernel<W, LEV_MODE_PREFIX>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

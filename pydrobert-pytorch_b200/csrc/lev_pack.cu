@@ -42,6 +42,8 @@ struct LevPackArgs {
     int ref_group, G;
     int* ghist;
     int bv_check;  // exit if the bit-vector kernels, enqueued first, took the batch
+    int slice;     // positions per warp and chunk: 32, or 16 / 8 for T <= 64 / 32
+    int hist_bins;  // > 0: a CTA walks many blocks and collects the histogram in shared memory
 };
 
 // ---- epilogue pieces shared by both layouts ----------------------------------------------
@@ -49,7 +51,7 @@ struct LevPackArgs {
 // (class, length) histogram for the group kernel's global bucketing (the reference lengths
 // were produced by the launch before this one).  Returns the warning flags it raises.
 __device__ __forceinline__ int lev_pack_owner(const LevPackArgs& a, int ref_len, int64_t n,
-                                              int first) {
+                                              int first, int* cta_hist = nullptr) {
     int len = first, flags = 0;
     if (a.has_eos && a.include_eos) {
         if (len == (int)a.T)
@@ -58,7 +60,8 @@ __device__ __forceinline__ int lev_pack_owner(const LevPackArgs& a, int ref_len,
             len += 1;
     }
     a.lens[n] = len;
-    if (a.ghist != nullptr) atomicAdd(&a.ghist[lev_group_bin(ref_len, len, a.G, (int)a.T)], 1);
+    if (a.ghist != nullptr)
+        atomicAdd(&(cta_hist ? cta_hist : a.ghist)[lev_group_bin(ref_len, len, a.G, (int)a.T)], 1);
     return flags;
 }
 
@@ -116,16 +119,17 @@ struct LevPackSeen {
     int first, wacc, lo, hi;
 };
 
-// One 32-position slice of one sequence: 2 batches of NB coalesced loads, tokens narrowed
-// into the lane's row of the shared tile.  GUARD adds the t < T predicate (last slice only).
-template <typename TT, bool GUARD>
+// One SW-position slice of one sequence: batches of NB coalesced loads, tokens narrowed into
+// the lane's row of the shared tile.  GUARD adds the t < T predicate (last slice only).
+// SW = 32 for long sequences; 16 / 8 keep all four warps busy when T <= 64 / 32.
+template <typename TT, bool GUARD, int SW>
 __device__ __forceinline__ void lev_pack_slice(const TT* __restrict__ src, int st, int t0,
                                                int Ti, bool eos_fast, int eos32, int* trow,
                                                LevPackSeen& seen) {
-    constexpr int NB = LEV_PACK_NB;
+    constexpr int NB = SW < LEV_PACK_NB ? SW : LEV_PACK_NB;
     LEV_OPAQUE_PTR(src);
 #pragma unroll
-    for (int h = 0; h < 32 / NB; ++h) {
+    for (int h = 0; h < SW / NB; ++h) {
         TT raw[NB];
 #pragma unroll
         for (int u = 0; u < NB; ++u)
@@ -170,6 +174,11 @@ __global__ void __launch_bounds__(128, 8) lev_pack_seqfirst_kernel(const LevPack
     __shared__ int first_s[32];
     __shared__ unsigned blk_u, blk_n;
     __shared__ int blk_flags;
+    // A million sequences fall into a few hundred (class, length) bins: one global atomic per
+    // sequence queues up behind the others on the same address (+120 us at 1 M x T=31).  A CTA
+    // that walks many blocks counts in shared memory and adds each bin once at the end.
+    LEV_DYN_SMEM(int, cta_hist);
+    for (int b = threadIdx.x; b < a.hist_bins; b += blockDim.x) cta_hist[b] = 0;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     // a CTA walks blocks of 32 sequences (a few each: the grid stays small, so that standing by
     // for the bit-vector path costs a 1000-CTA launch and not one of N / 32 CTAs)
@@ -195,22 +204,35 @@ __global__ void __launch_bounds__(128, 8) lev_pack_seqfirst_kernel(const LevPack
         blk_flags = 0;
     }
     __syncthreads();
-    for (int tb = 0; tb < Ti; tb += LEV_PACK_CHUNK) {
-        const int t0 = tb + 32 * w;
-        if (t0 + 32 <= Ti)
-            lev_pack_slice<TT, false>(seq + (int64_t)t0 * st, st, t0, Ti, eos_fast, eos32, &tile[lane][32 * w], seen);
-        else
-            lev_pack_slice<TT, true>(seq + (int64_t)t0 * st, st, t0, Ti, eos_fast, eos32, &tile[lane][32 * w], seen);
+    const int sw = a.slice, chunk = 4 * sw;
+    for (int tb = 0; tb < Ti; tb += chunk) {
+        const int t0 = tb + sw * w;
+        const TT* sp = seq + (int64_t)t0 * st;
+        int* trow = &tile[lane][sw * w];
+        const bool full = t0 + sw <= Ti;
+#define LEV_PACK_SLICE(SW_)                                                                      \
+    if (full)                                                                                    \
+        lev_pack_slice<TT, false, SW_>(sp, st, t0, Ti, eos_fast, eos32, trow, seen);             \
+    else                                                                                         \
+        lev_pack_slice<TT, true, SW_>(sp, st, t0, Ti, eos_fast, eos32, trow, seen);
+        if (sw == 32) {
+            LEV_PACK_SLICE(32)
+        } else if (sw == 16) {
+            LEV_PACK_SLICE(16)
+        } else {
+            LEV_PACK_SLICE(8)
+        }
+#undef LEV_PACK_SLICE
         __syncthreads();
-        if (threadIdx.x == 0 && tb + LEV_PACK_CHUNK >= Ti) {
+        if (threadIdx.x == 0 && tb + chunk >= Ti) {
             // a recent copy of the range words; the load completes under the row stores
             cur_u = lev_ldg_l2(reinterpret_cast<const unsigned*>(a.state) + 1);
             cur_n = lev_ldg_l2(reinterpret_cast<const unsigned*>(a.state) + 2);
         }
         // rows are 16-byte aligned and padded to a multiple of 4 (8 for the 16-bit table);
         // positions T..Tp-1 receive zeros
-        const int width = Tp - tb < LEV_PACK_CHUNK ? Tp - tb : LEV_PACK_CHUNK;
-        const int width16 = Tp16 - tb < LEV_PACK_CHUNK ? Tp16 - tb : LEV_PACK_CHUNK;
+        const int width = Tp - tb < chunk ? Tp - tb : chunk;
+        const int width16 = Tp16 - tb < chunk ? Tp16 - tb : chunk;
         for (int r = w; r < rows; r += 4) {
             int32_t* __restrict__ row32 = a.packed + (n0 + r) * a.Tp + tb;
             for (int c = lane; 4 * c < width; c += 32)
@@ -232,8 +254,8 @@ __global__ void __launch_bounds__(128, 8) lev_pack_seqfirst_kernel(const LevPack
         // rare: a low-word match may be a wide token (or eos itself is wide) -- rescan this
         // lane's slices with the exact comparison
         seen.first = Ti;
-        for (int tb = 0; tb < Ti; tb += LEV_PACK_CHUNK)
-            for (int t = tb + 32 * w; t < Ti && t < tb + 32 * w + 32; ++t)
+        for (int tb = 0; tb < Ti; tb += chunk)
+            for (int t = tb + sw * w; t < Ti && t < tb + sw * w + sw; ++t)
                 if ((int64_t)seq[(int64_t)t * st] == a.eos) {
                     seen.first = t < seen.first ? t : seen.first;
                     break;
@@ -252,13 +274,15 @@ __global__ void __launch_bounds__(128, 8) lev_pack_seqfirst_kernel(const LevPack
     }
     __syncthreads();
     if (w == 0) {
-        int flags = valid_seq ? lev_pack_owner(a, ref_len, n, first_s[lane]) : 0;
+        int flags = valid_seq ? lev_pack_owner(a, ref_len, n, first_s[lane], a.hist_bins ? cta_hist : nullptr) : 0;
         unsigned umax = blk_u, nmax = blk_n;
         lev_pack_warp_reduce(flags, umax, nmax);
         if (lane == 0) lev_pack_publish(a, flags | blk_flags, umax, nmax, cur_u, cur_n);
     }
     __syncthreads();  // the next block re-initialises the shared scalars
     }
+    for (int b = threadIdx.x; b < a.hist_bins; b += blockDim.x)
+        if (cta_hist[b] != 0) atomicAdd(&a.ghist[b], cta_hist[b]);
 }
 
 // ---- any other layout: one warp per sequence, lanes along the sequence axis -------------
@@ -328,20 +352,32 @@ int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int inc
     a.G = G;
     a.ghist = ghist;
     a.bv_check = bv_check;
+    a.slice = t->T <= 32 ? 8 : (t->T <= 64 ? 16 : 32);
     // unit stride along the batch axis => register-tile transpose; otherwise (batch_first,
     // or an arbitrary view) one warp per sequence.
     const bool seqfirst = (t->stride_n == 1 && t->stride_t != 1 && t->stride_t > -((int64_t)1 << 31) &&
                            t->stride_t < ((int64_t)1 << 31));
     const dim3 block(128, 1, 1);
     int64_t nblk = seqfirst ? (t->N + 31) / 32 : (t->N + 3) / 4;
-    if (seqfirst && bv_check && nblk > 148 * 8) {  // stand-by duty: equal shares, 8 CTAs per SM
-        const int64_t per_cta = (nblk + 148 * 8 - 1) / (148 * 8);
+    int64_t cap = 148 * 8;
+    if (const char* e = getenv("B200LEV_PACK_CTAS")) cap = atoll(e) > 0 ? atoll(e) : cap;  // tests
+    a.hist_bins = 0;
+    size_t smem = 0;
+    // few CTAs walking many blocks: on stand-by duty (a small grid exits faster), and for big
+    // batches, where the histogram is then collected per CTA
+    if (seqfirst && nblk > cap && (bv_check || nblk >= 8 * cap)) {
+        const int64_t per_cta = (nblk + cap - 1) / cap;
         nblk = (nblk + per_cta - 1) / per_cta;
+        const int64_t bins = (int64_t)LEV_GROUP_NCLS * (t->T + 1);
+        if (ghist != nullptr && per_cta >= 4 && bins <= 8192) {
+            a.hist_bins = (int)bins;
+            smem = sizeof(int) * (size_t)bins;
+        }
     }
     const dim3 grid((unsigned)nblk, 1, 1);
 #define LEV_PACK_CASE(TT)                                                \
     if (seqfirst)                                                        \
-        lev_launch(lev_pack_seqfirst_kernel<TT>, grid, block, 0, st, a); \
+        lev_launch(lev_pack_seqfirst_kernel<TT>, grid, block, smem, st, a); \
     else                                                                 \
         lev_launch(lev_pack_rows_kernel<TT>, grid, block, 0, st, a);
     switch (t->elem_bytes) {

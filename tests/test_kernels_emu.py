@@ -212,11 +212,50 @@ def test_bitvec_device_selected(F, shape, shared, monkeypatch):
     PC.check_nbest_batch(F, DEV, seed=R + H, R=R, H=H, n_utts=n_utts, nbest=nbest, shared=shared)
 
 
+def test_bitvec_degenerate_shapes(F, monkeypatch):
+    """Forced bit-vector path on the shapes the reference's tests poke at: empty hypotheses,
+    one-token references, batches that are not a multiple of 32, all-eos columns."""
+    monkeypatch.setenv("B200LEV_BITVEC", "1")
+    monkeypatch.setenv("B200LEV_BITVEC_MIN_PAIRS", "1")
+    from oracle import oracle as O
+
+    h = torch.tensor([[1, 2, 3], [2, 2, 2]])
+    z = torch.zeros((0, 3), dtype=torch.long)
+    assert F.edit_distance(h, z).tolist() == [2.0, 2.0, 2.0]  # empty hyp: all deletions
+    assert F.prefix_edit_distances(h, z).shape == (1, 3)
+    assert F.prefix_edit_distances(h, z).tolist() == [[2.0, 2.0, 2.0]]
+    rng = np.random.default_rng(2)
+    for R, H, N in ((1, 1, 1), (1, 40, 33), (128, 1, 31), (7, 3, 65)):
+        ref = rng.integers(0, 3, size=(R, N))
+        hyp = rng.integers(0, 3, size=(H, N))
+        ref[:, 0] = 0  # eos everywhere: an empty reference (norm: SM:360-366)
+        for kw in (dict(eos=0, include_eos=False, norm=True), dict(eos=0, include_eos=True, norm=False),
+                   dict(eos=None, norm=True)):
+            exp = O.prefix_error_rates(ref, hyp, padding=-5, **kw)
+            act = F.prefix_error_rates(torch.from_numpy(ref), torch.from_numpy(hyp), padding=-5,
+                                       warn=False, **kw)
+            PC.assert_same(act, exp, True, f"degenerate {R}x{H}x{N} {kw}")
+            exp = O.error_rate(ref, hyp, **kw)
+            act = F.error_rate(torch.from_numpy(ref), torch.from_numpy(hyp), warn=False, **kw)
+            PC.assert_same(act, exp, True, f"degenerate final {R}x{H}x{N} {kw}")
+
+
 def test_bitvec_golden(F, golden_sm, monkeypatch):
     monkeypatch.setenv("B200LEV_BITVEC", "1")
     monkeypatch.setenv("B200LEV_BITVEC_MIN_PAIRS", "1")
     names = [n for n in golden_sm.params if n.startswith("s")] + ["cfg1", "cfg2r", "cfg4r", "wide"]
     assert PC.check_golden_string_matching(F, DEV, golden_sm, names) >= 300
+
+
+def test_pack_persistent_ctas_and_cta_histogram(F, monkeypatch):
+    """Big batches: a pack CTA walks many blocks of 32 sequences and collects the (class,
+    length) histogram in shared memory (forced here with a 2-CTA grid)."""
+    monkeypatch.setenv("B200LEV_GROUP_MIN_PAIRS", "1")
+    monkeypatch.setenv("B200LEV_PACK_CTAS", "2")
+    monkeypatch.setenv("B200LEV_BITVEC", "0")
+    for R, H, N in ((31, 31, 700), (70, 40, 530)):
+        PC.check_vs_oracle(F, DEV, seed=R + N, R=R, H=H, N=N, V=6, costs=(1, 1, 1), do_mask=False,
+                           include_eos=True, norm=True, min_frac=0.1)
 
 
 def test_group_kernel_n_best_and_wide(F, monkeypatch):
