@@ -133,10 +133,12 @@ __device__ __forceinline__ bool lev_bv_uid_block(const LevBvArgs& a, int4* keys4
         const bool other = prev_col != (int)rcol;
         const int eos_lo = (int)a.eos, eos_hi = (int)(a.eos >> 32);
         int dacc = 0, wacc = 0;  // differences to the left neighbour / to a sign extension
-        auto observe = [&](const TT (&buf)[8], int t0) {
+        // (this pass needs no table yet, so its registers go into deeper batches: halves of 16)
+        constexpr int DH = 16;
+        auto observe = [&](const TT (&buf)[DH], int t0) {
             unsigned eos_bits = 0, empty_bits = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < DH; ++k) {
                 const int64_t x = (int64_t)buf[k];
                 const int lo = (int)x, hi = (int)(x >> 32);
                 dacc |= lo ^ __shfl_up_sync(LEV_FULL_MASK, lo, 1);
@@ -149,30 +151,21 @@ __device__ __forceinline__ bool lev_bv_uid_block(const LevBvArgs& a, int4* keys4
             }
             // positions past R were loaded as 0 (= what the neighbour loaded): mask them out
             const int live = a.R - t0;
-            if (live < 8) eos_bits &= live > 0 ? (1u << live) - 1u : 0u;
+            if (live < DH) eos_bits &= live > 0 ? (1u << live) - 1u : 0u;
             if (a.has_eos && eos_bits != 0 && first_eos == a.R) first_eos = t0 + __ffs((int)eos_bits) - 1;
             if (empty_bits) exact0 = 1;
         };
         const TT* rp = rsrc;
-        TT bufA[8], bufB[8];
+        TT bufA[DH], bufB[DH];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) bufA[k] = (k < a.R) ? rp[(int64_t)k * rst] : (TT)0;
+        for (int k = 0; k < DH; ++k) bufA[k] = (k < a.R) ? rp[(int64_t)k * rst] : (TT)0;
 #pragma unroll 1
-        for (int t0 = 0; t0 < a.R; t0 += 16) {
+        for (int t0 = 0; t0 < a.R; t0 += 2 * DH) {
             LEV_OPAQUE_PTR(rp);
-            // 8 loads per lane in flight do not cover DRAM latency at 20 warps per SM: ask L2
-            // for the rows three groups ahead (a hint: no register, nothing to wait for)
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-                if (t0 + 48 + k < a.R) lev_prefetch_l2(rp + (int64_t)(48 + k) * rst);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) bufB[k] = (t0 + 8 + k < a.R) ? rp[(int64_t)(8 + k) * rst] : (TT)0;
+            for (int k = 0; k < DH; ++k)
+                bufB[k] = (t0 + DH + k < a.R) ? rp[(int64_t)(DH + k) * rst] : (TT)0;
             observe(bufA, t0);
-            rp += 16 * (int64_t)rst;
-            LEV_OPAQUE_PTR(rp);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) bufA[k] = (t0 + 16 + k < a.R) ? rp[(int64_t)k * rst] : (TT)0;
-            observe(bufB, t0 + 8);
             if (a.check_state && t0 == 0) {
                 // unrelated references differ within their first tokens: such a batch is
                 // handed back to the wavefront path after one group of loads per warp
@@ -182,6 +175,12 @@ __device__ __forceinline__ bool lev_bv_uid_block(const LevBvArgs& a, int4* keys4
                     return false;
                 }
             }
+            rp += 2 * DH * (int64_t)rst;
+            LEV_OPAQUE_PTR(rp);
+#pragma unroll
+            for (int k = 0; k < DH; ++k)
+                bufA[k] = (t0 + 2 * DH + k < a.R) ? rp[(int64_t)k * rst] : (TT)0;
+            observe(bufB, t0 + DH);
         }
         diff = dacc != 0 && other;
         if (wacc != 0) exact0 = 1;
