@@ -64,16 +64,11 @@ struct LevBvArgs {
 // position bytes settle a probe -- no loop, so 32 lanes with 32 different tokens cost the same
 // as one.  A run leader builds its table with the first of a few multipliers under which no
 // bucket overflows (load <= 1 token per bucket on average: a couple of tries at most).
-constexpr int LEV_BV_TRIES = 6;
+// (a build with R = 128 distinct tokens in 128 buckets fails with p = 0.38: 16 tries leave
+// 2e-7 of the runs to the slow exact path; the typical R ~ 100 needs 1.2 tries on average)
+constexpr int LEV_BV_TRIES = 16;
 __device__ __forceinline__ unsigned lev_bv_mult(int seed) {
-    switch (seed) {
-        case 0: return 0x9E3779B1u;
-        case 1: return 0x85EBCA6Bu;
-        case 2: return 0xC2B2AE35u;
-        case 3: return 0x27D4EB2Fu;
-        case 4: return 0x165667B1u;
-        default: return 0xD3A2646Du;
-    }
+    return (0x9E3779B1u * (2u * (unsigned)seed + 1u)) ^ ((unsigned)seed * 0x85EBCA6Au);
 }
 __device__ __forceinline__ unsigned lev_bv_hash(int v, unsigned mult, int buckets_log2) {
     return ((unsigned)v * mult) >> (32 - buckets_log2);
@@ -186,7 +181,9 @@ __device__ __forceinline__ bool lev_bv_uid_block(const LevBvArgs& a, int4* keys4
         if (wacc != 0) exact0 = 1;
     }
     const LevBvRuns runs = lev_bv_runs(!diff, lane);
-    if (a.check_state && runs.count > LEV_BV_NT) {
+    // device-selected mode: more runs than tables, or reference tokens the 32-bit keys cannot
+    // hold (the exact path below is correct but slow: leave those to the wavefront kernels)
+    if (a.check_state && (runs.count > LEV_BV_NT || __any_sync(LEV_FULL_MASK, exact0 != 0))) {
         if (lane == 0) atomicExch(a.state + 3, 1);
         return false;
     }

@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(256) lev_warp_kernel(const LevParams p) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
-    const int Hs = p.H + 64;
+    // (even: every warp's slice starts 8-byte aligned, the 64-bit-token path stores int64)
+    const int Hs = (p.H + 65) & ~1;
     constexpr int NB = LevBufs<V, COUNT, MODE>::NB;
     int* hyp_s = smem + (size_t)warp * (2 + NB) * Hs;  // 2*Hs ints: room for int64 tokens
     V* bufs = reinterpret_cast<V*>(hyp_s + 2 * Hs);
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(256) lev_warp_kernel(const LevParams p) {
 template <typename V, bool COUNT, int MODE, int CMASK>
 static int lev_launch_variant(const LevParams& p, cudaStream_t st) {
     constexpr int NB = LevBufs<V, COUNT, MODE>::NB;
-    const size_t per_warp = (size_t)(2 + NB) * (size_t)(p.H + 64) * sizeof(int);
+    const size_t per_warp = (size_t)(2 + NB) * (size_t)((p.H + 65) & ~1) * sizeof(int);
     const size_t budget = 200 * 1024;
     if (per_warp > budget) {
         lev_set_error("hypothesis length %d needs %zu bytes of shared memory per warp (max %zu)",

@@ -214,7 +214,7 @@ def check_wide_tokens(F, dev):
                               O.edit_distance(ref.astype(np.int32), hyp.astype(np.int32), eos=0))
 
 
-def check_nbest_batch(F, dev, seed, R, H, n_utts, nbest, V=30, shared=True, **kw):
+def check_nbest_batch(F, dev, seed, R, H, n_utts, nbest, V=30, shared=True, wide=False, **kw):
     """prefix_error_rates / error_rate on an n-best shaped batch: every reference repeated
     `nbest` times along the batch axis (`shared`), or a batch of unrelated references -- the two
     shapes between which the device-side path selection of lev_bitvec.cu decides."""
@@ -225,6 +225,10 @@ def check_nbest_batch(F, dev, seed, R, H, n_utts, nbest, V=30, shared=True, **kw
         ref = np.repeat(ref, nbest, axis=1)
     else:
         ref = random_tokens(rng, R, n_utts * nbest, V, 0, -2, 0, 0.1)
+    if wide:  # tokens outside int32 whose low words collide with ordinary tokens
+        ref[min(3, R - 1), :nbest] = (1 << 40) + 5
+        hyp[min(2, H - 1), 1] = (1 << 40) + 5
+        hyp[min(2, H - 1), 2] = 5
     tr, th = torch.from_numpy(ref).to(dev), torch.from_numpy(hyp).to(dev)
     for func, okw in (("prefix_error_rates", dict(padding=-7)), ("error_rate", {}),
                       ("prefix_edit_distances", dict(padding=-7, exclude_last=True)),

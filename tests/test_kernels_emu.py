@@ -210,6 +210,9 @@ def test_bitvec_device_selected(F, shape, shared, monkeypatch):
     monkeypatch.setenv("B200LEV_GROUP_MIN_PAIRS", "1")
     R, H, n_utts, nbest = shape
     PC.check_nbest_batch(F, DEV, seed=R + H, R=R, H=H, n_utts=n_utts, nbest=nbest, shared=shared)
+    # a reference token outside int32: vetoed on the device, the 64-bit wavefront kernel answers
+    PC.check_nbest_batch(F, DEV, seed=R + H, R=R, H=H, n_utts=n_utts, nbest=nbest, shared=shared,
+                         wide=True)
 
 
 def test_bitvec_degenerate_shapes(F, monkeypatch):
