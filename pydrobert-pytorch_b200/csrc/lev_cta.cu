@@ -405,9 +405,11 @@ static int lev_cta_launch_one(const LevParams& p, cudaStream_t st) {
 // Returns 1 if the CTA-per-pair kernel took the job, 0 if it does not apply, < 0 on error.
 int lev_launch_cta(const LevParams& p, int mode, bool count_mode, bool float_path, cudaStream_t st) {
     if (mode == LEV_MODE_MASK) return 0;
-    // worth it when one warp per pair cannot fill the chip (few pairs) or rows are long;
-    // B200LEV_CTA_KERNEL=0/1 forces the choice (tests)
-    bool use = (p.R >= 48) && ((int64_t)p.P < 148 * 16 || p.R > 512);
+    // worth it when rows are long: measured crossover against the warp-per-pair kernel
+    // (scripts/micro/k1_vs_k2.py, square pairs): R >= 400 for P <= 128, R >= 800 for
+    // P <= 1024, R >= 1600 at P = 2048; below R = 300 one warp per pair always wins (a
+    // 512 x 101 batch: 42 us against 88).  B200LEV_CTA_KERNEL=0/1 forces the choice (tests).
+    bool use = (p.R >= 640 && (int64_t)p.P <= 1536) || (p.R >= 384 && p.P <= 256) || p.R >= 1400;
     if (const char* e = getenv("B200LEV_CTA_KERNEL")) use = atoi(e) != 0;
     if (!use) return 0;
     if (!float_path) {
