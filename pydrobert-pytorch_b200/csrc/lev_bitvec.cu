@@ -525,7 +525,7 @@ __device__ __forceinline__ void lev_bv_dp_block(const LevBvArgs& a, unsigned* M,
                     if (j < r) {
                         const unsigned u = (q[k >> 2] >> (8 * (k & 3))) & 0xffu;
                         const int b = j + o;
-                        M[(u * W + (b >> 5)) * NT + tb] |= 1u << (b & 31);
+                        M[(u * NT + tb) * W + (b >> 5)] |= 1u << (b & 31);
                     }
                 }
             }
@@ -575,8 +575,23 @@ __device__ __forceinline__ void lev_bv_dp_block(const LevBvArgs& a, unsigned* M,
                 unsigned u = (q[k >> 2] >> (8 * (k & 3))) & 0xffu;
                 u = u < (unsigned)Z ? u : (unsigned)Z;
                 unsigned eq[W];
+                // a row's W words are adjacent: one 128-bit (W = 4) or 64-bit (W = 2) read; the
+                // lanes of a run read the same address (broadcast)
+                const unsigned* row = M + (u * NT + tb) * W;
+                if (W == 4) {
+                    const uint4 e = *reinterpret_cast<const uint4*>(row);
+                    eq[0] = e.x;
+                    eq[W > 1 ? 1 : 0] = e.y;
+                    eq[W > 2 ? 2 : 0] = e.z;
+                    eq[W > 3 ? 3 : 0] = e.w;
+                } else if (W == 2) {
+                    const uint2 e = *reinterpret_cast<const uint2*>(row);
+                    eq[0] = e.x;
+                    eq[W > 1 ? 1 : 0] = e.y;
+                } else {
 #pragma unroll
-                for (int w = 0; w < W; ++w) eq[w] = M[(u * W + w) * NT + tb];
+                    for (int w = 0; w < W; ++w) eq[w] = row[w];
+                }
                 score += lev_bv_step<W>(eq, pv, mv);
                 if (MODE == LEV_MODE_PREFIX) {
                     emit(i, score);
@@ -604,7 +619,7 @@ __global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_dp_kernel(const LevB
     if (a.check_state && !lev_bv_took(a.state)) return;
     LEV_DYN_SMEM(unsigned, smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // per warp: Peq[(R + 1)][W][NT tables]; row R stays zero (no match)
+    // per warp: Peq[(R + 1)][NT tables][W]; row R stays zero (no match)
     const int tab_words = (a.R + 1) * W * LEV_BV_NT;
     unsigned* M = smem + (size_t)warp * tab_words;
     const int64_t nblocks = ((int64_t)a.P + 31) / 32;
