@@ -217,6 +217,24 @@ const int32_t *b200lev_workspace_hyp_lens(const b200lev_tokens_t *ref,
 int b200lev_after_eos_mask(const int64_t *tokens, int64_t outer, int64_t T, int64_t inner,
                            int64_t eos, unsigned char *mask, void *stream);
 
+/* sequence_log_probs, tensor path (_decoding.py:1516-1548; "next #1" of the hot-path scope):
+ *   out[a, b] = sum over the steps t that count of log_softmax(logits[a, t, b, :])[hyp[a, t, b]]
+ * A step counts if its token lies in [0, V) and t <= the first eos of the sequence (a, b)
+ * (has_eos; the eos step itself counts).  logits: contiguous (outer, T, inner, V) of `dtype`
+ * (B200LEV_F32/F16/BF16/F64); hyp: contiguous int64 (outer, T, inner); out: (outer, inner) in
+ * the dtype of logits.  Scratch supplied by the caller: len int32[outer*inner]; row_lp and
+ * row_lse, (outer*T*inner) elements of the ACCUMULATION type (fp32; fp64 for F64) -- row_lse and
+ * len are what the backward call needs.  Backward: grad_logits (same shape/dtype as logits) =
+ * grad_out[a, b] * (onehot(hyp) - softmax) on the steps that count, 0 elsewhere. */
+int b200lev_seqlp_forward(const void *logits, int32_t dtype, int64_t outer, int64_t T,
+                          int64_t inner, int64_t V, const int64_t *hyp, int32_t has_eos,
+                          int64_t eos, int32_t *len, void *row_lp, void *row_lse, void *out,
+                          void *stream);
+int b200lev_seqlp_backward(const void *logits, int32_t dtype, int64_t outer, int64_t T,
+                           int64_t inner, int64_t V, const int64_t *hyp, const int32_t *len,
+                           const void *row_lse, const void *grad_out, void *grad_logits,
+                           void *stream);
+
 /* Host-side plumbing for callers whose tensors live in HOST memory (the reference API accepts
  * CPU tensors: SM:146 has no device requirement): one strided 2-D copy between host and
  * device on `stream`, so that a caller can move a COLUMN block of a (T, N) tensor -- all

@@ -385,3 +385,43 @@ def minimum_error_rate_loss(
     ge = go * er
     grad = p * (ge - (p * ge).sum(1, keepdims=True))
     return loss, grad
+
+
+def sequence_log_probs(logits, hyp, dim=0, eos=None, grad_out=None):
+    """float64 restatement of _sequence_log_probs_tensor (_decoding.py:1516-1548).
+
+    ``logits`` (A*, T, B*, V), ``hyp`` (A*, T, B*) int.  A step counts if its token is in
+    [0, V) (:1530) and it is not past the first eos (:1531-1544, the eos step counts).
+    Returns the (A*, B*) sums (:1548); with ``grad_out`` also d(sum . grad_out)/d logits."""
+    logits = np.asarray(logits, dtype=np.float64)
+    hyp = np.asarray(hyp)
+    nd = hyp.ndim
+    if dim < -nd or dim > nd - 1:
+        raise RuntimeError(
+            "Dimension out of range (expected to be in range of [{}, {}], but "
+            "got {})".format(-nd, nd - 1, dim))
+    dim = (nd + dim) % nd
+    V = logits.shape[-1]
+    hyp_m = np.moveaxis(hyp, dim, 0)              # (T, rest...)
+    z = np.moveaxis(logits, dim, 0)               # (T, rest..., V)
+    T = hyp_m.shape[0]
+    m = z.max(axis=-1, keepdims=True)
+    m = np.where(np.isfinite(m), m, 0.0)
+    lse = m[..., 0] + np.log(np.exp(z - m).sum(axis=-1))
+    ok = (hyp_m >= 0) & (hyp_m < V)
+    if eos is not None:
+        is_eos = hyp_m == eos
+        seen_before = np.cumsum(is_eos, axis=0) - is_eos > 0   # an eos strictly before t
+        ok &= ~seen_before
+    tok = np.where(ok, hyp_m, 0)
+    picked = np.take_along_axis(z, tok[..., None], axis=-1)[..., 0]
+    lp = np.where(ok, picked - lse, 0.0)
+    out = lp.sum(axis=0)
+    if grad_out is None:
+        return out
+    g = np.asarray(grad_out, dtype=np.float64)
+    soft = np.exp(z - lse[..., None])
+    onehot = np.zeros_like(z)
+    np.put_along_axis(onehot, tok[..., None], 1.0, axis=-1)
+    gz = np.where(ok[..., None], g[None, ..., None] * (onehot - soft), 0.0)
+    return out, np.moveaxis(gz, 0, dim)

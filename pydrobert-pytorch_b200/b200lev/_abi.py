@@ -70,6 +70,10 @@ SIGNATURES = {
     "b200lev_workspace_ref_lens": (c_vp, [_PT, _PT, c_vp]),
     "b200lev_workspace_hyp_lens": (c_vp, [_PT, _PT, c_vp]),
     "b200lev_after_eos_mask": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "b200lev_seqlp_forward": (ctypes.c_int, [c_vp, c_i32, c_i64, c_i64, c_i64, c_i64, c_vp, c_i32,
+                                             c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b200lev_seqlp_backward": (ctypes.c_int, [c_vp, c_i32, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp,
+                                              c_vp, c_vp, c_vp, c_vp]),
     "b200lev_copy2d_async": (ctypes.c_int, [c_vp, c_sz, c_vp, c_sz, c_sz, c_sz, c_i32, c_vp]),
     "b200lev_profile": (ctypes.c_int, [ctypes.c_int]),
     "b200lev_profile_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.c_int]),

@@ -303,6 +303,72 @@ ocd_loss.register_autograd(_ocd_backward, setup_context=_ocd_setup)
 
 
 # ---------------------------------------------------------------------------------------
+# sequence_log_probs, tensor path (_decoding.py:1516-1548)
+# ---------------------------------------------------------------------------------------
+@torch.library.custom_op("b200lev::sequence_log_probs", mutates_args=())
+def sequence_log_probs(logits: Tensor, hyp: Tensor, eos: Optional[int]) -> Tuple[Tensor, Tensor, Tensor]:
+    """``logits`` (outer, T, inner, V) float, ``hyp`` (outer, T, inner) int64, both contiguous.
+    Returns ``(out (outer, inner), row_lse, len)``; the last two are saved for the backward."""
+    dev = _check_device(logits, hyp)
+    outer, T, inner, V = logits.shape
+    logits, hyp = logits.detach(), hyp.detach()
+    acc = _acc_dtype(logits)
+    length = torch.empty(max(outer * inner, 1), dtype=torch.int32, device=dev)
+    row_lp = torch.empty(max(outer * T * inner, 1), dtype=acc, device=dev)
+    row_lse = torch.empty(max(outer * T * inner, 1), dtype=acc, device=dev)
+    out = torch.zeros((outer, inner), dtype=logits.dtype, device=dev)
+    with _DeviceGuard(dev):
+        _abi.check(_abi.lib().b200lev_seqlp_forward(
+            logits.data_ptr(), _float_code(logits), outer, T, inner, V, hyp.data_ptr(),
+            int(eos is not None), 0 if eos is None else int(eos), length.data_ptr(),
+            row_lp.data_ptr(), row_lse.data_ptr(), out.data_ptr(), _stream(dev)))
+    return out, row_lse, length
+
+
+@sequence_log_probs.register_fake
+def _(logits, hyp, eos):
+    outer, T, inner, _ = logits.shape
+    acc = _acc_dtype(logits)
+    return (logits.new_empty((outer, inner)),
+            logits.new_empty((max(outer * T * inner, 1),), dtype=acc),
+            logits.new_empty((max(outer * inner, 1),), dtype=torch.int32))
+
+
+@torch.library.custom_op("b200lev::sequence_log_probs_backward", mutates_args=())
+def sequence_log_probs_backward(grad_out: Tensor, logits: Tensor, hyp: Tensor, row_lse: Tensor,
+                                length: Tensor) -> Tensor:
+    dev = _check_device(logits, hyp)
+    outer, T, inner, V = logits.shape
+    logits, hyp = logits.detach(), hyp.detach()
+    go = grad_out.detach().to(logits.dtype).contiguous()
+    grad = torch.empty_like(logits)
+    with _DeviceGuard(dev):
+        _abi.check(_abi.lib().b200lev_seqlp_backward(
+            logits.data_ptr(), _float_code(logits), outer, T, inner, V, hyp.data_ptr(),
+            length.data_ptr(), row_lse.data_ptr(), go.data_ptr(), grad.data_ptr(), _stream(dev)))
+    return grad
+
+
+@sequence_log_probs_backward.register_fake
+def _(grad_out, logits, hyp, row_lse, length):
+    return logits.new_empty(logits.shape)
+
+
+def _seqlp_setup(ctx, inputs, output):
+    logits, hyp, _ = inputs
+    _, row_lse, length = output
+    ctx.save_for_backward(logits, hyp, row_lse, length)
+
+
+def _seqlp_backward(ctx, g_out, g_lse, g_len):
+    logits, hyp, row_lse, length = ctx.saved_tensors
+    return sequence_log_probs_backward(g_out, logits, hyp, row_lse, length), None, None
+
+
+sequence_log_probs.register_autograd(_seqlp_backward, setup_context=_seqlp_setup)
+
+
+# ---------------------------------------------------------------------------------------
 # MWER epilogue (forward / backward)
 # ---------------------------------------------------------------------------------------
 @torch.library.custom_op("b200lev::mwer_loss", mutates_args=())

@@ -31,6 +31,7 @@ __all__ = [
     "optimal_completion",
     "prefix_edit_distances",
     "prefix_error_rates",
+    "sequence_log_probs",
 ]
 
 
@@ -428,3 +429,42 @@ def fill_after_eos(
     (tok_d, out_d), back = _offload(tokens, out)
     fill_mask = _ops.after_eos_mask(tok_d, int(eos), int(dim))
     return back(out_d.masked_fill(fill_mask, fill_))
+
+
+def sequence_log_probs(logits, hyp: torch.Tensor, dim: int = 0, eos: Optional[int] = None) -> torch.Tensor:
+    """Functional version of SequenceLogProbabilities, tensor path (_decoding.py:1516-1548,
+    1579-1633): joint log-probability of the token sequences in ``hyp`` (``(A*, T, B*)``, step
+    axis ``dim``) under the categorical distributions ``logits`` (``(A*, T, B*, V)``).  Tokens
+    outside ``[0, V)`` are padding; with ``eos`` the first eos step is the last one counted.
+    Differentiable with respect to ``logits``.
+
+    Only tensors: the reference's PackedSequence branch (_decoding.py:1551-1576) is a host-side
+    re-packing of the same sum and is not part of the hot-path scope."""
+    if not isinstance(logits, torch.Tensor):
+        raise RuntimeError("logits must be a Tensor (the PackedSequence path is not implemented "
+                           "by b200lev)")
+    hyp_dim = hyp.dim()
+    if dim < -hyp_dim or dim > hyp_dim - 1:  # _decoding.py:1521-1525
+        raise RuntimeError(
+            "Dimension out of range (expected to be in range of [{}, {}], but "
+            "got {})".format(-hyp_dim, hyp_dim - 1, dim)
+        )
+    dim = (hyp_dim + dim) % hyp_dim
+    if logits.dim() != hyp_dim + 1 or tuple(logits.shape[:-1]) != tuple(hyp.shape):
+        raise RuntimeError(
+            "logits must have the shape of hyp plus a class axis: got {} and {}".format(
+                tuple(logits.shape), tuple(hyp.shape)))
+    if not logits.is_floating_point():
+        raise RuntimeError("logits must be floating point")
+    (logits_d, hyp_d), back = _offload(logits, hyp)
+    outer = 1
+    for d in hyp.shape[:dim]:
+        outer *= d
+    inner = 1
+    for d in hyp.shape[dim + 1:]:
+        inner *= d
+    T, V = hyp.shape[dim], logits.shape[-1]
+    out, _, _ = _ops.sequence_log_probs(
+        logits_d.contiguous().view(outer, T, inner, V),
+        hyp_d.to(torch.long).contiguous().view(outer, T, inner), eos)
+    return back(out.view(tuple(hyp.shape[:dim]) + tuple(hyp.shape[dim + 1:])))

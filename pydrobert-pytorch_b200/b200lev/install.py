@@ -12,8 +12,12 @@ import importlib
 from . import functional as _F
 from . import modules as _M
 
-_FUNCS = tuple(_F.__all__)
-_CLASSES = tuple(_M.__all__)
+# sequence_log_probs / SequenceLogProbabilities cover the tensor path only (the reference also
+# accepts a PackedSequence there), so they are offered by name but not rebound behind the
+# reference's back
+_NOT_REBOUND = ("sequence_log_probs", "SequenceLogProbabilities")
+_FUNCS = tuple(n for n in _F.__all__ if n not in _NOT_REBOUND)
+_CLASSES = tuple(n for n in _M.__all__ if n not in _NOT_REBOUND)
 _saved = {}
 
 

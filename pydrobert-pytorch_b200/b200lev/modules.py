@@ -24,6 +24,7 @@ __all__ = [
     "OptimalCompletion",
     "PrefixEditDistances",
     "PrefixErrorRates",
+    "SequenceLogProbabilities",
 ]
 
 _REDUCTIONS = ("mean", "sum", "none")
@@ -291,3 +292,28 @@ class MinimumErrorRateLoss(torch.nn.Module):
         return F.minimum_error_rate_loss(
             log_probs, ref, hyp, self.eos, self.include_eos, self.sub_avg, self.batch_first,
             self.norm, self.ins_cost, self.del_cost, self.sub_cost, self.reduction, warn)
+
+
+class SequenceLogProbabilities(torch.nn.Module):
+    """Calculate joint log probability of sequences (_decoding.py:1636-1721), tensor inputs"""
+
+    __constants__ = "dim", "eos"
+    dim: int
+    eos: Optional[int]
+
+    def __init__(self, dim: int = 0, eos: Optional[int] = None):
+        dim = argcheck.is_int(dim, "dim")
+        if eos is not None:
+            eos = argcheck.is_int(eos, "eos")
+        super().__init__()
+        self.dim = dim
+        self.eos = eos
+
+    def extra_repr(self) -> str:
+        s = f"dim={self.dim}"
+        if self.eos is not None:
+            s += f", eos={self.eos}"
+        return s
+
+    def forward(self, logits: torch.Tensor, hyp: torch.Tensor) -> torch.Tensor:
+        return F.sequence_log_probs(logits, hyp, self.dim, self.eos)

@@ -71,6 +71,23 @@ def main():
     cells = int((np.repeat(rl, 8) * hl).sum())
     out.append(dict(cfg=2, call="minimum_error_rate_loss fwd+bwd", pairs=512, ms=ms,
                     gcups=cells / ms / 1e6, hyps_per_s=512 / ms * 1e3))
+    # "next #1": sequence_log_probs on the same batch, bf16 logits with vocab 10 k (1.02 GB)
+    lg = (torch.randn(101, 512, 10000, device=dev) * 2).to(torch.bfloat16).requires_grad_(True)
+    h512 = torch.from_numpy(h).to(dev)
+    ms = timed(lambda: F.sequence_log_probs(lg.detach(), h512, 0, eos=0), 20)
+    rows = int(np.minimum(hl, 101).sum())  # rows that count (the others are never read)
+    out.append(dict(cfg=2, call="sequence_log_probs fwd (bf16, V=10k)", pairs=512, ms=ms,
+                    gbs_all_rows=lg.numel() * 2 / ms / 1e6, gbs_rows_read=rows * 10000 * 2 / ms / 1e6))
+
+    def slp():
+        o = F.sequence_log_probs(lg, h512, 0, eos=0)
+        o.sum().backward()
+        lg.grad = None
+
+    ms = timed(slp, 10)
+    out.append(dict(cfg=2, call="sequence_log_probs fwd+bwd (bf16, V=10k)", pairs=512, ms=ms,
+                    gbs_3_passes=3 * lg.numel() * 2 / ms / 1e6))
+    del lg
     trx = torch.from_numpy(np.repeat(r, 8, axis=1)).to(dev)
     th2 = torch.from_numpy(h).to(dev)
     ms = timed(lambda: F.prefix_error_rates(trx, th2, eos=0, warn=False), 50, flush)

@@ -61,5 +61,10 @@ def golden_loss():
 
 
 @pytest.fixture(scope="session")
+def golden_seqlp():
+    return Golden("seqlp.npz")
+
+
+@pytest.fixture(scope="session")
 def golden_sclite():
     return np.load(os.path.join(GOLDEN, "sclite.npz"))

@@ -284,7 +284,52 @@ def gen_sclite():
     print("sclite.npz:", len(utts), "utterances, total", total)
 
 
+def gen_seqlp_cases():
+    """sequence_log_probs, tensor path (_decoding.py:1516-1548): outputs and gradients of the
+    reference for every float dtype, several step axes, with and without eos, padding tokens
+    outside [0, V), plus the reference's own known-answer test (tests/test_decoding.py:844-876
+    builds its expectation the same way: masked gather of a log_softmax)."""
+    g = np.random.default_rng(20240917)
+    store, params = {}, {}
+    shapes = [((6,), 0), ((5, 3), 0), ((4, 7), 1), ((3, 9, 4), 1), ((2, 5, 3, 2), -2), ((1, 1), 0),
+              ((33, 5), 0)]
+    k = 0
+    for shape, dim in shapes:
+        for V in (7, 40):
+            for eos in (None, 0, 3):
+                for dt in ("float32", "float64", "bfloat16", "float16"):
+                    if (k % 4) and dt in ("float64", "float16"):  # thin the grid a little
+                        k += 1
+                        continue
+                    k += 1
+                    name = f"q{len(params)}"
+                    hyp = g.integers(-2, V + 2, size=shape)
+                    tdt = getattr(torch, dt)
+                    logits = torch.tensor(g.standard_normal(shape + (V,)) * 3.0).to(tdt)
+                    logits.requires_grad_(True)
+                    out = F.sequence_log_probs(logits, torch.tensor(hyp), dim, eos)
+                    go = torch.tensor(g.standard_normal(tuple(out.shape))).to(tdt)
+                    (out * go).sum().backward()
+                    # (every dtype but float64 is exactly representable in float32)
+                    sdt = torch.float64 if dt == "float64" else torch.float32
+                    store[name + ".logits"] = logits.detach().to(sdt).numpy()
+                    store[name + ".hyp"] = hyp.astype(np.int16)
+                    store[name + ".out"] = out.detach().to(sdt).numpy()
+                    store[name + ".grad_out"] = go.to(sdt).numpy()
+                    store[name + ".grad"] = logits.grad.to(sdt).numpy()
+                    params[name] = dict(dim=dim, eos=eos, dtype=dt, V=V)
+    store["params"] = np.array(json.dumps(params))
+    np.savez_compressed(os.path.join(HERE, "seqlp.npz"), **store)
+    print("seqlp.npz:", len(params), "cases")
+
+
 if __name__ == "__main__":
-    gen_string_cases()
-    gen_loss_cases()
-    gen_sclite()
+    which = sys.argv[1:] or ["string", "loss", "sclite", "seqlp"]
+    if "string" in which:
+        gen_string_cases()
+    if "loss" in which:
+        gen_loss_cases()
+    if "sclite" in which:
+        gen_sclite()
+    if "seqlp" in which:
+        gen_seqlp_cases()

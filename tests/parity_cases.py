@@ -236,3 +236,50 @@ def check_nbest_batch(F, dev, seed, R, H, n_utts, nbest, V=30, shared=True, wide
         exp = getattr(O, func)(ref, hyp, eos=0, include_eos=True, **okw, **kw)
         act = getattr(F, func)(tr, th, eos=0, include_eos=True, warn=False, **okw, **kw)
         assert_same(act, exp, True, f"{func} nbest seed={seed} shared={shared}")
+
+
+# ---- sequence_log_probs ("next #1", _decoding.py:1516-1548) --------------------------------
+# tolerances: fp64 1e-12; fp32 2e-6 relative (+2e-6 absolute: log_softmax of ~10-magnitude
+# logits in fp32); bf16 / fp16 one unit in the last place of the result (each step is rounded
+# to the dtype before the fp32 sum, as torch does, but torch's summation order differs).
+SEQLP_TOL = {"float64": (1e-12, 1e-12), "float32": (2e-6, 2e-6), "bfloat16": (1.6e-2, 1e-2),
+             "float16": (2e-3, 2e-3)}
+
+
+def check_golden_seqlp(F, dev, golden, grads=True):
+    n = 0
+    for name, p in golden.params.items():
+        dt = getattr(torch, p["dtype"])
+        rtol, atol = SEQLP_TOL[p["dtype"]]
+        logits = torch.from_numpy(golden.get(name, "logits")).to(dev).to(dt).requires_grad_(grads)
+        hyp = torch.from_numpy(golden.get(name, "hyp").astype(np.int64)).to(dev)
+        out = F.sequence_log_probs(logits, hyp, p["dim"], p["eos"])
+        exp = golden.get(name, "out")
+        assert out.dtype == dt and tuple(out.shape) == tuple(exp.shape), name
+        np.testing.assert_allclose(out.detach().double().cpu().numpy(), exp, rtol=rtol, atol=atol,
+                                   err_msg=f"{name} {p}")
+        if grads:
+            go = torch.from_numpy(golden.get(name, "grad_out")).to(dev).to(dt)
+            (out * go).sum().backward()
+            # gradients are |g| * softmax-sized: absolute tolerance scaled by |g|
+            scale = float(np.abs(golden.get(name, "grad_out")).max()) if exp.size else 1.0
+            np.testing.assert_allclose(logits.grad.double().cpu().numpy(), golden.get(name, "grad"),
+                                       rtol=rtol, atol=atol * max(scale, 1.0), err_msg=f"grad {name} {p}")
+        n += 1
+    return n
+
+
+def check_seqlp_vs_oracle(F, dev, seed, shape, dim, V, eos, dtype=torch.float32):
+    rng = np.random.default_rng(seed)
+    hyp = rng.integers(-1, V + 1, size=shape)
+    lg = torch.tensor(rng.standard_normal(shape + (V,)) * 2.0).to(dtype)
+    logits = lg.clone().to(dev).requires_grad_(True)
+    out = F.sequence_log_probs(logits, torch.from_numpy(hyp).to(dev), dim, eos)
+    g = rng.standard_normal(tuple(out.shape))
+    (out * torch.tensor(g).to(dev).to(dtype)).sum().backward()
+    exp, gexp = O.sequence_log_probs(lg.double().numpy(), hyp, dim, eos,
+                                     grad_out=torch.tensor(g).to(dtype).double().numpy())
+    rtol, atol = SEQLP_TOL[str(dtype).split(".")[-1]]
+    np.testing.assert_allclose(out.detach().double().cpu().numpy(), exp, rtol=rtol, atol=atol * 4)
+    np.testing.assert_allclose(logits.grad.double().cpu().numpy(), gexp, rtol=rtol,
+                               atol=atol * max(1.0, float(np.abs(g).max()) if g.size else 1.0))

@@ -386,3 +386,56 @@ def test_cfg5_full_batch_properties(F, dev):
     exp = O.prefix_error_rates(ref[:, idx], hyp[:, idx], **kw)
     act = F.prefix_error_rates(tr[:, idx], th[:, idx], warn=False, **kw)
     PC.assert_same(act, exp, True, "cfg5 sample")
+
+
+# ---- sequence_log_probs ("next #1", _decoding.py:1516-1548) --------------------------------
+def test_seqlp_golden(F, dev, golden_seqlp):
+    assert PC.check_golden_seqlp(F, dev, golden_seqlp) == 84
+
+
+@pytest.mark.parametrize("case", [((7, 5), 0, 33, 2), ((3, 6, 4), 1, 264, None), ((2, 4, 3, 2), -1, 9, 0),
+                                  ((40,), 0, 1000, 5), ((5, 0), 0, 7, None), ((64, 33), 0, 1001, 3)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16, torch.float64])
+def test_seqlp_vs_oracle(F, dev, case, dtype):
+    shape, dim, V, eos = case
+    PC.check_seqlp_vs_oracle(F, dev, seed=V, shape=shape, dim=dim, V=V, eos=eos, dtype=dtype)
+
+
+def _seqlp_torch(logits, hyp, dim, eos):
+    """The same sum written with stock torch ops on the GPU (a float reference for sizes the
+    oracle is too slow for): masked gather of a log_softmax."""
+    V = logits.shape[-1]
+    lp = torch.log_softmax(logits, -1)
+    bad = (hyp < 0) | (hyp >= V)
+    if eos is not None:
+        is_eos = hyp == eos
+        bad |= (is_eos.cumsum(dim) - is_eos.long()) > 0
+    picked = lp.gather(-1, hyp.masked_fill(bad, 0).unsqueeze(-1)).squeeze(-1).masked_fill(bad, 0.0)
+    return picked.sum(dim)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_seqlp_full_size_cfg2(F, dev, dtype):
+    """cfg2's MWER front end: (T=100, 64 x 8 = 512, V=10000) logits (1 GB in bf16), ragged
+    eos-terminated hypotheses; forward and gradient against stock torch ops."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    T, N, V = 100, 512, 10000
+    hyp = torch.randint(1, V, (T, N), generator=g)
+    lens = torch.randint(50, T + 1, (N,), generator=g)
+    hyp[torch.arange(T)[:, None] >= (lens - 1)[None, :]] = 0
+    hyp[3, 7] = -5  # a padding token
+    hyp = hyp.to(dev)
+    logits = (torch.randn(T, N, V, generator=g) * 2).to(dtype).to(dev).requires_grad_(True)
+    go = torch.randn(N, generator=g).to(dtype).to(dev)
+    out = F.sequence_log_probs(logits, hyp, 0, eos=0)
+    (out * go).sum().backward()
+    grad = logits.grad.clone()
+    logits.grad = None
+    exp = _seqlp_torch(logits, hyp, 0, 0)
+    (exp * go).sum().backward()
+    rtol, atol = PC.SEQLP_TOL[str(dtype).split(".")[-1]]
+    torch.testing.assert_close(out.float(), exp.float(), rtol=rtol, atol=atol * 50)
+    # compare gradients where they are not both exactly zero (skipped rows) in fp32
+    torch.testing.assert_close(grad.float(), logits.grad.float(), rtol=rtol * 4, atol=atol)
+    skipped = torch.arange(T, device=dev)[:, None] >= lens.to(dev)[None, :]
+    assert float(grad[skipped].abs().max()) == 0.0

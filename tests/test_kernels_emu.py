@@ -284,3 +284,32 @@ def test_cta_kernel_vs_oracle(F, shape, costs, monkeypatch):
 def test_warp_kernel_when_cta_disabled(F, monkeypatch):
     monkeypatch.setenv("B200LEV_CTA_KERNEL", "0")
     PC.check_vs_oracle(F, DEV, seed=3, R=130, H=40, N=4, V=5, costs=(1, 2, 3), do_mask=False)
+
+
+def test_seqlp_golden(F, golden_seqlp):
+    assert PC.check_golden_seqlp(F, DEV, golden_seqlp) == 84
+
+
+@pytest.mark.parametrize("case", [((7, 5), 0, 33, 2), ((3, 6, 4), 1, 264, None), ((2, 4, 3, 2), -1, 9, 0),
+                                  ((40,), 0, 1000, 5), ((5, 0), 0, 7, None), ((0, 5), 0, 7, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_seqlp_vs_oracle(F, case, dtype):
+    """Vector (16-byte) and scalar row paths (V a multiple of the vector width or not), all
+    step axes, empty axes."""
+    shape, dim, V, eos = case
+    PC.check_seqlp_vs_oracle(F, DEV, seed=V, shape=shape, dim=dim, V=V, eos=eos, dtype=dtype)
+
+
+def test_seqlp_errors_and_module(F):
+    import b200lev.modules as M
+
+    lg, hyp = torch.randn(4, 3, 5), torch.randint(0, 5, (4, 3))
+    with pytest.raises(RuntimeError, match="Dimension out of range"):
+        F.sequence_log_probs(lg, hyp, 2)
+    with pytest.raises(RuntimeError, match="class axis"):
+        F.sequence_log_probs(lg[:, :2], hyp, 0)
+    m = M.SequenceLogProbabilities(1, eos=2)
+    assert "dim=1, eos=2" in repr(m)
+    assert torch.equal(m(lg, hyp), F.sequence_log_probs(lg, hyp, 1, 2))
+    with pytest.raises(ValueError):
+        M.SequenceLogProbabilities("x")

@@ -248,3 +248,21 @@ def test_fill_after_eos():
         assert (out[n:, n] == V - 1).all()
         assert (out2[: n + 1, n] == logits[: n + 1, n]).all()
         assert (out2[n + 1:, n] == V - 1).all()
+
+
+def test_seqlp_oracle_matches_reference_fixtures(golden_seqlp):
+    """oracle.sequence_log_probs (float64 restatement of _decoding.py:1516-1548) against the
+    reference's outputs and gradients; the fixture dtype bounds the agreement."""
+    import parity_cases as PC
+
+    n = 0
+    for name, p in golden_seqlp.params.items():
+        rtol, atol = PC.SEQLP_TOL[p["dtype"]]
+        out, grad = O.sequence_log_probs(golden_seqlp.get(name, "logits"), golden_seqlp.get(name, "hyp"),
+                                         p["dim"], p["eos"], grad_out=golden_seqlp.get(name, "grad_out"))
+        np.testing.assert_allclose(out, golden_seqlp.get(name, "out"), rtol=rtol, atol=atol, err_msg=name)
+        scale = max(1.0, float(np.abs(golden_seqlp.get(name, "grad_out")).max())) if out.size else 1.0
+        np.testing.assert_allclose(grad, golden_seqlp.get(name, "grad"), rtol=rtol, atol=atol * scale,
+                                   err_msg=name)
+        n += 1
+    assert n == 84
