@@ -79,6 +79,15 @@ def main():
     out.append(dict(cfg=2, call="sequence_log_probs fwd (bf16, V=10k)", pairs=512, ms=ms,
                     gbs_all_rows=lg.numel() * 2 / ms / 1e6, gbs_rows_read=rows * 10000 * 2 / ms / 1e6))
 
+    def slp_torch():  # the same sum with stock torch ops (what the reference runs on a GPU)
+        lp = torch.log_softmax(lg.detach(), -1)
+        is_eos = h512 == 0
+        bad = (is_eos.cumsum(0) - is_eos.long()) > 0
+        return lp.gather(-1, h512.unsqueeze(-1)).squeeze(-1).masked_fill(bad, 0.0).sum(0)
+
+    ms_t = timed(slp_torch, 10)
+    out[-1]["stock_torch_ops_ms"] = ms_t
+
     def slp():
         o = F.sequence_log_probs(lg, h512, 0, eos=0)
         o.sum().backward()
