@@ -88,6 +88,18 @@ __device__ __forceinline__ void slp_unpack(const uint4& raw,
 #pragma unroll
     for (int k = 0; k < VEC; ++k) x[k] = SlpElem<DT>::ld(&tmp[k]);
 }
+#ifndef B200LEV_EMU
+// bf16 -> fp32 is a 16-bit shift: one SHF (low half) or one LOP3 (high half) per value
+template <>
+__device__ __forceinline__ void slp_unpack<B200LEV_BF16>(const uint4& raw, float (&x)[8]) {
+    const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        x[2 * k] = __uint_as_float(w[k] << 16);
+        x[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+    }
+}
+#endif
 template <int DT>
 __device__ __forceinline__ void slp_load_vec(const typename SlpElem<DT>::T* p,
                                              typename SlpElem<DT>::Acc (&x)[SlpElem<DT>::VEC]) {
@@ -173,15 +185,40 @@ __device__ __forceinline__ typename SlpElem<DT>::Acc slp_row_lse(const typename 
     if (aligned) {
         const int64_t nvec = V / VEC;
         int64_t c = lane;
-        for (; c + 224 < nvec; c += 256) {  // eight 128-bit loads in flight per lane
-            uint4 raw[8];
+        // two groups of four 128-bit loads ping-pong: one group is in flight while the other
+        // is being summed
+        if (c + 96 < nvec) {
+            uint4 ra[4], rb[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) raw[u] = *reinterpret_cast<const uint4*>(z + (c + 32 * u) * VEC);
+            for (int u = 0; u < 4; ++u) ra[u] = *reinterpret_cast<const uint4*>(z + (c + 32 * u) * VEC);
+            c += 128;
+            while (true) {
+                const bool more_b = c + 96 < nvec;
+                if (more_b) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                A x[VEC];
-                slp_unpack<DT>(raw[u], x);
-                feed(x, VEC);
+                    for (int u = 0; u < 4; ++u) rb[u] = *reinterpret_cast<const uint4*>(z + (c + 32 * u) * VEC);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    A x[VEC];
+                    slp_unpack<DT>(ra[u], x);
+                    feed(x, VEC);
+                }
+                if (!more_b) break;
+                c += 128;
+                const bool more_a = c + 96 < nvec;
+                if (more_a) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) ra[u] = *reinterpret_cast<const uint4*>(z + (c + 32 * u) * VEC);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    A x[VEC];
+                    slp_unpack<DT>(rb[u], x);
+                    feed(x, VEC);
+                }
+                if (!more_a) break;
+                c += 128;
             }
         }
         for (; c < nvec; c += 32) {
