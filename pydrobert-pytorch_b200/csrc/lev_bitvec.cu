@@ -14,22 +14,28 @@
 // tok[t][n0 + l] is one coalesced row, and the (H', N) output row of 32 neighbouring pairs is
 // one 128-byte store.  K0 (lev_pack.cu) is not needed on this path.
 //
-//   lev_bv_uid_kernel   per lane: an open-addressing hash of the pair's reference tokens in
-//       shared memory (slot-major, lane-minor: every lane stays in its own bank).  Emits, 16
-//       positions per 128-bit store, ref_uid[j] = first position holding ref[j]'s token and
-//       hyp_uid[i] = first reference position matching hyp[i] (0xff: none); finds the
-//       lengths (SM:137-143, 195-228) and raises the warning flags on the way.  Reads the
-//       raw tokens once: HBM-bound.
-//   lev_bv_dp_kernel    per lane: the match masks Peq[uid] of its reference in shared memory
-//       (same interleaving), then one Myers step per hypothesis token.  The reference is
-//       RIGHT-aligned in the 32*W-bit vector: the o = 32W - r low bits start with Pv = 0 and
-//       never match, which makes each of them a copy of the boundary row D[0][i] = i, so the
-//       boundary enters the first real bit through the ordinary shift and the score is always
-//       read at the top bit of the last word.
+//   lev_bv_uid_kernel   per warp (32 consecutive pairs): one coalesced pass over the reference
+//       columns finds the RUNS of identical references (an n-best batch repeats every
+//       reference nbest times), their lengths (SM:137-143, 195-228) and the warnings.  The
+//       lanes of a run build ONE hash table for it together (buckets of 4 ways in shared
+//       memory, a way is claimed with a CAS on its key word, a build with an overflowing
+//       bucket is retried under another multiplier); then every lane looks its own
+//       hypothesis tokens up with one 128-bit read of the keys and one 32-bit read of the
+//       position bytes -- no probe loop.  Emits 1 uid byte per token (the table row of the
+//       token; 0xff: not in the reference), 16 per 128-bit store.  Reads the raw tokens once.
+//   lev_bv_dp_kernel    per run one table of match masks Peq[uid] in shared memory, per lane
+//       one Myers step per hypothesis token.  The reference is RIGHT-aligned in the 32*W-bit
+//       vector: the o = 32W - r low bits start with Pv = 0 and never match, which makes each
+//       of them a copy of the boundary row D[0][i] = i, so the boundary enters the first real
+//       bit through the ordinary shift and the score is always read at the top bit of the
+//       last word.
 //
-// Eligibility (lev_bitvec_launch): unit costs after SM:168-174, final or prefix mode, at most
+// Eligibility (lev_bitvec_eligible): unit costs after SM:168-174, final or prefix mode, at most
 // 128 reference positions, unit stride along the batch axis of both token tensors and of
-// the prefix output.  Everything else keeps the wavefront kernels.
+// the prefix output.  The kernels are enqueued AHEAD of the wavefront path and decide on the
+// device (lev_bv_took, lev_common.cuh): a block of 32 pairs with more than 4 distinct
+// references, or a reference token the 32-bit keys cannot hold, vetoes, and the wavefront
+// kernels -- which otherwise exit at once -- do the work.
 #include "lev_common.cuh"
 
 #define LEV_BV_NOMATCH 0xffu
