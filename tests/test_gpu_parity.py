@@ -356,7 +356,8 @@ def test_bitvec_device_selected(F, dev, shared):
     """Default mode at sizes where both paths are eligible: n-best shaped batches are taken by
     the bit-vector kernels, unrelated references (and references with tokens outside int32)
     are vetoed on the device and answered by the wavefront kernels.  Same numbers."""
-    for R, H, n_utts, nbest in ((101, 101, 600, 8), (40, 60, 300, 16), (128, 30, 1100, 4)):
+    for R, H, n_utts, nbest in ((101, 101, 600, 8), (40, 60, 300, 16), (128, 30, 1100, 4),
+                                (100, 600, 520, 8), (1, 50, 600, 8), (33, 1, 520, 8)):
         PC.check_nbest_batch(F, dev, seed=R, R=R, H=H, n_utts=n_utts, nbest=nbest, shared=shared)
         PC.check_nbest_batch(F, dev, seed=R, R=R, H=H, n_utts=n_utts, nbest=nbest, shared=shared,
                              wide=True)
