@@ -415,8 +415,10 @@ __device__ __forceinline__ bool lev_bv_uid_block(const LevBvArgs& a, int4* keys4
 
 // Warps are independent and walk the blocks of 32 pairs with a grid stride: the grid stays
 // small (a vetoed launch, or this kernel standing by, drains in a few microseconds).
+// (4 CTAs per SM on purpose: with 128 registers the compiler keeps both load batches and the
+// look-up temporaries in registers -- 118 -> 100 us on cfg2 against 5 CTAs at 96 registers)
 template <typename TT>
-__global__ void __launch_bounds__(32 * LEV_BV_WARPS) lev_bv_uid_kernel(const LevBvArgs a) {
+__global__ void __launch_bounds__(32 * LEV_BV_WARPS, 4) lev_bv_uid_kernel(const LevBvArgs a) {
     LEV_DYN_SMEM(int, smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nb = 1 << a.slots_log2;  // buckets per table
