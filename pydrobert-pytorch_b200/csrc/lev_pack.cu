@@ -285,6 +285,81 @@ __global__ void __launch_bounds__(128, 8) lev_pack_seqfirst_kernel(const LevPack
         if (cta_hist[b] != 0) atomicAdd(&a.ghist[b], cta_hist[b]);
 }
 
+// ---- sequence-first, short sequences (T <= 64): a WARP owns 32 sequences ------------------
+// With only one or two 32-position slices per sequence the four-warp chunk above leaves warps
+// idle and pays two block barriers per 1 K tokens (cfg4: 1 M sequences of 31).  Here every warp
+// runs its own 32 sequences start to finish -- slice loads, its private [32][36] tile, row
+// stores that cover 4 (int32) or 8 (uint16) rows per instruction, lane-local lengths -- and
+// only __syncwarp stands between the phases.
+template <typename TT>
+__global__ void __launch_bounds__(128, 8) lev_pack_warpseq_kernel(const LevPackArgs a) {
+    if (a.bv_check && lev_bv_took(a.state)) return;
+    __shared__ __align__(16) int tiles[4][32][36];
+    LEV_DYN_SMEM(int, cta_hist);
+    for (int b = threadIdx.x; b < a.hist_bins; b += blockDim.x) cta_hist[b] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int(*tile)[36] = tiles[w];
+    const int Ti = (int)a.T, Tp = (int)a.Tp, Tp16 = (int)a.Tp16;
+    const int st = (int)a.st;
+    const int eos32 = (int)a.eos;
+    const bool eos_fast = a.has_eos && (int64_t)eos32 == a.eos;
+    for (int64_t n0 = ((int64_t)blockIdx.x * 4 + w) * 32; n0 < a.N; n0 += (int64_t)gridDim.x * 128) {
+        const int64_t n = n0 + lane;
+        const bool valid_seq = n < a.N;
+        const int rows = (int)(a.N - n0 < 32 ? a.N - n0 : 32);
+        const TT* __restrict__ seq = reinterpret_cast<const TT*>(a.tok) + (valid_seq ? n : 0);
+        LevPackSeen seen = {Ti, 0, 0x7fffffff, (int)0x80000000};
+        const int ref_len = (valid_seq && a.ghist != nullptr) ? a.ref_len[n / a.ref_group] : 0;
+        unsigned cur_u = 0u, cur_n = 0u;
+        for (int tb = 0; tb < Ti; tb += 32) {
+            if (tb + 32 <= Ti)
+                lev_pack_slice<TT, false, 32>(seq + (int64_t)tb * st, st, tb, Ti, eos_fast, eos32, &tile[lane][0], seen);
+            else
+                lev_pack_slice<TT, true, 32>(seq + (int64_t)tb * st, st, tb, Ti, eos_fast, eos32, &tile[lane][0], seen);
+            __syncwarp();
+            if (lane == 0 && tb + 32 >= Ti) {  // a recent copy of the range words (see above)
+                cur_u = lev_ldg_l2(reinterpret_cast<const unsigned*>(a.state) + 1);
+                cur_n = lev_ldg_l2(reinterpret_cast<const unsigned*>(a.state) + 2);
+            }
+            const int cpr = (Tp - tb < 32 ? Tp - tb : 32) >> 2;  // 16-byte chunks per int32 row
+            for (int i = lane; i < rows * cpr; i += 32) {
+                const int r = i / cpr, c = i - r * cpr;
+                *reinterpret_cast<int4*>(a.packed + (n0 + r) * a.Tp + tb + 4 * c) =
+                    *reinterpret_cast<const int4*>(&tile[r][4 * c]);
+            }
+            if (a.packed16 != nullptr) {
+                const int cpr16 = (Tp16 - tb < 32 ? Tp16 - tb : 32) >> 3;
+                for (int i = lane; i < rows * cpr16; i += 32) {
+                    const int r = i / cpr16, c = i - r * cpr16;
+                    const int4 x = *reinterpret_cast<const int4*>(&tile[r][8 * c]);
+                    const int4 y = *reinterpret_cast<const int4*>(&tile[r][8 * c + 4]);
+                    *reinterpret_cast<uint4*>(a.packed16 + (n0 + r) * a.Tp16 + tb + 8 * c) =
+                        make_uint4(__byte_perm(x.x, x.y, 0x5410), __byte_perm(x.z, x.w, 0x5410),
+                                   __byte_perm(y.x, y.y, 0x5410), __byte_perm(y.z, y.w, 0x5410));
+                }
+            }
+            __syncwarp();
+        }
+        if (a.has_eos && (!eos_fast || (sizeof(TT) == 8 && seen.wacc != 0))) {
+            seen.first = Ti;  // rare: exact rescan (wide tokens / wide eos)
+            for (int t = 0; t < Ti; ++t)
+                if ((int64_t)seq[(int64_t)t * st] == a.eos) {
+                    seen.first = t;
+                    break;
+                }
+        }
+        int flags = seen.wacc != 0 ? B200LEV_FLAG_WIDE_TOKENS : 0;
+        if (valid_seq) flags |= lev_pack_owner(a, ref_len, n, seen.first, a.hist_bins ? cta_hist : nullptr);
+        unsigned umax = (unsigned)seen.hi + 0x80000000u, nmax = ~((unsigned)seen.lo + 0x80000000u);
+        lev_pack_warp_reduce(flags, umax, nmax);
+        if (lane == 0) lev_pack_publish(a, flags, umax, nmax, cur_u, cur_n);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < a.hist_bins; b += blockDim.x)
+        if (cta_hist[b] != 0) atomicAdd(&a.ghist[b], cta_hist[b]);
+}
+
 // ---- any other layout: one warp per sequence, lanes along the sequence axis -------------
 template <typename TT>
 __global__ void __launch_bounds__(128) lev_pack_rows_kernel(const LevPackArgs a) {
@@ -375,8 +450,28 @@ int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int inc
         }
     }
     const dim3 grid((unsigned)nblk, 1, 1);
+    const bool warpseq = seqfirst && t->T <= 64;
+    if (warpseq) {  // a warp per 32 sequences: 4 blocks per CTA and iteration
+        int64_t n = ((t->N + 31) / 32 + 3) / 4;
+        const bool many = n > cap && (bv_check || n >= 8 * cap);
+        if (many) {
+            const int64_t per_cta = (n + cap - 1) / cap;
+            n = (n + per_cta - 1) / per_cta;
+        }
+        if (!a.hist_bins) {  // (the branch above sized it for 32-sequence CTAs)
+            const int64_t bins = (int64_t)LEV_GROUP_NCLS * (t->T + 1);
+            if (ghist != nullptr && many && bins <= 8192) {
+                a.hist_bins = (int)bins;
+                smem = sizeof(int) * (size_t)bins;
+            }
+        }
+        nblk = n;
+    }
+    const dim3 wgrid((unsigned)nblk, 1, 1);
 #define LEV_PACK_CASE(TT)                                                \
-    if (seqfirst)                                                        \
+    if (warpseq)                                                         \
+        lev_launch(lev_pack_warpseq_kernel<TT>, wgrid, block, smem, st, a); \
+    else if (seqfirst)                                                   \
         lev_launch(lev_pack_seqfirst_kernel<TT>, grid, block, smem, st, a); \
     else                                                                 \
         lev_launch(lev_pack_rows_kernel<TT>, grid, block, 0, st, a);
