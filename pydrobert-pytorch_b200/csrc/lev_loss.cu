@@ -100,36 +100,66 @@ lev_ocd_fwd_kernel(const typename LevElem<DT>::T* __restrict__ logits, int64_t r
 }
 
 // mean (SM:1242-1246): mean over sequences of (sum over steps / #steps with targets);
-// sum (SM:1247-1248).  Single CTA, fixed summation order (deterministic).
+// sum (SM:1247-1248).  Single CTA, fixed summation order (deterministic): blocks of 32
+// sequences on the lanes (coalesced when the sequence axis is the inner one), the 32 warps
+// take every 32nd step (four loads in flight each: the kernel is pure load latency), warp 0
+// adds the 32 partials of each sequence in order.
 template <typename A>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 lev_ocd_reduce_kernel(const A* __restrict__ per, int64_t Adim, int64_t Bdim,
                       const int64_t* __restrict__ targets, int64_t U, int64_t ts_a, int64_t ts_b,
                       int64_t ignore_index, int reduction, int seq_axis, A* __restrict__ denom,
                       A* __restrict__ loss) {
-    __shared__ A part[256];
-    const int tid = threadIdx.x;
+    __shared__ A psum[32][32];
+    __shared__ int phave[32][32];
+    __shared__ A part[1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t nseq = seq_axis == 0 ? Bdim : Adim;   // number of sequences
     const int64_t nstep = seq_axis == 0 ? Adim : Bdim;  // steps per sequence
-    A acc = (A)0;
-    for (int64_t q = tid; q < nseq; q += 256) {
+    A acc = (A)0;  // (warp 0 only) this lane's sequences, in order
+    for (int64_t q0 = 0; q0 < nseq; q0 += 32) {
+        const int64_t q = q0 + lane;
         A s = (A)0;
-        int64_t have = 0;
-        for (int64_t t = 0; t < nstep; ++t) {
-            const int64_t a = seq_axis == 0 ? t : q, b = seq_axis == 0 ? q : t;
-            s += per[a * Bdim + b];
-            if (U > 0 && targets[a * ts_a + b * ts_b] != ignore_index) have += 1;
+        int have = 0;
+        if (q < nseq)
+            for (int64_t t0 = warp; t0 < nstep; t0 += 128) {
+                A v[4];
+                int64_t g[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int64_t t = t0 + 32 * k;
+                    const bool in = t < nstep;
+                    const int64_t a = seq_axis == 0 ? t : q, b = seq_axis == 0 ? q : t;
+                    v[k] = in ? per[a * Bdim + b] : (A)0;
+                    g[k] = (in && U > 0) ? targets[a * ts_a + b * ts_b] : ignore_index;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    s += v[k];
+                    have += g[k] != ignore_index;
+                }
+            }
+        psum[warp][lane] = s;
+        phave[warp][lane] = have;
+        __syncthreads();
+        if (warp == 0 && q < nseq) {
+            A tot = (A)0;
+            int h = 0;
+            for (int w = 0; w < 32; ++w) {
+                tot += psum[w][lane];
+                h += phave[w][lane];
+            }
+            const A d = (A)(h > 1 ? h : 1);
+            denom[q] = d;
+            acc += (reduction == B200LEV_REDUCE_MEAN) ? tot / d : tot;
         }
-        const A d = (A)(have > 1 ? have : 1);
-        denom[q] = d;
-        acc += (reduction == B200LEV_REDUCE_MEAN) ? s / d : s;
-    }
-    part[tid] = acc;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (tid < o) part[tid] += part[tid + o];
         __syncthreads();
     }
+    if (warp == 0) {
+        acc = lev_warp_sum(acc);
+        if (lane == 0) part[0] = acc;
+    }
+    __syncthreads();
     if (tid == 0) loss[0] = (reduction == B200LEV_REDUCE_MEAN) ? part[0] / (A)nseq : part[0];
 }
 
@@ -201,7 +231,7 @@ static int lev_ocd_forward_t(const void* logits, int64_t A_, int64_t B, int64_t 
                    ts_b, weight, ignore_index, (A*)per, (A*)lse);
     }
     if (reduction != B200LEV_REDUCE_NONE)
-        lev_launch(lev_ocd_reduce_kernel<A>, dim3(1), dim3(256), 0, st, (const A*)per, A_, B, targets,
+        lev_launch(lev_ocd_reduce_kernel<A>, dim3(1), dim3(1024), 0, st, (const A*)per, A_, B, targets,
                    U, ts_a, ts_b, ignore_index, reduction, seq_axis, (A*)denom, (A*)loss);
     return lev_check_cuda("lev_ocd_fwd_kernel");
 }
