@@ -273,6 +273,39 @@ def main():
               "prefix_finalize": prof[4], "standby_wide": prof[5], "bitvec_uid": prof[6],
               "bitvec_dp": prof[7]}
 
+    # the same call with the bit-vector kernels switched off: north_star's target is quoted on
+    # the wavefront kernel, so it is measured live next to the path that actually ships
+    wave = None
+    if bitvec:
+        saved = os.environ.get("B200LEV_BITVEC")
+        os.environ["B200LEV_BITVEC"] = "0"
+        try:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record()
+            for _ in range(nprof):
+                step()
+            w1.record()
+            torch.cuda.synchronize()
+            wave = {"ms_per_step": w0.elapsed_time(w1) / nprof}
+            wprof = np.zeros(8, dtype=np.float64)
+            _abi.check(L.b200lev_profile(1))
+            for _ in range(nprof):
+                step()
+                _abi.check(L.b200lev_profile_read(buf, 8))
+                wprof += np.array([max(x, 0.0) for x in buf])
+            _abi.check(L.b200lev_profile(0))
+            wprof /= nprof
+            wave["kernel_ms"] = float(wprof[3])
+            wave["pack_ms"] = float(wprof[0] + wprof[1])
+        finally:
+            if saved is None:
+                del os.environ["B200LEV_BITVEC"]
+            else:
+                os.environ["B200LEV_BITVEC"] = saved
+
     def timed(fn, reps):
         for _ in range(3):
             fn()
@@ -417,6 +450,22 @@ def main():
         }
         if roofline_dp is not None:
             line["roofline_dp"] = roofline_dp
+            if wave is not None and wave["kernel_ms"] > 0:
+                wops = cells / (wave["kernel_ms"] * 1e-3) * OPS_PER_CELL / 1e12
+                line["roofline_wavefront"] = {
+                    "bound": "int32_issue",
+                    "kernel": "lev_group_kernel<cost,PREFIX,packed16> (B200LEV_BITVEC=0: the "
+                              "wavefront path, taken by every batch the bit-vector path declines)",
+                    "achieved": wops, "peak": int32_peak, "unit": "Tint32op/s",
+                    "frac": wops / int32_peak, "traffic": traffic_all.get("lev_group_kernel"),
+                    "ops_per_cell": OPS_PER_CELL, "kernel_ms": wave["kernel_ms"],
+                    "kernel_gcups": cells / (wave["kernel_ms"] * 1e-3) / 1e9,
+                    "whole_call_ms": wave["ms_per_step"],
+                    "whole_call_gcups": cells / (wave["ms_per_step"] * 1e-3) / 1e9,
+                    "pack_ms": wave["pack_ms"],
+                    "pack_gbs": (in_bytes + in_bytes // 2) / (wave["pack_ms"] * 1e-3) / 1e9,
+                    "note": "algorithmic 5 INT32 ops/cell (SURVEY 8d); the kernel issues 2.5 "
+                            "instructions per cell (2 cells per 16x2 DPX instruction)"}
         else:
             line["roofline_pack"] = {"bound": "hbm",
                                      "kernel": "lev_pack_seqfirst_kernel<int64> x2 (ref, hyp)",
