@@ -6,7 +6,7 @@ signatures; ``b200lev.install()`` rebinds them inside an installed ``pydrobert.t
 All computation happens in ``libb200lev.so`` (hand-written CUDA behind the C ABI of
 ``include/b200lev.h``); there is no CPU fallback.
 """
-from . import config, functional, modules  # noqa: F401
+from . import config, functional, modules, scoring  # noqa: F401
 from ._abi import B200LevError  # noqa: F401
 from .install import install, uninstall  # noqa: F401
 

@@ -15,3 +15,9 @@ DEFT_DEL_COST = 1.0
 
 DEFT_SUB_COST = 1.0
 """Default substitution cost in error rate/distance computations (config.py:162)"""
+
+DEFT_FILE_PREFIX = ""
+"""Default prefix of a torch data file in a data directory (config.py:86)"""
+
+DEFT_FILE_SUFFIX = ".pt"
+"""Default suffix of a torch data file in a data directory (config.py:89)"""

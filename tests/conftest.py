@@ -66,5 +66,11 @@ def golden_seqlp():
 
 
 @pytest.fixture(scope="session")
+def golden_scoring():
+    with open(os.path.join(GOLDEN, "scoring.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def golden_sclite():
     return np.load(os.path.join(GOLDEN, "sclite.npz"))

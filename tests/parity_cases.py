@@ -9,6 +9,7 @@ losses and gradients (stated at each assert).
 import warnings
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import oracle as O
@@ -283,3 +284,70 @@ def check_seqlp_vs_oracle(F, dev, seed, shape, dim, V, eos, dtype=torch.float32)
     np.testing.assert_allclose(out.detach().double().cpu().numpy(), exp, rtol=rtol, atol=atol * 4)
     np.testing.assert_allclose(logits.grad.double().cpu().numpy(), gexp, rtol=rtol,
                                atol=atol * max(1.0, float(np.abs(g).max()) if g.size else 1.0))
+
+
+# ---- bulk-scoring front end (b200lev.scoring) against the reference command's own output ----
+def _scoring_tensor(seq, kind):
+    t = torch.tensor(seq, dtype=torch.long)
+    if kind == "col1":
+        return t.unsqueeze(-1)
+    if kind == "timed":
+        n = t.shape[0]
+        start = torch.arange(n) * 3
+        return torch.stack([t, start, start + 2], -1) if n else torch.zeros((0, 3), dtype=torch.long)
+    return t
+
+
+def build_scoring_dirs(golden, tmp):
+    """Rebuild the token data directories make_golden_scoring.py ran the reference on."""
+    import os
+
+    def write(root, utts, prefix="", suffix=".pt", drop_ref=(), drop_hyp=()):
+        for side, drop in (("ref", drop_ref), ("hyp", drop_hyp)):
+            os.makedirs(os.path.join(root, side), exist_ok=True)
+            for utt, d in utts.items():
+                if utt not in drop:
+                    torch.save(_scoring_tensor(d[side], d[side + "_kind"]),
+                               os.path.join(root, side, prefix + utt + suffix))
+            torch.save(torch.zeros(2, dtype=torch.long), os.path.join(root, side, "stray.bin"))
+
+    A, B = golden["corpora"]["A"], golden["corpora"]["B"]
+    for name, text in golden["files"].items():
+        with open(os.path.join(tmp, name), "w") as f:
+            f.write(text)
+    write(os.path.join(tmp, "A"), A)
+    write(os.path.join(tmp, "B"), B)
+    write(os.path.join(tmp, "Apre"), A, prefix="tok_", suffix=".tok")
+    write(os.path.join(tmp, "Amiss"), A, **golden["missing"])
+
+
+def check_golden_scoring(scoring, golden, tmp):
+    import os
+    import warnings
+
+    tmp = str(tmp)
+    build_scoring_dirs(golden, tmp)
+    n = 0
+    for case in golden["cases"]:
+        where, opts = case["where"], case["opts"]
+        if "+" in where:
+            dirs = [os.path.join(tmp, x) for x in where.split("+")]
+        else:
+            dirs = [os.path.join(tmp, where, "ref"), os.path.join(tmp, where, "hyp")]
+        out = os.path.join(tmp, f"out{n}.txt")
+        args = dirs + [out] + [os.path.join(tmp, o[1:]) if o.startswith("@") else o for o in opts]
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            if "raises" in case:
+                exc = {"ValueError": ValueError, "ZeroDivisionError": ZeroDivisionError}[case["raises"]]
+                with pytest.raises(exc) as info:
+                    scoring.compute_torch_token_data_dir_error_rates(args)
+                assert str(info.value) == case["message"].replace("{tmp}", tmp), (where, opts)
+            else:
+                assert scoring.compute_torch_token_data_dir_error_rates(args) == case["rc"], (where, opts)
+                with open(out) as f:
+                    assert f.read() == case["out"], (where, opts)
+        missing = sorted(str(x.message) for x in w if "does not contain" in str(x.message))
+        assert missing == [m.replace("{tmp}", tmp) for m in case["warned_missing"]], (where, opts)
+        n += 1
+    return n

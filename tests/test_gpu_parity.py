@@ -440,3 +440,38 @@ def test_seqlp_full_size_cfg2(F, dev, dtype):
     torch.testing.assert_close(grad.float(), logits.grad.float(), rtol=rtol * 4, atol=atol)
     skipped = torch.arange(T, device=dev)[:, None] >= lens.to(dev)[None, :]
     assert float(grad[skipped].abs().max()) == 0.0
+
+
+# ---- bulk-scoring front end ---------------------------------------------
+def test_scoring_golden_command_outputs(F, golden_scoring, tmp_path):
+    import b200lev.scoring as S
+
+    assert PC.check_golden_scoring(S, golden_scoring, tmp_path) == 30
+
+
+def test_scoring_large_corpus_matches_direct_call(F, dev):
+    """200 k utterances from flat arrays (int16 codes, length-sorted batches, host pipeline)
+    against error_rate on the padded int64 matrices built the plain way."""
+    import b200lev.scoring as S
+
+    rng = np.random.default_rng(11)
+    N, T, V = 200_000, 31, 5000
+    rl = rng.integers(1, T + 1, N)
+    hl = rng.integers(0, T + 1, N)
+    ref = np.full((T + 1, N), -2, dtype=np.int64)
+    hyp = np.full((T + 1, N), -2, dtype=np.int64)
+    rt = rng.integers(0, V, (T, N))
+    ht = np.where(rng.random((T, N)) < 0.7, rt, rng.integers(0, V, (T, N)))
+    rows = np.arange(T)[:, None]
+    ref[:T][rows < rl] = rt[rows < rl]
+    hyp[:T][rows < hl] = ht[rows < hl]
+    ref[rl, np.arange(N)] = -1
+    hyp[hl, np.arange(N)] = -1
+    exp = F.error_rate(torch.from_numpy(ref).to(dev), torch.from_numpy(hyp).to(dev), eos=-1, norm=False)
+    ids = [f"u{i:07d}" for i in range(N)]
+    rc = S.TokenCorpus(ids, ref[:T].T[(rows < rl).T], np.concatenate([[0], np.cumsum(rl)]), "r")
+    hc = S.TokenCorpus(ids, hyp[:T].T[(rows < hl).T], np.concatenate([[0], np.cumsum(hl)]), "h")
+    for budget in (S._CELL_BUDGET, 1 << 21):
+        got, lens = S.score_corpora(rc, hc, quiet=True, cell_budget=budget)
+        np.testing.assert_array_equal(got, exp.cpu().numpy())
+        np.testing.assert_array_equal(lens, rl)

@@ -313,3 +313,76 @@ def test_seqlp_errors_and_module(F):
     assert torch.equal(m(lg, hyp), F.sequence_log_probs(lg, hyp, 1, 2))
     with pytest.raises(ValueError):
         M.SequenceLogProbabilities("x")
+
+
+# ---- bulk-scoring front end ---------------------------------------------
+@pytest.fixture(scope="module")
+def scoring(F):
+    import b200lev.scoring as S
+
+    return S
+
+
+def test_scoring_golden_command_outputs(scoring, golden_scoring, tmp_path):
+    """Every option set the reference command was run on: same text, same exceptions."""
+    assert PC.check_golden_scoring(scoring, golden_scoring, tmp_path) == 30
+
+
+def test_scoring_batches_by_cell_budget(scoring, golden_scoring):
+    """A tiny budget splits the corpus into many length-sorted calls: same numbers."""
+    A = golden_scoring["corpora"]["A"]
+    utts = sorted(A)
+    ref = scoring.TokenCorpus.from_sequences(utts, [A[u]["ref"] for u in utts], "r")
+    hyp = scoring.TokenCorpus.from_sequences(utts, [A[u]["hyp"] for u in utts], "h")
+    one, rl1 = scoring.score_corpora(ref, hyp, quiet=True)
+    many, rl2 = scoring.score_corpora(ref, hyp, quiet=True, cell_budget=64)
+    np.testing.assert_array_equal(one, many)
+    np.testing.assert_array_equal(rl1, rl2)
+    from oracle import oracle as O
+
+    for k, u in enumerate(utts):  # unit costs, no eos: the plain Levenshtein distance
+        r, h = np.array(A[u]["ref"], dtype=np.int64), np.array(A[u]["hyp"], dtype=np.int64)
+        if h.size:
+            exp = np.asarray(O.edit_distance(r[:, None], h[:, None]))[0]
+        else:
+            exp = r.size
+        assert one[k] == exp and rl1[k] == r.size, u
+
+
+def test_scoring_corpus_helpers(scoring):
+    c = scoring.TokenCorpus.from_sequences(["a", "b", "c", "d"], [[1, 2, 3], [], [4], [5, 6]], "x")
+    s = c.select(np.array([0, 2, 3]))
+    assert s.utt_ids == ["a", "c", "d"] and s.tokens.tolist() == [1, 2, 3, 4, 5, 6]
+    assert s.offsets.tolist() == [0, 3, 4, 6]
+    e = c.select(np.array([1]))
+    assert e.tokens.shape == (0,) and e.offsets.tolist() == [0, 0]
+    with pytest.raises(ValueError, match="not aligned"):
+        scoring.score_corpora(c, s)
+    with pytest.raises(ValueError, match="offsets"):
+        scoring.TokenCorpus(["a"], np.arange(3), np.array([0, 2]))
+
+
+def test_scoring_recode_paths_agree(scoring, golden_scoring, monkeypatch):
+    """Plain shift, dense table and sort-based ranking of the ids give the same errors,
+    for ids that are negative, sparse or wider than 32 bits."""
+    A = golden_scoring["corpora"]["A"]
+    utts = sorted(A)
+    base_r, base_h = [A[u]["ref"] for u in utts], [A[u]["hyp"] for u in utts]
+
+    def corpora(f):
+        return (scoring.TokenCorpus.from_sequences(utts, [[f(t) for t in s] for s in base_r], "r"),
+                scoring.TokenCorpus.from_sequences(utts, [[f(t) for t in s] for s in base_h], "h"))
+
+    want, lens = scoring.score_corpora(*corpora(lambda t: t), quiet=True)
+    rep, ign = {3: 5, 9: 100}, {0, -2}
+    want_ri, lens_ri = scoring.score_corpora(*corpora(lambda t: t), replace=rep, ignore=ign, quiet=True)
+    assert (lens_ri < lens).any()
+    for f in (lambda t: t * 1000 - 7, lambda t: t * (1 << 40) - 5, lambda t: t + (1 << 33)):
+        got, _ = scoring.score_corpora(*corpora(f), quiet=True)
+        np.testing.assert_array_equal(got, want)
+        for span in (1 << 26, 4):  # dense table / np.unique
+            monkeypatch.setattr(scoring, "_DENSE_SPAN", span)
+            got, gl = scoring.score_corpora(*corpora(f), replace={f(k): f(v) for k, v in rep.items()},
+                                            ignore={f(t) for t in ign}, quiet=True)
+            np.testing.assert_array_equal(got, want_ri)
+            np.testing.assert_array_equal(gl, lens_ri)
