@@ -217,6 +217,15 @@ const int32_t *b200lev_workspace_hyp_lens(const b200lev_tokens_t *ref,
 int b200lev_after_eos_mask(const int64_t *tokens, int64_t outer, int64_t T, int64_t inner,
                            int64_t eos, unsigned char *mask, void *stream);
 
+/* Bulk-scoring batches ("next #2" of the hot-path scope): what command_line.py:1110-1121 builds
+ * on the host with torch.tensor(transcript + [eos]) per utterance and pad_sequence.  The
+ * corpus is flat (tokens of elem_bytes 2, 4 or 8; offsets[k] .. offsets[k+1] = utterance k);
+ * row u of out (n, T) row-major = utterance sel[u] (u if sel is NULL), then eos, then pad.
+ * T must exceed every selected utterance's length.  All pointers are device pointers. */
+int b200lev_ragged_to_padded(const void *flat, int32_t elem_bytes, const int64_t *offsets,
+                             const int64_t *sel, int64_t n, int64_t T, int64_t eos, int64_t pad,
+                             void *out, void *stream);
+
 /* sequence_log_probs, tensor path (_decoding.py:1516-1548; "next #1" of the hot-path scope):
  *   out[a, b] = sum over the steps t that count of log_softmax(logits[a, t, b, :])[hyp[a, t, b]]
  * A step counts if its token lies in [0, V) and t <= the first eos of the sequence (a, b)

@@ -70,6 +70,8 @@ SIGNATURES = {
     "b200lev_workspace_ref_lens": (c_vp, [_PT, _PT, c_vp]),
     "b200lev_workspace_hyp_lens": (c_vp, [_PT, _PT, c_vp]),
     "b200lev_after_eos_mask": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "b200lev_ragged_to_padded": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64,
+                                                c_vp, c_vp]),
     "b200lev_seqlp_forward": (ctypes.c_int, [c_vp, c_i32, c_i64, c_i64, c_i64, c_i64, c_vp, c_i32,
                                              c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b200lev_seqlp_backward": (ctypes.c_int, [c_vp, c_i32, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp,

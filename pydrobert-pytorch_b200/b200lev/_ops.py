@@ -464,6 +464,29 @@ def _(tokens, eos, dim):
     return tokens.new_empty(tokens.shape, dtype=torch.bool)
 
 
+def ragged_to_padded(flat: Tensor, offsets: Tensor, sel: Optional[Tensor], first: int, count: int, T: int,
+                     eos: int, pad: int) -> Tensor:
+    """``(count, T)`` token matrix: row u = utterance ``sel[u]`` (``first + u`` without
+    ``sel``) of the flat corpus, then ``eos``, then ``pad`` (what command_line.py:1110-1121
+    builds with pad_sequence).  ``flat`` int16/int32/int64, ``offsets`` int64, same device."""
+    dev = _check_device(flat, offsets) if sel is None else _check_device(flat, offsets, sel)
+    if flat.dtype not in (torch.int16, torch.int32, torch.int64) or offsets.dtype != torch.int64:
+        raise _abi.B200LevError("ragged_to_padded: flat must be int16/int32/int64 and offsets int64")
+    if not (flat.is_contiguous() and offsets.is_contiguous() and (sel is None or sel.is_contiguous())):
+        raise _abi.B200LevError("ragged_to_padded: arguments must be contiguous")
+    if sel is not None and (sel.dtype != torch.int64 or sel.numel() != count):
+        raise _abi.B200LevError("ragged_to_padded: sel must hold `count` int64 indices")
+    if count < 0 or T < 1 or (sel is None and not (0 <= first and first + count <= offsets.numel() - 1)):
+        raise _abi.B200LevError("ragged_to_padded: utterance range outside offsets")
+    out = torch.empty((count, T), dtype=flat.dtype, device=dev)
+    off_ptr = offsets.data_ptr() + (0 if sel is not None else 8 * first)
+    with _DeviceGuard(dev):
+        _abi.check(_abi.lib().b200lev_ragged_to_padded(
+            flat.data_ptr(), flat.element_size(), off_ptr, 0 if sel is None else sel.data_ptr(), count, T,
+            int(eos), int(pad), out.data_ptr(), _stream(dev)))
+    return out
+
+
 @torch.library.custom_op("b200lev::error_sums", mutates_args=())
 def error_sums(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: bool, batch_first: bool,
                ins_cost: float, del_cost: float, sub_cost: float, norm: bool,

@@ -9,13 +9,12 @@ tensor of shape ``(L,)``, ``(L, 1)`` or ``(L, 3)`` = token / start / end).
 The reference walks Python lists token by token (a ``defaultdict`` token->id map, one
 ``pad_sequence`` + ``error_rate`` per 100 utterances).  Here a corpus is two flat arrays
 (tokens, offsets); ``--id2token`` / ``--replace`` / ``--ignore`` are applied once per
-DISTINCT token and pushed through the corpus as a look-up table; utterances are laid out
-as padded ``(N, T)`` int16/int32 matrices (eos ``-1``, padding ``-2``: codes are >= 0, so no
-token can collide with either; sorted by length when one call cannot hold the corpus, so
-that the padding stays small), and every matrix
-is ONE ``error_rate`` call -- host tensors, i.e. the three-stream column-block pipeline of
-``functional._string_matching_pipelined``.  Outputs (per-utterance lines, corpus rate)
-are formatted exactly as the reference prints them.
+DISTINCT token and pushed through the corpus as a look-up table; the coded corpus goes to
+the device flat (int16 when the vocabulary allows) and the padded ``(N, T)`` batches (eos
+``-1``, padding ``-2``: codes are >= 0, so no token can collide with either) are built there
+by ``lev_ragged.cu``; every batch is ONE ``error_rate`` call (the whole corpus when it fits
+the cell budget, else length-sorted runs so that the padding stays small).  Outputs
+(per-utterance lines, corpus rate) are formatted exactly as the reference prints them.
 """
 import argparse
 import os
@@ -27,7 +26,7 @@ from typing import Dict, Hashable, Iterable, List, Optional, Sequence, Set, Tupl
 import numpy as np
 import torch
 
-from . import config
+from . import _ops, config
 from . import functional as F
 
 __all__ = [
@@ -239,23 +238,10 @@ def _filtered(c: TokenCorpus, code: np.ndarray, keep: Optional[np.ndarray]) -> T
     return code[keep], csum[c.offsets]
 
 
-def _padded(flat: np.ndarray, off: np.ndarray, sel: np.ndarray, dtype) -> torch.Tensor:
-    """(len(sel), T) page-locked matrix, one utterance per ROW (``batch_first``): its codes,
-    then eos, then padding.  Row-major, so the codes of consecutive utterances land in
-    memory order -- one masked assignment."""
-    lens = (off[1:] - off[:-1])[sel]
-    n = sel.shape[0]
-    T = int(lens.max()) + 1 if n else 1
-    mat = torch.empty((n, T), dtype=dtype, pin_memory=torch.cuda.is_available())
-    m = mat.numpy()
-    m.fill(_PAD)
-    if n and int(sel[-1]) - int(sel[0]) == n - 1 and (n == 1 or bool((np.diff(sel) == 1).all())):
-        vals = flat[off[sel[0]]:off[sel[-1] + 1]]  # a run of consecutive utterances: a slice
-    else:
-        vals = flat[_ragged_arange(off[:-1][sel], lens)]
-    m[np.arange(T, dtype=np.int64)[None, :] < lens[:, None]] = vals
-    m[np.arange(n), lens] = _EOS
-    return mat
+def _to_device(a: np.ndarray) -> torch.Tensor:
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    (moved,), _ = F._offload(t)  # raises without a CUDA device: there is no CPU path
+    return moved
 
 
 def score_corpora(ref: TokenCorpus, hyp: TokenCorpus, id2token: Optional[Dict[int, str]] = None,
@@ -273,23 +259,30 @@ def score_corpora(ref: TokenCorpus, hyp: TokenCorpus, id2token: Optional[Dict[in
     hflat, hoff = _filtered(hyp, code[1], keep[1])
     rlen, hlen = np.diff(roff), np.diff(hoff)
     errors = np.zeros(N, dtype=np.float32)
-    dtype = torch.int16 if ncodes < (1 << 15) else torch.int32
-    if N and (int(rlen.max()) + int(hlen.max()) + 2) * N <= cell_budget:
-        order = np.arange(N)  # one call holds the corpus: keep the order (no gather)
+    if N == 0:
+        return errors, rlen
+    # the corpus goes to the device flat (int16 codes when the vocabulary allows: a quarter of
+    # the int64 bytes); the padded batches are built there (lev_ragged.cu)
+    rdev, hdev = _to_device(rflat), _to_device(hflat)
+    roff_d, hoff_d = _to_device(roff), _to_device(hoff)
+    if (int(rlen.max()) + int(hlen.max()) + 2) * N <= cell_budget:
+        order = None  # one call holds the corpus: rows in corpus order
     else:
         order = np.argsort(np.maximum(rlen, hlen), kind="stable")  # short ones together
     a = 0
     while a < N:
         # longest run of utterances (in `order`) whose two padded matrices fit the budget
-        width = np.maximum.accumulate(rlen[order[a:]] + 1) + np.maximum.accumulate(hlen[order[a:]] + 1)
+        rl, hl = (rlen[a:], hlen[a:]) if order is None else (rlen[order[a:]], hlen[order[a:]])
+        width = np.maximum.accumulate(rl + 1) + np.maximum.accumulate(hl + 1)
         fits = np.flatnonzero(width * np.arange(1, N - a + 1) <= cell_budget)
-        b = a + (int(fits[-1]) + 1 if fits.size else 1)
-        sel = order[a:b]
-        er = F.error_rate(_padded(rflat, roff, sel, dtype), _padded(hflat, hoff, sel, dtype), eos=_EOS,
-                          include_eos=False, norm=False, batch_first=True, ins_cost=costs[0],
-                          del_cost=costs[1], sub_cost=costs[2], warn=not quiet)
-        errors[sel] = er.cpu().numpy()
-        a = b
+        n = int(fits[-1]) + 1 if fits.size else 1
+        sel = None if order is None else _to_device(order[a:a + n])
+        rm = _ops.ragged_to_padded(rdev, roff_d, sel, a, n, int(rl[:n].max()) + 1, _EOS, _PAD)
+        hm = _ops.ragged_to_padded(hdev, hoff_d, sel, a, n, int(hl[:n].max()) + 1, _EOS, _PAD)
+        er = F.error_rate(rm, hm, eos=_EOS, include_eos=False, norm=False, batch_first=True,
+                          ins_cost=costs[0], del_cost=costs[1], sub_cost=costs[2], warn=not quiet)
+        errors[slice(a, a + n) if order is None else order[a:a + n]] = er.cpu().numpy()
+        a += n
     return errors, rlen
 
 

@@ -56,15 +56,30 @@ def main():
                       "ms": whole * 1e3, "utts_per_s": N / whole}))
     t_recode = timed(lambda: S._recode(ref, hyp, None, None, None))
     code, keep, ncodes = S._recode(ref, hyp, None, None, None)
-    rflat, roff2 = S._filtered(ref, code[0], keep[0])
-    hflat, hoff2 = S._filtered(hyp, code[1], keep[1])
-    sel = np.arange(N)
-    t_pad = timed(lambda: (S._padded(rflat, roff2, sel, torch.int16), S._padded(hflat, hoff2, sel, torch.int16)))
-    rm, hm = S._padded(rflat, roff2, sel, torch.int16), S._padded(hflat, hoff2, sel, torch.int16)
-    t_call = timed(lambda: S.F.error_rate(rm, hm, eos=-1, norm=False, batch_first=True, warn=False))
-    print(json.dumps({"stage": "parts", "recode_ms": t_recode * 1e3, "pad_ms": t_pad * 1e3,
-                      "error_rate_host_tensors_ms": t_call * 1e3,
-                      "h2d_bytes": int(rm.numel() + hm.numel()) * 2}))
+    t_h2d = timed(lambda: (S._to_device(code[0]), S._to_device(code[1]), S._to_device(ref.offsets),
+                           S._to_device(hyp.offsets)))
+    rd, hd, ro, ho = (S._to_device(code[0]), S._to_device(code[1]), S._to_device(ref.offsets),
+                      S._to_device(hyp.offsets))
+
+    def dev_ms(fn, reps=20):
+        fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    Tr, Th = int(rl.max()) + 1, int(hl.max()) + 1
+    ms_pad = dev_ms(lambda: (S._ops.ragged_to_padded(rd, ro, None, 0, N, Tr, -1, -2),
+                             S._ops.ragged_to_padded(hd, ho, None, 0, N, Th, -1, -2)))
+    rm, hm = S._ops.ragged_to_padded(rd, ro, None, 0, N, Tr, -1, -2), S._ops.ragged_to_padded(hd, ho, None, 0, N, Th, -1, -2)
+    ms_call = dev_ms(lambda: S.F.error_rate(rm, hm, eos=-1, norm=False, batch_first=True, warn=False))
+    pad_bytes = (rm.numel() + hm.numel()) * 2 + (rd.numel() + hd.numel()) * 2 + 2 * 8 * N
+    print(json.dumps({"stage": "parts", "recode_ms": t_recode * 1e3, "h2d_flat_ms": t_h2d * 1e3,
+                      "ragged_to_padded_x2_ms": ms_pad, "ragged_GBps": pad_bytes / ms_pad / 1e6,
+                      "error_rate_device_ms": ms_call, "h2d_bytes": int(rd.numel() + hd.numel()) * 2 + 16 * N}))
     if a.files > 0:
         with tempfile.TemporaryDirectory() as tmp:
             for i in range(a.files):

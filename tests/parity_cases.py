@@ -351,3 +351,47 @@ def check_golden_scoring(scoring, golden, tmp):
         assert missing == [m.replace("{tmp}", tmp) for m in case["warned_missing"]], (where, opts)
         n += 1
     return n
+
+
+def check_ragged_to_padded(dev, seed=0):
+    """b200lev_ragged_to_padded against pad_sequence over (utterance + [eos]), the reference's
+    own construction (command_line.py:1110-1121)."""
+    from b200lev import _abi, _ops
+
+    rng = np.random.default_rng(seed)
+    n = 0
+    for dtype in (torch.int16, torch.int32, torch.int64):
+        for N, L in ((1, 0), (7, 5), (300, 40), (33, 1)):
+            lens = rng.integers(0, L + 1, N)
+            seqs = [torch.from_numpy(rng.integers(0, 1000, int(k))).to(dtype) for k in lens]
+            off = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)).to(dev)
+            flat = (torch.cat(seqs) if N else torch.zeros(0, dtype=dtype)).to(dev)
+            T = int(lens.max()) + 1 + int(rng.integers(0, 3))
+            eos = torch.tensor([-1], dtype=dtype)
+
+            def expect(idx):
+                rows = torch.nn.utils.rnn.pad_sequence([torch.cat([seqs[i], eos]) for i in idx],
+                                                       padding_value=-2, batch_first=True)
+                full = torch.full((len(idx), T), -2, dtype=dtype)
+                full[:, :rows.shape[1]] = rows
+                return full
+
+            got = _ops.ragged_to_padded(flat, off, None, 0, N, T, -1, -2)
+            assert got.dtype == dtype and torch.equal(got.cpu(), expect(range(N)))
+            a, b = N // 3, N - N // 4
+            got = _ops.ragged_to_padded(flat, off, None, a, b - a, T, -1, -2)
+            assert torch.equal(got.cpu(), expect(range(a, b)))
+            sel = rng.permutation(N)[: max(1, N // 2)]
+            got = _ops.ragged_to_padded(flat, off, torch.from_numpy(sel).to(dev), 0, len(sel), T, -1, -2)
+            assert torch.equal(got.cpu(), expect(sel.tolist()))
+            n += 3
+    flat = torch.zeros(4, dtype=torch.int32, device=dev)
+    off = torch.tensor([0, 4], dtype=torch.int64, device=dev)
+    with pytest.raises(_abi.B200LevError, match="int16/int32/int64"):
+        _ops.ragged_to_padded(flat.to(torch.int8), off, None, 0, 1, 5, -1, -2)
+    with pytest.raises(_abi.B200LevError, match="outside offsets"):
+        _ops.ragged_to_padded(flat, off, None, 1, 1, 5, -1, -2)
+    with pytest.raises(_abi.B200LevError, match="sel must hold"):
+        _ops.ragged_to_padded(flat, off, torch.zeros(2, dtype=torch.int64, device=dev), 0, 1, 5, -1, -2)
+    assert _ops.ragged_to_padded(flat, off, None, 0, 0, 3, -1, -2).shape == (0, 3)
+    return n

@@ -475,3 +475,7 @@ def test_scoring_large_corpus_matches_direct_call(F, dev):
         got, lens = S.score_corpora(rc, hc, quiet=True, cell_budget=budget)
         np.testing.assert_array_equal(got, exp.cpu().numpy())
         np.testing.assert_array_equal(lens, rl)
+
+
+def test_ragged_to_padded(F, dev):
+    assert PC.check_ragged_to_padded(dev) == 36

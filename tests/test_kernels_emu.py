@@ -386,3 +386,7 @@ def test_scoring_recode_paths_agree(scoring, golden_scoring, monkeypatch):
                                             ignore={f(t) for t in ign}, quiet=True)
             np.testing.assert_array_equal(got, want_ri)
             np.testing.assert_array_equal(gl, lens_ri)
+
+
+def test_ragged_to_padded(F):
+    assert PC.check_ragged_to_padded(DEV) == 36
