@@ -179,6 +179,22 @@ def _check_known(c: TokenCorpus, id2token: Dict[int, str]) -> None:
 _DENSE_SPAN = 1 << 26
 
 
+_CHUNK = 1 << 22  # tokens per host task: numpy releases the GIL inside these loops
+_POOL = None
+
+
+def _chunked(fn, *arrays):
+    """fn over aligned slices of the arrays, on a few host threads when there is enough work."""
+    global _POOL
+    n = arrays[0].shape[0]
+    if n <= _CHUNK:
+        return [fn(*arrays)] if n else []
+    if _POOL is None:
+        _POOL = ThreadPoolExecutor(min(8, os.cpu_count() or 1))
+    cuts = range(0, n, _CHUNK)
+    return list(_POOL.map(lambda c: fn(*(a[c:c + _CHUNK] for a in arrays)), cuts))
+
+
 def _recode(ref: TokenCorpus, hyp: TokenCorpus, id2token: Optional[Dict[int, str]],
             replace: Optional[Dict[Hashable, Hashable]], ignore: Optional[Set[Hashable]]):
     """Token ids -> ((ref, hyp) codes >= 0, (ref, hyp) keep masks or None, #codes).  Equal codes <=> equal tokens
@@ -193,14 +209,17 @@ def _recode(ref: TokenCorpus, hyp: TokenCorpus, id2token: Optional[Dict[int, str
     if ref.tokens.size + hyp.tokens.size == 0:
         z = np.zeros(0, dtype=np.int32)
         return (z, z), (None, None), 0
-    lo = min(int(t.min()) for t in sides if t.size)
-    hi = max(int(t.max()) for t in sides if t.size)
+    ranges = [r for t in sides for r in _chunked(lambda a: (int(a.min()), int(a.max())), t)]
+    lo, hi = min(r[0] for r in ranges), max(r[1] for r in ranges)
     span = hi - lo + 1
     if id2token is None and not replace and not ignore and span < (1 << 31):
         # (t - lo) evaluated in the narrow type: exact modulo 2^16 / 2^32, and the result fits
         dt = np.int16 if span < (1 << 15) else np.int32
         lo_n = np.int64(lo).astype(dt)  # wrapped, like the tokens the narrow subtraction reads
-        return tuple(np.subtract(t, lo_n, dtype=dt, casting="unsafe") for t in sides), (None, None), span
+        outs = tuple(np.empty(t.shape, dtype=dt) for t in sides)
+        for t, o in zip(sides, outs):
+            _chunked(lambda a, b: np.subtract(a, lo_n, out=b, dtype=dt, casting="unsafe"), t, o)
+        return outs, (None, None), span
     if span <= _DENSE_SPAN:
         present = np.zeros(span, dtype=bool)
         rel = tuple(t - lo for t in sides)
