@@ -395,4 +395,5 @@ def compute_torch_token_data_dir_error_rates(args: Optional[Sequence[str]] = Non
             raise ZeroDivisionError("float division by zero")
         tot, denom = float(errs.sum()), (len(ref) if options.distances else float(rlen.sum()))
         options.out.write("{}\n".format(tot / denom))
+    options.out.flush()  # the reference leaves this to the file object's finaliser
     return None  # as the reference does on success (a console-script exit status of 0)

@@ -346,7 +346,8 @@ def check_golden_scoring(scoring, golden, tmp):
             else:
                 assert scoring.compute_torch_token_data_dir_error_rates(args) == case["rc"], (where, opts)
                 with open(out) as f:
-                    assert f.read() == case["out"], (where, opts)
+                    got = f.read()
+                assert got == case["out"], (where, opts, got[:200])
         missing = sorted(str(x.message) for x in w if "does not contain" in str(x.message))
         assert missing == [m.replace("{tmp}", tmp) for m in case["warned_missing"]], (where, opts)
         n += 1
