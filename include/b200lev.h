@@ -244,6 +244,21 @@ int b200lev_seqlp_backward(const void *logits, int32_t dtype, int64_t outer, int
                            const void *row_lse, const void *grad_out, void *grad_logits,
                            void *stream);
 
+/* ctc_greedy_search (_decoding.py:507-560; "next #4" of the hot-path scope).  logits:
+ * contiguous (outer, T, inner, V) of `dtype`; sequence q = (a, b) of (outer, inner); in_lens:
+ * int64[outer*inner] or NULL (every step valid); blank in [0, V).  Outputs: paths int64
+ * (outer, T, inner) = the arg max per step with blanks and repeats dropped, compacted to the
+ * front (positions >= out_lens keep the raw arg max, as the reference's masked_scatter_
+ * does); out_lens int64[outer*inner]; max_out[outer*inner] in the dtype of logits = the sum
+ * over valid steps of max(log_softmax) -- or, with is_probs, the product of the maxima.
+ * Scratch: arg int64 and row_val, row_lse accumulation-type (fp32; fp64 for F64), all
+ * (outer*T*inner); len int32[outer*inner] (clamped in_lens).  arg, row_lse and len are what
+ * b200lev_seqlp_backward needs (hyp := arg) for the gradient of max_out w.r.t. the logits. */
+int b200lev_ctc_greedy(const void *logits, int32_t dtype, int64_t outer, int64_t T, int64_t inner,
+                       int64_t V, const int64_t *in_lens, int64_t blank, int32_t is_probs,
+                       int64_t *arg, void *row_val, void *row_lse, int32_t *len, int64_t *paths,
+                       int64_t *out_lens, void *max_out, void *stream);
+
 /* Host-side plumbing for callers whose tensors live in HOST memory (the reference API accepts
  * CPU tensors: SM:146 has no device requirement): one strided 2-D copy between host and
  * device on `stream`, so that a caller can move a COLUMN block of a (T, N) tensor -- all

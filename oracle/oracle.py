@@ -425,3 +425,61 @@ def sequence_log_probs(logits, hyp, dim=0, eos=None, grad_out=None):
     np.put_along_axis(onehot, tok[..., None], 1.0, axis=-1)
     gz = np.where(ok[..., None], g[None, ..., None] * (onehot - soft), 0.0)
     return out, np.moveaxis(gz, 0, dim)
+
+
+def ctc_greedy_search(logits, in_lens=None, blank_idx=-1, batch_first=False, is_probs=False, grad_out=None):
+    """float64 restatement of ctc_greedy_search (_decoding.py:507-560).
+
+    Per step the arg max class (:531; first of equal maxima) of the log-softmax of ``logits``
+    (``(T, N, V)``; ``(N, T, V)`` if ``batch_first``) -- of ``logits`` itself with ``is_probs``
+    (:524-526); a step is kept unless it is blank or repeats the step before it (:532-534) or lies
+    beyond ``in_lens`` (:536-540); kept classes are moved to the front of ``paths``, whose other
+    positions keep the raw arg max (:546,555); ``max_`` = sum (product) of the maxima over the
+    valid steps (:541-554).  With ``grad_out`` (logits only) also d(max_ . grad_out)/d logits =
+    g (onehot(arg max) - softmax) on the valid steps -- the reference's own backward raises
+    (its in-place masked_scatter_ invalidates the saved arg max)."""
+    z = np.asarray(logits, dtype=np.float64)
+    if z.ndim != 3:
+        raise RuntimeError("logits must be 3-dimensional")
+    V = z.shape[2]
+    if blank_idx < -V or blank_idx > V - 1:
+        raise RuntimeError(
+            "Blank index out of range (expected to be in the range of "
+            f"[-{V},{V-1}], but got {blank_idx})")
+    blank = (blank_idx + V) % V
+    if not batch_first:
+        z = z.transpose(1, 0, 2)                       # (N, T, V)
+    N, T, _ = z.shape
+    arg = z.argmax(axis=2) if T else np.zeros((N, 0), dtype=np.int64)
+    if is_probs:
+        val = z.max(axis=2) if T else np.zeros((N, 0))
+    else:
+        m = z.max(axis=2, keepdims=True) if T else np.zeros((N, 0, 1))
+        m = np.where(np.isfinite(m), m, 0.0)
+        lse = m[..., 0] + np.log(np.exp(z - m).sum(axis=2))
+        val = np.take_along_axis(z, arg[..., None], axis=2)[..., 0] - lse if T else np.zeros((N, 0))
+    keep = arg != blank
+    if T > 1:
+        keep[:, 1:] &= arg[:, 1:] != arg[:, :-1]
+    valid = np.ones((N, T), dtype=bool)
+    if in_lens is not None:
+        valid = np.arange(T)[None, :] < np.asarray(in_lens).reshape(N, 1)
+        keep &= valid
+    out_lens = keep.sum(axis=1).astype(np.int64)
+    paths = arg.astype(np.int64).copy()
+    for n in range(N):
+        paths[n, :out_lens[n]] = arg[n][keep[n]]
+    max_ = np.where(valid, val, 1.0).prod(axis=1) if is_probs else np.where(valid, val, 0.0).sum(axis=1)
+    if not batch_first:
+        paths = paths.T
+    if grad_out is None:
+        return max_, paths, out_lens
+    if is_probs:
+        raise RuntimeError("gradient restated for logits only")
+    g = np.asarray(grad_out, dtype=np.float64).reshape(N, 1, 1)
+    onehot = np.zeros_like(z)
+    np.put_along_axis(onehot, arg[..., None], 1.0, axis=2)
+    gz = np.where(valid[..., None], g * (onehot - np.exp(z - lse[..., None])), 0.0)
+    if not batch_first:
+        gz = gz.transpose(1, 0, 2)
+    return max_, paths, out_lens, gz

@@ -369,6 +369,69 @@ sequence_log_probs.register_autograd(_seqlp_backward, setup_context=_seqlp_setup
 
 
 # ---------------------------------------------------------------------------------------
+# ctc_greedy_search (_decoding.py:507-560)
+# ---------------------------------------------------------------------------------------
+@torch.library.custom_op("b200lev::ctc_greedy_search", mutates_args=())
+def ctc_greedy_search(logits: Tensor, in_lens: Optional[Tensor], blank: int, is_probs: bool
+                      ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """``logits`` contiguous (outer, T, inner, V); ``in_lens`` int64 (outer*inner) or None.
+    Returns ``(max_ (outer, inner), paths (outer, T, inner), out_lens (outer, inner), arg,
+    row_lse, len)``; the last three are saved for the backward."""
+    dev = _check_device(logits) if in_lens is None else _check_device(logits, in_lens)
+    outer, T, inner, V = logits.shape
+    logits = logits.detach()
+    acc = _acc_dtype(logits)
+    n, rows = max(outer * inner, 1), max(outer * T * inner, 1)
+    arg = torch.empty(rows, dtype=torch.int64, device=dev)
+    row_val = torch.empty(rows, dtype=acc, device=dev)
+    row_lse = torch.empty(rows, dtype=acc, device=dev)
+    length = torch.empty(n, dtype=torch.int32, device=dev)
+    paths = torch.empty((outer, T, inner), dtype=torch.int64, device=dev)
+    out_lens = torch.zeros((outer, inner), dtype=torch.int64, device=dev)
+    max_ = torch.zeros((outer, inner), dtype=logits.dtype, device=dev)
+    lens = None if in_lens is None else in_lens.detach().to(torch.int64).contiguous()
+    with _DeviceGuard(dev):
+        _abi.check(_abi.lib().b200lev_ctc_greedy(
+            logits.data_ptr(), _float_code(logits), outer, T, inner, V,
+            0 if lens is None else lens.data_ptr(), int(blank), int(is_probs), arg.data_ptr(),
+            row_val.data_ptr(), row_lse.data_ptr(), length.data_ptr(), paths.data_ptr(),
+            out_lens.data_ptr(), max_.data_ptr(), _stream(dev)))
+    return max_, paths, out_lens, arg, row_lse, length
+
+
+@ctc_greedy_search.register_fake
+def _(logits, in_lens, blank, is_probs):
+    outer, T, inner, _ = logits.shape
+    acc = _acc_dtype(logits)
+    n, rows = max(outer * inner, 1), max(outer * T * inner, 1)
+    return (logits.new_empty((outer, inner)), logits.new_empty((outer, T, inner), dtype=torch.int64),
+            logits.new_empty((outer, inner), dtype=torch.int64), logits.new_empty((rows,), dtype=torch.int64),
+            logits.new_empty((rows,), dtype=acc), logits.new_empty((n,), dtype=torch.int32))
+
+
+def _ctc_setup(ctx, inputs, output):
+    logits, _, _, is_probs = inputs
+    _, _, _, arg, row_lse, length = output
+    ctx.is_probs = is_probs
+    ctx.save_for_backward(logits, arg, row_lse, length)
+
+
+def _ctc_backward(ctx, g_max, g_paths, g_lens, g_arg, g_lse, g_len):
+    if ctx.is_probs:
+        raise _abi.B200LevError("ctc_greedy_search: the gradient of the path probability is implemented "
+                                "for logits only (is_probs=False)")
+    logits, arg, row_lse, length = ctx.saved_tensors
+    outer, T, inner, _ = logits.shape
+    # d max_ / d logits = g * (onehot(arg max) - softmax) on the valid steps: the same kernel as
+    # sequence_log_probs' backward with the greedy path as the hypothesis
+    return (sequence_log_probs_backward(g_max, logits, arg.view(outer, T, inner), row_lse, length),
+            None, None, None)
+
+
+ctc_greedy_search.register_autograd(_ctc_backward, setup_context=_ctc_setup)
+
+
+# ---------------------------------------------------------------------------------------
 # MWER epilogue (forward / backward)
 # ---------------------------------------------------------------------------------------
 @torch.library.custom_op("b200lev::mwer_loss", mutates_args=())

@@ -16,7 +16,7 @@ no CPU implementation.
 from __future__ import annotations
 
 import warnings
-from typing import Optional
+from typing import Optional, Tuple
 
 import torch
 
@@ -32,6 +32,7 @@ __all__ = [
     "prefix_edit_distances",
     "prefix_error_rates",
     "sequence_log_probs",
+    "ctc_greedy_search",
 ]
 
 
@@ -468,3 +469,35 @@ def sequence_log_probs(logits, hyp: torch.Tensor, dim: int = 0, eos: Optional[in
         logits_d.contiguous().view(outer, T, inner, V),
         hyp_d.to(torch.long).contiguous().view(outer, T, inner), eos)
     return back(out.view(tuple(hyp.shape[:dim]) + tuple(hyp.shape[dim + 1:])))
+
+
+def ctc_greedy_search(logits: torch.Tensor, in_lens: Optional[torch.Tensor] = None, blank_idx: int = -1,
+                      batch_first: bool = False, is_probs: bool = False
+                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Functional version of CTCGreedySearch (_decoding.py:507-560): per step the most likely
+    class of ``logits`` (``(T, N, V)``, or ``(N, T, V)`` if ``batch_first``); returns the path
+    score ``max_ (N,)`` (sum of the chosen log-probabilities; product of the chosen
+    probabilities with ``is_probs``), ``paths`` (``(T, N)`` / ``(N, T)`` long: blanks and repeats
+    removed, compacted to the front) and ``out_lens (N,)``.  Equal maxima resolve to the lowest
+    class index.  ``max_`` is differentiable w.r.t. ``logits`` when ``is_probs`` is false."""
+    if logits.dim() != 3:
+        raise RuntimeError("logits must be 3-dimensional")
+    V = logits.size(2)
+    if blank_idx < -V or blank_idx > (V - 1):
+        raise RuntimeError(
+            "Blank index out of range (expected to be in the range of "
+            f"[-{V},{V-1}], but got {blank_idx})"
+        )
+    if not logits.is_floating_point():
+        raise RuntimeError("logits must be floating point")
+    blank = (blank_idx + V) % V
+    N = logits.size(0) if batch_first else logits.size(1)
+    T = logits.size(1) if batch_first else logits.size(0)
+    if in_lens is not None and tuple(in_lens.shape) != (N,):
+        raise RuntimeError(f"in_lens must have shape ({N},), got {tuple(in_lens.shape)}")
+    (logits_d, lens_d), back = _offload(logits, in_lens)
+    outer, inner = (N, 1) if batch_first else (1, N)
+    max_, paths, out_lens, _, _, _ = _ops.ctc_greedy_search(
+        logits_d.contiguous().view(outer, T, inner, V), lens_d, blank, is_probs)
+    shape = (N, T) if batch_first else (T, N)
+    return back(max_.view(N)), back(paths.view(shape)), back(out_lens.view(N))

@@ -14,8 +14,9 @@ from . import modules as _M
 
 # sequence_log_probs / SequenceLogProbabilities cover the tensor path only (the reference also
 # accepts a PackedSequence there), so they are offered by name but not rebound behind the
-# reference's back
-_NOT_REBOUND = ("sequence_log_probs", "SequenceLogProbabilities")
+# reference's back; ctc_greedy_search / CTCGreedySearch differentiate logits only (not
+# is_probs=True) and are offered the same way
+_NOT_REBOUND = ("sequence_log_probs", "SequenceLogProbabilities", "ctc_greedy_search", "CTCGreedySearch")
 _FUNCS = tuple(n for n in _F.__all__ if n not in _NOT_REBOUND)
 _CLASSES = tuple(n for n in _M.__all__ if n not in _NOT_REBOUND)
 _saved = {}

@@ -8,7 +8,7 @@ forward calls the functional of the same name, which dispatches to the sm_100a k
 from __future__ import annotations
 
 import abc
-from typing import Optional
+from typing import Optional, Tuple
 
 import torch
 
@@ -25,6 +25,7 @@ __all__ = [
     "PrefixEditDistances",
     "PrefixErrorRates",
     "SequenceLogProbabilities",
+    "CTCGreedySearch",
 ]
 
 _REDUCTIONS = ("mean", "sum", "none")
@@ -317,3 +318,29 @@ class SequenceLogProbabilities(torch.nn.Module):
 
     def forward(self, logits: torch.Tensor, hyp: torch.Tensor) -> torch.Tensor:
         return F.sequence_log_probs(logits, hyp, self.dim, self.eos)
+
+
+class CTCGreedySearch(torch.nn.Module):
+    """CTC greedy search (_decoding.py:563-633): the most likely class per step with blanks and
+    repeats removed, and the (log-)probability of that path"""
+
+    __constants__ = "blank_idx", "batch_first", "is_probs"
+    blank_idx: int
+    batch_first: bool
+    is_probs: bool
+
+    def __init__(self, blank_idx: int = -1, batch_first: bool = False, is_probs: bool = False):
+        blank_idx = argcheck.is_int(blank_idx, "blank_idx")
+        batch_first = argcheck.is_bool(batch_first, "batch_first")
+        is_probs = argcheck.is_bool(is_probs, "is_probs")
+        super().__init__()
+        self.blank_idx = blank_idx
+        self.batch_first = batch_first
+        self.is_probs = is_probs
+
+    def extra_repr(self) -> str:
+        return ", ".join(f"{x}={getattr(self, x)}" for x in self.__constants__)
+
+    def forward(self, logits: torch.Tensor, in_lens: Optional[torch.Tensor] = None
+                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        return F.ctc_greedy_search(logits, in_lens, self.blank_idx, self.batch_first, self.is_probs)

@@ -450,3 +450,205 @@ extern "C" int b200lev_seqlp_backward(const void* logits, int32_t dtype, int64_t
     SLP_DT_SWITCH(dtype, CALL)
 #undef CALL
 }
+
+// ======================= ctc_greedy_search (_decoding.py:507-560) ========================
+// Row pass (one warp per (sequence, step) row of V classes, one read of the logits): the
+// arg max (first index among equal maxima), the value the reference sums -- max - logsumexp
+// for logits (DC:524-526,531), the max itself for probabilities -- and the row's logsumexp
+// for the backward pass.  Path pass (one warp per sequence): blanks and repeats dropped
+// (DC:532-534), steps beyond in_lens ignored (DC:536-545), survivors compacted to the front
+// in order (DC:546-555: masked_select + masked_scatter_, so positions >= out_lens keep the raw
+// arg max), values summed / multiplied over the valid steps (DC:551-554).
+template <int DT>
+struct SlpTop {
+    typename SlpElem<DT>::Acc m, s;
+    int64_t i;
+};
+
+template <int DT, bool PROBS>
+__device__ __forceinline__ SlpTop<DT> slp_row_top(const typename SlpElem<DT>::T* z, int64_t V, int lane) {
+    typedef typename SlpElem<DT>::Acc A;
+    constexpr int VEC = SlpElem<DT>::VEC;
+    A m = -(A)INFINITY, ms = -(A)INFINITY, s = (A)0;
+    int64_t arg = 0;
+    bool any = false;
+    auto feed = [&](const A* x, int n, int64_t base) {
+        A cm = x[0];
+        int ck = 0;
+        for (int k = 1; k < n; ++k)
+            if (x[k] > cm) {
+                cm = x[k];
+                ck = k;
+            }
+        if (cm > m || !any) {  // strictly greater: the first of equal maxima stays
+            if (!PROBS && any) s *= slp_exp(m - cm);
+            m = cm;
+            ms = slp_scale(cm);
+            arg = base + ck;
+            any = true;
+        }
+        if (!PROBS && m > -(A)INFINITY)
+            for (int k = 0; k < n; ++k) s += slp_expm(x[k], ms);
+    };
+    const bool aligned = ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
+    int64_t v0 = 0;
+    if (aligned) {
+        const int64_t nvec = V / VEC;
+        int64_t c = lane;
+        for (; c + 96 < nvec; c += 128) {  // four 128-bit loads in flight per lane
+            uint4 r[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) r[u] = *reinterpret_cast<const uint4*>(z + (c + 32 * u) * VEC);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                A x[VEC];
+                slp_unpack<DT>(r[u], x);
+                feed(x, VEC, (c + 32 * u) * VEC);
+            }
+        }
+        for (; c < nvec; c += 32) {
+            A x[VEC];
+            slp_load_vec<DT>(z + c * VEC, x);
+            feed(x, VEC, c * VEC);
+        }
+        v0 = nvec * VEC;
+    }
+    for (int64_t v = v0 + lane; v < V; v += 32) {
+        A x[1] = {(A)SlpElem<DT>::ld(z + v)};
+        feed(x, 1, v);
+    }
+    // butterfly: larger maximum wins, equal maxima -> smaller index; sums rescaled to the winner
+    for (int o = 16; o > 0; o >>= 1) {
+        const A m2 = __shfl_xor_sync(0xffffffffu, m, o);
+        const A s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        const int64_t i2 = __shfl_xor_sync(0xffffffffu, arg, o);
+        const bool a2 = __shfl_xor_sync(0xffffffffu, (int)any, o) != 0;
+        if (a2 && (!any || m2 > m || (m2 == m && i2 < arg))) {
+            if (!PROBS) s = (any && m > -(A)INFINITY ? s * slp_exp(m - m2) : (A)0) + s2;
+            m = m2;
+            arg = i2;
+            any = true;
+        } else if (a2 && !PROBS) {
+            s += (m2 > -(A)INFINITY ? s2 * slp_exp(m2 - m) : (A)0);
+        }
+    }
+    SlpTop<DT> r;
+    r.m = m;
+    r.s = s;
+    r.i = arg;
+    return r;
+}
+
+template <int DT, bool PROBS>
+__global__ void __launch_bounds__(256)
+lev_ctc_row_kernel(const typename SlpElem<DT>::T* __restrict__ logits, int64_t rows, int64_t V,
+                   int64_t* __restrict__ arg, typename SlpElem<DT>::Acc* __restrict__ row_val,
+                   typename SlpElem<DT>::Acc* __restrict__ row_lse) {
+    typedef typename SlpElem<DT>::Acc A;
+    const int lane = threadIdx.x & 31;
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+         row += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        const SlpTop<DT> top = slp_row_top<DT, PROBS>(logits + row * V, V, lane);
+        if (lane == 0) {
+            arg[row] = top.i;
+            if (PROBS) {
+                row_val[row] = top.m;
+                row_lse[row] = (A)0;
+            } else {
+                const A lse = top.m + slp_log(top.s);
+                row_lse[row] = lse;
+                row_val[row] = SlpElem<DT>::round(top.m - lse);  // log_softmax in the logits' dtype
+            }
+        }
+    }
+}
+
+template <int DT, bool PROBS>
+__global__ void __launch_bounds__(256)
+lev_ctc_path_kernel(const int64_t* __restrict__ arg, const typename SlpElem<DT>::Acc* __restrict__ row_val,
+                    const int64_t* __restrict__ in_lens, int64_t outer, int64_t T, int64_t inner,
+                    int64_t blank, int32_t* __restrict__ len, int64_t* __restrict__ paths,
+                    int64_t* __restrict__ out_lens, typename SlpElem<DT>::T* __restrict__ max_out) {
+    typedef typename SlpElem<DT>::Acc A;
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= outer * inner) return;
+    const int64_t a = q / inner, b = q - a * inner;
+    int64_t n = T;
+    if (in_lens != nullptr) n = in_lens[q];
+    const int64_t nv = n < 0 ? 0 : (n > T ? T : n);  // arange(T) < in_lens
+    int64_t count = 0, last = -1;
+    A acc = PROBS ? (A)1 : (A)0;
+    for (int64_t t0 = 0; t0 < T; t0 += 32) {
+        const int64_t t = t0 + lane;
+        const int64_t cur = t < T ? arg[(a * T + t) * inner + b] : (int64_t)-1;
+        int64_t prev = __shfl_up_sync(0xffffffffu, cur, 1);
+        if (lane == 0) prev = last;
+        last = __shfl_sync(0xffffffffu, cur, 31);
+        const bool keep = t < nv && cur != blank && (t == 0 || cur != prev);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) paths[(a * T + count + __popc(bal & ((1u << lane) - 1u))) * inner + b] = cur;
+        count += __popc(bal);
+        if (t < nv) {
+            const A v = row_val[(a * T + t) * inner + b];
+            acc = PROBS ? SlpElem<DT>::round(acc * v) : acc + v;
+        }
+    }
+    // positions past the reduced path keep the raw arg max (masked_scatter_ leaves them)
+    for (int64_t t = count + lane; t < T; t += 32) paths[(a * T + t) * inner + b] = arg[(a * T + t) * inner + b];
+    // fixed butterfly over the lanes' partial sums / products
+    for (int o = 16; o > 0; o >>= 1) {
+        const A other = __shfl_xor_sync(0xffffffffu, acc, o);
+        acc = PROBS ? SlpElem<DT>::round(acc * other) : acc + other;
+    }
+    if (lane == 0) {
+        out_lens[q] = count;
+        len[q] = (int32_t)nv;
+        SlpElem<DT>::st(max_out + q, acc);
+    }
+}
+
+template <int DT>
+static int slp_ctc(const void* logits, int64_t outer, int64_t T, int64_t inner, int64_t V,
+                   const int64_t* in_lens, int64_t blank, int32_t probs, int64_t* arg, void* row_val,
+                   void* row_lse, int32_t* len, int64_t* paths, int64_t* out_lens, void* max_out,
+                   cudaStream_t st) {
+    typedef typename SlpElem<DT>::T Tt;
+    typedef typename SlpElem<DT>::Acc A;
+    const int64_t rows = outer * inner * T, nseq = outer * inner;
+    if (rows > 0) {
+        if (probs)
+            lev_launch(lev_ctc_row_kernel<DT, true>, dim3(slp_row_grid(rows)), dim3(256), 0, st,
+                       (const Tt*)logits, rows, V, arg, (A*)row_val, (A*)row_lse);
+        else
+            lev_launch(lev_ctc_row_kernel<DT, false>, dim3(slp_row_grid(rows)), dim3(256), 0, st,
+                       (const Tt*)logits, rows, V, arg, (A*)row_val, (A*)row_lse);
+    }
+    const dim3 grid((unsigned)((nseq + 7) / 8));
+    if (probs)
+        lev_launch(lev_ctc_path_kernel<DT, true>, grid, dim3(256), 0, st, (const int64_t*)arg,
+                   (const A*)row_val, in_lens, outer, T, inner, blank, len, paths, out_lens, (Tt*)max_out);
+    else
+        lev_launch(lev_ctc_path_kernel<DT, false>, grid, dim3(256), 0, st, (const int64_t*)arg,
+                   (const A*)row_val, in_lens, outer, T, inner, blank, len, paths, out_lens, (Tt*)max_out);
+    return lev_check_cuda("lev_ctc_greedy");
+}
+
+extern "C" int b200lev_ctc_greedy(const void* logits, int32_t dtype, int64_t outer, int64_t T,
+                                  int64_t inner, int64_t V, const int64_t* in_lens, int64_t blank,
+                                  int32_t is_probs, int64_t* arg, void* row_val, void* row_lse,
+                                  int32_t* len, int64_t* paths, int64_t* out_lens, void* max_out,
+                                  void* stream) {
+    if (outer < 0 || T < 0 || inner < 0 || V < 1 || blank < 0 || blank >= V) {
+        lev_set_error("b200lev_ctc_greedy: bad dimensions or blank index");
+        return B200LEV_ERR_ARG;
+    }
+    if (outer * inner == 0) return B200LEV_OK;
+    if ((T > 0 && (!logits || !arg || !row_val || !row_lse || !paths)) || !len || !out_lens || !max_out) {
+        lev_set_error("b200lev_ctc_greedy: NULL buffer");
+        return B200LEV_ERR_ARG;
+    }
+#define CALL(DT_) slp_ctc<DT_>(logits, outer, T, inner, V, in_lens, blank, is_probs, arg, row_val, row_lse, len, paths, out_lens, max_out, (cudaStream_t)stream)
+    SLP_DT_SWITCH(dtype, CALL)
+#undef CALL
+}

@@ -96,6 +96,22 @@ def main():
     ms = timed(slp, 10)
     out.append(dict(cfg=2, call="sequence_log_probs fwd+bwd (bf16, V=10k)", pairs=512, ms=ms,
                     gbs_3_passes=3 * lg.numel() * 2 / ms / 1e6))
+    # "next #4": ctc_greedy_search on the same logits (one read: 1.01 GB)
+    ms = timed(lambda: F.ctc_greedy_search(lg.detach(), None, 0), 20)
+    out.append(dict(cfg=2, call="ctc_greedy_search fwd (bf16, V=10k)", pairs=512, ms=ms,
+                    gbs=lg.numel() * 2 / ms / 1e6))
+
+    def ctc_torch():  # the reference's op sequence (_decoding.py:524-555) on the device
+        RF_lp = lg.detach().log_softmax(2).transpose(0, 1)
+        mx, am = RF_lp.max(2)
+        keep = am != 0
+        keep = torch.cat([keep[:, :1], keep[:, 1:] & (am[:, 1:] != am[:, :-1])], 1)
+        ol = keep.long().sum(1)
+        data = am.masked_select(keep)
+        olm = torch.arange(am.size(1), device=dev).unsqueeze(0) < ol.unsqueeze(1)
+        return mx.sum(1), am.masked_scatter_(olm, data).t(), ol
+
+    out[-1]["stock_torch_ops_ms"] = timed(ctc_torch, 10)
     del lg
     trx = torch.from_numpy(np.repeat(r, 8, axis=1)).to(dev)
     th2 = torch.from_numpy(h).to(dev)

@@ -66,6 +66,11 @@ def golden_seqlp():
 
 
 @pytest.fixture(scope="session")
+def golden_ctc():
+    return Golden("ctc.npz")
+
+
+@pytest.fixture(scope="session")
 def golden_scoring():
     with open(os.path.join(GOLDEN, "scoring.json")) as f:
         return json.load(f)

@@ -323,8 +323,48 @@ def gen_seqlp_cases():
     print("seqlp.npz:", len(params), "cases")
 
 
+def gen_ctc_cases():
+    """ctc_greedy_search (_decoding.py:507-560): max_, paths (whole tensor: positions past
+    out_lens keep the raw arg max) and out_lens of the reference; small class counts so that
+    blanks and repeats are frequent.  No gradients: the reference's backward raises (its
+    in-place masked_scatter_ invalidates the arg max saved for max's backward)."""
+    g = np.random.default_rng(20240918)
+    store, params = {}, {}
+    for (T, N, V) in ((1, 1, 2), (7, 3, 3), (20, 5, 4), (45, 4, 6), (70, 2, 3), (33, 6, 40), (12, 3, 300)):
+        for batch_first in (False, True):
+            for lens_kind in ("none", "ragged"):
+                for is_probs in (False, True):
+                    for blank_idx in (-1, 0):
+                        for dt in ("float32", "float64"):
+                            if dt == "float64" and (len(params) % 3):
+                                continue
+                            if T * N * V > 1000 and (lens_kind == "none" or blank_idx == 0 or dt == "float64"):
+                                continue  # the wide-row cases only in a few combinations
+                            name = f"c{len(params)}"
+                            tdt = getattr(torch, dt)
+                            # values exactly representable in float32: the fixture stores float32
+                            x = torch.tensor(g.standard_normal((T, N, V)) * 2.0).float().to(tdt)
+                            if is_probs:
+                                x = x.softmax(2).float().to(tdt)
+                            if batch_first:
+                                x = x.transpose(0, 1).contiguous()
+                            lens = None if lens_kind == "none" else torch.tensor(g.integers(0, T + 3, N))
+                            max_, paths, out_lens = F.ctc_greedy_search(x, lens, blank_idx, batch_first, is_probs)
+                            store[name + ".logits"] = x.float().numpy()
+                            if lens is not None:
+                                store[name + ".in_lens"] = lens.numpy().astype(np.int16)
+                            store[name + ".max"] = max_.numpy()
+                            store[name + ".paths"] = paths.numpy().astype(np.int16)
+                            store[name + ".out_lens"] = out_lens.numpy().astype(np.int16)
+                            params[name] = dict(batch_first=batch_first, is_probs=is_probs, blank_idx=blank_idx,
+                                                dtype=dt, lens=lens is not None)
+    store["params"] = np.array(json.dumps(params))
+    np.savez_compressed(os.path.join(HERE, "ctc.npz"), **store)
+    print("ctc.npz:", len(params), "cases")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["string", "loss", "sclite", "seqlp"]
+    which = sys.argv[1:] or ["string", "loss", "sclite", "seqlp", "ctc"]
     if "string" in which:
         gen_string_cases()
     if "loss" in which:
@@ -333,3 +373,5 @@ if __name__ == "__main__":
         gen_sclite()
     if "seqlp" in which:
         gen_seqlp_cases()
+    if "ctc" in which:
+        gen_ctc_cases()

@@ -396,3 +396,54 @@ def check_ragged_to_padded(dev, seed=0):
         _ops.ragged_to_padded(flat, off, torch.zeros(2, dtype=torch.int64, device=dev), 0, 1, 5, -1, -2)
     assert _ops.ragged_to_padded(flat, off, None, 0, 0, 3, -1, -2).shape == (0, 3)
     return n
+
+
+# ---- ctc_greedy_search (_decoding.py:507-560) ------------------------------------------------
+# relative, on a sum / product over T steps; a log-probability is max - logsumexp, so in logits
+# mode each step also carries an absolute error of the order eps * |logsumexp| (1e-6 per step)
+CTC_TOL = {"float32": 2e-6, "float64": 1e-12}
+
+
+def _ctc_case(golden, name):
+    p = golden.params[name]
+    dt = getattr(torch, p["dtype"])
+    logits = torch.from_numpy(golden.get(name, "logits")).to(dt)
+    lens = torch.from_numpy(golden.get(name, "in_lens").astype(np.int64)) if p["lens"] else None
+    return p, logits, lens
+
+
+def check_golden_ctc(F, dev, golden):
+    n = 0
+    for name in golden.params:
+        p, logits, lens = _ctc_case(golden, name)
+        max_, paths, out_lens = F.ctc_greedy_search(logits.to(dev), None if lens is None else lens.to(dev),
+                                                    p["blank_idx"], p["batch_first"], p["is_probs"])
+        assert max_.dtype == logits.dtype and paths.dtype == torch.long and out_lens.dtype == torch.long
+        np.testing.assert_array_equal(paths.cpu().numpy(), golden.get(name, "paths"), err_msg=f"{name} {p}")
+        np.testing.assert_array_equal(out_lens.cpu().numpy(), golden.get(name, "out_lens"), err_msg=name)
+        T = logits.shape[1 if p["batch_first"] else 0]
+        tol = CTC_TOL[p["dtype"]]
+        np.testing.assert_allclose(max_.double().cpu().numpy(), golden.get(name, "max").astype(np.float64),
+                                   rtol=tol, atol=1e-30 if p["is_probs"] else tol * T, err_msg=f"{name} {p}")
+        n += 1
+    return n
+
+
+def check_ctc_vs_oracle(F, dev, seed, T, N, V, batch_first, dtype=torch.float32, with_lens=True):
+    """Forward and the gradient of max_ (logits mode) against the float64 oracle."""
+    rng = np.random.default_rng(seed)
+    shape = (N, T, V) if batch_first else (T, N, V)
+    x = torch.tensor(rng.standard_normal(shape) * 2.0).to(dtype)
+    lens = torch.from_numpy(rng.integers(0, T + 2, N)) if with_lens else None
+    g = rng.standard_normal(N)
+    logits = x.clone().to(dev).requires_grad_(True)
+    max_, paths, out_lens = F.ctc_greedy_search(logits, None if lens is None else lens.to(dev), 1, batch_first)
+    (max_ * torch.tensor(g).to(dev).to(dtype)).sum().backward()
+    e_max, e_paths, e_lens, e_grad = O.ctc_greedy_search(x.double().numpy(), None if lens is None else lens.numpy(),
+                                                         1, batch_first, False, grad_out=g)
+    np.testing.assert_array_equal(paths.cpu().numpy(), e_paths)
+    np.testing.assert_array_equal(out_lens.cpu().numpy(), e_lens)
+    rtol, atol = SEQLP_TOL[str(dtype).replace("torch.", "")]
+    np.testing.assert_allclose(max_.detach().double().cpu().numpy(), e_max, rtol=max(rtol, 2e-6), atol=max(atol, 2e-6 * T))
+    np.testing.assert_allclose(logits.grad.double().cpu().numpy(), e_grad, rtol=rtol,
+                               atol=atol * max(1.0, float(np.abs(g).max())))

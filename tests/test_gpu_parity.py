@@ -479,3 +479,36 @@ def test_scoring_large_corpus_matches_direct_call(F, dev):
 
 def test_ragged_to_padded(F, dev):
     assert PC.check_ragged_to_padded(dev) == 36
+
+
+# ---- ctc_greedy_search -----------------------------------------------------
+def test_ctc_golden(F, dev, golden_ctc):
+    assert PC.check_golden_ctc(F, dev, golden_ctc) == 106
+
+
+@pytest.mark.parametrize("batch_first", [False, True])
+@pytest.mark.parametrize("shape", [(9, 4, 5), (40, 3, 37), (5, 2, 300), (70, 2, 3), (120, 7, 1003)])
+def test_ctc_vs_oracle_with_gradient(F, dev, shape, batch_first):
+    PC.check_ctc_vs_oracle(F, dev, seed=sum(shape), T=shape[0], N=shape[1], V=shape[2], batch_first=batch_first)
+    PC.check_ctc_vs_oracle(F, dev, seed=1 + sum(shape), T=shape[0], N=shape[1], V=shape[2],
+                           batch_first=batch_first, dtype=torch.float64, with_lens=False)
+
+
+def test_ctc_full_size_against_torch_ops(F, dev):
+    """cfg2-sized logits (100, 512, 10 000) bf16: paths, lengths and score against the same
+    computation written with stock torch ops on the device (fp32 log-softmax of the bf16 values)."""
+    g = torch.Generator(device="cpu").manual_seed(3)
+    T, N, V = 100, 512, 10_000
+    x = (torch.randn((T, N, V), generator=g, dtype=torch.float32) * 2).to(torch.bfloat16).to(dev)
+    lens = torch.randint(0, T + 1, (N,), generator=g).to(dev)
+    max_, paths, out_lens = F.ctc_greedy_search(x, lens, 0)
+    lp = x.float().log_softmax(2)
+    val, arg = lp.max(2)
+    valid = torch.arange(T, device=dev)[:, None] < lens[None, :]
+    keep = (arg != 0) & valid
+    keep[1:] &= arg[1:] != arg[:-1]
+    assert torch.equal(out_lens, keep.sum(0))
+    for n in range(0, N, 37):
+        assert torch.equal(paths[: int(out_lens[n]), n], arg[:, n][keep[:, n]])
+    exp = torch.where(valid, val, torch.zeros_like(val)).sum(0)
+    torch.testing.assert_close(max_.float(), exp, rtol=2e-2, atol=1e-2)

@@ -392,3 +392,46 @@ def test_scoring_recode_paths_agree(scoring, golden_scoring, monkeypatch):
 
 def test_ragged_to_padded(F):
     assert PC.check_ragged_to_padded(DEV) == 36
+
+
+# ---- ctc_greedy_search -----------------------------------------------------
+def test_ctc_golden(F, golden_ctc):
+    assert PC.check_golden_ctc(F, DEV, golden_ctc) == 106
+
+
+@pytest.mark.parametrize("batch_first", [False, True])
+@pytest.mark.parametrize("shape", [(9, 4, 5), (40, 3, 37), (5, 2, 300), (70, 2, 3)])
+def test_ctc_vs_oracle_with_gradient(F, shape, batch_first):
+    PC.check_ctc_vs_oracle(F, DEV, seed=sum(shape), T=shape[0], N=shape[1], V=shape[2], batch_first=batch_first)
+    PC.check_ctc_vs_oracle(F, DEV, seed=1 + sum(shape), T=shape[0], N=shape[1], V=shape[2],
+                           batch_first=batch_first, dtype=torch.float64, with_lens=False)
+
+
+def test_ctc_low_precision_ties_and_errors(F):
+    """bf16 rows with many equal maxima: the lowest class index wins (as the oracle's arg max)."""
+    from b200lev import _abi
+
+    rng = np.random.default_rng(5)
+    x = torch.tensor(rng.integers(-2, 3, (30, 4, 9)).astype(np.float32)).to(torch.bfloat16)
+    max_, paths, out_lens = F.ctc_greedy_search(x, None, 0)
+    e_max, e_paths, e_lens = PC.O.ctc_greedy_search(x.float().numpy(), None, 0)
+    np.testing.assert_array_equal(paths.numpy(), e_paths)
+    np.testing.assert_array_equal(out_lens.numpy(), e_lens)
+    np.testing.assert_allclose(max_.float().numpy(), e_max, rtol=2e-2)
+    with pytest.raises(RuntimeError, match="3-dimensional"):
+        F.ctc_greedy_search(torch.zeros(3, 4))
+    with pytest.raises(RuntimeError, match=r"Blank index out of range \(expected to be in the range of \[-5,4\], but got 5\)"):
+        F.ctc_greedy_search(torch.zeros(3, 4, 5), None, 5)
+    with pytest.raises(RuntimeError, match="in_lens must have shape"):
+        F.ctc_greedy_search(torch.zeros(3, 4, 5), torch.zeros(3, dtype=torch.long))
+    p = torch.full((3, 2, 4), 0.25, requires_grad=True)
+    m, _, _ = F.ctc_greedy_search(p, None, -1, False, True)
+    with pytest.raises(_abi.B200LevError, match="logits only"):
+        m.sum().backward()
+    m, paths, lens = F.ctc_greedy_search(torch.zeros(0, 2, 4))
+    assert m.tolist() == [0.0, 0.0] and paths.shape == (0, 2) and lens.tolist() == [0, 0]
+    import b200lev.modules as M
+
+    mod = M.CTCGreedySearch(blank_idx=0, batch_first=True)
+    assert "blank_idx=0, batch_first=True, is_probs=False" == mod.extra_repr()
+    assert mod(torch.zeros(2, 3, 4))[2].tolist() == [0, 0]

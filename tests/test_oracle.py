@@ -266,3 +266,21 @@ def test_seqlp_oracle_matches_reference_fixtures(golden_seqlp):
                                    err_msg=name)
         n += 1
     assert n == 84
+
+
+def test_ctc_greedy_oracle_against_reference_fixture(golden_ctc):
+    """oracle.ctc_greedy_search reproduces every case make_golden.py ran through the
+    reference: paths (whole tensor), out_lens, max_."""
+    import parity_cases as PC
+
+    for name in golden_ctc.params:
+        p, logits, lens = PC._ctc_case(golden_ctc, name)
+        max_, paths, out_lens = O.ctc_greedy_search(logits.numpy(), None if lens is None else lens.numpy(),
+                                                    p["blank_idx"], p["batch_first"], p["is_probs"])
+        np.testing.assert_array_equal(paths, golden_ctc.get(name, "paths"), err_msg=name)
+        np.testing.assert_array_equal(out_lens, golden_ctc.get(name, "out_lens"), err_msg=name)
+        np.testing.assert_allclose(max_, golden_ctc.get(name, "max").astype(np.float64),
+                                   rtol=3e-6 if p["dtype"] == "float32" else 1e-12,
+                                   atol=1e-30 if p["is_probs"] else (3e-6 if p["dtype"] == "float32" else 1e-12)
+                                   * logits.shape[1 if p["batch_first"] else 0], err_msg=name)
+    assert len(golden_ctc.params) == 106
