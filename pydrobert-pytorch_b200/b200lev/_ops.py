@@ -607,3 +607,19 @@ def optimal_completion_fast(*args):
     if _needs_dispatcher():
         return optimal_completion(*args)
     return optimal_completion._init_fn(*args)
+
+
+def _wants_grad(t: Tensor) -> bool:
+    return torch.is_grad_enabled() and t.requires_grad
+
+
+def sequence_log_probs_fast(logits, hyp, eos):
+    if _needs_dispatcher() or _wants_grad(logits):
+        return sequence_log_probs(logits, hyp, eos)
+    return sequence_log_probs._init_fn(logits, hyp, eos)
+
+
+def ctc_greedy_search_fast(logits, in_lens, blank, is_probs):
+    if _needs_dispatcher() or _wants_grad(logits):
+        return ctc_greedy_search(logits, in_lens, blank, is_probs)
+    return ctc_greedy_search._init_fn(logits, in_lens, blank, is_probs)

@@ -465,7 +465,7 @@ def sequence_log_probs(logits, hyp: torch.Tensor, dim: int = 0, eos: Optional[in
     for d in hyp.shape[dim + 1:]:
         inner *= d
     T, V = hyp.shape[dim], logits.shape[-1]
-    out, _, _ = _ops.sequence_log_probs(
+    out, _, _ = _ops.sequence_log_probs_fast(
         logits_d.contiguous().view(outer, T, inner, V),
         hyp_d.to(torch.long).contiguous().view(outer, T, inner), eos)
     return back(out.view(tuple(hyp.shape[:dim]) + tuple(hyp.shape[dim + 1:])))
@@ -497,7 +497,7 @@ def ctc_greedy_search(logits: torch.Tensor, in_lens: Optional[torch.Tensor] = No
         raise RuntimeError(f"in_lens must have shape ({N},), got {tuple(in_lens.shape)}")
     (logits_d, lens_d), back = _offload(logits, in_lens)
     outer, inner = (N, 1) if batch_first else (1, N)
-    max_, paths, out_lens, _, _, _ = _ops.ctc_greedy_search(
+    max_, paths, out_lens, _, _, _ = _ops.ctc_greedy_search_fast(
         logits_d.contiguous().view(outer, T, inner, V), lens_d, blank, is_probs)
     shape = (N, T) if batch_first else (T, N)
     return back(max_.view(N)), back(paths.view(shape)), back(out_lens.view(N))

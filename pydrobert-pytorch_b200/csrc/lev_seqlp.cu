@@ -474,13 +474,12 @@ __device__ __forceinline__ SlpTop<DT> slp_row_top(const typename SlpElem<DT>::T*
     bool any = false;
     auto feed = [&](const A* x, int n, int64_t base) {
         A cm = x[0];
-        int ck = 0;
-        for (int k = 1; k < n; ++k)
-            if (x[k] > cm) {
-                cm = x[k];
-                ck = k;
-            }
+        for (int k = 1; k < n; ++k) cm = slp_max(cm, x[k]);
         if (cm > m || !any) {  // strictly greater: the first of equal maxima stays
+            int ck = 0;         // (rare after the first few vectors: the index is found here only)
+            for (int k = n - 1; k > 0; --k)
+                if (x[k] == cm) ck = k;
+            if (x[0] == cm) ck = 0;
             if (!PROBS && any) s *= slp_exp(m - cm);
             m = cm;
             ms = slp_scale(cm);
