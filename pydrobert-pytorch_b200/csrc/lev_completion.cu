@@ -83,27 +83,63 @@ int lev_launch_uid(const b200lev_tokens_t* ref, const int32_t* ref_len, int32_t*
     return lev_check_cuda("lev_uid_kernel");
 }
 
+// One thread per (hypothesis prefix i, pair n) lists the distinct next tokens of its row.
+// STAGED: the 32 lists of a warp go through shared memory and leave as one contiguous
+// run of 32 * U values (rows of consecutive n are adjacent in the output), so every store
+// instruction of the warp fills whole sectors; a thread writing its own U values directly
+// touches 32 different sectors per instruction, a quarter of each.
+template <bool STAGED>
 __global__ void __launch_bounds__(256)
 lev_completion_fill_kernel(const uint32_t* __restrict__ dbits, const int64_t* __restrict__ dtok,
                            int64_t Rp, int64_t rows /* Hout*P */, int64_t P, int64_t Wd,
                            int ref_group, int64_t U, int64_t padding, int64_t* __restrict__ out,
                            int64_t out_si, int64_t out_sn) {
+    LEV_DYN_SMEM(int64_t, lev_fill_smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows) return;
+    const int64_t idx0 = idx - lane;  // first row of this warp
+    if (idx0 >= rows) return;
+    const bool live = idx < rows;
     const int64_t i = idx / P, n = idx - i * P;
-    const uint32_t* __restrict__ w = dbits + idx * Wd;
-    const int64_t* __restrict__ dt = dtok + (n / ref_group) * Rp;
-    int64_t* __restrict__ o = out + i * out_si + n * out_sn;
-    int64_t k = 0;
-    for (int64_t q = 0; q < Wd && k < U; ++q) {
-        uint32_t bits = w[q];
-        while (bits && k < U) {
-            const int b = __ffs((int)bits) - 1;
-            bits &= bits - 1;
-            o[k++] = dt[q * 32 + b];
+    const int64_t Us = U | 1;  // odd row pitch: the lanes' 8-byte stores spread over the banks
+    int64_t* __restrict__ buf = lev_fill_smem + (int64_t)warp * 32 * Us;
+    // staged only when the warp's 32 rows are one contiguous piece of the output
+    const int64_t i0 = idx0 / P;
+    const bool run = STAGED && out_sn == U && idx0 + 31 < rows && (idx0 + 31) / P == i0;
+    int64_t* __restrict__ o = run ? buf + (int64_t)lane * Us : out + i * out_si + n * out_sn;
+    if (live) {
+        const uint32_t* __restrict__ w = dbits + idx * Wd;
+        const int64_t* __restrict__ dt = dtok + (n / ref_group) * Rp;
+        int64_t k = 0;
+        for (int64_t q = 0; q < Wd && k < U; ++q) {
+            uint32_t bits = w[q];
+            while (bits && k < U) {
+                const int b = __ffs((int)bits) - 1;
+                bits &= bits - 1;
+                o[k++] = dt[q * 32 + b];
+            }
+        }
+        for (; k < U; ++k) o[k] = padding;
+    }
+    if (STAGED) {
+        __syncwarp();
+        if (run) {
+            int64_t* __restrict__ dst = out + i0 * out_si + (idx0 - i0 * P) * U;
+            int64_t row = 0, k = lane;
+            while (k >= U) {
+                k -= U;
+                ++row;
+            }
+            for (int64_t e = lane; e < 32 * U; e += 32) {
+                dst[e] = buf[row * Us + k];
+                k += 32;
+                while (k >= U) {
+                    k -= U;
+                    ++row;
+                }
+            }
         }
     }
-    for (; k < U; ++k) o[k] = padding;
 }
 
 int lev_launch_completion_fill(const uint32_t* dbits, const int64_t* dtok, int64_t Rp,
@@ -113,7 +149,16 @@ int lev_launch_completion_fill(const uint32_t* dbits, const int64_t* dtok, int64
     const int64_t rows = Hout * P;
     if (rows <= 0 || U <= 0) return B200LEV_OK;
     dim3 block(256), grid((unsigned)((rows + 255) / 256));
-    lev_launch(lev_completion_fill_kernel, grid, block, 0, st, dbits, dtok, Rp, rows, P, Wd,
-               ref_group, U, padding, out, out_si, out_sn);
+    const size_t smem = (size_t)8 * 32 * (size_t)(U | 1) * sizeof(int64_t);
+    if (smem <= 96 * 1024) {
+        auto kern = lev_completion_fill_kernel<true>;
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lev_launch(kern, grid, block, smem, st, dbits, dtok, Rp, rows, P, Wd, ref_group, U, padding, out,
+                   out_si, out_sn);
+    } else {
+        lev_launch(lev_completion_fill_kernel<false>, grid, block, 0, st, dbits, dtok, Rp, rows, P, Wd,
+                   ref_group, U, padding, out, out_si, out_sn);
+    }
     return lev_check_cuda("lev_completion_fill_kernel");
 }

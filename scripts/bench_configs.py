@@ -164,6 +164,31 @@ def main():
     ms = timed(lambda: F.prefix_edit_distances(tr, th, eos=0, ins_cost=0.7, del_cost=1.1, sub_cost=1.3), 3, flush)
     out.append(dict(cfg=5, call="prefix_edit_distances (0.7,1.1,1.3) fp32", pairs=256, ms=ms,
                     gcups=cells / ms / 1e6))
+    del tr, th
+    # saturated variants (SURVEY 8d iii): the same per-pair shapes with the batch replicated
+    # until the chip is full (cfg2's is bench.py itself)
+    r, rl = seqs(rng, 51, 65536, 30, 25, 50, 0, 0)
+    h, hl = seqs(rng, 51, 65536, 30, 25, 50, 0, 0)
+    tr, th = torch.from_numpy(r).to(dev), torch.from_numpy(h).to(dev)
+    ms = timed(lambda: F.error_rate(tr, th, eos=0, warn=False), 20, flush)
+    cells = int(((rl - 1).astype(np.int64) * (hl - 1)).sum())
+    out.append(dict(cfg=1, call="error_rate, saturated", pairs=65536, ms=ms, gcups=cells / ms / 1e6,
+                    hyps_per_s=65536 / ms * 1e3))
+    r, rl = seqs(rng, 201, 8192, 32, 100, 200, 0, 0)
+    h, hl = seqs(rng, 201, 8192, 32, 100, 200, 0, 0)
+    tr, th = torch.from_numpy(r).to(dev), torch.from_numpy(h).to(dev)
+    ms = timed(lambda: F.optimal_completion(tr, th, eos=0, warn=False), 5, flush)
+    cells = int((rl.astype(np.int64) * hl).sum())
+    out.append(dict(cfg=3, call="optimal_completion, saturated", pairs=8192, ms=ms, gcups=cells / ms / 1e6,
+                    hyps_per_s=8192 / ms * 1e3))
+    r, rl = seqs(rng, 2001, 1184, 64, 200, 2000, 0, 0)
+    h, hl = seqs(rng, 2001, 1184, 64, 200, 2000, 0, 0)
+    tr, th = torch.from_numpy(r).to(dev), torch.from_numpy(h).to(dev)
+    cells = int((rl.astype(np.int64) * hl).sum())
+    ms = timed(lambda: F.prefix_edit_distances(tr, th, eos=0, ins_cost=3, del_cost=3, sub_cost=4, warn=False), 3,
+               flush)
+    out.append(dict(cfg=5, call="prefix_edit_distances (3,3,4), saturated", pairs=1184, ms=ms,
+                    gcups=cells / ms / 1e6))
     for o in out:
         print(json.dumps(o))
 

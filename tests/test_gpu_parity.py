@@ -512,3 +512,11 @@ def test_ctc_full_size_against_torch_ops(F, dev):
         assert torch.equal(paths[: int(out_lens[n]), n], arg[:, n][keep[:, n]])
     exp = torch.where(valid, val, torch.zeros_like(val)).sum(0)
     torch.testing.assert_close(max_.float(), exp, rtol=2e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("N,batch_first", [(70, False), (33, True), (1000, False)])
+def test_completion_fill_staged_rows(F, dev, N, batch_first):
+    PC.check_vs_oracle(F, dev, seed=N, R=31, H=29, N=N, V=7, costs=(1, 1, 1), include_eos=True,
+                       batch_first=batch_first, exclude_last=False, min_frac=0.3)
+    PC.check_vs_oracle(F, dev, seed=N + 1, R=14, H=6, N=N, V=3, costs=(1, 2, 3), include_eos=False,
+                       batch_first=batch_first, exclude_last=True, min_frac=0.0, padding=-7)

@@ -435,3 +435,13 @@ def test_ctc_low_precision_ties_and_errors(F):
     mod = M.CTCGreedySearch(blank_idx=0, batch_first=True)
     assert "blank_idx=0, batch_first=True, is_probs=False" == mod.extra_repr()
     assert mod(torch.zeros(2, 3, 4))[2].tolist() == [0, 0]
+
+
+@pytest.mark.parametrize("N,batch_first", [(70, False), (33, True), (64, False)])
+def test_completion_fill_staged_rows(F, N, batch_first):
+    """Enough pairs that whole warps of the fill kernel own 32 adjacent output rows (the
+    shared-memory staged path), plus the ragged last warp and rows that straddle two prefixes."""
+    PC.check_vs_oracle(F, DEV, seed=N, R=11, H=9, N=N, V=5, costs=(1, 1, 1), include_eos=True,
+                       batch_first=batch_first, exclude_last=False, min_frac=0.3)
+    PC.check_vs_oracle(F, DEV, seed=N + 1, R=14, H=6, N=N, V=3, costs=(1, 2, 3), include_eos=False,
+                       batch_first=batch_first, exclude_last=True, min_frac=0.0, padding=-7)
