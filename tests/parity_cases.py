@@ -447,3 +447,20 @@ def check_ctc_vs_oracle(F, dev, seed, T, N, V, batch_first, dtype=torch.float32,
     np.testing.assert_allclose(max_.detach().double().cpu().numpy(), e_max, rtol=max(rtol, 2e-6), atol=max(atol, 2e-6 * T))
     np.testing.assert_allclose(logits.grad.double().cpu().numpy(), e_grad, rtol=rtol,
                                atol=atol * max(1.0, float(np.abs(g).max())))
+
+
+def check_ctc_masked_classes(F, dev):
+    """-inf logits (masked classes), including rows that START with -inf vectors and a class
+    count that leaves a scalar tail: arg max, lengths and score against the oracle."""
+    rng = np.random.default_rng(12)
+    for V in (5, 37, 300, 1031):
+        x = rng.standard_normal((11, 3, V)) * 2.0
+        x[:, :, : V // 2] = -np.inf          # the first half of every row is masked
+        x[rng.random((11, 3, V)) < 0.2] = -np.inf
+        x[:, :, V - 1] = np.where(np.isinf(x).all(axis=2), 0.0, x[:, :, V - 1])  # no all-masked row
+        t = torch.tensor(x, dtype=torch.float32)
+        max_, paths, out_lens = F.ctc_greedy_search(t.to(dev), None, V - 1)
+        e_max, e_paths, e_lens = O.ctc_greedy_search(t.double().numpy(), None, V - 1)
+        np.testing.assert_array_equal(paths.cpu().numpy(), e_paths)
+        np.testing.assert_array_equal(out_lens.cpu().numpy(), e_lens)
+        np.testing.assert_allclose(max_.double().cpu().numpy(), e_max, rtol=2e-6, atol=2e-5)

@@ -520,3 +520,7 @@ def test_completion_fill_staged_rows(F, dev, N, batch_first):
                        batch_first=batch_first, exclude_last=False, min_frac=0.3)
     PC.check_vs_oracle(F, dev, seed=N + 1, R=14, H=6, N=N, V=3, costs=(1, 2, 3), include_eos=False,
                        batch_first=batch_first, exclude_last=True, min_frac=0.0, padding=-7)
+
+
+def test_ctc_masked_classes(F, dev):
+    PC.check_ctc_masked_classes(F, dev)
