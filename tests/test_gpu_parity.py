@@ -524,3 +524,28 @@ def test_completion_fill_staged_rows(F, dev, N, batch_first):
 
 def test_ctc_masked_classes(F, dev):
     PC.check_ctc_masked_classes(F, dev)
+
+
+def test_bench_batch_all_dp_paths_agree(F, dev, monkeypatch):
+    """bench.py's own batch (cfg2 shape x 131 072 pairs): the device-selected default, the
+    forced bit-vector kernels and the wavefront kernels are three independent routes to the same
+    numbers -- bit-identical prefix rates and final rates; plus the oracle on a strided sample
+    and d(x, x) = 0 through the n-best (shared reference) layout."""
+    import bench
+
+    ref_np, hyp_np, _ = bench.make_batch(16384, seed=0)
+    ref = torch.from_numpy(np.repeat(ref_np, bench.NBEST, axis=1)).to(dev)
+    hyp = torch.from_numpy(hyp_np).to(dev)
+    outs = {}
+    for mode in ("2", "1", "0"):
+        monkeypatch.setenv("B200LEV_BITVEC", mode)
+        outs[mode] = (F.prefix_error_rates(ref, hyp, eos=0, warn=False),
+                      F.error_rate(ref, hyp, eos=0, include_eos=True, warn=False))
+    for mode in ("1", "0"):
+        assert torch.equal(outs["2"][0], outs[mode][0]), f"prefix rates differ: default vs BITVEC={mode}"
+        assert torch.equal(outs["2"][1], outs[mode][1]), f"final rates differ: default vs BITVEC={mode}"
+    monkeypatch.setenv("B200LEV_BITVEC", "2")
+    idx = torch.arange(0, hyp.shape[1], 1013, device=dev)
+    exp = O.prefix_error_rates(ref[:, idx].cpu().numpy(), hyp[:, idx].cpu().numpy(), eos=0)
+    assert np.array_equal(outs["2"][0][:, idx].cpu().numpy(), np.asarray(exp, dtype=np.float32))
+    assert F.error_rate(ref, ref, eos=0, include_eos=True, warn=False).abs().sum().item() == 0
