@@ -408,7 +408,7 @@ def main():
                            "note": "algorithmic 5 INT32 ops/cell (SURVEY 8d); Myers' bit-vector "
                                    "recurrence advances 32 cells with ~17 instructions, so frac "
                                    "exceeds 1; ncu: ALU pipe 78 % busy"}
-            launches = 9  # 2 bit-vector kernels + 7 wavefront kernels standing by (exit at once)
+            launches = 10  # 2 bit-vector kernels + 8 wavefront kernels standing by (exit at once)
         else:
             roofline = {"bound": "int32_issue",
                         "kernel": "lev_group_kernel<cost,PREFIX,packed16> (+ its 32-bit twin's "
@@ -424,7 +424,7 @@ def main():
             roofline_dp = None
             # 2 pack, 1 bucketing, 2 DP builds (one exits at once), 1 prefix finalize, 1 stand-by
             # 64-bit-token kernel (+ 2 bit-vector kernels that vetoed, when they were eligible)
-            launches = 7 + (2 if prof[6] > 0 else 0)
+            launches = 7 + (3 if prof[6] > 0 else 0)
         line = {
             "metric": "edit-distance cell-updates/s", "value": cells_all / (ms * 1e-3) / 1e9,
             "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -1,6 +1,7 @@
 // lev_abi.cu -- the extern "C" boundary declared in include/b200lev.h: argument
 // checking, the uniform-cost shortcut (SM:168-174), int/float path selection, workspace
 // carving and kernel sequencing.  No device allocation, no host synchronisation.
+#include <mutex>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -260,13 +261,72 @@ static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
 // Unit costs, short references, sequence-first tensors: the bit-vector path (lev_bitvec.cu)
 // takes the whole call -- lengths, warnings and DP -- straight from the raw tokens.
 // Returns 0 if it does not apply, 1 if it ran unconditionally (forced mode: the call is
+// Device-selected mode forks: once the uid pre-pass has finished the veto is final, so the
+// wavefront path's stand-by chain (seven launches that exit at once when the bit-vector
+// kernels took the call) runs on a side stream NEXT TO the bit-vector DP kernel instead of
+// behind it, and the caller's stream joins at the end.  In the vetoed case the DP kernel
+// exits at once and the chain does the work.  Nothing the chain touches before its kernels
+// have checked the veto overlaps what the DP kernel reads (lev_group.cu clears its tables in
+// a kernel that stands by too).  One side stream and two events per device, made once.
+// (the side stream and its events are shared by every caller on the device: calls that fork
+// are enqueued one at a time)
+static std::mutex g_fork_mu;
+struct LevFork {
+    cudaStream_t side;
+    void* after_uid;
+    void* joined;
+};
+#ifndef B200LEV_EMU
+static bool lev_fork_get(LevFork* f) {
+    static LevFork cache[64];
+    static bool have[64];
+    if (const char* e = getenv("B200LEV_FORK"))
+        if (atoi(e) == 0) return false;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    if (!have[dev]) {
+        cudaEvent_t a, b;
+        cudaStream_t s2;
+        if (cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&a, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        cache[dev].side = s2;
+        cache[dev].after_uid = (void*)a;
+        cache[dev].joined = (void*)b;
+        have[dev] = true;
+    }
+    *f = cache[dev];
+    return true;
+}
+// the chain goes to the side stream once the uid kernel is done; returns the stream to use
+static cudaStream_t lev_fork_begin(const LevFork& f, bool on) {
+    if (!on) return nullptr;
+    if (cudaStreamWaitEvent(f.side, (cudaEvent_t)f.after_uid, 0) != cudaSuccess) return nullptr;
+    return f.side;
+}
+static int lev_fork_join(const LevFork& f, cudaStream_t st) {
+    if (cudaEventRecord((cudaEvent_t)f.joined, f.side) != cudaSuccess ||
+        cudaStreamWaitEvent(st, (cudaEvent_t)f.joined, 0) != cudaSuccess)
+        return lev_check_cuda("fork join");
+    return B200LEV_OK;
+}
+#else
+static bool lev_fork_get(LevFork*) { return false; }
+static cudaStream_t lev_fork_begin(const LevFork&, bool) { return nullptr; }
+static int lev_fork_join(const LevFork&, cudaStream_t) { return B200LEV_OK; }
+#endif
+
 // done), 2 if its kernels were enqueued in device-selected mode (the caller goes on to
 // enqueue the wavefront path with bv_check set; the state words are already cleared),
 // < 0 on error.
 static int lev_try_bitvec(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
                           const b200lev_opts_t* o, const LevLayout& L, char* ws, int32_t* flags,
                           cudaStream_t st, int mode, float* out, int64_t out_si, int64_t out_sn,
-                          int Hout) {
+                          int Hout, LevFork* fork, bool* forked) {
+    *forked = false;
     if (!L.off_bv_ref) return 0;
     LevParams tmp;
     memset(&tmp, 0, sizeof(tmp));
@@ -283,10 +343,11 @@ static int lev_try_bitvec(const b200lev_tokens_t* ref, const b200lev_tokens_t* h
         const size_t clear = sizeof(int32_t) * (size_t)(4 + L.nbins);
         if (cudaMemsetAsync(state, 0, clear, st) != cudaSuccess) return lev_check_cuda("memset");
     }
+    *forked = !forced && lev_fork_get(fork);
     const int rc = lev_bitvec_launch(ref, hyp, o, mode, tmp.mult, (int32_t*)(ws + L.off_ref_len),
                                      (int32_t*)(ws + L.off_hyp_len), ws + L.off_bv_ref,
                                      ws + L.off_hyp_tok, ws + L.off_slots, forced ? nullptr : state,
-                                     flags, out, out_si, Hout, st);
+                                     flags, out, out_si, Hout, st, *forked ? fork->after_uid : nullptr);
     if (rc) return rc;
     return forced ? 1 : 2;
 }
@@ -311,18 +372,29 @@ static int lev_final_impl(const b200lev_tokens_t* ref, const b200lev_tokens_t* h
     b200lev_opts_t o = *opts;
     o.exclude_last = 0;  // SM:165
     int bv = 0;
+    LevFork fork;
+    bool forked = false;
+    std::lock_guard<std::mutex> fork_lock(g_fork_mu);
     if (do_pack) {
         bv = lev_try_bitvec(ref, hyp, &o, L, lev_ws_base(workspace), flags, st, LEV_MODE_FINAL, out,
-                            0, 1, 0);
+                            0, 1, 0, &fork, &forked);
         if (bv < 0) return bv;
         if (bv == 1) return B200LEV_OK;
     }
-    rc = lev_prepare(ref, hyp, &o, L, lev_ws_base(workspace), flags, st, &p, do_pack, bv == 2);
-    if (rc) return rc;
-    bool cm, fp;
-    lev_classify_costs(&o, L.R, L.H, &p, &cm, &fp);
-    p.out = out;
-    return lev_launch_dp(p, LEV_MODE_FINAL, cm, fp, st);
+    cudaStream_t side = lev_fork_begin(fork, forked && bv == 2);
+    cudaStream_t cs = side ? side : st;  // the wavefront chain's stream
+    rc = lev_prepare(ref, hyp, &o, L, lev_ws_base(workspace), flags, cs, &p, do_pack, bv == 2);
+    if (rc == B200LEV_OK) {
+        bool cm, fp;
+        lev_classify_costs(&o, L.R, L.H, &p, &cm, &fp);
+        p.out = out;
+        rc = lev_launch_dp(p, LEV_MODE_FINAL, cm, fp, cs);
+    }
+    if (side) {
+        const int jr = lev_fork_join(fork, st);
+        if (rc == B200LEV_OK) rc = jr;
+    }
+    return rc;
 }
 
 extern "C" int b200lev_final(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
@@ -371,21 +443,32 @@ static int lev_prefix_impl(const b200lev_tokens_t* ref, const b200lev_tokens_t* 
     cudaStream_t st = (cudaStream_t)stream;
     LevParams p;
     int bv = 0;
+    LevFork fork;
+    bool forked = false;
+    std::lock_guard<std::mutex> fork_lock(g_fork_mu);
     if (do_pack) {
         bv = lev_try_bitvec(ref, hyp, opts, L, lev_ws_base(workspace), flags, st, LEV_MODE_PREFIX,
-                            out, out_stride_i, out_stride_n, (int)L.Hout);
+                            out, out_stride_i, out_stride_n, (int)L.Hout, &fork, &forked);
         if (bv < 0) return bv;
         if (bv == 1) return B200LEV_OK;
     }
-    rc = lev_prepare(ref, hyp, opts, L, lev_ws_base(workspace), flags, st, &p, do_pack, bv == 2);
-    if (rc) return rc;
-    bool cm, fp;
-    lev_classify_costs(opts, L.R, L.H, &p, &cm, &fp);
-    p.out = out;
-    p.out_si = out_stride_i;
-    p.out_sn = out_stride_n;
-    p.Hout = (int)L.Hout;
-    return lev_launch_dp(p, LEV_MODE_PREFIX, cm, fp, st);
+    cudaStream_t side = lev_fork_begin(fork, forked && bv == 2);
+    cudaStream_t cs = side ? side : st;  // the wavefront chain's stream
+    rc = lev_prepare(ref, hyp, opts, L, lev_ws_base(workspace), flags, cs, &p, do_pack, bv == 2);
+    if (rc == B200LEV_OK) {
+        bool cm, fp;
+        lev_classify_costs(opts, L.R, L.H, &p, &cm, &fp);
+        p.out = out;
+        p.out_si = out_stride_i;
+        p.out_sn = out_stride_n;
+        p.Hout = (int)L.Hout;
+        rc = lev_launch_dp(p, LEV_MODE_PREFIX, cm, fp, cs);
+    }
+    if (side) {
+        const int jr = lev_fork_join(fork, st);
+        if (rc == B200LEV_OK) rc = jr;
+    }
+    return rc;
 }
 
 extern "C" int b200lev_prefix(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,

@@ -709,7 +709,7 @@ int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
                       const b200lev_opts_t* o, int mode, float mult, int32_t* ref_len,
                       int32_t* hyp_len, void* uid_ref, void* uid_hyp, void* lead,
                       int32_t* state, int32_t* flags, float* out, int64_t out_si, int Hout,
-                      cudaStream_t st) {
+                      cudaStream_t st, void* after_uid) {
     LevBvArgs a;
     memset(&a, 0, sizeof(a));
     a.ref = ref->data;
@@ -758,6 +758,13 @@ int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     lev_prof_end(LEV_PROF_BV_UID, st);
     int rc = lev_check_cuda("lev_bv_uid_kernel");
     if (rc) return rc;
+#ifndef B200LEV_EMU
+    // the veto is final once this kernel is done: the stand-by chain forks from here
+    if (after_uid != nullptr && cudaEventRecord((cudaEvent_t)after_uid, st) != cudaSuccess)
+        return lev_check_cuda("cudaEventRecord");
+#else
+    (void)after_uid;
+#endif
     lev_prof_begin(LEV_PROF_BV_DP, st);
     const int W = (a.R + 31) / 32;
     switch (W) {

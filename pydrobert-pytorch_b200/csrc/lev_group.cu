@@ -249,6 +249,17 @@ __device__ __forceinline__ void levg_run16(const LevParams& p, const int G, cons
 // ---------------------------------------------------------------------------------------
 // bucketing: scan the (class, length) histogram and scatter the pairs into task slots
 // ---------------------------------------------------------------------------------------
+// what two memsets do on the plain path (cursors + meta := 0, slot table := all ones), as a
+// kernel that stands by when the bit-vector kernels took the call
+__global__ void __launch_bounds__(256)
+lev_group_clear_kernel(const LevParams p, const int64_t ncursor, const int64_t nslots) {
+    if (p.bv_check && lev_bv_took(p.wide_flag)) return;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = tid; k < ncursor; k += stride) p.gcursor[k] = 0;
+    for (int64_t k = tid; k < nslots; k += stride) p.slots[k] = make_int4(-1, -1, -1, -1);
+}
+
 #define LEVG_SORT_PER_THREAD 2
 __global__ void __launch_bounds__(256)
 lev_sort_kernel(const LevParams p, const LevGroupGeom geo, const int count_mode) {
@@ -632,8 +643,13 @@ int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t
     tmp = geo;
     if (geo.allow16 && levg_geometry(p, true, &tmp) > 200 * 1024) geo.allow16 = 0;
     // bucketing: clear the scatter cursors + meta and the slot table, then scan + scatter
-    if (cudaMemsetAsync(p.gcursor, 0, sizeof(int) * (size_t)(p.nbins + 16), st) != cudaSuccess ||
-        cudaMemsetAsync(p.slots, 0xff, 16 * (size_t)(p.P + LEVG_NCLS * 32), st) != cudaSuccess)
+    if (p.bv_check) {
+        // stand-by mode: the slot table shares its bytes with the bit-vector path's tables and
+        // this chain may run beside that path's DP kernel, so the clearing stands by as well
+        lev_launch(lev_group_clear_kernel, dim3(148 * 2), dim3(256), 0, st, p,
+                   (int64_t)(p.nbins + 16), (int64_t)(p.P + LEVG_NCLS * 32));
+    } else if (cudaMemsetAsync(p.gcursor, 0, sizeof(int) * (size_t)(p.nbins + 16), st) != cudaSuccess ||
+               cudaMemsetAsync(p.slots, 0xff, 16 * (size_t)(p.P + LEVG_NCLS * 32), st) != cudaSuccess)
         return lev_check_cuda("memset");
     lev_prof_begin(LEV_PROF_SORT, st);
     {

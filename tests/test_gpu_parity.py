@@ -549,3 +549,31 @@ def test_bench_batch_all_dp_paths_agree(F, dev, monkeypatch):
     exp = O.prefix_error_rates(ref[:, idx].cpu().numpy(), hyp[:, idx].cpu().numpy(), eos=0)
     assert np.array_equal(outs["2"][0][:, idx].cpu().numpy(), np.asarray(exp, dtype=np.float32))
     assert F.error_rate(ref, ref, eos=0, include_eos=True, warn=False).abs().sum().item() == 0
+
+
+def test_device_selected_fork_ordering(F, dev, monkeypatch):
+    """The stand-by chain runs on a side stream beside the bit-vector DP kernel: back-to-back
+    calls on a non-default stream, alternating batches the bit-vector kernels take (n-best) and
+    veto (unrelated references), no synchronisation in between -- every result equals the
+    single-stream (B200LEV_FORK=0) result of the same batch."""
+    import bench
+
+    ref_np, hyp_np, _ = bench.make_batch(1024, seed=5)
+    hyp = torch.from_numpy(hyp_np).to(dev)
+    shared = torch.from_numpy(np.repeat(ref_np, bench.NBEST, axis=1)).to(dev)
+    unrelated = torch.from_numpy(bench.make_batch(1024, seed=6)[1]).to(dev)
+    monkeypatch.setenv("B200LEV_FORK", "0")
+    want = [F.prefix_error_rates(r, hyp, eos=0, warn=False) for r in (shared, unrelated)]
+    want_f = [F.error_rate(r, hyp, eos=0, warn=False) for r in (shared, unrelated)]
+    torch.cuda.synchronize()
+    monkeypatch.setenv("B200LEV_FORK", "1")
+    s = torch.cuda.Stream(dev)
+    got = []
+    with torch.cuda.stream(s):
+        for k in range(12):
+            r = (shared, unrelated)[k % 2]
+            got.append((k % 2, F.prefix_error_rates(r, hyp, eos=0, warn=False),
+                        F.error_rate(r, hyp, eos=0, warn=False)))
+    s.synchronize()
+    for which, pe, er in got:
+        assert torch.equal(pe, want[which]) and torch.equal(er, want_f[which])
