@@ -577,3 +577,38 @@ def test_device_selected_fork_ordering(F, dev, monkeypatch):
     s.synchronize()
     for which, pe, er in got:
         assert torch.equal(pe, want[which]) and torch.equal(er, want_f[which])
+
+
+@pytest.mark.parametrize("which", ["nbest", "unrelated_refs"])
+def test_device_selected_call_in_cuda_graph(F, dev, which):
+    """The fork/join of the device-selected mode is a capturable pattern: the public call,
+    captured into a CUDA graph after a warm-up call and replayed on fresh inputs copied into the
+    captured buffers, gives the eager result."""
+    import bench
+
+    ref_np, hyp_np, _ = bench.make_batch(1024, seed=8)
+    hyp = torch.from_numpy(hyp_np).to(dev)
+    if which == "nbest":
+        ref = torch.from_numpy(np.repeat(ref_np, bench.NBEST, axis=1)).to(dev)
+    else:
+        ref = torch.from_numpy(bench.make_batch(1024, seed=9)[1]).to(dev)
+    want = F.prefix_error_rates(ref, hyp, eos=0, warn=False)  # (also the warm-up call)
+    s = torch.cuda.Stream(dev)
+    s.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(s):
+        F.prefix_error_rates(ref, hyp, eos=0, warn=False)
+    torch.cuda.current_stream(dev).wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = F.prefix_error_rates(ref, hyp, eos=0, warn=False)
+    out.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+    # new data through the same graph
+    hyp2 = torch.from_numpy(bench.make_batch(1024, seed=10)[1]).to(dev)
+    want2 = F.prefix_error_rates(ref, hyp2, eos=0, warn=False)
+    hyp.copy_(hyp2)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want2)
