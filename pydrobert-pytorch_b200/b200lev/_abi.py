@@ -86,9 +86,6 @@ SIGNATURES = {
 }
 
 _lib: Optional[ctypes.CDLL] = None
-# True only when a test has swapped in the SIMT-emulated build of the same sources
-# (tests/emu); the product never sets it.
-EMULATED = False
 
 
 class B200LevError(RuntimeError):
@@ -117,16 +114,6 @@ def lib() -> ctypes.CDLL:
         if _lib.b200lev_abi_version() != 1:
             raise B200LevError("libb200lev.so ABI version mismatch")
     return _lib
-
-
-def _set_library_for_tests(path: Optional[str]) -> None:
-    """Test seam: load the emulated build of the kernels (tests/emu) instead of the
-    CUDA library.  Never called by product code."""
-    global _lib, EMULATED
-    if path is None:
-        _lib, EMULATED = None, False
-    else:
-        _lib, EMULATED = _bind(ctypes.CDLL(path)), True
 
 
 def check(status: int) -> None:

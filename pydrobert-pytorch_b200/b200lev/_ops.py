@@ -1,14 +1,19 @@
 """Host side of the custom-op layer: tensor plumbing around the C ABI.
 
-Each public call of the reference's string-matching family maps to ONE registered
-torch op (``torch.ops.b200lev.*``) whose body allocates the outputs/workspace with
-torch, hands raw device pointers, strides and the current CUDA stream to
-``libb200lev.so`` and returns.  PyTorch is used for device memory, streams and
-autograd wiring only; every number is produced by the hand-written kernels.
+Each public call of the reference's string-matching family maps to registered torch ops
+(``torch.ops.b200lev.*``) whose bodies allocate the outputs/workspace with torch, hand
+raw device pointers, strides and the current CUDA stream to ``libb200lev.so`` and return.
+PyTorch is used for device memory, streams and autograd wiring only; every number is
+produced by the hand-written kernels.
 
-There is no CPU fallback: tensors must live on a CUDA device (host tensors are
-accepted by the *functional* layer, which copies them to the current device and the
-result back -- see ``functional._offload``).
+The ops are what ``torch.jit.script`` / ``torch.jit.trace`` / ``torch.compile`` see: one
+opaque node per call, shapes and checks inside, so nothing data- or shape-dependent is
+baked into a graph.  Each op is a plain Python function (``*_impl``) registered with
+``torch.library.custom_op``; plain eager code may call the ``*_impl`` function directly
+and skip the dispatcher round trip.
+
+There is no CPU fallback: the computation always runs on a CUDA device.  Tensors that live
+on the host are copied to the current CUDA device and the results back (``_host.Placement``).
 """
 from __future__ import annotations
 
@@ -18,9 +23,9 @@ from typing import List, Optional, Tuple
 import torch
 from torch import Tensor
 
-from . import _abi
+from . import _abi, _host
 
-_INT_DTYPES = (torch.int64, torch.int32, torch.int16, torch.int8)
+_INT_DTYPES = _host._INT_DTYPES
 _FLOAT_CODES = {torch.float32: _abi.F32, torch.float16: _abi.F16, torch.bfloat16: _abi.BF16,
                 torch.float64: _abi.F64}
 
@@ -37,34 +42,12 @@ def _as_tokens(t: Tensor) -> Tensor:
     return t.to(torch.long)
 
 
-def _check_device(*ts: Tensor) -> torch.device:
-    dev = ts[0].device
-    for t in ts:
-        if t.device != dev:
-            raise RuntimeError(f"expected all tensors on {dev}, got one on {t.device}")
-    if dev.type != "cuda" and not _abi.EMULATED:
-        raise _abi.B200LevError(
-            f"b200lev kernels need CUDA tensors (got {dev}); there is no CPU fallback")
-    return dev
-
-
 def _stream(dev: torch.device) -> int:
-    if dev.type == "cuda":
-        return torch.cuda.current_stream(dev).cuda_stream
-    return 0
+    return torch.cuda.current_stream(dev).cuda_stream
 
 
-class _DeviceGuard:
-    def __init__(self, dev: torch.device):
-        self.g = torch.cuda.device(dev) if dev.type == "cuda" else None
-
-    def __enter__(self):
-        if self.g is not None:
-            self.g.__enter__()
-
-    def __exit__(self, *a):
-        if self.g is not None:
-            self.g.__exit__(*a)
+def _DeviceGuard(dev: torch.device):
+    return torch.cuda.device(dev)
 
 
 def _tok_struct(t: Tensor, batch_first: bool) -> _abi.Tokens:
@@ -99,18 +82,14 @@ def _shapes(ref: Tensor, hyp: Tensor, batch_first: bool, ref_group: int) -> Tupl
 # ---------------------------------------------------------------------------------------
 # string matching: final / prefix
 # ---------------------------------------------------------------------------------------
-@torch.library.custom_op("b200lev::string_matching", mutates_args=())
-def string_matching(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: bool,
-                    batch_first: bool, ins_cost: float, del_cost: float, sub_cost: float,
-                    norm: bool, prefix: bool, exclude_last: bool, padding: int,
-                    return_mistakes: bool, ref_group: int) -> Tuple[Tensor, Tensor]:
-    """``_string_matching`` (_string.py:146-406) minus the mask mode.
-
-    Returns ``(out, flags)``: fp32 ``(N,)`` or ``(H', N)`` / ``(N, H')`` and the int32[1]
-    warning flags (``_abi.FLAG_*``)."""
-    R, H, n = _shapes(ref, hyp, batch_first, ref_group)
-    ref, hyp = _as_tokens(ref), _as_tokens(hyp)
-    dev = _check_device(ref, hyp)
+def _string_matching_device(ref: Tensor, hyp: Tensor, dev: torch.device, eos: Optional[int],
+                            include_eos: bool, batch_first: bool, ins_cost: float, del_cost: float,
+                            sub_cost: float, norm: bool, prefix: bool, exclude_last: bool,
+                            padding: int, return_mistakes: bool, ref_group: int
+                            ) -> Tuple[Tensor, Tensor]:
+    """Device tensors in, device tensors out (the body shared by the ops below)."""
+    H = hyp.shape[1] if batch_first else hyp.shape[0]
+    n = hyp.shape[0] if batch_first else hyp.shape[1]
     L = _abi.lib()
     with _DeviceGuard(dev):
         rt, ht = _tok_struct(ref, batch_first), _tok_struct(hyp, batch_first)
@@ -139,6 +118,34 @@ def string_matching(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: b
     return out, flags
 
 
+def string_matching_impl(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: bool,
+                         batch_first: bool, ins_cost: float, del_cost: float, sub_cost: float,
+                         norm: bool, prefix: bool, exclude_last: bool, padding: int,
+                         return_mistakes: bool, ref_group: int) -> Tuple[Tensor, Tensor]:
+    """``_string_matching`` (_string.py:146-406) minus the mask mode.
+
+    Returns ``(out, flags)``: fp32 ``(N,)`` or ``(H', N)`` / ``(N, H')`` and the int32[1]
+    warning flags (``_abi.FLAG_*``), both on the device of ``ref``.  ``ref_group`` > 1 means
+    reference column ``pair // ref_group`` serves the pair (an n-best batch whose
+    reference is not physically repeated, _string.py:1426/1439)."""
+    _shapes(ref, hyp, batch_first, ref_group)
+    ref, hyp = _as_tokens(ref), _as_tokens(hyp)
+    args = (eos, include_eos, batch_first, ins_cost, del_cost, sub_cost, norm, prefix, exclude_last,
+            padding, return_mistakes, ref_group)
+    plan = _host.block_plan(ref, hyp, batch_first, ref_group)
+    if plan is not None:  # big host batch: blocks through three streams
+        return _host.string_matching_blocks(
+            plan, ref, hyp, lambda r, h: _string_matching_device(r, h, r.device, *args),
+            batch_first, prefix, exclude_last, ref_group)
+    pl = _host.Placement(ref, hyp)
+    out, flags = _string_matching_device(pl.to_dev(ref), pl.to_dev(hyp), pl.dev, *args)
+    return pl.back(out), pl.back(flags)
+
+
+string_matching = torch.library.custom_op("b200lev::string_matching", string_matching_impl,
+                                          mutates_args=())
+
+
 @string_matching.register_fake
 def _(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost, sub_cost, norm, prefix,
       exclude_last, padding, return_mistakes, ref_group):
@@ -157,15 +164,15 @@ def _(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost, sub_cost, nor
 # ---------------------------------------------------------------------------------------
 # optimal completion
 # ---------------------------------------------------------------------------------------
-@torch.library.custom_op("b200lev::optimal_completion", mutates_args=())
-def optimal_completion(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: bool,
-                       batch_first: bool, ins_cost: float, del_cost: float, sub_cost: float,
-                       padding: int, exclude_last: bool) -> Tuple[Tensor, Tensor]:
+def optimal_completion_impl(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: bool,
+                            batch_first: bool, ins_cost: float, del_cost: float, sub_cost: float,
+                            padding: int, exclude_last: bool) -> Tuple[Tensor, Tensor]:
     """``optimal_completion`` (_string.py:464-517): ``(targets, flags)`` with targets int64
     ``(H', N, U)`` or ``(N, H', U)``.  One host read of U, as the reference has at :511."""
     R, H, n = _shapes(ref, hyp, batch_first, 1)
     ref, hyp = _as_tokens(ref), _as_tokens(hyp)
-    dev = _check_device(ref, hyp)
+    pl = _host.Placement(ref, hyp)
+    ref, hyp, dev = pl.to_dev(ref), pl.to_dev(hyp), pl.dev
     L = _abi.lib()
     with _DeviceGuard(dev):
         rt, ht = _tok_struct(ref, batch_first), _tok_struct(hyp, batch_first)
@@ -189,7 +196,11 @@ def optimal_completion(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos
             si, sn = n * U, U
         _abi.check(L.b200lev_completion_fill(ctypes.byref(rt), ctypes.byref(ht), ctypes.byref(o),
                                              ws.data_ptr(), nbytes, U, out.data_ptr(), si, sn, st))
-    return out, flags
+    return pl.back(out), pl.back(flags)
+
+
+optimal_completion = torch.library.custom_op("b200lev::optimal_completion", optimal_completion_impl,
+                                             mutates_args=())
 
 
 @optimal_completion.register_fake
@@ -222,18 +233,23 @@ def _rowmajor_last(t: Tensor) -> Tensor:
     return t if t.stride(-1) == 1 or t.size(-1) <= 1 else t.contiguous()
 
 
+def _weight_on(w: Optional[Tensor], dev: torch.device) -> Optional[Tensor]:
+    return None if w is None else w.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
 @torch.library.custom_op("b200lev::ocd_loss", mutates_args=())
 def ocd_loss(logits: Tensor, targets: Tensor, weight: Optional[Tensor], ignore_index: int,
              reduction: int, seq_axis: int) -> Tuple[Tensor, Tensor, Tensor]:
     """_string.py:1229-1251 given the optimal-completion targets.  Returns
     ``(loss, lse, denom)`` (lse/denom are saved for the backward)."""
-    dev = _check_device(logits, targets)
+    pl = _host.Placement(logits, targets)
+    dev = pl.dev
     A, B, V = logits.shape
     U = targets.size(-1)
-    logits = _rowmajor_last(logits.detach())
-    targets = targets.contiguous()
+    logits = _rowmajor_last(pl.to_dev(logits.detach()))
+    targets = pl.to_dev(targets).contiguous()
     acc = _acc_dtype(logits)
-    w = None if weight is None else weight.detach().to(device=dev, dtype=torch.float32).contiguous()
+    w = _weight_on(weight, dev)
     per = torch.empty((A, B), dtype=acc, device=dev)
     lse = torch.empty((A, B), dtype=acc, device=dev)
     denom = torch.empty(max(B if seq_axis == 0 else A, 1), dtype=acc, device=dev)
@@ -245,7 +261,7 @@ def ocd_loss(logits: Tensor, targets: Tensor, weight: Optional[Tensor], ignore_i
             None if w is None else w.data_ptr(), ignore_index, reduction, seq_axis,
             per.data_ptr(), lse.data_ptr(), denom.data_ptr(), loss.data_ptr(), _stream(dev)))
     out = per if reduction == 0 else loss
-    return out.to(logits.dtype), lse, denom
+    return pl.back(out.to(logits.dtype)), pl.back(lse), pl.back(denom)
 
 
 @ocd_loss.register_fake
@@ -261,14 +277,16 @@ def _(logits, targets, weight, ignore_index, reduction, seq_axis):
 def ocd_loss_backward(grad_out: Tensor, logits: Tensor, targets: Tensor, weight: Optional[Tensor],
                       ignore_index: int, reduction: int, seq_axis: int, lse: Tensor,
                       denom: Tensor) -> Tensor:
-    dev = _check_device(logits, targets)
+    pl = _host.Placement(logits, targets)
+    dev = pl.dev
     A, B, V = logits.shape
     U = targets.size(-1)
-    logits = _rowmajor_last(logits.detach())
-    targets = targets.contiguous()
+    logits = _rowmajor_last(pl.to_dev(logits.detach()))
+    targets = pl.to_dev(targets).contiguous()
     acc = _acc_dtype(logits)
-    w = None if weight is None else weight.detach().to(device=dev, dtype=torch.float32).contiguous()
-    go = grad_out.detach().to(acc).contiguous()
+    w = _weight_on(weight, dev)
+    go = grad_out.detach().to(device=dev, dtype=acc).contiguous()
+    lse, denom = lse.to(dev), denom.to(dev)
     grad = torch.empty((A, B, V), dtype=logits.dtype, device=dev)
     with _DeviceGuard(dev):
         _abi.check(_abi.lib().b200lev_ocd_backward(
@@ -276,7 +294,7 @@ def ocd_loss_backward(grad_out: Tensor, logits: Tensor, targets: Tensor, weight:
             targets.data_ptr(), U, targets.stride(0), targets.stride(1),
             None if w is None else w.data_ptr(), ignore_index, reduction, seq_axis,
             lse.data_ptr(), denom.data_ptr(), go.data_ptr(), grad.data_ptr(), _stream(dev)))
-    return grad
+    return pl.back(grad)
 
 
 @ocd_loss_backward.register_fake
@@ -305,13 +323,14 @@ ocd_loss.register_autograd(_ocd_backward, setup_context=_ocd_setup)
 # ---------------------------------------------------------------------------------------
 # sequence_log_probs, tensor path (_decoding.py:1516-1548)
 # ---------------------------------------------------------------------------------------
-@torch.library.custom_op("b200lev::sequence_log_probs", mutates_args=())
-def sequence_log_probs(logits: Tensor, hyp: Tensor, eos: Optional[int]) -> Tuple[Tensor, Tensor, Tensor]:
+def sequence_log_probs_impl(logits: Tensor, hyp: Tensor, eos: Optional[int]
+                            ) -> Tuple[Tensor, Tensor, Tensor]:
     """``logits`` (outer, T, inner, V) float, ``hyp`` (outer, T, inner) int64, both contiguous.
     Returns ``(out (outer, inner), row_lse, len)``; the last two are saved for the backward."""
-    dev = _check_device(logits, hyp)
+    pl = _host.Placement(logits, hyp)
+    dev = pl.dev
     outer, T, inner, V = logits.shape
-    logits, hyp = logits.detach(), hyp.detach()
+    logits, hyp = pl.to_dev(logits.detach()), pl.to_dev(hyp.detach())
     acc = _acc_dtype(logits)
     length = torch.empty(max(outer * inner, 1), dtype=torch.int32, device=dev)
     row_lp = torch.empty(max(outer * T * inner, 1), dtype=acc, device=dev)
@@ -322,7 +341,11 @@ def sequence_log_probs(logits: Tensor, hyp: Tensor, eos: Optional[int]) -> Tuple
             logits.data_ptr(), _float_code(logits), outer, T, inner, V, hyp.data_ptr(),
             int(eos is not None), 0 if eos is None else int(eos), length.data_ptr(),
             row_lp.data_ptr(), row_lse.data_ptr(), out.data_ptr(), _stream(dev)))
-    return out, row_lse, length
+    return pl.back(out), pl.back(row_lse), pl.back(length)
+
+
+sequence_log_probs = torch.library.custom_op("b200lev::sequence_log_probs", sequence_log_probs_impl,
+                                             mutates_args=())
 
 
 @sequence_log_probs.register_fake
@@ -337,16 +360,18 @@ def _(logits, hyp, eos):
 @torch.library.custom_op("b200lev::sequence_log_probs_backward", mutates_args=())
 def sequence_log_probs_backward(grad_out: Tensor, logits: Tensor, hyp: Tensor, row_lse: Tensor,
                                 length: Tensor) -> Tensor:
-    dev = _check_device(logits, hyp)
+    pl = _host.Placement(logits, hyp)
+    dev = pl.dev
     outer, T, inner, V = logits.shape
-    logits, hyp = logits.detach(), hyp.detach()
-    go = grad_out.detach().to(logits.dtype).contiguous()
+    logits, hyp = pl.to_dev(logits.detach()), pl.to_dev(hyp.detach())
+    go = grad_out.detach().to(device=dev, dtype=logits.dtype).contiguous()
+    row_lse, length = row_lse.to(dev), length.to(dev)
     grad = torch.empty_like(logits)
     with _DeviceGuard(dev):
         _abi.check(_abi.lib().b200lev_seqlp_backward(
             logits.data_ptr(), _float_code(logits), outer, T, inner, V, hyp.data_ptr(),
             length.data_ptr(), row_lse.data_ptr(), go.data_ptr(), grad.data_ptr(), _stream(dev)))
-    return grad
+    return pl.back(grad)
 
 
 @sequence_log_probs_backward.register_fake
@@ -371,15 +396,15 @@ sequence_log_probs.register_autograd(_seqlp_backward, setup_context=_seqlp_setup
 # ---------------------------------------------------------------------------------------
 # ctc_greedy_search (_decoding.py:507-560)
 # ---------------------------------------------------------------------------------------
-@torch.library.custom_op("b200lev::ctc_greedy_search", mutates_args=())
-def ctc_greedy_search(logits: Tensor, in_lens: Optional[Tensor], blank: int, is_probs: bool
-                      ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+def ctc_greedy_search_impl(logits: Tensor, in_lens: Optional[Tensor], blank: int, is_probs: bool
+                           ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """``logits`` contiguous (outer, T, inner, V); ``in_lens`` int64 (outer*inner) or None.
     Returns ``(max_ (outer, inner), paths (outer, T, inner), out_lens (outer, inner), arg,
     row_lse, len)``; the last three are saved for the backward."""
-    dev = _check_device(logits) if in_lens is None else _check_device(logits, in_lens)
+    pl = _host.Placement(logits, in_lens)
+    dev = pl.dev
     outer, T, inner, V = logits.shape
-    logits = logits.detach()
+    logits = pl.to_dev(logits.detach())
     acc = _acc_dtype(logits)
     n, rows = max(outer * inner, 1), max(outer * T * inner, 1)
     arg = torch.empty(rows, dtype=torch.int64, device=dev)
@@ -389,14 +414,19 @@ def ctc_greedy_search(logits: Tensor, in_lens: Optional[Tensor], blank: int, is_
     paths = torch.empty((outer, T, inner), dtype=torch.int64, device=dev)
     out_lens = torch.zeros((outer, inner), dtype=torch.int64, device=dev)
     max_ = torch.zeros((outer, inner), dtype=logits.dtype, device=dev)
-    lens = None if in_lens is None else in_lens.detach().to(torch.int64).contiguous()
+    lens = None if in_lens is None else pl.to_dev(in_lens.detach()).to(torch.int64).contiguous()
     with _DeviceGuard(dev):
         _abi.check(_abi.lib().b200lev_ctc_greedy(
             logits.data_ptr(), _float_code(logits), outer, T, inner, V,
             0 if lens is None else lens.data_ptr(), int(blank), int(is_probs), arg.data_ptr(),
             row_val.data_ptr(), row_lse.data_ptr(), length.data_ptr(), paths.data_ptr(),
             out_lens.data_ptr(), max_.data_ptr(), _stream(dev)))
-    return max_, paths, out_lens, arg, row_lse, length
+    return (pl.back(max_), pl.back(paths), pl.back(out_lens), pl.back(arg), pl.back(row_lse),
+            pl.back(length))
+
+
+ctc_greedy_search = torch.library.custom_op("b200lev::ctc_greedy_search", ctc_greedy_search_impl,
+                                            mutates_args=())
 
 
 @ctc_greedy_search.register_fake
@@ -437,10 +467,11 @@ ctc_greedy_search.register_autograd(_ctc_backward, setup_context=_ctc_setup)
 @torch.library.custom_op("b200lev::mwer_loss", mutates_args=())
 def mwer_loss(er: Tensor, log_probs: Tensor, sub_avg: bool, reduction: int) -> Tensor:
     """_string.py:1463-1471 on the (N, M) error rates."""
-    dev = _check_device(er, log_probs)
+    pl = _host.Placement(er, log_probs)
+    dev = pl.dev
     N, M = log_probs.shape
-    er = er.detach().reshape(N, M).contiguous()
-    lp = log_probs.detach()
+    er = pl.to_dev(er.detach()).reshape(N, M).contiguous()
+    lp = pl.to_dev(log_probs.detach())
     acc = _acc_dtype(lp)
     per = torch.empty((N, M), dtype=acc, device=dev)
     loss = torch.zeros((), dtype=acc, device=dev)
@@ -448,7 +479,7 @@ def mwer_loss(er: Tensor, log_probs: Tensor, sub_avg: bool, reduction: int) -> T
         _abi.check(_abi.lib().b200lev_mwer_forward(
             er.data_ptr(), lp.data_ptr(), _float_code(lp), N, M, lp.stride(0), lp.stride(1),
             int(sub_avg), reduction, per.data_ptr(), loss.data_ptr(), _stream(dev)))
-    return per if reduction == 0 else loss
+    return pl.back(per if reduction == 0 else loss)
 
 
 @mwer_loss.register_fake
@@ -460,18 +491,19 @@ def _(er, log_probs, sub_avg, reduction):
 @torch.library.custom_op("b200lev::mwer_loss_backward", mutates_args=())
 def mwer_loss_backward(grad_out: Tensor, er: Tensor, log_probs: Tensor, sub_avg: bool,
                        reduction: int) -> Tensor:
-    dev = _check_device(er, log_probs)
+    pl = _host.Placement(er, log_probs)
+    dev = pl.dev
     N, M = log_probs.shape
-    er = er.detach().reshape(N, M).contiguous()
-    lp = log_probs.detach()
+    er = pl.to_dev(er.detach()).reshape(N, M).contiguous()
+    lp = pl.to_dev(log_probs.detach())
     acc = _acc_dtype(lp)
-    go = grad_out.detach().to(acc).contiguous()
+    go = grad_out.detach().to(device=dev, dtype=acc).contiguous()
     grad = torch.empty((N, M), dtype=lp.dtype, device=dev)
     with _DeviceGuard(dev):
         _abi.check(_abi.lib().b200lev_mwer_backward(
             er.data_ptr(), lp.data_ptr(), _float_code(lp), N, M, lp.stride(0), lp.stride(1),
             int(sub_avg), reduction, go.data_ptr(), grad.data_ptr(), _stream(dev)))
-    return grad
+    return pl.back(grad)
 
 
 @mwer_loss_backward.register_fake
@@ -499,12 +531,16 @@ mwer_loss.register_autograd(_mwer_backward, setup_context=_mwer_setup)
 # ---------------------------------------------------------------------------------------
 # fill_after_eos scan, bulk error sums, INT32 microbenchmark
 # ---------------------------------------------------------------------------------------
-@torch.library.custom_op("b200lev::after_eos_mask", mutates_args=())
-def after_eos_mask(tokens: Tensor, eos: int, dim: int) -> Tensor:
+def after_eos_mask_impl(tokens: Tensor, eos: int, dim: int) -> Tensor:
     """bool mask, True strictly after the first ``eos`` along ``dim`` (_string.py:41)."""
-    dev = _check_device(tokens)
-    dim = dim % max(tokens.dim(), 1)
-    tok = tokens.detach()
+    pl = _host.Placement(tokens)
+    dev = pl.dev
+    nd = tokens.dim()
+    if nd and not (-nd <= dim < nd):
+        raise IndexError(f"Dimension out of range (expected to be in range of [{-nd}, {nd - 1}], "
+                         f"but got {dim})")
+    dim = dim % max(nd, 1)
+    tok = pl.to_dev(tokens.detach())
     tok = tok.to(torch.long) if tok.dtype != torch.long else tok
     tok = tok.contiguous()
     shape = tok.shape
@@ -519,7 +555,11 @@ def after_eos_mask(tokens: Tensor, eos: int, dim: int) -> Tensor:
     with _DeviceGuard(dev):
         _abi.check(_abi.lib().b200lev_after_eos_mask(tok.data_ptr(), outer, T, inner, int(eos),
                                                      mask.data_ptr(), _stream(dev)))
-    return mask.bool()
+    return pl.back(mask.bool())
+
+
+after_eos_mask = torch.library.custom_op("b200lev::after_eos_mask", after_eos_mask_impl,
+                                         mutates_args=())
 
 
 @after_eos_mask.register_fake
@@ -532,7 +572,10 @@ def ragged_to_padded(flat: Tensor, offsets: Tensor, sel: Optional[Tensor], first
     """``(count, T)`` token matrix: row u = utterance ``sel[u]`` (``first + u`` without
     ``sel``) of the flat corpus, then ``eos``, then ``pad`` (what command_line.py:1110-1121
     builds with pad_sequence).  ``flat`` int16/int32/int64, ``offsets`` int64, same device."""
-    dev = _check_device(flat, offsets) if sel is None else _check_device(flat, offsets, sel)
+    pl = _host.Placement(flat, offsets, sel)
+    if pl.moved:
+        raise _abi.B200LevError("ragged_to_padded: arguments must be CUDA tensors")
+    dev = pl.dev
     if flat.dtype not in (torch.int16, torch.int32, torch.int64) or offsets.dtype != torch.int64:
         raise _abi.B200LevError("ragged_to_padded: flat must be int16/int32/int64 and offsets int64")
     if not (flat.is_contiguous() and offsets.is_contiguous() and (sel is None or sel.is_contiguous())):
@@ -556,11 +599,12 @@ def error_sums(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: bool, 
                return_mistakes: bool, ref_group: int) -> Tuple[Tensor, Tensor, Tensor]:
     """Bulk scoring (command_line.py:1124-1147 without the per-utterance host reads):
     ``(er, acc, flags)`` with ``er`` the per-pair values of ``string_matching`` and
-    ``acc = [sum(er), sum(ref_lens), #pairs]`` in fp64 on the device, ready for a single
-    all-reduce.  The reference lengths come from the same packing pass as the DP."""
+    ``acc = [sum(er), sum(ref_lens), #pairs]`` in fp64 ON THE COMPUTE DEVICE, ready for a
+    single all-reduce.  The reference lengths come from the same packing pass as the DP."""
     R, H, n = _shapes(ref, hyp, batch_first, ref_group)
     ref, hyp = _as_tokens(ref), _as_tokens(hyp)
-    dev = _check_device(ref, hyp)
+    pl = _host.Placement(ref, hyp)
+    ref, hyp, dev = pl.to_dev(ref), pl.to_dev(hyp), pl.dev
     L = _abi.lib()
     with _DeviceGuard(dev):
         rt, ht = _tok_struct(ref, batch_first), _tok_struct(hyp, batch_first)
@@ -576,7 +620,7 @@ def error_sums(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: bool, 
                                    out.data_ptr(), ws.data_ptr(), nbytes, flags.data_ptr(), st))
         lens = L.b200lev_workspace_ref_lens(ctypes.byref(rt), ctypes.byref(ht), ws.data_ptr())
         _abi.check(L.b200lev_err_sum(out.data_ptr(), lens, n, ref_group, acc.data_ptr(), st))
-    return out, acc, flags
+    return pl.back(out), acc, pl.back(flags)
 
 
 @error_sums.register_fake
@@ -590,36 +634,12 @@ def _(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost, sub_cost, nor
 # ---------------------------------------------------------------------------------------
 # eager fast path
 # ---------------------------------------------------------------------------------------
-def _needs_dispatcher() -> bool:
-    """The registered ops exist so that tracing / torch.compile see ONE opaque op per public
-    call.  In plain eager mode the dispatcher round trip (~20-30 us) is pure overhead next to
-    kernels that take a few microseconds, so the op bodies are called directly."""
+def needs_dispatcher() -> bool:
+    """The registered ops exist so that scripting / tracing / torch.compile see ONE opaque op
+    per call.  In plain eager mode the dispatcher round trip (~20-30 us) is pure overhead next
+    to kernels that take a few microseconds, so the ``*_impl`` bodies are called directly."""
     return torch.jit.is_tracing() or torch.compiler.is_compiling()
 
 
-def string_matching_fast(*args):
-    if _needs_dispatcher():
-        return string_matching(*args)
-    return string_matching._init_fn(*args)
-
-
-def optimal_completion_fast(*args):
-    if _needs_dispatcher():
-        return optimal_completion(*args)
-    return optimal_completion._init_fn(*args)
-
-
-def _wants_grad(t: Tensor) -> bool:
+def wants_grad(t: Tensor) -> bool:
     return torch.is_grad_enabled() and t.requires_grad
-
-
-def sequence_log_probs_fast(logits, hyp, eos):
-    if _needs_dispatcher() or _wants_grad(logits):
-        return sequence_log_probs(logits, hyp, eos)
-    return sequence_log_probs._init_fn(logits, hyp, eos)
-
-
-def ctc_greedy_search_fast(logits, in_lens, blank, is_probs):
-    if _needs_dispatcher() or _wants_grad(logits):
-        return ctc_greedy_search(logits, in_lens, blank, is_probs)
-    return ctc_greedy_search._init_fn(logits, in_lens, blank, is_probs)

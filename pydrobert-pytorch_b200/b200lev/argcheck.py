@@ -1,50 +1,60 @@
 """The constructor checks the string-matching modules use.
 
-Same behaviour and messages as the reference's ``pydrobert/torch/argcheck.py``
-(``_type_check_factory`` :202-223, ``is_in`` :316-325): a value of an accepted type is
-returned converted to the canonical type, anything else raises
-``ValueError("<name> (<val>) is not a[n] <type>")``.
+Written against the reference's observable contract (``pydrobert/torch/argcheck.py``):
+``is_<kind>(val, name=None, allow_none=False)`` returns ``val`` converted to the canonical
+Python type of the kind, or raises ``ValueError("<what> is not a[n] <kind>")`` where
+``<what>`` is ``name (val)``, just ``val`` without a name, strings quoted, one-element
+tensors shown by value and larger tensors by name only; ``is_in`` raises
+``ValueError("<what> is not one of <collection>")``.
 """
-from typing import Any, Collection, Optional
+from typing import Any, Collection, Optional, Tuple
 
 import numpy as np
 import torch
 
 
-def _nv(name: Optional[str], val: Any) -> str:
+def _describe(val: Any, name: Optional[str]) -> str:
+    """How a rejected value is shown in the message."""
+    if isinstance(val, torch.Tensor) and val.numel() != 1:
+        return "tensor" if name is None else name
     if isinstance(val, torch.Tensor):
-        if val.numel() == 1:
-            return f"{val.item()}" if name is None else f"{name} ({val.item()})"
-        return name if name is not None else "tensor"
-    if isinstance(val, str):
-        val = f"'{val}'"
-    return f"{val}" if name is None else f"{name} ({val})"
+        shown = str(val.item())
+    elif isinstance(val, str):
+        shown = "'" + val + "'"
+    else:
+        shown = str(val)
+    return shown if name is None else "{} ({})".format(name, shown)
 
 
-def _type_check(t, *ts):
-    ts = (t,) + ts
+class _Kind:
+    """One accepted kind of constructor argument: the canonical type it is returned as and
+    the other types that convert to it."""
 
-    def check(val, name=None, allow_none=False):
+    def __init__(self, canonical: type, also: Tuple[type, ...] = ()):
+        self.canonical = canonical
+        self.accepted = (canonical,) + tuple(also)
+        label = canonical.__name__
+        self.phrase = ("an " if label[0] in "aeiou" else "a ") + label
+
+    def __call__(self, val: Any, name: Optional[str] = None, allow_none: bool = False) -> Any:
         if val is None and allow_none:
-            return val
-        if isinstance(val, ts):
-            return val if (type(val) is t) else t(val)
-        tname = t.__name__
-        x = "n" if tname.startswith(("a", "e", "i", "o", "u")) else ""
-        raise ValueError(f"{_nv(name, val)} is not a{x} {tname}")
-
-    return check
+            return None
+        if not isinstance(val, self.accepted):
+            raise ValueError("{} is not {}".format(_describe(val, name), self.phrase))
+        if type(val) is not self.canonical:
+            val = self.canonical(val)
+        return val
 
 
-is_int = _type_check(int, np.integer)
-is_bool = _type_check(bool)
-is_float = _type_check(float, int, np.integer, np.floating)
-is_tensor = _type_check(torch.Tensor)
+is_int = _Kind(int, (np.integer,))
+is_bool = _Kind(bool)
+is_float = _Kind(float, (int, np.integer, np.floating))
+is_tensor = _Kind(torch.Tensor)
 
 
-def is_in(val, collection: Collection, name=None, allow_none=False):
-    if allow_none and val is None:
+def is_in(val: Any, collection: Collection, name: Optional[str] = None, allow_none: bool = False) -> Any:
+    if val is None and allow_none:
         return None
-    if val not in collection:
-        raise ValueError(f"{_nv(name, val)} is not one of {collection}")
-    return val
+    if val in collection:
+        return val
+    raise ValueError("{} is not one of {}".format(_describe(val, name), collection))

@@ -74,8 +74,7 @@ def bulk_error_rate(ref: torch.Tensor, hyp: torch.Tensor, eos: Optional[int] = N
     ``compute-torch-token-data-dir-error-rates`` (command_line.py:1141-1147) is
     ``totals[0] / totals[1]`` (or ``/ totals[2]`` with ``distances``).
     """
-    (ref_d, hyp_d), back = F._offload(ref, hyp)
-    er, acc, flags = _ops.error_sums(ref_d, hyp_d, eos, include_eos, batch_first,
+    er, acc, flags = _ops.error_sums(ref, hyp, eos, include_eos, batch_first,
                                      float(ins_cost), float(del_cost), float(sub_cost), False,
                                      not distances, 1)
     if warn:
@@ -87,4 +86,4 @@ def bulk_error_rate(ref: torch.Tensor, hyp: torch.Tensor, eos: Optional[int] = N
             acc = host.to(acc.device)
         else:
             dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=process_group)
-    return back(er), acc
+    return er, acc

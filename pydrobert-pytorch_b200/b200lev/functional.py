@@ -1,26 +1,30 @@
-"""The eight functionals of the reference's string-matching family, same signatures.
+"""The functionals of the reference's string-matching family, same signatures.
 
 Mirrors ``pydrobert.torch.functional`` (functional.py:49-58 of the reference) for the
 names backed by ``pydrobert/torch/_string.py`` ("SM" below): argument meaning,
 defaults, shapes, dtypes, error messages and the three data-dependent warnings are
 the reference's; the numbers come from the sm_100a kernels behind ``torch.ops.b200lev``.
 
-Host tensors: the reference runs wherever its inputs live.  Here a CPU tensor is
-copied to the current CUDA device (asynchronously when it is pinned), the kernels run
-there and the result is copied back -- the ``e2e`` path of ``bench.py``.  Large host
-batches of the final / prefix modes are cut into blocks of the batch axis that flow
-through three streams (copy in, kernels, copy out), so that the PCIe transfers of both
-directions and the kernels overlap.  Without a CUDA device the call raises; there is
-no CPU implementation.
+Every function here compiles under ``torch.jit.script`` (the reference scripts its
+modules, tests/conftest.py:166-174) and is wrapped in ``torch.jit.script_if_tracing`` as
+the reference's are (_compat.py:189,300), so a traced module keeps its shape checks,
+group sizes and warnings dynamic instead of baking the example's into the graph.  The
+body is therefore TorchScript: no closures, no dict globals, one ``torch.ops.b200lev``
+call per step.  In plain eager mode the ``if not torch.jit.is_scripting()`` branches call
+the op bodies directly (no dispatcher round trip).
+
+Host tensors: the reference runs wherever its inputs live.  Here a CPU tensor is copied
+to the current CUDA device inside the op, the kernels run there and the result is copied
+back (``_host.py``).  Without a CUDA device the call raises; there is no CPU
+implementation.
 """
-from __future__ import annotations
 
 import warnings
-from typing import Optional, Tuple
+from typing import Any, Optional, Tuple
 
 import torch
 
-from . import _abi, _ops, config
+from . import _ops, config
 
 __all__ = [
     "edit_distance",
@@ -35,145 +39,40 @@ __all__ = [
     "ctc_greedy_search",
 ]
 
-
-def _offload(*tensors):
-    """Move host tensors to the current CUDA device; returns (tensors, back) where
-    ``back`` maps a result to the device the caller's inputs were on."""
-    first = next(t for t in tensors if t is not None)
-    if first.device.type == "cuda" or _abi.EMULATED:
-        return tensors, (lambda x: x)
-    if not torch.cuda.is_available():
-        raise _abi.B200LevError(
-            "b200lev needs a CUDA device: the string-matching kernels have no CPU fallback")
-    dev = torch.device("cuda", torch.cuda.current_device())
-    moved = tuple(None if t is None else t.to(dev, non_blocking=True) for t in tensors)
-
-    def back(x):
-        # D2H into page-locked memory (torch's caching host allocator recycles the block):
-        # one DMA, no staging copy through a pageable buffer
-        host = torch.empty(x.shape, dtype=x.dtype, device="cpu", pin_memory=True)
-        host.copy_(x, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        return host
-
-    return moved, back
+script = torch.jit.script_if_tracing
 
 
-# ---- host tensors, large batches: three-stream pipeline over blocks of the batch ----------
-_PIPE_MIN_BYTES = 16 << 20  # below this one copy each way is as fast
-_PIPE_BLOCKS = 16  # measured on cfg2 (212 MB in): 4 -> 4.35 ms, 8 -> 4.58, 16 -> 4.29, 32 -> 4.79 (CPU-bound)
-_pipe_streams = {}
-
-
-def _pipe_streams_for(dev: torch.device):
-    if dev.index not in _pipe_streams:
-        _pipe_streams[dev.index] = tuple(torch.cuda.Stream(dev) for _ in range(3))
-    return _pipe_streams[dev.index]
-
-
-def _pipe_plan(ref, hyp, batch_first, ref_group):
-    """Block boundaries (in reference sequences) or None when the single-copy path is the
-    right one (small batch, odd shapes that the op itself must reject, emulation)."""
-    if _abi.EMULATED or ref.device.type != "cpu" or hyp.device.type != "cpu":
-        return None
-    if not torch.cuda.is_available() or ref.dim() != 2 or hyp.dim() != 2:
-        return None
-    bdim = 0 if batch_first else 1
-    nr, n = ref.shape[bdim], hyp.shape[bdim]
-    if nr * ref_group != n or ref.shape[1 - bdim] == 0 or hyp.shape[1 - bdim] == 0:
-        return None
-    if ref.dtype not in _ops._INT_DTYPES or hyp.dtype not in _ops._INT_DTYPES:
-        return None
-    nbytes = ref.numel() * ref.element_size() + hyp.numel() * hyp.element_size()
-    if nbytes < _PIPE_MIN_BYTES or nr < 2 * 256:
-        return None
-    blocks = min(_PIPE_BLOCKS, nr // 256)
-    step = -(-nr // blocks)
-    step = -(-step // 32) * 32
-    return [(a, min(a + step, nr)) for a in range(0, nr, step)]
-
-
-def _copy_block(lib, dev_t, host_t, batch_first, a, b, to_device, stream):
-    """One DMA between rows/columns [a, b) of the batch axis of a host matrix (inner stride
-    1) and the contiguous device matrix of that block."""
-    es = host_t.element_size()
-    if host_t.dim() == 1:
-        base, pitch, width, height = a * es, (b - a) * es, (b - a) * es, 1
-    elif batch_first:
-        base, pitch, width, height = a * host_t.stride(0) * es, host_t.stride(0) * es, \
-            host_t.shape[1] * es, b - a
-    else:
-        base, pitch, width, height = a * es, host_t.stride(0) * es, (b - a) * es, host_t.shape[0]
-    hp, dp = host_t.data_ptr() + base, dev_t.data_ptr()
-    if to_device:
-        _abi.check(lib.b200lev_copy2d_async(dp, width, hp, pitch, width, height, 1, stream))
-    else:
-        _abi.check(lib.b200lev_copy2d_async(hp, pitch, dp, width, width, height, 0, stream))
-
-
-def _string_matching_pipelined(plan, ref, hyp, op_args, batch_first, prefix, exclude_last,
-                               ref_group):
-    """Blocks of the batch through (H2D, kernels, D2H) on three streams; same numbers as one
-    call on the whole batch (pairs are independent).  Returns (host result, flags)."""
-    lib = _abi.lib()
-    dev = torch.device("cuda", torch.cuda.current_device())
-    s_in, s_run, s_out = _pipe_streams_for(dev)
-    if ref.dim() == 2 and ref.stride(1) != 1:
-        ref = ref.contiguous()
-    if hyp.stride(1) != 1:
-        hyp = hyp.contiguous()
-    bdim = 0 if batch_first else 1
-    n = hyp.shape[bdim]
-    hout = hyp.shape[1 - bdim] + (0 if exclude_last else 1)
-    if not prefix:
-        shape = (n,)
-    else:
-        shape = (n, hout) if batch_first else (hout, n)
-    host_out = torch.empty(shape, dtype=torch.float32, device="cpu", pin_memory=True)
-    flags = None
-    keep = []  # blocks stay referenced until the last stream drains
-    here = torch.cuda.current_stream(dev)
-    s_in.wait_stream(here)
-    for (a, b) in plan:
-        ha, hb = a * ref_group, b * ref_group
-        with torch.cuda.stream(s_in):
-            rshape = (b - a, ref.shape[1]) if batch_first else (ref.shape[0], b - a)
-            hshape = (hb - ha, hyp.shape[1]) if batch_first else (hyp.shape[0], hb - ha)
-            ref_d = torch.empty(rshape, dtype=ref.dtype, device=dev)
-            hyp_d = torch.empty(hshape, dtype=hyp.dtype, device=dev)
-            _copy_block(lib, ref_d, ref, batch_first, a, b, True, s_in.cuda_stream)
-            _copy_block(lib, hyp_d, hyp, batch_first, ha, hb, True, s_in.cuda_stream)
-            arrived = s_in.record_event()
-        with torch.cuda.stream(s_run):
-            s_run.wait_event(arrived)
-            out_d, f = _ops.string_matching_fast(ref_d, hyp_d, *op_args)
-            flags = f if flags is None else flags.bitwise_or_(f)
-            done = s_run.record_event()
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(done)
-            _copy_block(lib, out_d, host_out, batch_first, ha, hb, False, s_out.cuda_stream)
-        keep.append((ref_d, hyp_d, out_d, f))
-    s_out.synchronize()
-    s_run.synchronize()
-    del keep
-    return host_out, flags
+def _reduction_code(reduction: str) -> int:
+    """SM:1250, 1471: the message of a bad ``reduction``; the codes are the C ABI's."""
+    if reduction == "none":
+        return 0
+    elif reduction == "mean":
+        return 1
+    elif reduction == "sum":
+        return 2
+    raise RuntimeError(f"'{reduction}' is not a valid value for reduction")
 
 
 def _warn_flags(flags: torch.Tensor, eos: Optional[int], include_eos: bool, norm: bool,
                 prefix: bool) -> None:
-    """The data-dependent warnings of SM:202-217, 361-366, 398-404 (one 4-byte D2H)."""
-    if torch.jit.is_tracing():
-        return
+    """The data-dependent warnings of SM:202-217, 361-366, 398-404 (one 4-byte read of the
+    flag word the kernels wrote: bit 0/1 = a ref/hyp sequence without eos, bit 2 = an empty
+    reference)."""
     f = int(flags.item())
     if eos is not None and include_eos:
-        for bit, name in ((_abi.FLAG_REF_NO_EOS, "ref"), (_abi.FLAG_HYP_NO_EOS, "hyp")):
-            if f & bit:
-                warnings.warn(
-                    "include_eos=True, but a transcription in {} did not "
-                    "contain the eos symbol ({}). To suppress this "
-                    "warning, set warn=False".format(name, eos)
-                )
-    if norm and (f & _abi.FLAG_EMPTY_REF):
+        if (f & 1) != 0:
+            warnings.warn(
+                "include_eos=True, but a transcription in ref did not "
+                "contain the eos symbol ({}). To suppress this "
+                "warning, set warn=False".format(eos)
+            )
+        if (f & 2) != 0:
+            warnings.warn(
+                "include_eos=True, but a transcription in hyp did not "
+                "contain the eos symbol ({}). To suppress this "
+                "warning, set warn=False".format(eos)
+            )
+    if norm and (f & 4) != 0:
         if prefix:
             warnings.warn(
                 "ref contains empty transcripts. Error rates will be "
@@ -188,36 +87,52 @@ def _warn_flags(flags: torch.Tensor, eos: Optional[int], include_eos: bool, norm
             )
 
 
-def _string_matching(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost, sub_cost, warn,
-                     norm=False, return_prf_dsts=False, exclude_last=False,
-                     padding=config.INDEX_PAD_VALUE, return_mistakes=False, ref_group=1):
+def _string_matching(
+    ref: torch.Tensor,
+    hyp: torch.Tensor,
+    eos: Optional[int],
+    include_eos: bool,
+    batch_first: bool,
+    ins_cost: float,
+    del_cost: float,
+    sub_cost: float,
+    warn: bool,
+    norm: bool = False,
+    return_prf_dsts: bool = False,
+    exclude_last: bool = False,
+    padding: int = config.INDEX_PAD_VALUE,
+    return_mistakes: bool = False,
+    ref_group: int = 1,
+) -> torch.Tensor:
     """SM:146-406 for the final and prefix modes (the mask mode is folded into
     :func:`optimal_completion`)."""
     if ref.dim() != 2 or hyp.dim() != 2:
         raise RuntimeError("ref and hyp must be 2 dimensional")
-    uniform = ins_cost == del_cost == sub_cost > 0.0
+    uniform = (ins_cost == del_cost) and (del_cost == sub_cost) and (sub_cost > 0.0)
     if not uniform and return_mistakes and warn:  # SM:175-180
         warnings.warn(
             "The behaviour for non-uniform error rates has changed after v0.3.0. "
             "Please switch to edit_distance functions for old behaviour. Set "
             "warn=False to suppress this warning"
         )
-    op_args = (eos, include_eos, batch_first, float(ins_cost), float(del_cost), float(sub_cost),
-               norm, return_prf_dsts, exclude_last, int(padding), return_mistakes, ref_group)
-    plan = _pipe_plan(ref, hyp, batch_first, ref_group)
-    if plan is not None:
-        out, flags = _string_matching_pipelined(plan, ref, hyp, op_args, batch_first,
-                                                return_prf_dsts, exclude_last, ref_group)
-        if warn:
-            _warn_flags(flags, eos, include_eos, norm, return_prf_dsts)
-        return out
-    (ref_d, hyp_d), back = _offload(ref, hyp)
-    out, flags = _ops.string_matching_fast(ref_d, hyp_d, *op_args)
+    if not torch.jit.is_scripting():
+        if not _ops.needs_dispatcher():
+            out, flags = _ops.string_matching_impl(
+                ref, hyp, eos, include_eos, batch_first, float(ins_cost), float(del_cost),
+                float(sub_cost), norm, return_prf_dsts, exclude_last, int(padding),
+                return_mistakes, ref_group)
+            if warn:
+                _warn_flags(flags, eos, include_eos, norm, return_prf_dsts)
+            return out
+    out, flags = torch.ops.b200lev.string_matching(
+        ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost, sub_cost, norm,
+        return_prf_dsts, exclude_last, padding, return_mistakes, ref_group)
     if warn:
         _warn_flags(flags, eos, include_eos, norm, return_prf_dsts)
-    return back(out)
+    return out
 
 
+@script
 def error_rate(
     ref: torch.Tensor,
     hyp: torch.Tensor,
@@ -232,9 +147,10 @@ def error_rate(
 ) -> torch.Tensor:
     """Functional version of ErrorRate (SM:409-434)."""
     return _string_matching(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost,
-                            sub_cost, warn, norm=norm, return_mistakes=True)
+                            sub_cost, warn, norm, False, False, config.INDEX_PAD_VALUE, True, 1)
 
 
+@script
 def edit_distance(
     ref: torch.Tensor,
     hyp: torch.Tensor,
@@ -249,9 +165,10 @@ def edit_distance(
 ) -> torch.Tensor:
     """Functional version of EditDistance (SM:437-461)."""
     return _string_matching(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost,
-                            sub_cost, warn, norm=norm)
+                            sub_cost, warn, norm, False, False, config.INDEX_PAD_VALUE, False, 1)
 
 
+@script
 def prefix_error_rates(
     ref: torch.Tensor,
     hyp: torch.Tensor,
@@ -268,10 +185,10 @@ def prefix_error_rates(
 ) -> torch.Tensor:
     """Functional version of PrefixErrorRates (SM:520-550)."""
     return _string_matching(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost,
-                            sub_cost, warn, norm=norm, return_prf_dsts=True,
-                            exclude_last=exclude_last, padding=padding, return_mistakes=True)
+                            sub_cost, warn, norm, True, exclude_last, padding, True, 1)
 
 
+@script
 def prefix_edit_distances(
     ref: torch.Tensor,
     hyp: torch.Tensor,
@@ -288,10 +205,41 @@ def prefix_edit_distances(
 ) -> torch.Tensor:
     """Functional version of PrefixEditDistances (SM:553-583)."""
     return _string_matching(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost,
-                            sub_cost, warn, norm=norm, return_prf_dsts=True,
-                            exclude_last=exclude_last, padding=padding, return_mistakes=False)
+                            sub_cost, warn, norm, True, exclude_last, padding, False, 1)
 
 
+def _optimal_completion(
+    ref: torch.Tensor,
+    hyp: torch.Tensor,
+    eos: Optional[int],
+    include_eos: bool,
+    batch_first: bool,
+    ins_cost: float,
+    del_cost: float,
+    sub_cost: float,
+    padding: int,
+    exclude_last: bool,
+    warn: bool,
+) -> torch.Tensor:
+    if ref.dim() != 2 or hyp.dim() != 2:
+        raise RuntimeError("ref and hyp must be 2 dimensional")
+    if not torch.jit.is_scripting():
+        if not _ops.needs_dispatcher():
+            out, flags = _ops.optimal_completion_impl(
+                ref, hyp, eos, include_eos, batch_first, float(ins_cost), float(del_cost),
+                float(sub_cost), int(padding), exclude_last)
+            if warn:
+                _warn_flags(flags, eos, include_eos, False, False)
+            return out
+    out, flags = torch.ops.b200lev.optimal_completion(
+        ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost, sub_cost, padding,
+        exclude_last)
+    if warn:
+        _warn_flags(flags, eos, include_eos, False, False)
+    return out
+
+
+@script
 def optimal_completion(
     ref: torch.Tensor,
     hyp: torch.Tensor,
@@ -306,17 +254,11 @@ def optimal_completion(
     warn: bool = True,
 ) -> torch.Tensor:
     """Functional version of OptimalCompletion (SM:464-517)."""
-    if ref.dim() != 2 or hyp.dim() != 2:
-        raise RuntimeError("ref and hyp must be 2 dimensional")
-    (ref_d, hyp_d), back = _offload(ref, hyp)
-    out, flags = _ops.optimal_completion_fast(ref_d, hyp_d, eos, include_eos, batch_first,
-                                              float(ins_cost), float(del_cost), float(sub_cost),
-                                              int(padding), exclude_last)
-    if warn:
-        _warn_flags(flags, eos, include_eos, False, False)
-    return back(out)
+    return _optimal_completion(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost,
+                               sub_cost, padding, exclude_last, warn)
 
 
+@script
 def hard_optimal_completion_distillation_loss(
     logits: torch.Tensor,
     ref: torch.Tensor,
@@ -342,20 +284,15 @@ def hard_optimal_completion_distillation_loss(
             raise RuntimeError(f"If include_eos=True, eos ({eos}) must be a class idx")
         if eos is not None and eos == ignore_index:
             raise RuntimeError(f"If include_eos=True, eos cannot equal ignore_index ({eos}")
-    if reduction not in _abi.REDUCE:
-        raise RuntimeError(f"'{reduction}' is not a valid value for reduction")
-    (logits_d, ref_d, hyp_d, weight_d), back = _offload(logits, ref, hyp, weight)
-    optimals, flags = _ops.optimal_completion_fast(ref_d, hyp_d, eos, include_eos, batch_first,
-                                                   float(ins_cost), float(del_cost),
-                                                   float(sub_cost), int(ignore_index),
-                                                   True)  # SM:1216-1228
-    if warn:
-        _warn_flags(flags, eos, include_eos, False, False)
-    loss, _, _ = _ops.ocd_loss(logits_d, optimals, weight_d, int(ignore_index),
-                               _abi.REDUCE[reduction], 1 if batch_first else 0)
-    return back(loss)
+    code = _reduction_code(reduction)
+    optimals = _optimal_completion(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost,
+                                   sub_cost, ignore_index, True, warn)  # SM:1216-1228
+    loss, _, _ = torch.ops.b200lev.ocd_loss(logits, optimals, weight, ignore_index, code,
+                                            1 if batch_first else 0)
+    return loss
 
 
+@script
 def minimum_error_rate_loss(
     log_probs: torch.Tensor,
     ref: torch.Tensor,
@@ -379,20 +316,22 @@ def minimum_error_rate_loss(
         raise RuntimeError("log_probs must be 2 dimensional")
     if hyp.dim() != 3:
         raise RuntimeError("hyp must be 3 dimensional")
-    if ref.dim() not in (2, 3):
+    if ref.dim() != 2 and ref.dim() != 3:
         raise RuntimeError("ref must be 2 or 3 dimensional")
     if batch_first:
-        batch_size, samples, max_hyp_steps = hyp.shape
-        rshape = tuple(ref.shape[:2]) if ref.dim() == 3 else (ref.shape[0], samples)
+        batch_size, samples, max_hyp_steps = hyp.size(0), hyp.size(1), hyp.size(2)
+        ref_batch = ref.size(0)
+        ref_samples = ref.size(1) if ref.dim() == 3 else samples
     else:
-        max_hyp_steps, batch_size, samples = hyp.shape
-        rshape = tuple(ref.shape[1:]) if ref.dim() == 3 else (ref.shape[1], samples)
-    if rshape != (batch_size, samples) or rshape != tuple(log_probs.shape):
+        max_hyp_steps, batch_size, samples = hyp.size(0), hyp.size(1), hyp.size(2)
+        ref_batch = ref.size(1)
+        ref_samples = ref.size(2) if ref.dim() == 3 else samples
+    if (ref_batch != batch_size or ref_samples != samples or log_probs.size(0) != batch_size
+            or log_probs.size(1) != samples):
         raise RuntimeError("ref and hyp batch_size and sample dimensions must match")
     if samples < 2:
         raise RuntimeError(f"Batch must have at least two samples, got {samples}")
-    if reduction not in _abi.REDUCE:
-        raise RuntimeError(f"'{reduction}' is not a valid value for reduction")
+    code = _reduction_code(reduction)
     group = samples if ref.dim() == 2 else 1
     if batch_first:
         hyp2 = hyp.reshape(-1, max_hyp_steps)
@@ -400,23 +339,12 @@ def minimum_error_rate_loss(
     else:
         hyp2 = hyp.reshape(max_hyp_steps, -1)
         ref2 = ref if ref.dim() == 2 else ref.reshape(ref.size(0), -1)
-    (lp_d, ref_d, hyp_d), back = _offload(log_probs, ref2, hyp2)
-    uniform = ins_cost == del_cost == sub_cost > 0.0
-    if not uniform and warn:  # SM:175-180 via error_rate
-        warnings.warn(
-            "The behaviour for non-uniform error rates has changed after v0.3.0. "
-            "Please switch to edit_distance functions for old behaviour. Set "
-            "warn=False to suppress this warning"
-        )
-    er, flags = _ops.string_matching_fast(ref_d, hyp_d, eos, include_eos, batch_first,
-                                          float(ins_cost), float(del_cost), float(sub_cost), norm,
-                                          False, False, 0, True, group)  # SM:1451-1462
-    if warn:
-        _warn_flags(flags, eos, include_eos, norm, False)
-    loss = _ops.mwer_loss(er, lp_d, sub_avg, _abi.REDUCE[reduction])
-    return back(loss)
+    er = _string_matching(ref2, hyp2, eos, include_eos, batch_first, ins_cost, del_cost, sub_cost,
+                          warn, norm, False, False, 0, True, group)  # SM:1451-1462
+    return torch.ops.b200lev.mwer_loss(er, log_probs, sub_avg, code)
 
 
+@script
 def fill_after_eos(
     tokens: torch.Tensor,
     eos: int,
@@ -427,23 +355,20 @@ def fill_after_eos(
     """Functional version of FillAfterEndOfSequence (SM:30-42)."""
     out = tokens if value is None else value
     fill_ = float(eos) if fill is None else fill
-    (tok_d, out_d), back = _offload(tokens, out)
-    fill_mask = _ops.after_eos_mask(tok_d, int(eos), int(dim))
-    return back(out_d.masked_fill(fill_mask, fill_))
+    fill_mask = torch.ops.b200lev.after_eos_mask(tokens, eos, dim)
+    return out.masked_fill(fill_mask, fill_)
 
 
-def sequence_log_probs(logits, hyp: torch.Tensor, dim: int = 0, eos: Optional[int] = None) -> torch.Tensor:
-    """Functional version of SequenceLogProbabilities, tensor path (_decoding.py:1516-1548,
-    1579-1633): joint log-probability of the token sequences in ``hyp`` (``(A*, T, B*)``, step
-    axis ``dim``) under the categorical distributions ``logits`` (``(A*, T, B*, V)``).  Tokens
-    outside ``[0, V)`` are padding; with ``eos`` the first eos step is the last one counted.
-    Differentiable with respect to ``logits``.
+def _prod(sizes: Tuple[int, ...]) -> int:
+    n = 1
+    for s in sizes:
+        n *= s
+    return n
 
-    Only tensors: the reference's PackedSequence branch (_decoding.py:1551-1576) is a host-side
-    re-packing of the same sum and is not part of the hot-path scope."""
-    if not isinstance(logits, torch.Tensor):
-        raise RuntimeError("logits must be a Tensor (the PackedSequence path is not implemented "
-                           "by b200lev)")
+
+def _sequence_log_probs_tensor(logits: torch.Tensor, hyp: torch.Tensor, dim: int,
+                               eos: Optional[int]) -> torch.Tensor:
+    """_decoding.py:1516-1548"""
     hyp_dim = hyp.dim()
     if dim < -hyp_dim or dim > hyp_dim - 1:  # _decoding.py:1521-1525
         raise RuntimeError(
@@ -457,18 +382,61 @@ def sequence_log_probs(logits, hyp: torch.Tensor, dim: int = 0, eos: Optional[in
                 tuple(logits.shape), tuple(hyp.shape)))
     if not logits.is_floating_point():
         raise RuntimeError("logits must be floating point")
-    (logits_d, hyp_d), back = _offload(logits, hyp)
-    outer = 1
-    for d in hyp.shape[:dim]:
-        outer *= d
-    inner = 1
-    for d in hyp.shape[dim + 1:]:
-        inner *= d
+    outer, inner = _prod(tuple(hyp.shape[:dim])), _prod(tuple(hyp.shape[dim + 1:]))
     T, V = hyp.shape[dim], logits.shape[-1]
-    out, _, _ = _ops.sequence_log_probs_fast(
-        logits_d.contiguous().view(outer, T, inner, V),
-        hyp_d.to(torch.long).contiguous().view(outer, T, inner), eos)
-    return back(out.view(tuple(hyp.shape[:dim]) + tuple(hyp.shape[dim + 1:])))
+    logits4 = logits.contiguous().view(outer, T, inner, V)
+    hyp3 = hyp.to(torch.long).contiguous().view(outer, T, inner)
+    if _ops.needs_dispatcher() or _ops.wants_grad(logits):
+        out, _, _ = _ops.sequence_log_probs(logits4, hyp3, eos)
+    else:
+        out, _, _ = _ops.sequence_log_probs_impl(logits4, hyp3, eos)
+    return out.view(tuple(hyp.shape[:dim]) + tuple(hyp.shape[dim + 1:]))
+
+
+def _sequence_log_probs_packed(logits: torch.nn.utils.rnn.PackedSequence, hyp: torch.Tensor,
+                               dim: int) -> torch.Tensor:
+    """_decoding.py:1551-1586: ``logits`` is a PackedSequence of per-step distributions
+    ``(sum(lens), V)`` and ``hyp`` the ``(T, N)`` (``dim == 0``) or ``(N, T)`` (``dim == 1``)
+    token matrix of the same sequences in their original order.
+
+    The packed data is a ragged view of the padded ``(T, N, V)`` tensor: a step that a sequence
+    does not have contributes nothing.  That is exactly what the tensor kernel does with a
+    token outside ``[0, V)``, so the packed rows are scattered into a padded logits tensor,
+    the steps beyond a sequence's length get token -1, and the tensor path does the rest
+    (its backward hands the padded gradient back through the same index map)."""
+    hyp_dim = hyp.dim()
+    if dim < -hyp_dim or dim > hyp_dim - 1:
+        raise RuntimeError(
+            "Dimension out of range (expected to be in range of [{}, {}], but "
+            "got {})".format(-hyp_dim, hyp_dim - 1, dim)
+        )
+    if hyp_dim != 2:
+        raise RuntimeError("hyp must be 2 dimensional when logits is a PackedSequence")
+    dim = (hyp_dim + dim) % hyp_dim
+    padded, lens = torch.nn.utils.rnn.pad_packed_sequence(logits, batch_first=bool(dim))
+    T = padded.size(dim)
+    hyp = hyp.narrow(dim, 0, T) if hyp.size(dim) >= T else hyp
+    steps = torch.arange(T, device=hyp.device)
+    lens = lens.to(hyp.device)
+    beyond = (steps.unsqueeze(1) >= lens.unsqueeze(0)) if dim == 0 else \
+        (steps.unsqueeze(0) >= lens.unsqueeze(1))
+    hyp = hyp.masked_fill(beyond, -1)
+    return _sequence_log_probs_tensor(padded, hyp, dim, None)
+
+
+def sequence_log_probs(logits: Any, hyp: torch.Tensor, dim: int = 0, eos: Optional[int] = None
+                       ) -> torch.Tensor:
+    """Functional version of SequenceLogProbabilities (_decoding.py:1516-1633): joint
+    log-probability of the token sequences in ``hyp`` (``(A*, T, B*)``, step axis ``dim``) under
+    the categorical distributions ``logits`` (``(A*, T, B*, V)``, or a PackedSequence of
+    ``(T, N)`` / ``(N, T)`` sequences).  Tokens outside ``[0, V)`` are padding; with ``eos`` the
+    first eos step is the last one counted (tensor ``logits`` only, as in the reference).
+    Differentiable with respect to ``logits``."""
+    if isinstance(logits, torch.Tensor):
+        return _sequence_log_probs_tensor(logits, hyp, dim, eos)
+    if isinstance(logits, torch.nn.utils.rnn.PackedSequence):
+        return _sequence_log_probs_packed(logits, hyp, dim)
+    raise RuntimeError("logits must be either a Tensor or PackedSequence")
 
 
 def ctc_greedy_search(logits: torch.Tensor, in_lens: Optional[torch.Tensor] = None, blank_idx: int = -1,
@@ -495,9 +463,11 @@ def ctc_greedy_search(logits: torch.Tensor, in_lens: Optional[torch.Tensor] = No
     T = logits.size(1) if batch_first else logits.size(0)
     if in_lens is not None and tuple(in_lens.shape) != (N,):
         raise RuntimeError(f"in_lens must have shape ({N},), got {tuple(in_lens.shape)}")
-    (logits_d, lens_d), back = _offload(logits, in_lens)
     outer, inner = (N, 1) if batch_first else (1, N)
-    max_, paths, out_lens, _, _, _ = _ops.ctc_greedy_search_fast(
-        logits_d.contiguous().view(outer, T, inner, V), lens_d, blank, is_probs)
+    logits4 = logits.contiguous().view(outer, T, inner, V)
+    if _ops.needs_dispatcher() or _ops.wants_grad(logits):
+        max_, paths, out_lens, _, _, _ = _ops.ctc_greedy_search(logits4, in_lens, blank, is_probs)
+    else:
+        max_, paths, out_lens, _, _, _ = _ops.ctc_greedy_search_impl(logits4, in_lens, blank, is_probs)
     shape = (N, T) if batch_first else (T, N)
-    return back(max_.view(N)), back(paths.view(shape)), back(out_lens.view(N))
+    return max_.view(N), paths.view(shape), out_lens.view(N)

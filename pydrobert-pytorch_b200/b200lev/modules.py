@@ -5,7 +5,6 @@ Same constructor signatures, validation (``argcheck``), ``__constants__``,
 of the reference; classes at _string.py:45-134, 680-1166, 1254-1378, 1475-1646).  Each
 forward calls the functional of the same name, which dispatches to the sm_100a kernels.
 """
-from __future__ import annotations
 
 import abc
 from typing import Optional, Tuple

@@ -26,7 +26,7 @@ from typing import Dict, Hashable, Iterable, List, Optional, Sequence, Set, Tupl
 import numpy as np
 import torch
 
-from . import _ops, config
+from . import _host, _ops, config
 from . import functional as F
 
 __all__ = [
@@ -259,8 +259,7 @@ def _filtered(c: TokenCorpus, code: np.ndarray, keep: Optional[np.ndarray]) -> T
 
 def _to_device(a: np.ndarray) -> torch.Tensor:
     t = torch.from_numpy(np.ascontiguousarray(a))
-    (moved,), _ = F._offload(t)  # raises without a CUDA device: there is no CPU path
-    return moved
+    return _host.Placement(t).to_dev(t)  # raises without a CUDA device: there is no CPU path
 
 
 def score_corpora(ref: TokenCorpus, hyp: TokenCorpus, id2token: Optional[Dict[int, str]] = None,

@@ -464,3 +464,133 @@ def check_ctc_masked_classes(F, dev):
         np.testing.assert_array_equal(paths.cpu().numpy(), e_paths)
         np.testing.assert_array_equal(out_lens.cpu().numpy(), e_lens)
         np.testing.assert_allclose(max_.double().cpu().numpy(), e_max, rtol=2e-6, atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------
+# fill_after_eos and the nn.Module shells under nojit / trace / script
+# ---------------------------------------------------------------------------------------
+def check_fill_after_eos(F, dev, seed=0):
+    """SM:30-42 against the oracle: every axis, negative axes, integer and float fills, a
+    broadcast ``value`` tensor, float "tokens" (the reference's trace placeholders), 1-D and
+    0-sized inputs."""
+    rng = np.random.default_rng(seed)
+    tok = rng.integers(0, 5, (7, 6, 3))
+    t = torch.from_numpy(tok).to(dev)
+    for dim in (0, 1, 2, -1, -3):
+        exp = O.fill_after_eos(tok, 2, dim=dim, fill=-9)
+        assert np.array_equal(F.fill_after_eos(t, 2, dim=dim, fill=-9).cpu().numpy(), exp), dim
+    assert np.array_equal(F.fill_after_eos(t, 3).cpu().numpy(), O.fill_after_eos(tok, 3))
+    val = rng.standard_normal((7, 6, 4)).astype(np.float32)
+    exp = O.fill_after_eos(tok[:, :, :1], 2, value=val)
+    act = F.fill_after_eos(t[:, :, :1], 2, value=torch.from_numpy(val).to(dev))
+    assert np.array_equal(act.cpu().numpy(), exp)
+    flt = F.fill_after_eos(t.float(), 2, dim=1, fill=0.5)
+    assert flt.dtype == torch.float32
+    assert np.array_equal(flt.cpu().numpy(), O.fill_after_eos(tok.astype(np.float32), 2, dim=1, fill=0.5))
+    one = torch.tensor([4, 1, 1, 3, 1], device=dev)
+    assert F.fill_after_eos(one, 1, fill=7).tolist() == [4, 1, 7, 7, 7]
+    assert F.fill_after_eos(torch.zeros((0, 3), dtype=torch.long, device=dev), 1).shape == (0, 3)
+    big = rng.integers(0, 50, (300, 257))
+    assert np.array_equal(F.fill_after_eos(torch.from_numpy(big).to(dev), 7, dim=0).cpu().numpy(),
+                          O.fill_after_eos(big, 7, dim=0))
+    assert np.array_equal(F.fill_after_eos(torch.from_numpy(big).to(dev), 7, dim=1).cpu().numpy(),
+                          O.fill_after_eos(big, 7, dim=1))
+
+
+def _jit(module, jit_type, example):
+    if jit_type == "script":
+        return torch.jit.script(module)
+    if jit_type == "trace":
+        return torch.jit.trace(module, example)
+    return module
+
+
+def check_modules(F, M, dev, jit_type):
+    """Every module of the family (modules.py:115-124 of the reference), plain, traced with the
+    tiny placeholder inputs the reference's tests use (TS:43, 86, 150, 219, 249-255) and
+    scripted: same numbers as the functional on inputs of OTHER shapes than the example's,
+    which is what catches shape logic baked into a graph."""
+    rng = np.random.default_rng(17)
+    eos = 0
+    ref_np, hyp_np = random_tokens(rng, 9, 6, 5, eos, -1), random_tokens(rng, 11, 6, 5, eos, -1)
+    ref, hyp = torch.from_numpy(ref_np).to(dev), torch.from_numpy(hyp_np).to(dev)
+    tok11 = (torch.full((1, 1), eos, dtype=torch.long, device=dev),) * 2
+    flt11 = (torch.zeros(1, 1, device=dev),) * 2  # the reference traces with float tokens too
+    cases = [
+        (M.ErrorRate(eos=eos, warn=False), flt11, F.error_rate, dict(eos=eos, warn=False)),
+        (M.ErrorRate(eos=eos, include_eos=True, norm=False, ins_cost=2.0, warn=False), tok11,
+         F.error_rate, dict(eos=eos, include_eos=True, norm=False, ins_cost=2.0, warn=False)),
+        (M.EditDistance(eos=eos, ins_cost=3.0, del_cost=3.0, sub_cost=4.0), tok11, F.edit_distance,
+         dict(eos=eos, ins_cost=3.0, del_cost=3.0, sub_cost=4.0)),
+        (M.PrefixErrorRates(eos=eos, padding=-3, warn=False), tok11, F.prefix_error_rates,
+         dict(eos=eos, padding=-3, warn=False)),
+        (M.PrefixEditDistances(eos=eos, exclude_last=True, norm=True, warn=False), tok11,
+         F.prefix_edit_distances, dict(eos=eos, exclude_last=True, norm=True, warn=False)),
+        (M.OptimalCompletion(eos=eos, padding=-7), tok11, F.optimal_completion,
+         dict(eos=eos, padding=-7)),
+        (M.OptimalCompletion(eos=None, exclude_last=True, include_eos=False), tok11,
+         F.optimal_completion, dict(eos=None, exclude_last=True, include_eos=False)),
+    ]
+    for mod, example, fn, kw in cases:
+        jm = _jit(mod, jit_type, example)
+        for r, h in ((ref, hyp), (ref[:, :3], hyp[:5, :3])):
+            want = fn(r, h, **kw)
+            got = jm(r, h)
+            assert got.shape == want.shape and torch.equal(got, want), (type(mod).__name__, jit_type)
+            assert np.array_equal(got.cpu().numpy(), getattr(O, fn.__name__)(
+                r.cpu().numpy(), h.cpu().numpy(), **{k: v for k, v in kw.items() if k != "warn"}))
+    # batch_first modules
+    mod = M.PrefixErrorRates(eos=eos, batch_first=True, warn=False)
+    jm = _jit(mod, jit_type, tok11)
+    assert torch.equal(jm(ref.t(), hyp.t()), F.prefix_error_rates(ref, hyp, eos=eos, warn=False).t())
+    # FillAfterEndOfSequence (TS:31-52: traced on 1-element float placeholders, run on 3-D)
+    fa = M.FillAfterEndOfSequence(4)
+    jf = _jit(fa, jit_type, (torch.empty(1, device=dev), torch.empty(1, device=dev)))
+    tok = torch.from_numpy(rng.integers(0, 5, (8, 6))).to(dev)
+    logits = torch.randn(8, 6, 5, device=dev)
+    if jit_type != "trace":  # a module traced with (tokens, value) takes exactly those two
+        assert np.array_equal(jf(tok).cpu().numpy(), O.fill_after_eos(tok.cpu().numpy(), 4))
+    assert np.array_equal(jf(tok.unsqueeze(2), logits).cpu().numpy(),
+                          O.fill_after_eos(tok.unsqueeze(2).cpu().numpy(), 4, value=logits.cpu().numpy()))
+    # HardOptimalCompletionDistillationLoss: forward + gradient, sizes other than the example's
+    V = 5
+    for reduction in ("mean", "sum", "none"):
+        ocd = M.HardOptimalCompletionDistillationLoss(eos=eos, reduction=reduction)
+        jo = _jit(ocd, jit_type, (torch.empty(1, 1, V, device=dev),) + tok11)
+        lg = torch.randn(11, 6, V, device=dev, requires_grad=True)
+        loss = jo(lg, ref, hyp)
+        exp_loss, exp_grad = O.hard_optimal_completion_distillation_loss(
+            lg.detach().cpu().numpy(), ref_np, hyp_np, eos=eos, reduction=reduction,
+            ignore_index=-100, grad_output=None)
+        assert np.allclose(loss.detach().cpu().numpy(), exp_loss, rtol=2e-6, atol=2e-6), reduction
+        (loss if reduction != "none" else loss.sum()).backward()
+        assert np.allclose(lg.grad.cpu().numpy(), exp_grad, rtol=2e-5, atol=1e-6), reduction
+    # MinimumErrorRateLoss: traced on (2, 2) / (2, 2, 2) placeholders, run on 6 x 4 samples,
+    # 2-D and 3-D references (TS:224-270)
+    nb, ns = 6, 4
+    hyp3_np = random_tokens(rng, 7, nb * ns, 5, eos, -1).reshape(7, nb, ns)
+    hyp3 = torch.from_numpy(hyp3_np).to(dev)
+    ex = (torch.empty(2, 2, device=dev), torch.zeros(2, 2, dtype=torch.long, device=dev),
+          torch.zeros(2, 2, 2, dtype=torch.long, device=dev))
+    for reduction, sub_avg in (("mean", True), ("sum", False), ("none", True)):
+        mw = M.MinimumErrorRateLoss(eos=eos, sub_avg=sub_avg, reduction=reduction)
+        jw = _jit(mw, jit_type, ex)
+        lp = torch.randn(nb, ns, device=dev, requires_grad=True)
+        for r3 in (ref, ref.unsqueeze(-1).repeat(1, 1, ns)):
+            lp.grad = None
+            loss = jw(lp, r3, hyp3)
+            exp_loss, exp_grad = O.minimum_error_rate_loss(
+                lp.detach().cpu().numpy(), ref_np, hyp3_np, eos=eos, sub_avg=sub_avg,
+                reduction=reduction,
+                grad_output=None)
+            assert np.allclose(loss.detach().cpu().numpy(), exp_loss, rtol=2e-6, atol=2e-6)
+            (loss if reduction != "none" else loss.sum()).backward()
+            assert np.allclose(lp.grad.cpu().numpy(), exp_grad, rtol=2e-5, atol=1e-6)
+    mb = M.MinimumErrorRateLoss(eos=eos, batch_first=True)
+    jb = _jit(mb, jit_type, ex)
+    lp = torch.randn(nb, ns, device=dev)
+    assert torch.allclose(jb(lp, ref.t(), hyp3.permute(1, 2, 0)),
+                          F.minimum_error_rate_loss(lp, ref, hyp3, eos=eos))
+    if jit_type != "nojit":  # the checks stay dynamic in a graph (SM:1417-1450)
+        with pytest.raises(Exception, match="sample dimensions must match"):
+            jw(torch.randn(nb, ns + 1, device=dev), ref, hyp3)

@@ -1,0 +1,40 @@
+"""pytest plugin (``-p ref_suite_plugin``) for running the REFERENCE's own test module
+against the B200 kernels: rebinds the reference's string-matching names to b200lev
+(``b200lev.install()``) before the test module is imported.  On a box without a GPU the
+kernels run on the SIMT emulator (test infrastructure, tests/emu) so the host layer --
+scripting, tracing, shapes, messages -- is exercised by the same 310 cases."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "pydrobert-pytorch_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+import b200lev  # noqa: E402
+
+_cm = None
+if not torch.cuda.is_available():
+    from emu_backend import emulated_kernels
+
+    _cm = emulated_kernels()
+    _cm.__enter__()
+else:
+    from b200lev import _abi
+
+    _abi.lib()  # the CUDA library, or fail loudly
+
+assert b200lev.install(), "pydrobert.torch (baseline/_ref) is not importable"
+
+import pydrobert.torch.functional as _rf  # noqa: E402
+import pydrobert.torch.modules as _rm  # noqa: E402
+
+assert _rm.ErrorRate is b200lev.modules.ErrorRate and _rf.error_rate is b200lev.functional.error_rate
+assert _rm.MinimumErrorRateLoss is b200lev.modules.MinimumErrorRateLoss
+
+
+def pytest_report_header(config):
+    return "reference names rebound to b200lev ({})".format(
+        "CUDA: " + torch.cuda.get_device_name(0) if torch.cuda.is_available() else "SIMT emulator")

@@ -6,6 +6,8 @@ costs -- distances, counts, prefix tables, completion targets; rtol 1e-6 for
 non-dyadic costs; 2e-6 / 2e-5 relative (with an absolute floor of 1e-6 x scale) for
 fp32 losses / gradients.  Nothing here reads /root/reference.
 """
+import sys
+
 import numpy as np
 import pytest
 import torch
@@ -21,7 +23,7 @@ def F():
     import b200lev.functional as F_
     from b200lev import _abi
 
-    assert not _abi.EMULATED
+    assert "emu_backend" not in sys.modules, "the GPU suite must never load the emulator seam"
     _abi.lib()  # fail loudly if the CUDA library is missing
     return F_
 
@@ -34,12 +36,14 @@ def dev():
 def test_library_is_the_cuda_build(F):
     from b200lev import _abi
 
-    assert _abi.lib().b200lev_device_count() >= 1
-    with pytest.raises(_abi.B200LevError, match="no CPU fallback"):
-        from b200lev import _ops
+    from b200lev import _host
 
-        _ops.string_matching(torch.zeros(2, 2, dtype=torch.long), torch.zeros(2, 2, dtype=torch.long),
-                             None, False, False, 1.0, 1.0, 1.0, False, False, False, 0, False, 1)
+    assert _abi.lib().b200lev_device_count() >= 1
+    assert _abi.lib()._name == _abi.LIB_PATH
+    # host tensors compute on the GPU (and come back); devices that are neither raise
+    assert _host.compute_device(torch.device("cpu")).type == "cuda"
+    with pytest.raises(_abi.B200LevError, match="no CPU fallback"):
+        _host.compute_device(torch.device("meta"))
 
 
 def test_golden_string_matching(F, dev, golden_sm):
@@ -263,14 +267,14 @@ def test_host_tensors_and_views(F, dev):
 def test_host_pipeline_matches_single_call(F, dev, batch_first, pinned, monkeypatch):
     """Large host batches flow through the three-stream block pipeline (functional.py); the
     numbers, the host-side result layout and the warnings are those of one call."""
-    import b200lev.functional as Fm
-    monkeypatch.setattr(Fm, "_PIPE_MIN_BYTES", 1 << 16)
+    from b200lev import _host as Fm
+    monkeypatch.setattr(Fm, "PIPE_MIN_BYTES", 1 << 16)
     rng = np.random.default_rng(11)
     n = 2000 + 37  # not a multiple of the block size
     ref = PC.random_tokens(rng, 40, n, 50, 0, -1)
     hyp = PC.random_tokens(rng, 45, n, 50, 0, -1)
     ref[:, 5] = 3  # a reference without eos: the warning must survive the blocks
-    assert Fm._pipe_plan(torch.from_numpy(ref), torch.from_numpy(hyp), False, 1) is not None
+    assert Fm.block_plan(torch.from_numpy(ref), torch.from_numpy(hyp), False, 1) is not None
     rt, ht = torch.from_numpy(ref), torch.from_numpy(hyp)
     if batch_first:
         rt, ht = rt.t().contiguous(), ht.t().contiguous()
@@ -299,19 +303,25 @@ def test_warnings_and_errors(F, dev):
     PC.check_errors(F, dev)
 
 
-def test_modules_trace(F, dev):
-    """The reference's tests trace every module (conftest.py:166-174)."""
+@pytest.mark.parametrize("jit_type", ["nojit", "trace", "script"])
+def test_modules_jit(F, dev, jit_type):
+    """Every module, plain / traced / scripted (the reference's tests do all three,
+    conftest.py:166-174), on shapes other than the trace examples'."""
     import b200lev.modules as M
 
-    rng = np.random.default_rng(8)
-    ref = torch.from_numpy(PC.random_tokens(rng, 9, 5, 6, 0, -1)).to(dev)
-    hyp = torch.from_numpy(PC.random_tokens(rng, 11, 5, 6, 0, -1)).to(dev)
-    m = M.ErrorRate(eos=0, warn=False)
-    tm = torch.jit.trace(m, (torch.zeros(1, 1, device=dev), torch.zeros(1, 1, device=dev)))
-    assert torch.equal(tm(ref, hyp), m(ref, hyp))
-    pm = M.PrefixErrorRates(eos=0, warn=False)
-    tpm = torch.jit.trace(pm, (torch.zeros(1, 1, dtype=torch.long, device=dev),) * 2)
-    assert torch.equal(tpm(ref, hyp), pm(ref, hyp))
+    PC.check_modules(F, M, dev, jit_type)
+
+
+def test_fill_after_eos(F, dev):
+    PC.check_fill_after_eos(F, dev)
+
+
+def test_modules_host_tensors(F, dev):
+    """Host tensors through the modules: computed on the GPU, returned on the host."""
+    import b200lev.modules as M
+
+    PC.check_modules(F, M, torch.device("cpu"), "script")
+    PC.check_fill_after_eos(F, torch.device("cpu"))
 
 
 def test_wide_tokens(F, dev):

@@ -107,18 +107,14 @@ def test_sclite(F, golden_sclite):
 
 
 def test_fill_after_eos(F):
-    from oracle import oracle as O
+    PC.check_fill_after_eos(F, DEV)
 
-    rng = np.random.default_rng(0)
-    tok = rng.integers(0, 5, (7, 6, 3))
-    for dim in (0, 1, 2, -1):
-        exp = O.fill_after_eos(tok, 2, dim=dim, fill=-9)
-        act = F.fill_after_eos(torch.from_numpy(tok), 2, dim=dim, fill=-9).numpy()
-        assert np.array_equal(act, exp)
-    val = rng.standard_normal((7, 6, 4)).astype(np.float32)
-    exp = O.fill_after_eos(tok[:, :, :1], 2, value=val)
-    act = F.fill_after_eos(torch.from_numpy(tok[:, :, :1].copy()), 2, value=torch.from_numpy(val))
-    assert np.array_equal(act.numpy(), exp)
+
+@pytest.mark.parametrize("jit_type", ["nojit", "trace", "script"])
+def test_modules_jit(F, jit_type):
+    import b200lev.modules as M
+
+    PC.check_modules(F, M, DEV, jit_type)
 
 
 def test_modules_match_functionals(F):
