@@ -1,30 +1,38 @@
 #!/usr/bin/env python
 """bench.py -- the hot path's headline metric on N B200s (one process per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1..5] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Metric (BASELINE.json): edit-distance cell-updates/s (GCUPS), cells = sum over pairs of
-ref_len * hyp_len on the valid (eos-terminated) lengths; N-best hyps/s is reported
-beside it.  Workload (BASELINE.json configs[1], "MinimumErrorRateLoss /
-prefix_error_rates: batch 64 x 8-best word hyps, T=100, vocab 10k"): the per-pair shape
-is the named one; the batch is replicated to 16384 utterances x 8-best = 131072 pairs
-per GPU so the chip is full and the inputs (212 MB int64) exceed the 126 MB L2
-(SURVEY 8d-iii).  The literal 64 x 8 batch is timed too and reported under "literal".
+ref_len * hyp_len on the valid (eos-terminated) lengths; hyps/s is reported beside it.
 
-A step = one `prefix_error_rates(ref (x) 8, hyp, eos=0)` call = 7 kernel launches: pack ref,
-pack hyp (+ length histogram), bucketing (scan + scatter), the wavefront DP kernel in its
-two builds (32-bit / packed 16x2; the device-side token range picks one, the other exits at
-once), the prefix finalize (normalise + transpose, 128-bit stores) and the stand-by 64-bit
-token kernel (exits at once).
+Workloads = BASELINE.json's configs, each at its per-pair shape with the batch
+replicated until the chip is full ("saturated"); the literal batch is timed too ("literal"):
 
-  value     device-resident inputs, CUDA events, max over ranks (whole job, all GPUs)
-  e2e       the same public call with HOST (pinned) int64 tensors: H2D of the inputs and
-            D2H of the (H+1, N) result inside the timed region
-  roofline  the DP kernel alone, timed with CUDA events on the launch stream (b200lev_profile):
-            achieved = cells/s x 5 INT32 ops against the INT32 issue rate
-            measured live by the library's microbenchmark kernel
-  cpu_baseline  the oracle port (C, OpenMP) on the box's host cores, same workload
+  --config 1  error_rate, char pairs T~50, V=30                    65 536 pairs / GPU   weak
+  --config 2  prefix_error_rates, 8-best word hyps, T=100, V=10k  131 072 pairs / GPU   weak   (default;
+              the configuration the metric is quoted on)
+  --config 3  optimal_completion, T=200, V=32, include_eos          8 192 pairs / GPU   weak
+  --config 4  bulk WER: error_rate + device error sums + ONE all-reduce of the 24-byte fp64
+              totals inside the timed step, 1 000 000 pairs sharded over the ranks      strong
+  --config 5  prefix_edit_distances, T=2000 ragged, costs 3/3/4     1 184 pairs / GPU   weak
+
+A step = one public call on one batch.
+
+  value         device-resident inputs, CUDA events, max over ranks (whole job, all GPUs)
+  e2e           the same public call with HOST (pinned) int64 tensors: H2D of the inputs and
+                D2H of the result inside the timed region
+  roofline      the dominant kernel alone, timed with CUDA events on the launch stream
+                (b200lev_profile): INT32-issue bound kernels as cells/s x 5 INT32 ops
+                against the issue rate measured live by the library's microbenchmark kernel,
+                HBM-bound kernels as algorithmic bytes/s against MEASURED_PEAKS.json
+  cpu_baseline  the oracle port (C, OpenMP) on the box's host cores, bounded sample
+
+--impl reference times the UNMODIFIED reference (sdrobert/pydrobert-pytorch installed into
+baseline/_ref by oracle/make_ref.sh): its own torch implementation of the same public call on
+the host cores (torch CPU ops, all threads), same per-pair shape, bounded pair count; and, when
+a GPU is present, the same reference code on CUDA tensors next to it ("reference_on_gpu").
 """
 import argparse
 import ctypes
@@ -42,26 +50,92 @@ for p in (ROOT, os.path.join(ROOT, "pydrobert-pytorch_b200")):
 
 import numpy as np  # noqa: E402
 
-T_LEN, V, NBEST = 100, 10000, 8
 OPS_PER_CELL = 5  # compare, select/add, add, add, 3-input min
+NBEST = 8
+PROF_SLOTS = ("pack_ref", "pack_hyp", "bucketing", "dp", "prefix_finalize", "standby_wide",
+              "bitvec_probe_or_uid", "bitvec_dp", "completion_uid", "completion_fill", "err_sum")
+
+
+# ---------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------
+def _seqs(rng, T, n, V, lo, hi, eos, pad):
+    """(T, n) int64 tokens in [1, V), lengths ~ U{lo..hi} INCLUDING one eos at len-1, tail pad."""
+    tok = rng.integers(1, V, size=(T, n), dtype=np.int64)
+    lens = rng.integers(lo, hi + 1, size=n)
+    pos = np.arange(T)[:, None]
+    tok[pos == (lens - 1)[None, :]] = eos
+    tok[pos > (lens - 1)[None, :]] = pad
+    return tok, lens
+
+
+class Workload:
+    """One BASELINE config: data, the public call (ours and the reference's), the oracle call."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        (self.name, self.T, self.V, self.lo, self.hi, self.eos, self.pad, self.sat_pairs,
+         self.lit_pairs, self.scaling, self.ref_pairs, self.port_pairs) = {
+            1: ("cfg1 error_rate: char-level pairs, T~50, vocab 30, eos-padded, unit costs",
+                51, 30, 25, 50, 0, 0, 65536, 32, "weak", 2048, 65536),
+            2: ("cfg2 prefix_error_rates N-best: 8-best word hyps, T=100, vocab 10k, include_eos, norm",
+                101, 10000, 50, 100, 0, 0, 131072, 512, "weak", 512, 131072),
+            3: ("cfg3 optimal_completion: char seqs T=200, V=32, include_eos",
+                201, 32, 100, 200, 0, 0, 8192, 128, "weak", 16, 8192),
+            4: ("cfg4 bulk WER scoring: error_rate(norm=False) + error sums, word pairs T~30, vocab 10k, "
+                "sharded over the ranks, one all-reduce of the totals",
+                31, 10000, 10, 30, -1, -2, 1000000, 1000000, "strong", 10000, 1000000),
+            5: ("cfg5 long-form prefix_edit_distances: T=2000 chars, ragged, costs ins=3 del=3 sub=4",
+                2001, 64, 200, 2000, 0, 0, 1184, 256, "weak", 2, 256),
+        }[cfg]
+        self.nbest = NBEST if cfg == 2 else 1
+
+    # include_eos of the call decides which lengths count as cells
+    @property
+    def include_eos(self):
+        return self.cfg in (2, 3, 5)
+
+    def make(self, pairs, seed):
+        rng = np.random.default_rng(seed)
+        n_ref = pairs // self.nbest
+        ref, rl = _seqs(rng, self.T, n_ref, self.V, self.lo, self.hi, self.eos, self.pad)
+        hyp, hl = _seqs(rng, self.T, pairs, self.V, self.lo, self.hi, self.eos, self.pad)
+        if self.nbest > 1:  # prefix_error_rates(ref (x) 8, hyp): the reference physically repeated
+            ref, rl = np.repeat(ref, self.nbest, axis=1), np.repeat(rl, self.nbest)
+        d = 0 if self.include_eos else 1
+        cells = int(((rl - d).astype(np.int64) * (hl - d).astype(np.int64)).sum())
+        return ref, hyp, cells
+
+    def kwargs(self):
+        return {1: dict(eos=0), 2: dict(eos=0), 3: dict(eos=0),
+                4: dict(eos=-1, include_eos=False, norm=False),
+                5: dict(eos=0, ins_cost=3.0, del_cost=3.0, sub_cost=4.0)}[self.cfg]
+
+    def fn_name(self):
+        return {1: "error_rate", 2: "prefix_error_rates", 3: "optimal_completion", 4: "error_rate",
+                5: "prefix_edit_distances"}[self.cfg]
+
+    def call(self, F, ref, hyp):
+        return getattr(F, self.fn_name())(ref, hyp, warn=False, **self.kwargs())
+
+    def oracle_call(self, O, ref, hyp):
+        return getattr(O, self.fn_name())(ref, hyp, **self.kwargs())
+
+    def config(self, pairs_per_gpu, extra=None):
+        c = {"workload": self.name, "cfg": self.cfg, "call": self.fn_name(), "T": self.T - 1,
+             "vocab": self.V, "nbest": self.nbest, "pairs_per_gpu": pairs_per_gpu}
+        c.update(extra or {})
+        return c
 
 
 def make_batch(n_utts, seed):
-    """cfg2 synthetic batch: ref (T+1, n_utts), hyp (T+1, n_utts*8) int64; len ~ U{50..100}
-    with one eos(0) at len-1, tail = 0 (eos-padded); hyps independent of refs."""
+    """cfg2 synthetic batch with the reference NOT repeated: ref (T+1, n_utts), hyp (T+1, n_utts*8)
+    int64, and the cells of the 8-best pairs (the tests build their own n-best / unrelated
+    pairings from it)."""
+    wl = Workload(2)
     rng = np.random.default_rng(seed)
-    T = T_LEN + 1
-
-    def seqs(n):
-        tok = rng.integers(1, V, size=(T, n), dtype=np.int64)
-        lens = rng.integers(50, T_LEN + 1, size=n)
-        pos = np.arange(T)[:, None]
-        tok[pos >= (lens - 1)[None, :]] = 0
-        return tok, lens
-
-    ref, rl = seqs(n_utts)
-    hyp, hl = seqs(n_utts * NBEST)
-    # include_eos=True: valid lengths include the eos token
+    ref, rl = _seqs(rng, wl.T, n_utts, wl.V, wl.lo, wl.hi, wl.eos, wl.pad)
+    hyp, hl = _seqs(rng, wl.T, n_utts * NBEST, wl.V, wl.lo, wl.hi, wl.eos, wl.pad)
     cells = int((np.repeat(rl, NBEST).astype(np.int64) * hl.astype(np.int64)).sum())
     return ref, hyp, cells
 
@@ -121,73 +195,147 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(ref, hyp, cells, min_seconds=3.0, max_runs=5):
-    """The oracle port on the host cores (all OpenMP threads), same call, same tensors."""
+# ---------------------------------------------------------------------------------------------
+# CPU arms
+# ---------------------------------------------------------------------------------------------
+def cpu_baseline(wl, seed, min_seconds=3.0, max_runs=5):
+    """The oracle port on the host cores (all OpenMP threads), same call, bounded sample."""
     from oracle import oracle as O
 
     O.use_all_cores()
-    refx = np.repeat(ref, NBEST, axis=1)
-    O.prefix_error_rates(refx[:, :64], hyp[:, :64], eos=0)  # build + warm
+    ref, hyp, cells = wl.make(wl.port_pairs, seed)
+    wl.oracle_call(O, ref[:, :64], hyp[:, :64])  # build + warm
     best, runs, t_total = None, 0, 0.0
     while runs < max_runs and (runs < 2 or t_total < min_seconds):
         t0 = time.perf_counter()
-        O.prefix_error_rates(refx, hyp, eos=0)
+        wl.oracle_call(O, ref, hyp)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
         t_total += dt
         runs += 1
-    return {"value": cells / best / 1e9, "unit": "GCUPS", "cores": O.num_threads(),
-            "kind": "port",
+    return {"value": cells / best / 1e9, "unit": "GCUPS", "cores": O.num_threads(), "kind": "port",
             "sample": f"{hyp.shape[1]} pairs of the same workload, best of {runs} "
                       f"({best * 1e3:.1f} ms); oracle/lev_oracle.c, OpenMP over pairs",
             "pairs_per_s": hyp.shape[1] / best}
 
 
+def _import_reference():
+    """The unmodified reference from baseline/_ref (installed by oracle/make_ref.sh)."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "pydrobert", "torch")):
+        return None, "baseline/_ref is absent (oracle/make_ref.sh needs /root/reference)"
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    try:
+        import pydrobert.torch.functional as RF  # noqa: N812
+    except Exception as e:  # pragma: no cover
+        return None, f"import of the reference failed: {e!r}"
+    return RF, None
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path = the oracle port
-    (the reference itself is pure Python on torch CPU ops and cannot travel to the box)."""
+    """--impl reference: the reference's own implementation of the path on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_utts = 2048  # bounded sample: 16384 pairs of the same per-pair shape
-    ref, hyp, cells = make_batch(n_utts, seed=3)
-    from oracle import oracle as O
+    import torch
 
-    O.use_all_cores()
-    refx = np.repeat(ref, NBEST, axis=1)
-    O.prefix_error_rates(refx[:, :64], hyp[:, :64], eos=0)
+    wl = Workload(args.config)
+    RF, why = _import_reference()
+    if RF is None:
+        print(json.dumps({"impl": "reference", "unavailable": why}))
+        return
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    pairs = wl.ref_pairs
+    ref, hyp, cells = wl.make(pairs, seed=3)
+    tr, th = torch.from_numpy(ref), torch.from_numpy(hyp)
+    kw = dict(wl.kwargs())
+    steps_of = None
+    if wl.cfg == 5:
+        # a full T=2000 call of the reference takes ~1 h (SURVEY 8d): time the first 16 hypothesis
+        # steps (the cost per step does not depend on the step, SM:286-318) and scale
+        steps_of = 16
+        th = th[:steps_of].contiguous()
+    fn = getattr(RF, wl.fn_name())
+
+    def step():
+        if wl.cfg == 4:  # the reference command scores in batches of 100 (command_line.py:1124)
+            tot = 0.0
+            for a in range(0, pairs, 100):
+                tot += float(fn(tr[:, a:a + 100], th[:, a:a + 100], warn=False, **kw).sum())
+            return tot
+        return fn(tr, th, warn=False, **kw)
+
     for _ in range(max(args.warmup, 1)):
-        O.prefix_error_rates(refx, hyp, eos=0)
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.prefix_error_rates(refx, hyp, eos=0)
+        step()
     dt = (time.perf_counter() - t0) / args.steps
-    val = cells / dt / 1e9
+    scale = 1.0
+    sample = f"{pairs} pairs per step, reference torch-CPU ops, {cores} threads"
+    if steps_of is not None:
+        scale = (wl.T) / steps_of
+        sample += f"; first {steps_of} of {wl.T} hypothesis steps timed, scaled x{scale:.1f} (extrapolated)"
+    dt_full = dt * scale
+    val = cells / dt_full / 1e9
     line = {
         "impl": "reference", "metric": "edit-distance cell-updates/s", "value": val,
         "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": dt_full * 1e3, "higher_is_better": True, "scaling": wl.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2 prefix_error_rates N-best: 8-best word hyps, T=100, "
-                               "vocab 10k; bounded sample of 2048 utterances x 8 = 16384 pairs",
-                   "pairs": int(hyp.shape[1]), "T": T_LEN, "nbest": NBEST, "vocab": V},
-        "hyps_per_s": hyp.shape[1] / dt,
-        "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": O.num_threads(), "kind": "port",
-                         "sample": "16384 pairs per step; oracle/lev_oracle.c, OpenMP over pairs"},
+        "config": wl.config(pairs, {"sample": "bounded pair count, same per-pair shape"}),
+        "hyps_per_s": pairs / dt_full,
+        "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": cores, "kind": "reference",
+                         "sample": sample},
         "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    # BASELINE.md 3(b): the same reference code on the B200 (CUDA tensors), when there is one
+    if torch.cuda.is_available() and not args.no_reference_on_gpu:
+        dev = torch.device("cuda", 0)
+        cr, ch = tr.to(dev), th.to(dev)
+
+        def gstep():
+            if wl.cfg == 4:
+                tot = torch.zeros((), device=dev)
+                for a in range(0, pairs, 100):
+                    tot += fn(cr[:, a:a + 100], ch[:, a:a + 100], warn=False, **kw).sum()
+                return tot
+            return fn(cr, ch, warn=False, **kw)
+
+        for _ in range(2):
+            gstep()
+        torch.cuda.synchronize()
+        reps = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            gstep()
+        torch.cuda.synchronize()
+        gdt = (time.perf_counter() - t0) / reps * scale
+        line["reference_on_gpu"] = {"value": cells / gdt / 1e9, "unit": "GCUPS", "ms_per_step": gdt * 1e3,
+                                    "device": torch.cuda.get_device_name(0),
+                                    "note": "the reference's torch code on CUDA tensors, same sample"}
+    # the C/OpenMP port beside it, for continuity with round 1's reference arm
+    if not args.no_cpu_baseline:
+        line["cpu_baseline_port"] = cpu_baseline(wl, seed=3, min_seconds=2.0, max_runs=3)
     print(json.dumps(line))
 
 
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--utts", type=int, default=16384, help="utterances per GPU (x8-best)")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (cfg4: in total); 0 = the config's")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-on-gpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -196,7 +344,8 @@ def main():
     import torch.distributed as dist
 
     import b200lev.functional as F
-    from b200lev import _abi, _ops
+    from b200lev import _abi
+    from b200lev import dist as D
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,74 +356,107 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         # one process per GPU: keep this rank's host buffers on its GPU's NUMA node
-        from b200lev.dist import bind_host_to_gpu
-        numa_node = bind_host_to_gpu(local)
+        numa_node = D.bind_host_to_gpu(local)
     L = _abi.lib()
-
-    ref_np, hyp_np, cells = make_batch(args.utts, seed=100 + rank)
-    refx_np = np.repeat(ref_np, NBEST, axis=1)
-    ref = torch.from_numpy(refx_np).to(dev)
+    wl = Workload(args.config)
+    total_pairs = args.pairs or wl.sat_pairs
+    if wl.scaling == "strong":  # cfg4: the million pairs are cut into contiguous shards
+        lo, hi = D.shard_bounds(total_pairs, rank, world)
+        my_pairs = hi - lo
+    else:
+        my_pairs = total_pairs
+    ref_np, hyp_np, cells = wl.make(my_pairs, seed=100 + rank)
+    ref = torch.from_numpy(ref_np).to(dev)
     hyp = torch.from_numpy(hyp_np).to(dev)
     P = hyp.shape[1]
     in_bytes = ref.numel() * 8 + hyp.numel() * 8
+    flush = None
+    if in_bytes < (160 << 20):  # inputs do not exceed L2: evict them between iterations
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    totals = {}
 
-    def step():
-        return F.prefix_error_rates(ref, hyp, eos=0, warn=False)
+    def step(r=ref, h=hyp):
+        if wl.cfg == 4:
+            # shard -> error_rate + device sums (K7) -> ONE all-reduce of [sum err, sum ref
+            # tokens, #pairs] (fp64, 24 bytes) on the NCCL stream, inside the step
+            er, acc = D.bulk_error_rate(r, h, eos=-1)
+            totals["acc"] = acc
+            return er
+        return wl.call(F, r, h)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_loop(fn, reps):
+        """K calls between two events; with `flush` the eviction write runs between calls and
+        its own (separately measured) time is subtracted."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if flush is None:
+            e0.record()
+            for _ in range(reps):
+                out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps, out
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / reps, out
+
     # ---- value: device-resident, whole public call ------------------------------------
+    # W untimed warm-up steps, then a short soak of the same step with the clock sampler already
+    # running (K steps of 0.2 ms are shorter than one nvidia-smi period, and the first calls
+    # after an idle GPU run below the clocks the load settles at), then EXACTLY K timed steps.
     for _ in range(max(args.warmup, 3)):
         out = step()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        out = step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1) / args.steps
-    # K steps of 0.3 ms are shorter than one nvidia-smi period: keep the same step running
-    # (untimed) under the sampler until it has seen the clocks this load settles at
+    soak_s = 0.5
     t_soak = time.perf_counter()
-    while time.perf_counter() - t_soak < 0.6:
-        for _ in range(20):
+    while time.perf_counter() - t_soak < soak_s:
+        for _ in range(10):
             out = step()
         torch.cuda.synchronize()
+    barrier()
+    ms, out = timed_loop(step, args.steps)
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
-        clocks["window"] = "the timed K steps plus 0.6 s of the same step, untimed"
+        clocks["window"] = f"{soak_s} s of the same step (untimed) followed by the timed K steps"
+    out_bytes = int(out.numel() * out.element_size())
 
-    # ---- roofline: per-kernel CUDA-event times of the same public call --------------------
-    # (b200lev_profile brackets every phase with events on the launch stream)
-    prof = np.zeros(8, dtype=np.float64)
-    buf = (ctypes.c_float * 8)()
-    _abi.check(L.b200lev_profile(1))
-    for _ in range(3):
-        step()
+    # ---- per-kernel CUDA-event times of the same public call (b200lev_profile) -------------
+    nslots = len(PROF_SLOTS)
+    buf = (ctypes.c_float * nslots)()
+
+    def profile(nprof):
+        acc = np.zeros(nslots, dtype=np.float64)
+        _abi.check(L.b200lev_profile(1))
+        for _ in range(3):
+            step()
+        for _ in range(nprof):
+            step()
+            _abi.check(L.b200lev_profile_read(buf, nslots))
+            acc += np.array([max(x, 0.0) for x in buf])
+        _abi.check(L.b200lev_profile(0))
+        return acc / nprof
+
     nprof = max(5, min(args.steps, 20))
-    for _ in range(nprof):
-        out = step()
-        _abi.check(L.b200lev_profile_read(buf, 8))
-        prof += np.array([max(x, 0.0) for x in buf])
-    _abi.check(L.b200lev_profile(0))
-    prof /= nprof
-    ms_pack = max(float(prof[0] + prof[1]), 1e-6)
-    bitvec = prof[7] > prof[3]  # which DP ran: the bit-vector kernels or the wavefront kernels
-    ms_dp = float(prof[7] if bitvec else prof[3])
-    phases = {"pack_ref": prof[0], "pack_hyp": prof[1], "bucketing": prof[2], "dp": prof[3],
-              "prefix_finalize": prof[4], "standby_wide": prof[5], "bitvec_uid": prof[6],
-              "bitvec_dp": prof[7]}
+    prof = profile(nprof)
+    phases = {k: round(float(v), 5) for k, v in zip(PROF_SLOTS, prof)}
+    bitvec = prof[7] > prof[3]  # which DP ran: the bit-vector kernel(s) or the wavefront kernels
 
-    # the same call with the bit-vector kernels switched off: north_star's target is quoted on
-    # the wavefront kernel, so it is measured live next to the path that actually ships
+    # cfg2: the same call with the bit-vector kernels switched off -- north_star's target is
+    # quoted on the wavefront kernel, so it is measured live next to the path that ships
     wave = None
     if bitvec:
         saved = os.environ.get("B200LEV_BITVEC")
@@ -283,23 +465,9 @@ def main():
             for _ in range(3):
                 step()
             torch.cuda.synchronize()
-            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            w0.record()
-            for _ in range(nprof):
-                step()
-            w1.record()
-            torch.cuda.synchronize()
-            wave = {"ms_per_step": w0.elapsed_time(w1) / nprof}
-            wprof = np.zeros(8, dtype=np.float64)
-            _abi.check(L.b200lev_profile(1))
-            for _ in range(nprof):
-                step()
-                _abi.check(L.b200lev_profile_read(buf, 8))
-                wprof += np.array([max(x, 0.0) for x in buf])
-            _abi.check(L.b200lev_profile(0))
-            wprof /= nprof
-            wave["kernel_ms"] = float(wprof[3])
-            wave["pack_ms"] = float(wprof[0] + wprof[1])
+            wms, _ = timed_loop(step, nprof)
+            wprof = profile(nprof)
+            wave = {"ms_per_step": wms, "kernel_ms": float(wprof[3]), "pack_ms": float(wprof[0] + wprof[1])}
         finally:
             if saved is None:
                 del os.environ["B200LEV_BITVEC"]
@@ -310,66 +478,85 @@ def main():
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / reps
+        return timed_loop(fn, reps)[0]
 
     st = torch.cuda.current_stream(dev).cuda_stream
-    outp = out
-
     # INT32 issue-rate peak, measured live (variant 2 = VIADDMNMX, 0 = IADD3, 3 = DP cell mix)
     sink = torch.zeros(4, dtype=torch.int32, device=dev)
     peaks = {}
     for name, var in (("iadd3", 0), ("viaddmnmx", 2), ("dp_cell_mix", 3)):
         ops = ctypes.c_double(0)
 
-        def k(var=var):
+        def k(var=var, ops=ops):
             _abi.check(L.b200lev_int32_peak_kernel(var, 148 * 8, 4096, sink.data_ptr(),
                                                    ctypes.byref(ops), st))
 
-        t = timed(k, 5)
-        peaks[name] = ops.value / (t * 1e-3) / 1e12  # T int32-op/s
-    # denominator = the ALU-pipe rate (VIADDMNMX / VIMNMX / ISETP live there): SURVEY 8(d)'s
+        for _ in range(3):
+            k()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            k()
+        b.record()
+        torch.cuda.synchronize()
+        peaks[name] = ops.value / (a.elapsed_time(b) / 5 * 1e-3) / 1e12  # T int32-op/s
+    # denominator = the ALU-pipe rate (VIADDMNMX / VIMNMX / ISETP / LOP3 live there): SURVEY 8(d)'s
     # "64 lanes/clk/SM".  Plain IADD3 also dual-issues on the FMA pipe (the iadd3 figure).
     int32_peak = peaks["viaddmnmx"]
 
     # ---- e2e: host (pinned) tensors through the public API -----------------------------
-    ref_h = torch.from_numpy(refx_np).pin_memory()
+    ref_h = torch.from_numpy(ref_np).pin_memory()
     hyp_h = torch.from_numpy(hyp_np).pin_memory()
     # warm-up in the timed loop's own pattern (the previous result is still referenced while
     # the next call runs), so that the page-locked result blocks of the steady state exist
     # before the clock starts: a first-time cudaHostAlloc of 53 MB costs tens of ms
     res = None
     for _ in range(max(args.warmup, 3)):
-        res = F.prefix_error_rates(ref_h, hyp_h, eos=0, warn=False)
+        res = step(ref_h, hyp_h)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_steps = max(3, min(args.steps, 10))
     e0.record()
     for _ in range(e2e_steps):
-        res = F.prefix_error_rates(ref_h, hyp_h, eos=0, warn=False)
+        res = step(ref_h, hyp_h)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1) / e2e_steps
     assert res.device.type == "cpu"
 
-    # ---- literal BASELINE shape (64 x 8): latency of the public call --------------------
-    lref_np, lhyp_np, lcells = make_batch(64, seed=7)
-    lref = torch.from_numpy(np.repeat(lref_np, NBEST, axis=1)).to(dev)
-    lhyp = torch.from_numpy(lhyp_np).to(dev)
-    ms_lit = timed(lambda: F.prefix_error_rates(lref, lhyp, eos=0, warn=False), 50)
+    # ---- literal BASELINE shape: latency of the public call --------------------------------
+    lit = None
+    if wl.lit_pairs != total_pairs and world == 1:
+        lref_np, lhyp_np, lcells = wl.make(wl.lit_pairs, seed=7)
+        lref, lhyp = torch.from_numpy(lref_np).to(dev), torch.from_numpy(lhyp_np).to(dev)
+        ms_lit = timed(lambda: wl.call(F, lref, lhyp), 30)
+        lit = {"workload": f"{wl.lit_pairs} pairs (the BASELINE config as written)", "ms_per_call": ms_lit,
+               "gcups": lcells / (ms_lit * 1e-3) / 1e9, "hyps_per_s": wl.lit_pairs / (ms_lit * 1e-3)}
+
+    # ---- cfg4: the reduced totals against the oracle on a slice ------------------------------
+    check = None
+    if wl.cfg == 4:
+        from oracle import oracle as O
+
+        n_chk = min(4096, P)
+        want = np.asarray(O.error_rate(ref_np[:, :n_chk], hyp_np[:, :n_chk], eos=-1, norm=False))
+        got = out[:n_chk].cpu().numpy()
+        acc = totals["acc"].cpu().numpy()
+        check = {"slice_pairs": n_chk, "slice_matches_oracle": bool(np.array_equal(got, want)),
+                 "sum_errors": float(acc[0]), "sum_ref_tokens": float(acc[1]), "pairs": float(acc[2]),
+                 "wer": float(acc[0] / max(acc[1], 1.0))}
+        assert check["slice_matches_oracle"], "cfg4: per-pair errors differ from the oracle"
+        assert int(acc[2]) == total_pairs, "cfg4: the all-reduced pair count is not the global one"
 
     # ---- reduce over ranks ---------------------------------------------------------------
-    stats = torch.tensor([ms, ms_e2e, ms_dp, ms_pack], dtype=torch.float64, device=dev)
+    dom_ms = float(prof[7] if bitvec else prof[3])
+    stats = torch.tensor([ms, ms_e2e, dom_ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(cells), float(P)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms, ms_e2e, ms_dp_max, ms_pack_max = stats.tolist()
+    ms, ms_e2e, _ = stats.tolist()
     cells_all, pairs_all = tot.tolist()
 
     if rank == 0:
@@ -377,103 +564,114 @@ def main():
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
         if os.path.exists(peaks_file):
             hbm_peak, hbm_src = json.load(open(peaks_file))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
-        achieved_ops = cells / (ms_dp * 1e-3) * OPS_PER_CELL / 1e12
         traffic_all = {}
         tf = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tf):  # dram bytes per launch from the last `ncu --set full` captures
+        if os.path.exists(tf):  # dram bytes per launch from the committed `ncu --set full` captures
             traffic_all = json.load(open(tf))
-        pack_gbs = (in_bytes + in_bytes // 2) / (ms_pack * 1e-3) / 1e9
         peak_note = ("measured live (b200lev_int32_peak_kernel), ALU pipe = viaddmnmx; T int32-op/s: "
                      f"{ {k: round(v, 2) for k, v in peaks.items()} }")
+
+        def int32_roofline(kernel, kernel_ms, note, traffic_key):
+            ops = cells / (kernel_ms * 1e-3) * OPS_PER_CELL / 1e12
+            return {"bound": "int32_issue", "kernel": kernel, "achieved": ops, "peak": int32_peak,
+                    "unit": "Tint32op/s", "frac": ops / int32_peak,
+                    "traffic": traffic_all.get(traffic_key), "traffic_source": "profiles/traffic.json (ncu --set full)",
+                    "ops_per_cell": OPS_PER_CELL, "kernel_ms": kernel_ms,
+                    "kernel_gcups": cells / (kernel_ms * 1e-3) / 1e9, "peak_source": peak_note, "note": note}
+
+        def hbm_roofline(kernel, kernel_ms, nbytes, note, traffic_key):
+            gbs = nbytes / (kernel_ms * 1e-3) / 1e9
+            return {"bound": "hbm", "kernel": kernel, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": gbs / hbm_peak, "traffic": traffic_all.get(traffic_key),
+                    "traffic_source": "profiles/traffic.json (ncu --set full)", "kernel_ms": kernel_ms,
+                    "algorithmic_bytes": int(nbytes), "peak_source": hbm_src, "note": note}
+
+        extra = {}
+        pack_ms = float(prof[0] + prof[1])
         if bitvec:
-            # n-best shaped batch: the bit-vector kernels took the call on the device.  The
-            # dominant kernel is the uid pre-pass (it reads the raw tokens once: HBM-bound);
-            # the DP kernel is reported next to it against the INT32 issue rate.
-            ms_uid = float(prof[6])
-            R1 = T_LEN + 1
-            uid_bytes = in_bytes + 2 * P * ((R1 + 15) // 16) * 16 + 2 * 4 * P + P
-            roofline = {"bound": "hbm", "kernel": "lev_bv_uid_kernel<int64>",
-                        "achieved": uid_bytes / (ms_uid * 1e-3) / 1e9, "peak": hbm_peak,
-                        "unit": "GB/s", "frac": uid_bytes / (ms_uid * 1e-3) / 1e9 / hbm_peak,
-                        "traffic": traffic_all.get("lev_bv_uid_kernel"), "kernel_ms": ms_uid,
-                        "algorithmic_bytes": uid_bytes, "peak_source": hbm_src,
-                        "note": "reads both raw int64 token tensors once, writes 1 uid byte per "
-                                "token + lengths; share of the step = kernel_ms / ms_per_step"}
-            roofline_dp = {"bound": "int32_issue", "kernel": "lev_bv_dp_kernel<W=4,PREFIX>",
-                           "achieved": achieved_ops, "peak": int32_peak, "unit": "Tint32op/s",
-                           "frac": achieved_ops / int32_peak,
-                           "traffic": traffic_all.get("lev_bv_dp_kernel"),
-                           "ops_per_cell": OPS_PER_CELL, "kernel_ms": ms_dp,
-                           "kernel_gcups": cells / (ms_dp * 1e-3) / 1e9, "peak_source": peak_note,
-                           "note": "algorithmic 5 INT32 ops/cell (SURVEY 8d); Myers' bit-vector "
-                                   "recurrence advances 32 cells with ~17 instructions, so frac "
-                                   "exceeds 1; ncu: ALU pipe 78 % busy"}
-            launches = 10  # 2 bit-vector kernels + 8 wavefront kernels standing by (exit at once)
+            fused = os.environ.get("B200LEV_BV_FUSED", "1") != "0"
+            if fused:
+                # one kernel: lengths, run detection, hash tables, Myers' recurrence, output rows
+                roofline = int32_roofline(
+                    "lev_bv_fused_kernel<int64,W=4,PREFIX>", float(prof[7]),
+                    "algorithmic 5 INT32 ops/cell (SURVEY 8d); Myers' bit-vector recurrence advances 128 "
+                    "cells with ~50 ALU instructions, so frac exceeds 1; the same kernel reads both raw "
+                    "int64 token tensors and writes the (H+1, N) fp32 rows (roofline_hbm)",
+                    "lev_bv_fused_kernel")
+                extra["roofline_hbm"] = hbm_roofline(
+                    "lev_bv_fused_kernel (its memory side)", float(prof[7]), in_bytes + out_bytes + 8 * P,
+                    "reads both raw int64 token tensors once, writes the output rows + lengths",
+                    "lev_bv_fused_kernel")
+                launches = 10  # probe + fused kernel + 8 wavefront kernels standing by (exit at once)
+            else:
+                R1 = wl.T
+                uid_bytes = in_bytes + 2 * P * ((R1 + 15) // 16) * 16 + 2 * 4 * P + P
+                roofline = hbm_roofline("lev_bv_uid_kernel<int64>", float(prof[6]), uid_bytes,
+                                        "two-kernel form (B200LEV_BV_FUSED=0): reads both raw int64 token "
+                                        "tensors once, writes 1 uid byte per token + lengths",
+                                        "lev_bv_uid_kernel")
+                extra["roofline_dp"] = int32_roofline("lev_bv_dp_kernel<W=4,PREFIX>", float(prof[7]),
+                                                      "Myers' recurrence on the uid bytes", "lev_bv_dp_kernel")
+                launches = 10
+            if wave is not None and wave["kernel_ms"] > 0:
+                w = int32_roofline(
+                    "lev_group_kernel<cost,PREFIX,packed16> (B200LEV_BITVEC=0: the wavefront path, taken "
+                    "by every batch the bit-vector path declines)", wave["kernel_ms"],
+                    "algorithmic 5 INT32 ops/cell (SURVEY 8d); the kernel issues 2.5 instructions per cell "
+                    "(2 cells per 16x2 DPX instruction)", "lev_group_kernel")
+                w.update({"whole_call_ms": wave["ms_per_step"],
+                          "whole_call_gcups": cells / (wave["ms_per_step"] * 1e-3) / 1e9,
+                          "pack_ms": wave["pack_ms"],
+                          "pack_gbs": (in_bytes + in_bytes // 2) / (wave["pack_ms"] * 1e-3) / 1e9})
+                extra["roofline_wavefront"] = w
         else:
-            roofline = {"bound": "int32_issue",
-                        "kernel": "lev_group_kernel<cost,PREFIX,packed16> (+ its 32-bit twin's "
-                                  "immediate exit)",
-                        "achieved": achieved_ops, "peak": int32_peak, "unit": "Tint32op/s",
-                        "frac": achieved_ops / int32_peak,
-                        "traffic": traffic_all.get("lev_group_kernel"),
-                        "ops_per_cell": OPS_PER_CELL, "kernel_ms": ms_dp,
-                        "kernel_gcups": cells / (ms_dp * 1e-3) / 1e9, "peak_source": peak_note,
-                        "note": "algorithmic 5 INT32 ops/cell (SURVEY 8d); the kernel issues 2.5 "
-                                "instructions per cell (2 cells per 16x2 DPX instruction), so "
-                                "frac can exceed 1"}
-            roofline_dp = None
-            # 2 pack, 1 bucketing, 2 DP builds (one exits at once), 1 prefix finalize, 1 stand-by
-            # 64-bit-token kernel (+ 2 bit-vector kernels that vetoed, when they were eligible)
-            launches = 7 + (3 if prof[6] > 0 else 0)
+            kname = {1: "lev_group_kernel<cost,FINAL,packed16>", 3: "lev_warp_kernel<int,MASK> (two passes)",
+                     4: "lev_group_kernel<cost,FINAL,packed16>", 5: "lev_cta_kernel<int,PREFIX> (TMA-staged)",
+                     2: "lev_group_kernel<cost,PREFIX,packed16>"}[wl.cfg]
+            roofline = int32_roofline(kname, float(prof[3]),
+                                      "algorithmic 5 INT32 ops/cell (SURVEY 8d) on the wavefront DP kernel",
+                                      kname.split("<")[0])
+            if pack_ms > 0:
+                extra["roofline_pack"] = hbm_roofline("lev_pack_*_kernel x2 (ref, hyp)", pack_ms,
+                                                      in_bytes + in_bytes // 2,
+                                                      "reads the raw int64 tokens, writes the packed int32 "
+                                                      "(+ 16-bit hypothesis) tables", "lev_pack_kernel")
+            if wl.cfg == 3 and prof[9] > 0:
+                # north_star item 4: achieved HBM GB/s of the kernel that writes the targets
+                extra["roofline_target_writer"] = hbm_roofline(
+                    "lev_completion_fill_kernel", float(prof[9]), out_bytes + 4 * (out_bytes // 8 // max(out.shape[-1], 1)),
+                    "writes the (H', N, U) int64 targets (128-bit staged stores), reads one bitmap word "
+                    "per row", "lev_completion_fill_kernel")
+            launches = int(sum(1 for v in prof if v > 0)) + 3
         line = {
             "metric": "edit-distance cell-updates/s", "value": cells_all / (ms * 1e-3) / 1e9,
             "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "soak_s": soak_s,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "cfg2 prefix_error_rates N-best (8-best word hyps, T=100, vocab "
-                                   "10k, include_eos, norm), batch replicated to "
-                                   f"{args.utts} utts x 8 = {P} pairs per GPU",
-                       "pairs_per_gpu": P, "T": T_LEN, "nbest": NBEST, "vocab": V,
-                       "cells_per_gpu": cells, "host_numa_node": numa_node,
-                       "l2": f"inputs {in_bytes / 1e6:.0f} MB per step exceed the 126 MB L2"},
+            "config": wl.config(P, {
+                "pairs_total": int(pairs_all), "cells_per_gpu": cells, "host_numa_node": numa_node,
+                "l2": (f"inputs {in_bytes / 1e6:.0f} MB per step exceed the 126 MB L2" if flush is None else
+                       f"inputs {in_bytes / 1e6:.0f} MB fit L2: a 256 MB buffer is rewritten between "
+                       "timed calls (each call timed by its own event pair)")}),
             "hyps_per_s": pairs_all / (ms * 1e-3),
             "e2e": {"value": cells_all / (ms_e2e * 1e-3) / 1e9, "unit": "GCUPS",
-                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": int(outp.numel() * 4),
+                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                     "ms_per_step": ms_e2e},
             "gpu_launches": launches * args.steps,
             "roofline": roofline,
-            "phases_ms": {k: round(float(v), 5) for k, v in phases.items()},
-            "literal": {"workload": "64 utts x 8-best = 512 pairs (BASELINE configs[1] as written)",
-                        "ms_per_call": ms_lit, "gcups": lcells / (ms_lit * 1e-3) / 1e9,
-                        "hyps_per_s": 512 / (ms_lit * 1e-3)},
+            "phases_ms": phases,
             "clocks": clocks,
         }
-        if roofline_dp is not None:
-            line["roofline_dp"] = roofline_dp
-            if wave is not None and wave["kernel_ms"] > 0:
-                wops = cells / (wave["kernel_ms"] * 1e-3) * OPS_PER_CELL / 1e12
-                line["roofline_wavefront"] = {
-                    "bound": "int32_issue",
-                    "kernel": "lev_group_kernel<cost,PREFIX,packed16> (B200LEV_BITVEC=0: the "
-                              "wavefront path, taken by every batch the bit-vector path declines)",
-                    "achieved": wops, "peak": int32_peak, "unit": "Tint32op/s",
-                    "frac": wops / int32_peak, "traffic": traffic_all.get("lev_group_kernel"),
-                    "ops_per_cell": OPS_PER_CELL, "kernel_ms": wave["kernel_ms"],
-                    "kernel_gcups": cells / (wave["kernel_ms"] * 1e-3) / 1e9,
-                    "whole_call_ms": wave["ms_per_step"],
-                    "whole_call_gcups": cells / (wave["ms_per_step"] * 1e-3) / 1e9,
-                    "pack_ms": wave["pack_ms"],
-                    "pack_gbs": (in_bytes + in_bytes // 2) / (wave["pack_ms"] * 1e-3) / 1e9,
-                    "note": "algorithmic 5 INT32 ops/cell (SURVEY 8d); the kernel issues 2.5 "
-                            "instructions per cell (2 cells per 16x2 DPX instruction)"}
-        else:
-            line["roofline_pack"] = {"bound": "hbm",
-                                     "kernel": "lev_pack_seqfirst_kernel<int64> x2 (ref, hyp)",
-                                     "achieved": pack_gbs, "peak": hbm_peak, "unit": "GB/s",
-                                     "frac": pack_gbs / hbm_peak, "kernel_ms": ms_pack,
-                                     "peak_source": hbm_src}
+        line.update(extra)
+        if lit is not None:
+            line["literal"] = lit
+        if check is not None:
+            line["check"] = check
+            line["collective"] = ("one all_reduce(sum) of 3 fp64 values per step on the NCCL stream" if world > 1
+                                  else "none (1 rank)")
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(ref_np, hyp_np, cells)
+            line["cpu_baseline"] = cpu_baseline(wl, seed=100)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

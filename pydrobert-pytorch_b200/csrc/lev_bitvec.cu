@@ -36,73 +36,7 @@
 // device (lev_bv_took, lev_common.cuh): a block of 32 pairs with more than 4 distinct
 // references, or a reference token the 32-bit keys cannot hold, vetoes, and the wavefront
 // kernels -- which otherwise exit at once -- do the work.
-#include "lev_common.cuh"
-
-#define LEV_BV_NOMATCH 0xffu
-#define LEV_BV_EMPTY ((int)0x80000000)  // key of a free way (a token with this value: exact path)
-constexpr int LEV_BV_NT = 4;     // tables per warp = runs of identical references per pass
-constexpr int LEV_BV_WARPS = 4;  // warps per CTA (independent: no block barrier anywhere)
-
-struct LevBvArgs {
-    const void* ref;  // raw token tensors, stride 1 along the batch axis
-    const void* hyp;
-    int64_t ref_st, hyp_st;  // elements between positions
-    int R, H, P, ref_group;
-    int has_eos;
-    int64_t eos;
-    int include_eos;
-    int32_t* ref_len;  // [Nref]  (same workspace slots K0 fills on the other paths)
-    int32_t* hyp_len;  // [P]
-    uint4* ref_uid;    // [ceil(R/16)][P]  16 uid bytes per (chunk, pair); run leaders only
-    uint4* hyp_uid;    // [ceil(H/16)][P]
-    unsigned char* lead;  // [P] lane (0..31) of the leader of the pair's run in its 32-block
-    int32_t* flags;    // caller's warning flags, may be NULL
-    int32_t* state;  // workspace state words; [3] != 0 = "not for this path" (lev_bv_took)
-    int check_state;   // device-selected mode: veto through state[3] instead of multi-pass
-    int slots_log2;    // hash buckets per table (power of two >= R), 4 ways each
-    int mode, norm, exclude_last, Hout;
-    float mult, padding;
-    float* out;
-    int64_t out_si;  // prefix: elements between output rows (pairs are adjacent)
-};
-
-// Bucketed hash: 4 ways per bucket, one 128-bit read of the keys and one 32-bit read of the
-// position bytes settle a probe -- no loop, so 32 lanes with 32 different tokens cost the same
-// as one.  A run leader builds its table with the first of a few multipliers under which no
-// bucket overflows (load <= 1 token per bucket on average: a couple of tries at most).
-// (a build with R = 128 distinct tokens in 128 buckets fails with p = 0.38: 16 tries leave
-// 2e-7 of the runs to the slow exact path; the typical R ~ 100 needs 1.2 tries on average)
-constexpr int LEV_BV_TRIES = 16;
-__device__ __forceinline__ unsigned lev_bv_mult(int seed) {
-    return (0x9E3779B1u * (2u * (unsigned)seed + 1u)) ^ ((unsigned)seed * 0x85EBCA6Au);
-}
-__device__ __forceinline__ unsigned lev_bv_hash(int v, unsigned mult, int buckets_log2) {
-    return ((unsigned)v * mult) >> (32 - buckets_log2);
-}
-
-// Runs of identical references inside a block of 32 consecutive pairs, from each lane's
-// "same as the lane before" bit: leader lane of the run, its index, number of runs.
-struct LevBvRuns {
-    int lead, index, count, len;
-    unsigned mask;  // the lanes of my run
-};
-__device__ __forceinline__ LevBvRuns lev_bv_runs(bool same, int lane) {
-    const unsigned starts = ~__ballot_sync(LEV_FULL_MASK, same && lane > 0);
-    const unsigned upto = starts & (0xffffffffu >> (31 - lane));
-    LevBvRuns r;
-    r.lead = 31 - __clz((int)upto);
-    r.index = __popc(upto) - 1;
-    r.count = __popc(starts);
-    const unsigned higher = r.lead == 31 ? 0u : (starts & ~(0xffffffffu >> (31 - r.lead)));
-    const int next = higher ? __ffs((int)higher) - 1 : 32;
-    r.len = next - r.lead;
-    r.mask = (r.len == 32 ? 0xffffffffu : ((1u << r.len) - 1u)) << r.lead;
-    return r;
-}
-
-__device__ __forceinline__ unsigned lev_bv_set_byte(unsigned word, unsigned byte, int k) {
-    return (word & ~(0xffu << (8 * k))) | (byte << (8 * k));
-}
+#include "lev_bitvec.cuh"
 
 // ---------------------------------------------------------------------------------------
 // uid pre-pass
@@ -436,66 +370,6 @@ __global__ void __launch_bounds__(32 * LEV_BV_WARPS, 4) lev_bv_uid_kernel(const 
 // ---------------------------------------------------------------------------------------
 // the DP
 // ---------------------------------------------------------------------------------------
-// sum = t + pv over W 32-bit words (carry chain in one asm block)
-template <int W>
-__device__ __forceinline__ void lev_bv_add(const unsigned (&t)[W], const unsigned (&pv)[W],
-                                           unsigned (&sum)[W]) {
-#ifdef B200LEV_EMU
-    unsigned long long carry = 0;
-    for (int w = 0; w < W; ++w) {
-        const unsigned long long s = (unsigned long long)t[w] + pv[w] + carry;
-        sum[w] = (unsigned)s;
-        carry = s >> 32;
-    }
-#else
-    if (W == 1) {
-        sum[0] = t[0] + pv[0];
-    } else if (W == 2) {
-        asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;"
-            : "=r"(sum[0]), "=r"(sum[W > 1 ? 1 : 0])
-            : "r"(t[0]), "r"(t[W > 1 ? 1 : 0]), "r"(pv[0]), "r"(pv[W > 1 ? 1 : 0]));
-    } else if (W == 3) {
-        asm("add.cc.u32 %0, %3, %6;\n\taddc.cc.u32 %1, %4, %7;\n\taddc.u32 %2, %5, %8;"
-            : "=r"(sum[0]), "=r"(sum[W > 1 ? 1 : 0]), "=r"(sum[W > 2 ? 2 : 0])
-            : "r"(t[0]), "r"(t[W > 1 ? 1 : 0]), "r"(t[W > 2 ? 2 : 0]), "r"(pv[0]),
-              "r"(pv[W > 1 ? 1 : 0]), "r"(pv[W > 2 ? 2 : 0]));
-    } else {
-        asm("add.cc.u32 %0, %4, %8;\n\taddc.cc.u32 %1, %5, %9;\n\taddc.cc.u32 %2, %6, %10;\n\t"
-            "addc.u32 %3, %7, %11;"
-            : "=r"(sum[0]), "=r"(sum[W > 1 ? 1 : 0]), "=r"(sum[W > 2 ? 2 : 0]),
-              "=r"(sum[W > 3 ? 3 : 0])
-            : "r"(t[0]), "r"(t[W > 1 ? 1 : 0]), "r"(t[W > 2 ? 2 : 0]), "r"(t[W > 3 ? 3 : 0]),
-              "r"(pv[0]), "r"(pv[W > 1 ? 1 : 0]), "r"(pv[W > 2 ? 2 : 0]), "r"(pv[W > 3 ? 3 : 0]));
-    }
-#endif
-}
-
-// One row of the recurrence; returns the score change at the top bit (reference column r).
-template <int W>
-__device__ __forceinline__ int lev_bv_step(const unsigned (&eq)[W], unsigned (&pv)[W],
-                                           unsigned (&mv)[W]) {
-    unsigned t[W], sum[W], ph[W], mh[W];
-#pragma unroll
-    for (int w = 0; w < W; ++w) t[w] = eq[w] & pv[w];
-    lev_bv_add<W>(t, pv, sum);
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-        const unsigned xh = (sum[w] ^ pv[w]) | eq[w];
-        ph[w] = mv[w] | ~(xh | pv[w]);
-        mh[w] = pv[w] & xh;
-    }
-    const int delta = (int)(ph[W - 1] >> 31) - (int)(mh[W - 1] >> 31);
-#pragma unroll
-    for (int w = W - 1; w >= 0; --w) {
-        const unsigned phs = w ? __funnelshift_l(ph[w - 1], ph[w], 1) : ((ph[0] << 1) | 1u);
-        const unsigned mhs = w ? __funnelshift_l(mh[w - 1], mh[w], 1) : (mh[0] << 1);
-        const unsigned xv = eq[w] | mv[w];
-        pv[w] = mhs | ~(xv | phs);
-        mv[w] = phs & xv;
-    }
-    return delta;
-}
-
 template <int W, int MODE>
 __device__ __forceinline__ void lev_bv_dp_block(const LevBvArgs& a, unsigned* M, const int tab_words,
                                                 const int64_t block, const int lane) {
@@ -741,6 +615,14 @@ int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     a.padding = (float)o->padding;
     a.out = out;
     a.out_si = out_si;
+    // B200LEV_BV_FUSED=0 keeps the two-kernel form (uid pre-pass + DP) for comparison
+    const char* fe = getenv("B200LEV_BV_FUSED");
+    if ((fe == nullptr || atoi(fe) != 0) && lev_bvfused_supports(ref->elem_bytes)) {
+        if (getenv("B200LEV_TRACE"))
+            fprintf(stderr, "b200lev: fused bit-vector kernel, mode %d, R=%d H=%d P=%d W=%d device-selected=%d\n",
+                    mode, a.R, a.H, a.P, (a.R + 31) / 32, a.check_state);
+        return lev_bvfused_launch(a, ref->elem_bytes, st, after_uid);
+    }
     const size_t smem_uid = (size_t)(1 << a.slots_log2) * LEV_BV_NT * 20 * LEV_BV_WARPS;
     if (getenv("B200LEV_TRACE"))
         fprintf(stderr, "b200lev: bit-vector path, mode %d, R=%d H=%d P=%d W=%d device-selected=%d\n",

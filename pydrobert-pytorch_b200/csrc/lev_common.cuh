@@ -157,7 +157,7 @@ struct LevParams {
 // around each phase; slots of b200lev_profile_read()
 enum LevProfSlot { LEV_PROF_PACK_REF = 0, LEV_PROF_PACK_HYP, LEV_PROF_SORT, LEV_PROF_DP,
                    LEV_PROF_FINALIZE, LEV_PROF_STANDBY, LEV_PROF_BV_UID, LEV_PROF_BV_DP,
-                   LEV_PROF_NSLOTS };
+                   LEV_PROF_COMP_UID, LEV_PROF_COMP_FILL, LEV_PROF_ERR_SUM, LEV_PROF_NSLOTS };
 void lev_prof_begin(int slot, cudaStream_t st);
 void lev_prof_end(int slot, cudaStream_t st);
 

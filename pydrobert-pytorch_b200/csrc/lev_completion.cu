@@ -62,6 +62,7 @@ int lev_launch_uid(const b200lev_tokens_t* ref, const int32_t* ref_len, int32_t*
         return B200LEV_ERR_UNSUPPORTED;
     }
     dim3 grid((unsigned)ref->N), block(256);
+    lev_prof_begin(LEV_PROF_COMP_UID, st);
 #define LEV_UID_CASE(TT)                                                                        \
     {                                                                                           \
         auto kern = lev_uid_kernel<TT>;                                                         \
@@ -80,6 +81,7 @@ int lev_launch_uid(const b200lev_tokens_t* ref, const int32_t* ref_len, int32_t*
             return B200LEV_ERR_ARG;
     }
 #undef LEV_UID_CASE
+    lev_prof_end(LEV_PROF_COMP_UID, st);
     return lev_check_cuda("lev_uid_kernel");
 }
 
@@ -150,6 +152,7 @@ int lev_launch_completion_fill(const uint32_t* dbits, const int64_t* dtok, int64
     if (rows <= 0 || U <= 0) return B200LEV_OK;
     dim3 block(256), grid((unsigned)((rows + 255) / 256));
     const size_t smem = (size_t)8 * 32 * (size_t)(U | 1) * sizeof(int64_t);
+    lev_prof_begin(LEV_PROF_COMP_FILL, st);
     if (smem <= 96 * 1024) {
         auto kern = lev_completion_fill_kernel<true>;
         if (smem > 48 * 1024)
@@ -160,5 +163,6 @@ int lev_launch_completion_fill(const uint32_t* dbits, const int64_t* dtok, int64
         lev_launch(lev_completion_fill_kernel<false>, grid, block, 0, st, dbits, dtok, Rp, rows, P, Wd,
                    ref_group, U, padding, out, out_si, out_sn);
     }
+    lev_prof_end(LEV_PROF_COMP_FILL, st);
     return lev_check_cuda("lev_completion_fill_kernel");
 }

@@ -466,8 +466,10 @@ extern "C" int b200lev_err_sum(const float* er, const int32_t* ref_lens, int64_t
     if (ref_group < 1) ref_group = 1;
     int64_t blocks = (P + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
+    lev_prof_begin(LEV_PROF_ERR_SUM, (cudaStream_t)stream);
     lev_launch(lev_err_sum_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, er,
                ref_lens, P, (int)ref_group, acc);
+    lev_prof_end(LEV_PROF_ERR_SUM, (cudaStream_t)stream);
     return lev_check_cuda("lev_err_sum_kernel");
 }
 

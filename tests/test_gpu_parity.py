@@ -345,9 +345,17 @@ def test_group_kernel_vs_oracle(F, dev, shape, costs, monkeypatch):
                                padding=-3, spread=spread, **flags)
 
 
+@pytest.fixture(params=["fused", "two_kernel"])
+def bv_form(request, monkeypatch):
+    """Both forms of the unit-cost bit-vector path: the fused kernel (lev_bvfused.cu, the
+    default) and the uid pre-pass + DP pair it replaced (lev_bitvec.cu, B200LEV_BV_FUSED=0)."""
+    monkeypatch.setenv("B200LEV_BV_FUSED", "1" if request.param == "fused" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("shape", [(20, 25, 300), (33, 30, 500), (64, 50, 300), (101, 101, 4200),
                                    (128, 60, 700)])
-def test_bitvec_path_vs_oracle(F, dev, shape, monkeypatch):
+def test_bitvec_path_vs_oracle(F, bv_form, dev, shape, monkeypatch):
     """The experimental unit-cost bit-vector path (lev_bitvec.cu, B200LEV_BITVEC=1): every word
     count, final + prefix, ragged lengths, narrow and wide token ranges, uniform multiplier."""
     monkeypatch.setenv("B200LEV_BITVEC", "1")
@@ -363,7 +371,7 @@ def test_bitvec_path_vs_oracle(F, dev, shape, monkeypatch):
 
 
 @pytest.mark.parametrize("shared", [True, False], ids=["nbest", "unrelated_refs"])
-def test_bitvec_device_selected(F, dev, shared):
+def test_bitvec_device_selected(F, bv_form, dev, shared):
     """Default mode at sizes where both paths are eligible: n-best shaped batches are taken by
     the bit-vector kernels, unrelated references (and references with tokens outside int32)
     are vetoed on the device and answered by the wavefront kernels.  Same numbers."""

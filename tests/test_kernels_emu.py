@@ -163,10 +163,18 @@ def test_group_kernel_vs_oracle(F, shape, costs, monkeypatch):
                                padding=-3, spread=spread, **flags)
 
 
+@pytest.fixture(params=["fused", "two_kernel"])
+def bv_form(request, monkeypatch):
+    """Both forms of the unit-cost bit-vector path: the fused kernel (lev_bvfused.cu, the
+    default) and the uid pre-pass + DP pair it replaced (lev_bitvec.cu, B200LEV_BV_FUSED=0)."""
+    monkeypatch.setenv("B200LEV_BV_FUSED", "1" if request.param == "fused" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("shape", [(1, 9, 33), (20, 25, 70), (32, 40, 64), (33, 30, 31), (64, 70, 40),
                                    (65, 20, 45), (96, 101, 35), (101, 101, 40), (128, 60, 34)])
 @pytest.mark.parametrize("costs", [(1, 1, 1), (3, 3, 3), (0.5, 0.5, 0.5)])
-def test_bitvec_kernels_vs_oracle(F, shape, costs, monkeypatch):
+def test_bitvec_kernels_vs_oracle(F, bv_form, shape, costs, monkeypatch):
     """The unit-cost bit-vector path (lev_bitvec.cu), forced on for small batches: every
     word count W = 1..4 with reference lengths on both sides of the word boundaries,
     final and prefix outputs, ragged lengths incl. empty sequences, missing eos, the uniform
@@ -185,7 +193,7 @@ def test_bitvec_kernels_vs_oracle(F, shape, costs, monkeypatch):
 
 
 @pytest.mark.parametrize("dtype", [torch.int32, torch.int16, torch.int8])
-def test_bitvec_token_dtypes_nbest_and_wide(F, dtype, monkeypatch):
+def test_bitvec_token_dtypes_nbest_and_wide(F, bv_form, dtype, monkeypatch):
     monkeypatch.setenv("B200LEV_BITVEC", "1")
     monkeypatch.setenv("B200LEV_BITVEC_MIN_PAIRS", "1")
     PC.check_vs_oracle(F, DEV, seed=5, R=40, H=45, N=37, V=9, costs=(1, 1, 1), do_mask=False,
@@ -197,7 +205,7 @@ def test_bitvec_token_dtypes_nbest_and_wide(F, dtype, monkeypatch):
 
 @pytest.mark.parametrize("shared", [True, False], ids=["nbest", "unrelated_refs"])
 @pytest.mark.parametrize("shape", [(30, 33, 12, 8), (101, 101, 9, 8), (64, 40, 5, 16), (90, 70, 20, 4)])
-def test_bitvec_device_selected(F, shape, shared, monkeypatch):
+def test_bitvec_device_selected(F, bv_form, shape, shared, monkeypatch):
     """Default mode: the bit-vector kernels are enqueued ahead of the wavefront path and decide
     on the device -- they take n-best shaped batches (<= 4 distinct references per 32 pairs)
     and veto the others, whose work the group kernels then do.  Same numbers either way."""
@@ -211,7 +219,7 @@ def test_bitvec_device_selected(F, shape, shared, monkeypatch):
                          wide=True)
 
 
-def test_bitvec_degenerate_shapes(F, monkeypatch):
+def test_bitvec_degenerate_shapes(F, bv_form, monkeypatch):
     """Forced bit-vector path on the shapes the reference's tests poke at: empty hypotheses,
     one-token references, batches that are not a multiple of 32, all-eos columns."""
     monkeypatch.setenv("B200LEV_BITVEC", "1")
@@ -239,7 +247,7 @@ def test_bitvec_degenerate_shapes(F, monkeypatch):
             PC.assert_same(act, exp, True, f"degenerate final {R}x{H}x{N} {kw}")
 
 
-def test_bitvec_golden(F, golden_sm, monkeypatch):
+def test_bitvec_golden(F, bv_form, golden_sm, monkeypatch):
     monkeypatch.setenv("B200LEV_BITVEC", "1")
     monkeypatch.setenv("B200LEV_BITVEC_MIN_PAIRS", "1")
     names = [n for n in golden_sm.params if n.startswith("s")] + ["cfg1", "cfg2r", "cfg4r", "wide"]
