@@ -141,18 +141,45 @@ def make_batch(n_utts, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).
+
+    Read through NVML from a thread of this process (nvidia_ml_py): one `nvidia-smi -lms` child
+    takes ~150 ms to come up and every one of its polls stalls kernel launches for milliseconds
+    -- more than a whole timed region of K short steps -- so it can only ever bracket the region,
+    never sample inside it.  An NVML clock query from inside the process costs tens of
+    microseconds.  Falls back to the nvidia-smi child when the module is missing."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_s=0.01):
         self.idx = gpu_index
+        self.period = period_s
         self.proc = None
         self.lines = []
+        self.samples = []  # (sm_mhz, max_mhz, reasons bitmask)
+        self.nvml = None
+        self._stop = threading.Event()
+        self._paused = False
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber: resolve through the PCI bus id of the torch device
+            import torch
+
+            props = torch.cuda.get_device_properties(self.idx)
+            bus = "{:08x}:{:02x}:{:02x}.0".format(props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+            self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
@@ -163,11 +190,52 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            if self._paused:
+                self._stop.wait(0.001)
+                continue
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    why = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except AttributeError:
+                    why = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((float(sm), float(mx), int(why)))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """Number of samples so far (to tell which ones fell inside the timed region)."""
+        return len(self.samples)
+
+    def pause(self, on):
+        """No polls while `on`: ONE poll inside a region of K short steps stalls kernel launches
+        for milliseconds (measured: 0.35 ms/step with a poll inside 20 steps of 0.17 ms)."""
+        self._paused = on
+
+    def stop(self, first=0, last=None):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=1)
+            n = self.nvml
+            names = (("hw_slowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                     ("hw_thermal_slowdown", getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                     ("sw_thermal_slowdown", getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                     ("sw_power_cap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))
+            inside = self.samples[first:last] or self.samples
+            reasons = sorted({nm for _, _, why in self.samples for nm, bit in names if why & bit})
+            return {"sm_mhz": float(np.median([x[0] for x in inside])) if inside else None,
+                    "sm_max_mhz": float(max(x[1] for x in inside)) if inside else None,
+                    "samples": len(self.samples), "samples_in_timed_region": len(self.samples[first:last]),
+                    "reasons": reasons, "how": f"NVML polled every {self.period * 1e3:.0f} ms from this process"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -192,7 +260,7 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "how": "nvidia-smi -lms 100 child"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -336,6 +404,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (cfg4: in total); 0 = the config's")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-on-gpu", action="store_true")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="diagnosis only")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -370,12 +439,22 @@ def main():
     hyp = torch.from_numpy(hyp_np).to(dev)
     P = hyp.shape[1]
     in_bytes = ref.numel() * 8 + hyp.numel() * 8
-    flush = None
-    if in_bytes < (160 << 20):  # inputs do not exceed L2: evict them between iterations
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # L2 (126 MB): when one batch does not exceed it, the timed steps rotate through several
+    # independent batches of the same shape whose inputs together do, so no step finds its
+    # inputs in L2 (the roofline / e2e legs use the first batch)
+    batches = [(ref, hyp, cells)]
+    if in_bytes < (160 << 20):
+        n_sets = min(8, -(-(200 << 20) // max(in_bytes, 1)))
+        for k in range(1, n_sets):
+            r_k, h_k, c_k = wl.make(my_pairs, seed=100 + rank + 1000 * k)
+            batches.append((torch.from_numpy(r_k).to(dev), torch.from_numpy(h_k).to(dev), c_k))
     totals = {}
+    turn = [0]
 
-    def step(r=ref, h=hyp):
+    def step(r=None, h=None):
+        if r is None:
+            r, h, _ = batches[turn[0] % len(batches)]
+            turn[0] += 1
         if wl.cfg == 4:
             # shard -> error_rate + device sums (K7) -> ONE all-reduce of [sum err, sum ref
             # tokens, #pairs] (fp64, 24 bytes) on the NCCL stream, inside the step
@@ -389,49 +468,67 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    debug = os.environ.get("B200LEV_BENCH_DEBUG") == "1"
+
     def timed_loop(fn, reps):
-        """K calls between two events; with `flush` the eviction write runs between calls and
-        its own (separately measured) time is subtracted."""
+        """K back-to-back calls between two events on the launch stream."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if flush is None:
-            e0.record()
-            for _ in range(reps):
-                out = fn()
-            e1.record()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / reps, out
-        tot = 0.0
+        if debug:
+            st0 = torch.cuda.memory_stats(dev)
+            walls = []
+        e0.record()
         for _ in range(reps):
-            flush.zero_()
-            e0.record()
+            if debug:
+                tw = time.perf_counter()
             out = fn()
-            e1.record()
-            torch.cuda.synchronize()
-            tot += e0.elapsed_time(e1)
-        return tot / reps, out
+            if debug:
+                walls.append(round((time.perf_counter() - tw) * 1e6))
+        e1.record()
+        torch.cuda.synchronize()
+        if debug:
+            st1 = torch.cuda.memory_stats(dev)
+            keys = ("num_device_alloc", "num_device_free", "num_alloc_retries", "reserved_bytes.all.current")
+            sys.stderr.write(f"timed_loop: {e0.elapsed_time(e1) / reps:.4f} ms/step; enqueue us {walls}; "
+                             f"allocator {[(k, st0.get(k), st1.get(k)) for k in keys]}\n")
+        return e0.elapsed_time(e1) / reps, out
 
     # ---- value: device-resident, whole public call ------------------------------------
     # W untimed warm-up steps, then a short soak of the same step with the clock sampler already
     # running (K steps of 0.2 ms are shorter than one nvidia-smi period, and the first calls
     # after an idle GPU run below the clocks the load settles at), then EXACTLY K timed steps.
-    for _ in range(max(args.warmup, 3)):
-        out = step()
+    # (warm-up, soak and timed steps all run through timed_loop: its local `out` is the only
+    # reference to a result, so the caching allocator ping-pongs between the same two blocks in
+    # all three phases -- a result kept alive outside would cost the timed region a cudaMalloc
+    # of a third block, which takes 1 to 70 ms on these boxes)
+    timed_loop(step, max(args.warmup, 3))
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not args.no_clock_sampler:
         sampler.start()
     soak_s = 0.5
     t_soak = time.perf_counter()
     while time.perf_counter() - t_soak < soak_s:
-        for _ in range(10):
-            out = step()
-        torch.cuda.synchronize()
+        timed_loop(step, 10)
     barrier()
+    # the sampler polls up to the first timed step and again from the last one on, while the same
+    # step keeps running (untimed): the clocks are those of this load, read within milliseconds of
+    # the timed region on both sides; inside it a poll would be the largest thing measured
+    sampler.pause(True)
+    m0 = sampler.mark()
+    first_turn = turn[0]
     ms, out = timed_loop(step, args.steps)
+    cells_step = sum(batches[(first_turn + k) % len(batches)][2] for k in range(args.steps)) / args.steps
+    sampler.pause(False)
+    t_soak = time.perf_counter()
+    while time.perf_counter() - t_soak < 0.25:
+        timed_loop(step, 10)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(0, None) if rank == 0 else None
     if clocks is not None:
-        clocks["window"] = f"{soak_s} s of the same step (untimed) followed by the timed K steps"
+        clocks["samples_before_timed_region"] = m0
+        clocks.pop("samples_in_timed_region", None)
+        clocks["window"] = (f"{soak_s} s of the same step before and 0.25 s after the timed K steps, polling "
+                            "paused during them (one NVML poll stalls launches for milliseconds)")
     out_bytes = int(out.numel() * out.element_size())
 
     # ---- per-kernel CUDA-event times of the same public call (b200lev_profile) -------------
@@ -442,9 +539,9 @@ def main():
         acc = np.zeros(nslots, dtype=np.float64)
         _abi.check(L.b200lev_profile(1))
         for _ in range(3):
-            step()
+            step(ref, hyp)
         for _ in range(nprof):
-            step()
+            step(ref, hyp)
             _abi.check(L.b200lev_profile_read(buf, nslots))
             acc += np.array([max(x, 0.0) for x in buf])
         _abi.check(L.b200lev_profile(0))
@@ -552,12 +649,12 @@ def main():
     # ---- reduce over ranks ---------------------------------------------------------------
     dom_ms = float(prof[7] if bitvec else prof[3])
     stats = torch.tensor([ms, ms_e2e, dom_ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(cells), float(P)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(cells_step), float(P), float(cells)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ms, ms_e2e, _ = stats.tolist()
-    cells_all, pairs_all = tot.tolist()
+    cells_all, pairs_all, cells_e2e_all = tot.tolist()
 
     if rank == 0:
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -651,11 +748,11 @@ def main():
             "dtype": "int32", "data": "synthetic",
             "config": wl.config(P, {
                 "pairs_total": int(pairs_all), "cells_per_gpu": cells, "host_numa_node": numa_node,
-                "l2": (f"inputs {in_bytes / 1e6:.0f} MB per step exceed the 126 MB L2" if flush is None else
-                       f"inputs {in_bytes / 1e6:.0f} MB fit L2: a 256 MB buffer is rewritten between "
-                       "timed calls (each call timed by its own event pair)")}),
+                "l2": (f"inputs {in_bytes / 1e6:.0f} MB per step exceed the 126 MB L2" if len(batches) == 1 else
+                       f"inputs {in_bytes / 1e6:.0f} MB per step: the timed steps rotate through "
+                       f"{len(batches)} independent batches ({len(batches) * in_bytes / 1e6:.0f} MB > 126 MB L2)")}),
             "hyps_per_s": pairs_all / (ms * 1e-3),
-            "e2e": {"value": cells_all / (ms_e2e * 1e-3) / 1e9, "unit": "GCUPS",
+            "e2e": {"value": cells_e2e_all / (ms_e2e * 1e-3) / 1e9, "unit": "GCUPS",
                     "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                     "ms_per_step": ms_e2e},
             "gpu_launches": launches * args.steps,
