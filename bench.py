@@ -685,7 +685,21 @@ def main():
 
         extra = {}
         pack_ms = float(prof[0] + prof[1])
-        if bitvec:
+        short = bitvec and wl.T <= 64 and os.environ.get("B200LEV_BV_SHORT", "1") != "0"
+        if short:
+            # R <= 64: one kernel, lane = pair, reference in registers, straight from the raw tokens
+            roofline = int32_roofline(
+                f"lev_bv_short_kernel<int64,W={1 if wl.T <= 32 else 2},{'PREFIX' if wl.cfg == 2 else 'FINAL'}>",
+                float(prof[7]),
+                "algorithmic 5 INT32 ops/cell (SURVEY 8d); the match masks come from 16-bit packed compares "
+                "against the reference registers (2 ALU + 1 FMA instruction per two positions), the "
+                "recurrence is Myers' bit-vector step; the same kernel reads both raw int64 token tensors "
+                "(roofline_hbm)", "lev_bv_short_kernel")
+            extra["roofline_hbm"] = hbm_roofline(
+                "lev_bv_short_kernel (its memory side)", float(prof[7]), in_bytes + out_bytes + 8 * P,
+                "reads both raw int64 token tensors once, writes the results + lengths", "lev_bv_short_kernel")
+            launches = 1 + (1 if wl.cfg == 4 else 0)
+        elif bitvec:
             fused = os.environ.get("B200LEV_BV_FUSED", "1") != "0"
             if fused:
                 # one kernel: lengths, run detection, hash tables, Myers' recurrence, output rows

@@ -332,8 +332,10 @@ static int lev_try_bitvec(const b200lev_tokens_t* ref, const b200lev_tokens_t* h
     memset(&tmp, 0, sizeof(tmp));
     bool cm, fp;
     lev_classify_costs(o, L.R, L.H, &tmp, &cm, &fp);
-    if (!lev_bitvec_eligible(ref, hyp, mode, cm, fp, tmp.ins_i, tmp.del_i, tmp.sub_i, out_sn)) return 0;
-    const bool forced = lev_bitvec_mode() == 1;
+    bool short_form = false;
+    if (!lev_bitvec_eligible(ref, hyp, mode, cm, fp, tmp.ins_i, tmp.del_i, tmp.sub_i, out_sn, &short_form)) return 0;
+    // the short-reference kernel takes any batch: nothing to select on the device, no chain behind it
+    const bool forced = lev_bitvec_mode() == 1 || short_form;
     int32_t* state = (int32_t*)(ws + L.off_flags);
     if (!forced) {
         // device-selected: only where the wavefront fallback is the group path, whose kernels
@@ -347,7 +349,8 @@ static int lev_try_bitvec(const b200lev_tokens_t* ref, const b200lev_tokens_t* h
     const int rc = lev_bitvec_launch(ref, hyp, o, mode, tmp.mult, (int32_t*)(ws + L.off_ref_len),
                                      (int32_t*)(ws + L.off_hyp_len), ws + L.off_bv_ref,
                                      ws + L.off_hyp_tok, ws + L.off_slots, forced ? nullptr : state,
-                                     flags, out, out_si, Hout, st, *forked ? fork->after_uid : nullptr);
+                                     flags, out, out_si, Hout, st, *forked ? fork->after_uid : nullptr,
+                                     short_form);
     if (rc) return rc;
     return forced ? 1 : 2;
 }

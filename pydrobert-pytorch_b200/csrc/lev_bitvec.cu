@@ -526,14 +526,23 @@ static int64_t lev_bv_min_pairs() {
     return v;
 }
 
+// the short-reference form (lev_bvshort.cu) has no tables to set up: worth it from a few warps on
+static int64_t lev_bvshort_min_pairs() {
+    int64_t v = 64;
+    if (const char* e = getenv("B200LEV_BVSHORT_MIN_PAIRS")) v = atoll(e);
+    return v;
+}
+
 bool lev_bitvec_eligible(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp, int mode,
                          bool count_mode, bool float_path, int ins_i, int del_i, int sub_i,
-                         int64_t out_sn) {
+                         int64_t out_sn, bool* short_form) {
+    *short_form = false;
     if (lev_bitvec_mode() == 0) return false;
     if (mode != LEV_MODE_FINAL && mode != LEV_MODE_PREFIX) return false;
     if (count_mode || float_path || ins_i != 1 || del_i != 1 || sub_i != 1) return false;
     if (ref->T > 128 || ref->T < 1 || hyp->T >= (1 << 20)) return false;
-    if (hyp->N < lev_bv_min_pairs()) return false;
+    *short_form = lev_bvshort_supports(ref->elem_bytes, ref->T) && hyp->N >= lev_bvshort_min_pairs();
+    if (!*short_form && hyp->N < lev_bv_min_pairs()) return false;
     if (ref->elem_bytes != hyp->elem_bytes) return false;
     if (ref->stride_t >= ((int64_t)1 << 31) || hyp->stride_t >= ((int64_t)1 << 31) ||
         ref->stride_t < 0 || hyp->stride_t < 0)
@@ -583,7 +592,7 @@ int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
                       const b200lev_opts_t* o, int mode, float mult, int32_t* ref_len,
                       int32_t* hyp_len, void* uid_ref, void* uid_hyp, void* lead,
                       int32_t* state, int32_t* flags, float* out, int64_t out_si, int Hout,
-                      cudaStream_t st, void* after_uid) {
+                      cudaStream_t st, void* after_uid, bool short_form) {
     LevBvArgs a;
     memset(&a, 0, sizeof(a));
     a.ref = ref->data;
@@ -615,6 +624,11 @@ int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     a.padding = (float)o->padding;
     a.out = out;
     a.out_si = out_si;
+    if (short_form) {  // R <= 64: lane = pair, reference in registers, no tables (lev_bvshort.cu)
+        if (getenv("B200LEV_TRACE"))
+            fprintf(stderr, "b200lev: short bit-vector kernel, mode %d, R=%d H=%d P=%d\n", mode, a.R, a.H, a.P);
+        return lev_bvshort_launch(a, ref->elem_bytes, st);
+    }
     // B200LEV_BV_FUSED=0 keeps the two-kernel form (uid pre-pass + DP) for comparison
     const char* fe = getenv("B200LEV_BV_FUSED");
     if ((fe == nullptr || atoi(fe) != 0) && lev_bvfused_supports(ref->elem_bytes)) {

@@ -133,6 +133,8 @@ __device__ __forceinline__ int lev_bv_step(const unsigned (&eq)[W], unsigned (&p
 // ---------------------------------------------------------------------------------------
 // pieces of the fused kernel (lev_bvfused.cu)
 // ---------------------------------------------------------------------------------------
+bool lev_bvshort_supports(int elem_bytes, int64_t R);
+int lev_bvshort_launch(const LevBvArgs& a, int elem_bytes, cudaStream_t st);
 bool lev_bvfused_supports(int elem_bytes);
 int lev_bvfused_launch(const LevBvArgs& a, int elem_bytes, cudaStream_t st, void* after_probe);
 

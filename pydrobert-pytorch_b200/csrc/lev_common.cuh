@@ -189,12 +189,12 @@ __device__ __forceinline__ bool lev_bv_took(const int* state) {
 // unit-cost bit-vector path (lev_bitvec.cu)
 bool lev_bitvec_eligible(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp, int mode,
                          bool count_mode, bool float_path, int ins_i, int del_i, int sub_i,
-                         int64_t out_sn);
+                         int64_t out_sn, bool* short_form);
 int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
                       const b200lev_opts_t* o, int mode, float mult, int32_t* ref_len,
                       int32_t* hyp_len, void* uid_ref, void* uid_hyp, void* lead,
                       int32_t* state, int32_t* flags, float* out, int64_t out_si, int Hout,
-                      cudaStream_t st, void* after_uid);
+                      cudaStream_t st, void* after_uid, bool short_form);
 // 0: off, 1: forced (tests; runs whatever the references look like), 2: device-selected
 int lev_bitvec_mode();
 int lev_launch_uid(const b200lev_tokens_t* ref, const int32_t* ref_len, int32_t* uid,

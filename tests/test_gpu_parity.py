@@ -345,11 +345,17 @@ def test_group_kernel_vs_oracle(F, dev, shape, costs, monkeypatch):
                                padding=-3, spread=spread, **flags)
 
 
-@pytest.fixture(params=["fused", "two_kernel"])
+@pytest.fixture(params=["fused", "two_kernel", "short"])
 def bv_form(request, monkeypatch):
-    """Both forms of the unit-cost bit-vector path: the fused kernel (lev_bvfused.cu, the
-    default) and the uid pre-pass + DP pair it replaced (lev_bitvec.cu, B200LEV_BV_FUSED=0)."""
-    monkeypatch.setenv("B200LEV_BV_FUSED", "1" if request.param == "fused" else "0")
+    """The forms of the unit-cost bit-vector path: the fused kernel (lev_bvfused.cu, the default
+    for R > 64), the uid pre-pass + DP pair it replaced (lev_bitvec.cu, B200LEV_BV_FUSED=0), and
+    the lane-per-pair short-reference kernel (lev_bvshort.cu, R <= 64; larger shapes of a
+    "short" run fall through to the fused kernel)."""
+    if request.param == "short":
+        monkeypatch.setenv("B200LEV_BVSHORT_MIN_PAIRS", "1")
+    else:
+        monkeypatch.setenv("B200LEV_BV_SHORT", "0")
+        monkeypatch.setenv("B200LEV_BV_FUSED", "1" if request.param == "fused" else "0")
     return request.param
 
 
