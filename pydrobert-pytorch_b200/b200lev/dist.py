@@ -87,3 +87,35 @@ def bulk_error_rate(ref: torch.Tensor, hyp: torch.Tensor, eos: Optional[int] = N
         else:
             dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=process_group)
     return er, acc
+
+
+def score_corpora_sharded(ref, hyp, process_group=None, **score_kwargs):
+    """``scoring.score_corpora`` over the ranks of a process group: the aligned corpora are cut
+    into contiguous blocks of utterances (:func:`shard_bounds`), every rank scores its block on
+    its own GPU, and ONE ``all_reduce(sum)`` of ``[sum(err), sum(ref_tokens), #utterances]``
+    (fp64) gives every rank the corpus totals that ``compute-torch-token-data-dir-error-rates``
+    prints (command_line.py:1135-1147).
+
+    Returns ``(lo, hi, errors[lo:hi], ref_lens[lo:hi], totals)``.  The token-to-code map is built
+    per rank from its block only: the edit distance depends on token equality inside a pair,
+    so the blocks do not have to agree on the codes."""
+    import numpy as np
+
+    from . import scoring as S
+
+    if ref.utt_ids != hyp.utt_ids:
+        raise ValueError("corpora are not aligned (see align_utterances)")
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(process_group), dist.get_world_size(process_group)
+    else:
+        rank, world = 0, 1
+    lo, hi = shard_bounds(len(ref), rank, world)
+    keep = np.arange(lo, hi, dtype=np.int64)
+    errors, rlens = S.score_corpora(ref.select(keep), hyp.select(keep), **score_kwargs)
+    totals = torch.tensor([float(errors.astype(np.float64).sum()), float(rlens.sum()), float(hi - lo)],
+                          dtype=torch.float64)
+    if world > 1:
+        if dist.get_backend(process_group) != "gloo":
+            totals = totals.to(torch.device("cuda", torch.cuda.current_device()))
+        dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=process_group)
+    return lo, hi, errors, rlens, totals.cpu()
