@@ -283,6 +283,28 @@ int b200lev_profile_read(float *ms, int n);
 int b200lev_int32_peak_kernel(int32_t variant, int64_t blocks, int64_t iters, int32_t *sink,
                               double *ops, void *stream);
 
+/* ---- N-best producers' step functions -------------------------------------
+ * b200lev_beam_topk   -- the top-k of reference _decoding.py:117-121 (beam_search_advance):
+ *   candidates log_probs_prev[n, k] + log_probs_t[n, k, v] (summed and rounded in the tensors'
+ *   dtype: 0 fp32, 1 fp16, 2 bf16, 3 fp64; element strides), the `width` best per batch element
+ *   in descending order, equal scores by ascending flat index k * V + v.  Writes
+ *   log_probs_next (N, width) in the same dtype, next_src (N, width) = k and y_t (N, width) = v
+ *   (int64); columns beyond min(width, Kp * V) get -inf / 0 / 0 (_decoding.py:143-152).
+ * b200lev_path_extend -- the gather / cat / scatter of _decoding.py:123-141 (and of
+ *   random_walk_advance, _decoding.py:1268-1281, with src = NULL): y_next (S_out, N, W) from
+ *   y_prev (S, N, Kp), both contiguous int64; src (N, W) or NULL (identity), lens_prev (N, Kp)
+ *   or NULL (all S), y_t (N, W); S_out is S or S + 1; lens_next (N, W) may be NULL.  Columns
+ *   k >= K are padding (zeros; the reference leaves them uninitialised).
+ */
+int b200lev_beam_topk(const void *log_probs_t, int32_t dtype, int64_t N, int64_t Kp, int64_t V,
+                      int64_t stride_n, int64_t stride_k, int64_t stride_v,
+                      const void *log_probs_prev, int64_t prev_stride_n, int64_t prev_stride_k,
+                      int64_t width, void *log_probs_next, int64_t *next_src, int64_t *y_t,
+                      void *stream);
+int b200lev_path_extend(const int64_t *y_prev, int64_t S, int64_t N, int64_t Kp, const int64_t *src,
+                        const int64_t *lens_prev, const int64_t *y_t, int64_t K, int64_t W,
+                        int64_t S_out, int64_t *y_next, int64_t *lens_next, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

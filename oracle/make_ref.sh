@@ -6,7 +6,7 @@
 # 1. installs the reference package, as it is, into baseline/_ref (the one offline install the
 #    build contract allows: pip --no-index --no-deps --target; the source tree is read-only, so
 #    the wheel is built from a copy under /tmp);
-# 2. copies the reference's own test module for the hot path (tests/test_string.py), its
+# 2. copies the reference's own test module for the hot path (tests/test_string.py; tests/test_decoding.py for the step functions of the N-best producers), its
 #    conftest.py and its pytest.ini (marker names) into oracle/_ref/tests/.
 #
 # Both directories are git-ignored (nothing of the reference enters this repository's history)
@@ -30,7 +30,7 @@ if [ ! -f "$ROOT/baseline/_ref/pydrobert/torch/_string.py" ] || [ "${FORCE:-0}" 
     rm -rf "$TMP"
 fi
 mkdir -p "$ROOT/oracle/_ref/tests"
-cp "$REF/tests/test_string.py" "$REF/tests/conftest.py" "$ROOT/oracle/_ref/tests/"
+cp "$REF/tests/test_string.py" "$REF/tests/test_decoding.py" "$REF/tests/conftest.py" "$ROOT/oracle/_ref/tests/"
 # the reference registers its markers (cpu / gpu / trace / script / nojit) in pytest.ini
 cp "$REF/pytest.ini" "$ROOT/oracle/_ref/tests/pytest.ini"
 echo "make_ref: baseline/_ref (package) and oracle/_ref/tests (test_string.py, conftest.py) ready"

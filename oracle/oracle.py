@@ -483,3 +483,68 @@ def ctc_greedy_search(logits, in_lens=None, blank_idx=-1, batch_first=False, is_
     if not batch_first:
         gz = gz.transpose(1, 0, 2)
     return max_, paths, out_lens, gz
+
+
+def beam_search_advance(log_probs_t, width, log_probs_prev, y_prev, y_prev_lens=None):
+    """_decoding.py:41-155 restated (numpy; test infrastructure).  Ties between equal candidate
+    scores resolve to the lower flat index ``k * V + v`` (the reference leaves the order of ties
+    to torch.topk).  The sum is formed in the arrays' dtype, as torch's add is.  Padding columns
+    (fewer than ``width`` extensions) hold -inf / length 0 / source 0 / token 0."""
+    lpt = np.asarray(log_probs_t)
+    lpp = np.asarray(log_probs_prev).astype(lpt.dtype)
+    y_prev = np.asarray(y_prev, dtype=np.int64)
+    N, Kp, V = lpt.shape
+    S = y_prev.shape[0]
+    K = min(width, Kp * V)
+    cand = (lpp[:, :, None] + lpt).astype(lpt.dtype).reshape(N, Kp * V)
+    # descending by value (NaN greatest, as torch.topk), ascending by index among equals
+    key = np.where(np.isnan(cand), np.inf, cand.astype(np.float64))
+    isnan = np.isnan(cand)
+    order = np.lexsort((np.arange(Kp * V)[None, :].repeat(N, 0), -key, ~isnan), axis=1)[:, :K]
+    lp_next = np.take_along_axis(cand, order, 1)
+    src = order // V
+    y_t = order % V
+    if y_prev_lens is None:
+        lens = np.full((N, Kp), S, dtype=np.int64)
+        S_out = S + 1
+    else:
+        lens = np.asarray(y_prev_lens, dtype=np.int64)
+        if S == 0:
+            if (lens != 0).any():
+                raise RuntimeError("Invalid lengths for t=0")
+            S_out = 1
+        else:
+            S_out = S + 1 if int(lens.max()) >= S else S
+    y_next = np.zeros((S_out, N, width), dtype=np.int64)
+    lens_next = np.zeros((N, width), dtype=np.int64)
+    for n in range(N):
+        for k in range(K):
+            f = src[n, k]
+            y_next[:S, n, k] = y_prev[:, n, f]
+            if S_out > S:
+                y_next[S, n, k] = y_t[n, k]  # cat([y_next, y_t]) leaves the token in the new row
+            y_next[lens[n, f], n, k] = y_t[n, k]
+            lens_next[n, k] = lens[n, f] + 1
+    lp_out = np.full((N, width), -np.inf, dtype=lpt.dtype)
+    lp_out[:, :K] = lp_next
+    src_out = np.zeros((N, width), dtype=np.int64)
+    src_out[:, :K] = src
+    return y_next, lens_next, lp_out, src_out
+
+
+def random_walk_advance(log_probs_t, log_probs_prev, y_prev, y_t, y_prev_lens=None):
+    """_decoding.py:1207-1283 restated GIVEN the drawn tokens ``y_t`` (N,): the draw itself is
+    torch.multinomial's."""
+    lpt = np.asarray(log_probs_t)
+    y_prev = np.asarray(y_prev, dtype=np.int64)
+    y_t = np.asarray(y_t, dtype=np.int64)
+    S, N = y_prev.shape
+    lp_next = np.asarray(log_probs_prev) + lpt[np.arange(N), y_t]
+    if S == 0:
+        return y_t[None, :].copy(), lp_next
+    if y_prev_lens is None:
+        return np.concatenate([y_prev, y_t[None, :]], 0), lp_next
+    lens = np.asarray(y_prev_lens, dtype=np.int64)
+    y_next = np.concatenate([y_prev, y_t[None, :]], 0) if int(lens.max()) >= S else y_prev.copy()
+    y_next[lens, np.arange(N)] = y_t
+    return y_next, lp_next

@@ -78,6 +78,10 @@ SIGNATURES = {
                                               c_vp, c_vp, c_vp, c_vp]),
     "b200lev_ctc_greedy": (ctypes.c_int, [c_vp, c_i32, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp,
                                           c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b200lev_beam_topk": (ctypes.c_int, [c_vp, c_i32, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64,
+                                         c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "b200lev_path_extend": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64,
+                                           c_vp, c_vp, c_vp]),
     "b200lev_copy2d_async": (ctypes.c_int, [c_vp, c_sz, c_vp, c_sz, c_sz, c_sz, c_i32, c_vp]),
     "b200lev_profile": (ctypes.c_int, [ctypes.c_int]),
     "b200lev_profile_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.c_int]),

@@ -632,6 +632,91 @@ def _(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost, sub_cost, nor
 
 
 # ---------------------------------------------------------------------------------------
+# N-best producers' step functions (_decoding.py:41-155, 1207-1283)
+# ---------------------------------------------------------------------------------------
+def _path_extend(pl, y_prev: Tensor, src: Optional[Tensor], lens_prev: Optional[Tensor], y_t: Tensor,
+                 K: int, W: int) -> Tuple[Tensor, Tensor]:
+    """Device tensors in and out: ``(y_next (S', N, W), lens_next (N, W))``."""
+    dev = pl.dev
+    S, N, Kp = y_prev.shape
+    if S == 0:
+        if lens_prev is not None and bool((lens_prev != 0).any()):
+            raise RuntimeError("Invalid lengths for t=0")  # _decoding.py:135-136
+        S_out = 1
+    elif lens_prev is None:
+        S_out = S + 1
+    else:  # don't make y bigger unless we have to (_decoding.py:129-131): one host read
+        S_out = S + 1 if int(lens_prev.max().item()) >= S else S
+    y_next = torch.empty((S_out, N, W), dtype=torch.long, device=dev)
+    lens_next = torch.empty((N, W), dtype=torch.long, device=dev)
+    with _DeviceGuard(dev):
+        _abi.check(_abi.lib().b200lev_path_extend(
+            y_prev.data_ptr() if S > 0 and y_prev.numel() else None, S, N, Kp,
+            None if src is None else src.data_ptr(), None if lens_prev is None else lens_prev.data_ptr(),
+            y_t.data_ptr(), K, W, S_out, y_next.data_ptr(), lens_next.data_ptr(), _stream(dev)))
+    return y_next, lens_next
+
+
+@torch.library.custom_op("b200lev::beam_search_advance", mutates_args=())
+def beam_search_advance(log_probs_t: Tensor, width: int, log_probs_prev: Tensor, y_prev: Tensor,
+                        y_prev_lens: Optional[Tensor]) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """``(y_next, y_next_lens, log_probs_next, next_src)`` of _decoding.py:41-155.  Shapes are
+    checked by the caller (functional.beam_search_advance)."""
+    pl = _host.Placement(log_probs_t, log_probs_prev, y_prev, y_prev_lens)
+    dev = pl.dev
+    N, Kp, V = log_probs_t.shape
+    lpt = pl.to_dev(log_probs_t.detach())
+    lpp = pl.to_dev(log_probs_prev.detach()).to(lpt.dtype)
+    yp = pl.to_dev(y_prev.detach()).to(torch.long).contiguous()
+    lens = None if y_prev_lens is None else pl.to_dev(y_prev_lens.detach()).to(torch.long).contiguous()
+    K = min(width, Kp * V)
+    lp_next = torch.empty((N, width), dtype=lpt.dtype, device=dev)
+    next_src = torch.empty((N, width), dtype=torch.long, device=dev)
+    y_t = torch.empty((N, width), dtype=torch.long, device=dev)
+    with _DeviceGuard(dev):
+        _abi.check(_abi.lib().b200lev_beam_topk(
+            lpt.data_ptr(), _float_code(lpt), N, Kp, V, lpt.stride(0), lpt.stride(1), lpt.stride(2),
+            lpp.data_ptr(), lpp.stride(0), lpp.stride(1), width, lp_next.data_ptr(), next_src.data_ptr(),
+            y_t.data_ptr(), _stream(dev)))
+    y_next, lens_next = _path_extend(pl, yp, next_src, lens, y_t, K, width)
+    return pl.back(y_next), pl.back(lens_next), pl.back(lp_next), pl.back(next_src)
+
+
+@beam_search_advance.register_fake
+def _(log_probs_t, width, log_probs_prev, y_prev, y_prev_lens):
+    N = log_probs_t.shape[0]
+    S = y_prev.shape[0]
+    S_out = S + 1 if y_prev_lens is None or S == 0 else torch.library.get_ctx().new_dynamic_size()
+    return (y_prev.new_empty((S_out, N, width), dtype=torch.long), y_prev.new_empty((N, width), dtype=torch.long),
+            log_probs_t.new_empty((N, width)), y_prev.new_empty((N, width), dtype=torch.long))
+
+
+@torch.library.custom_op("b200lev::random_walk_advance", mutates_args=())
+def random_walk_advance(log_probs_t: Tensor, log_probs_prev: Tensor, y_prev: Tensor,
+                        y_prev_lens: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """``(y_next, log_probs_next)`` of _decoding.py:1207-1283.  The draw itself is torch's
+    (``torch.multinomial`` on the compute device: the random stream is the reference's own, so a
+    seeded run reproduces it); the path bookkeeping is the same kernel as the beam's."""
+    pl = _host.Placement(log_probs_t, log_probs_prev, y_prev, y_prev_lens)
+    dev = pl.dev
+    N, V = log_probs_t.shape
+    lpt = pl.to_dev(log_probs_t.detach())
+    y_t = torch.multinomial(lpt.exp(), 1, True)  # (N, 1)   _decoding.py:1266
+    lp_next = pl.to_dev(log_probs_prev.detach()) + lpt.gather(1, y_t).squeeze(1)
+    yp = pl.to_dev(y_prev.detach()).to(torch.long).contiguous().unsqueeze(2)  # (S, N, 1)
+    lens = None if y_prev_lens is None else pl.to_dev(y_prev_lens.detach()).to(torch.long).contiguous().unsqueeze(1)
+    y_next, _ = _path_extend(pl, yp, None, lens, y_t.contiguous(), 1, 1)
+    return pl.back(y_next.squeeze(2)), pl.back(lp_next)
+
+
+@random_walk_advance.register_fake
+def _(log_probs_t, log_probs_prev, y_prev, y_prev_lens):
+    S, N = y_prev.shape
+    S_out = S + 1 if y_prev_lens is None or S == 0 else torch.library.get_ctx().new_dynamic_size()
+    return y_prev.new_empty((S_out, N), dtype=torch.long), log_probs_prev.new_empty((N,))
+
+
+# ---------------------------------------------------------------------------------------
 # eager fast path
 # ---------------------------------------------------------------------------------------
 def needs_dispatcher() -> bool:

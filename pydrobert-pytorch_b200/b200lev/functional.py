@@ -37,6 +37,8 @@ __all__ = [
     "prefix_error_rates",
     "sequence_log_probs",
     "ctc_greedy_search",
+    "beam_search_advance",
+    "random_walk_advance",
 ]
 
 script = torch.jit.script_if_tracing
@@ -471,3 +473,70 @@ def ctc_greedy_search(logits: torch.Tensor, in_lens: Optional[torch.Tensor] = No
         max_, paths, out_lens, _, _, _ = _ops.ctc_greedy_search_impl(logits4, in_lens, blank, is_probs)
     shape = (N, T) if batch_first else (T, N)
     return max_.view(N), paths.view(shape), out_lens.view(N)
+
+
+@script
+def beam_search_advance(
+    log_probs_t: torch.Tensor,
+    width: int,
+    log_probs_prev: torch.Tensor,
+    y_prev: torch.Tensor,
+    y_prev_lens: Optional[torch.Tensor] = None,
+) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Beam search step function (_decoding.py:41-155): the ``width`` best extensions of the
+    ``old_width`` prefixes ``y_prev`` (``(S, N, old_width)``) by one token of ``log_probs_t``
+    (``(N, old_width, V)``).  Returns ``(y_next, y_next_lens, log_probs_next, next_src)``.
+    Equal candidate scores resolve to the lower ``old_width * V`` index (the reference leaves
+    that order to ``torch.topk``); paths beyond ``old_width * V`` get ``-inf``, length 0 and
+    source 0, their tokens are zeros (uninitialised in the reference)."""
+    if log_probs_t.dim() != 3:
+        raise RuntimeError("log_probs_t must be 3 dimensional")
+    N, Kp, V = log_probs_t.shape
+    if width < 1:
+        raise RuntimeError(f"Expected width to be >= 1, got {width}")
+    if log_probs_prev.dim() != 2 or log_probs_prev.size(0) != N or log_probs_prev.size(1) != Kp:
+        raise RuntimeError(
+            f"Expected log_probs_prev to be of shape {(N, Kp)}, got "
+            f"{log_probs_prev.shape}"
+        )
+    if y_prev.dim() != 3:
+        raise RuntimeError("y_prev must be 3 dimensional")
+    if y_prev.size(1) != N or y_prev.size(2) != Kp:
+        raise RuntimeError(
+            f"Expected the last two dimensions of y_prev to be {(N, Kp)}, "
+            f"got {y_prev.shape[1:]}"
+        )
+    if y_prev_lens is not None and (y_prev_lens.dim() != 2 or y_prev_lens.size(0) != N
+                                    or y_prev_lens.size(1) != Kp):
+        raise RuntimeError(
+            f"Expected y_prev_lens to have shape {(N, Kp)}, got {y_prev_lens.shape}"
+        )
+    return torch.ops.b200lev.beam_search_advance(log_probs_t, width, log_probs_prev, y_prev, y_prev_lens)
+
+
+@script
+def random_walk_advance(
+    log_probs_t: torch.Tensor,
+    log_probs_prev: torch.Tensor,
+    y_prev: torch.Tensor,
+    y_prev_lens: Optional[torch.Tensor] = None,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Random walk step function (_decoding.py:1207-1283): one token per path drawn from
+    ``exp(log_probs_t)`` (``(N, V)``), appended to ``y_prev`` (``(S, N)``).  Returns
+    ``(y_next, log_probs_next)``."""
+    if log_probs_t.dim() != 2:
+        raise RuntimeError("log_probs_t must be 2-dimensional")
+    N, V = log_probs_t.shape
+    if log_probs_prev.dim() != 1 or log_probs_prev.size(0) != N:
+        raise RuntimeError(
+            f"Expected log_probs_prev to be of shape {(N,)}, got {log_probs_prev.shape}"
+        )
+    if y_prev.dim() != 2:
+        raise RuntimeError("y_prev must be 2-dimensional")
+    if y_prev.size(1) != N:
+        raise RuntimeError(f"Expected dim 1 of y_prev to be {N}, got {y_prev.size(-1)}")
+    if y_prev_lens is not None and (y_prev_lens.dim() != 1 or y_prev_lens.size(0) != N):
+        raise RuntimeError(
+            f"Expected y_prev_lens to have shape {(N,)}, got {y_prev_lens.shape}"
+        )
+    return torch.ops.b200lev.random_walk_advance(log_probs_t, log_probs_prev, y_prev, y_prev_lens)

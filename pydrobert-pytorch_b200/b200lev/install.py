@@ -1,9 +1,11 @@
 """Rebind the reference's string-matching names to the B200 kernels.
 
 ``install()`` patches an importable ``pydrobert.torch`` in place -- ``_string``,
-``functional`` and ``modules`` (functional.py:49-58, modules.py:115-124 of the
-reference) -- so that existing user code and the reference's own
-``tests/test_string.py`` run on ``libb200lev.so`` without edits.
+``_decoding``, ``functional`` and ``modules`` (functional.py:49-58, modules.py:115-124 of
+the reference) -- so that existing user code and the reference's own
+``tests/test_string.py`` run on ``libb200lev.so`` without edits.  Rebinding
+``_decoding.beam_search_advance`` / ``random_walk_advance`` also puts the step kernels under
+the reference's own ``BeamSearch`` / ``RandomWalk`` modules, whose loops call them by name.
 """
 from __future__ import annotations
 
@@ -12,10 +14,10 @@ import importlib
 from . import functional as _F
 from . import modules as _M
 
-# sequence_log_probs / SequenceLogProbabilities cover the tensor path only (the reference also
-# accepts a PackedSequence there), so they are offered by name but not rebound behind the
-# reference's back; ctc_greedy_search / CTCGreedySearch differentiate logits only (not
-# is_probs=True) and are offered the same way
+# sequence_log_probs / SequenceLogProbabilities are not TorchScript (the reference scripts its
+# Union[Tensor, PackedSequence] signature), ctc_greedy_search / CTCGreedySearch differentiate
+# logits only (not is_probs=True): they are offered by name but not rebound behind the
+# reference's back
 _NOT_REBOUND = ("sequence_log_probs", "SequenceLogProbabilities", "ctc_greedy_search", "CTCGreedySearch")
 _FUNCS = tuple(n for n in _F.__all__ if n not in _NOT_REBOUND)
 _CLASSES = tuple(n for n in _M.__all__ if n not in _NOT_REBOUND)
@@ -26,7 +28,7 @@ def install() -> bool:
     """Returns False if ``pydrobert.torch`` is not importable (nothing to patch)."""
     try:
         mods = [importlib.import_module(f"pydrobert.torch.{m}")
-                for m in ("_string", "functional", "modules")]
+                for m in ("_string", "_decoding", "functional", "modules")]
     except ImportError:
         return False
     for mod in mods:

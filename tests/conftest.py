@@ -71,6 +71,11 @@ def golden_ctc():
 
 
 @pytest.fixture(scope="session")
+def golden_decode():
+    return Golden("decode.npz")
+
+
+@pytest.fixture(scope="session")
 def golden_scoring():
     with open(os.path.join(GOLDEN, "scoring.json")) as f:
         return json.load(f)

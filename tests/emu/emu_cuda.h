@@ -292,6 +292,7 @@ static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline long long __double_as_longlong(double x) { long long r; memcpy(&r, &x, 8); return r; }
 static inline float __int_as_float(int x) { return emu::from_bits<float>((uint64_t)(uint32_t)x); }
 static inline int __float_as_int(float x) { return (int)(uint32_t)emu::to_bits(x); }
 using std::max;

@@ -594,3 +594,109 @@ def check_modules(F, M, dev, jit_type):
     if jit_type != "nojit":  # the checks stay dynamic in a graph (SM:1417-1450)
         with pytest.raises(Exception, match="sample dimensions must match"):
             jw(torch.randn(nb, ns + 1, device=dev), ref, hyp3)
+
+
+# ---------------------------------------------------------------------------------------
+# N-best producers' step functions
+# ---------------------------------------------------------------------------------------
+def _decode_case(golden, name):
+    p = golden.params[name]
+    get = lambda f: golden.get(name, f) if golden.has(name, f) else None  # noqa: E731
+    return p, get
+
+
+def check_golden_decode(F, dev, golden):
+    """tests/golden/decode.npz (outputs of the unmodified reference): beam_search_advance bit
+    for bit -- paths, lengths, sources, scores (the padding columns' tokens are uninitialised in
+    the reference and skipped); random_walk_advance replayed on the reference's random stream
+    where the device allows it (CPU tensors here are computed on the GPU, whose stream differs),
+    and checked against the oracle with the tokens torch drew."""
+    n = 0
+    for name in golden.names("beam"):
+        p, get = _decode_case(golden, name)
+        t = lambda a: None if a is None else torch.from_numpy(a).to(dev)  # noqa: E731
+        y_next, y_lens, lp, src = F.beam_search_advance(t(get("log_probs_t")), p["width"], t(get("log_probs_prev")),
+                                                        t(get("y_prev")), t(get("y_prev_lens")))
+        K = p["K"]
+        assert np.array_equal(y_next.cpu().numpy()[:, :, :K], get("y_next")[:, :, :K]), name
+        assert y_next.shape == get("y_next").shape, name
+        assert np.array_equal(y_lens.cpu().numpy(), get("y_next_lens")), name
+        assert np.array_equal(lp.cpu().numpy(), get("log_probs_next")), name
+        assert np.array_equal(src.cpu().numpy(), get("next_src")), name
+        assert lp.dtype == t(get("log_probs_t")).dtype
+        n += 1
+    for name in golden.names("walk"):
+        p, get = _decode_case(golden, name)
+        t = lambda a: None if a is None else torch.from_numpy(a).to(dev)  # noqa: E731
+        torch.manual_seed(p["seed"])
+        y_next, lp = F.random_walk_advance(t(get("log_probs_t")), t(get("log_probs_prev")), t(get("y_prev")),
+                                           t(get("y_prev_lens")))
+        assert y_next.shape == get("y_next").shape, name
+        N = y_next.shape[1]
+        lens = get("y_prev_lens")
+        pos = lens if lens is not None else np.full(N, get("y_prev").shape[0])
+        drawn = y_next.cpu().numpy()[pos, np.arange(N)]
+        ey, elp = O.random_walk_advance(get("log_probs_t"), get("log_probs_prev"), get("y_prev"), drawn, lens)
+        assert np.array_equal(y_next.cpu().numpy(), ey), name
+        assert np.allclose(lp.cpu().numpy(), elp, rtol=1e-6, atol=1e-6), name
+        if dev.type == "cpu" and y_next.device.type == "cpu" and not torch.cuda.is_available():
+            # same device, same stream as the reference's run: the draw itself reproduces
+            assert np.array_equal(y_next.numpy(), get("y_next")), name
+        n += 1
+    return n
+
+
+def check_decode_vs_oracle(F, dev, seed=0):
+    """Random shapes incl. ties (coarse dtypes), too-narrow candidate sets, strided inputs, a
+    vocabulary-sized step, and the error messages (_decoding.py:95-116, 1249-1265)."""
+    g = torch.Generator().manual_seed(seed)
+    for dtype in (torch.float32, torch.float64, torch.bfloat16, torch.float16):
+        for (N, Kp, V, W, S) in ((3, 4, 50, 6, 5), (2, 2, 3, 9, 2), (4, 8, 2000, 8, 10), (1, 1, 1, 1, 0)):
+            lpt = torch.randn(N, Kp, V, generator=g).to(dtype)
+            lpp = torch.randn(N, Kp, generator=g).to(dtype)
+            yp = torch.randint(0, V, (S, N, Kp), generator=g)
+            lens = torch.randint(0, S + 1, (N, Kp), generator=g)
+            for ln in (None, lens):
+                got = F.beam_search_advance(lpt.to(dev), W, lpp.to(dev), yp.to(dev), None if ln is None else ln.to(dev))
+                f64 = dtype == torch.float64
+                npd = lambda a: a.double().numpy() if f64 else a.float().numpy()  # noqa: E731
+                if dtype in (torch.bfloat16, torch.float16):
+                    # the oracle sums in fp32 and rounds like torch: emulate the rounding
+                    cand = (lpp.float().unsqueeze(2) + lpt.float()).to(dtype).float().numpy()
+                    exp = O.beam_search_advance(cand, W, np.zeros((N, Kp), np.float32), yp.numpy(),
+                                                None if ln is None else ln.numpy())
+                else:
+                    exp = O.beam_search_advance(npd(lpt), W, npd(lpp), yp.numpy(), None if ln is None else ln.numpy())
+                assert np.array_equal(got[0].cpu().numpy(), exp[0]), (dtype, N, Kp, V, W, S)
+                assert np.array_equal(got[1].cpu().numpy(), exp[1])
+                assert np.array_equal(got[2].float().cpu().numpy() if not f64 else got[2].cpu().numpy(),
+                                      exp[2].astype(np.float64 if f64 else np.float32))
+                assert np.array_equal(got[3].cpu().numpy(), exp[3])
+    # strided log-probabilities (a transposed view)
+    lpt = torch.randn(7, 3, 4, generator=g).permute(1, 2, 0)
+    got = F.beam_search_advance(lpt.to(dev), 5, torch.zeros(3, 4).to(dev), torch.zeros((0, 3, 4), dtype=torch.long).to(dev))
+    exp = O.beam_search_advance(lpt.numpy(), 5, np.zeros((3, 4), np.float32), np.zeros((0, 3, 4), np.int64))
+    assert np.array_equal(got[3].cpu().numpy(), exp[3]) and np.array_equal(got[0].cpu().numpy(), exp[0])
+    z = torch.zeros
+    with pytest.raises(RuntimeError, match="log_probs_t must be 3 dimensional"):
+        F.beam_search_advance(z(2, 3).to(dev), 1, z(2, 3).to(dev), z(0, 2, 3, dtype=torch.long).to(dev))
+    with pytest.raises(RuntimeError, match="Expected width to be >= 1"):
+        F.beam_search_advance(z(2, 3, 4).to(dev), 0, z(2, 3).to(dev), z(0, 2, 3, dtype=torch.long).to(dev))
+    with pytest.raises(RuntimeError, match="Expected log_probs_prev to be of shape"):
+        F.beam_search_advance(z(2, 3, 4).to(dev), 1, z(2, 4).to(dev), z(0, 2, 3, dtype=torch.long).to(dev))
+    with pytest.raises(RuntimeError, match="Invalid lengths for t=0"):
+        F.beam_search_advance(z(2, 3, 4).to(dev), 1, z(2, 3).to(dev), z(0, 2, 3, dtype=torch.long).to(dev),
+                              torch.ones(2, 3, dtype=torch.long).to(dev))
+    with pytest.raises(RuntimeError, match="log_probs_t must be 2-dimensional"):
+        F.random_walk_advance(z(2, 3, 4).to(dev), z(2).to(dev), z(0, 2, dtype=torch.long).to(dev))
+    with pytest.raises(RuntimeError, match="Expected dim 1 of y_prev"):
+        F.random_walk_advance(z(2, 3).to(dev), z(2).to(dev), z(0, 3, dtype=torch.long).to(dev))
+    # greedy decoding through the step function (tests/test_decoding.py:283-294 of the reference)
+    T, N, C = 9, 4, 20
+    logits = torch.randn(T, N, C, generator=g).to(dev)
+    y = torch.empty((0, N, 1), dtype=torch.long, device=dev)
+    lp = torch.zeros((N, 1), device=dev)
+    for lt in logits:
+        y, _, lp, _ = F.beam_search_advance(lt.unsqueeze(1), 1, lp, y)
+    mx, am = logits.max(2)
+    assert torch.equal(y.squeeze(2), am) and torch.allclose(lp.squeeze(1), mx.sum(0))

@@ -637,3 +637,11 @@ def test_device_selected_call_in_cuda_graph(F, dev, which):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, want2)
+
+
+def test_decode_steps_golden_and_oracle(F, dev, golden_decode):
+    """beam_search_advance / random_walk_advance against the reference's outputs
+    and the oracle, device and host tensors."""
+    assert PC.check_golden_decode(F, dev, golden_decode) == 26
+    PC.check_decode_vs_oracle(F, dev)
+    assert PC.check_golden_decode(F, torch.device("cpu"), golden_decode) == 26

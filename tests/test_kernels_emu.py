@@ -459,3 +459,10 @@ def test_completion_fill_staged_rows(F, N, batch_first):
 
 def test_ctc_masked_classes(F):
     PC.check_ctc_masked_classes(F, DEV)
+
+
+def test_decode_steps_golden_and_oracle(F, golden_decode):
+    """beam_search_advance / random_walk_advance against the reference's outputs
+    and the oracle."""
+    assert PC.check_golden_decode(F, DEV, golden_decode) == 26
+    PC.check_decode_vs_oracle(F, DEV)

@@ -284,3 +284,23 @@ def test_ctc_greedy_oracle_against_reference_fixture(golden_ctc):
                                    atol=1e-30 if p["is_probs"] else (3e-6 if p["dtype"] == "float32" else 1e-12)
                                    * logits.shape[1 if p["batch_first"] else 0], err_msg=name)
     assert len(golden_ctc.params) == 106
+
+
+def test_oracle_decode_steps_match_reference(golden_decode):
+    """oracle.beam_search_advance / random_walk_advance pinned by the reference's outputs."""
+    g = golden_decode
+    for name in g.names("beam"):
+        p = g.params[name]
+        lens = g.get(name, "y_prev_lens") if g.has(name, "y_prev_lens") else None
+        y, ln, lp, src = O.beam_search_advance(g.get(name, "log_probs_t"), p["width"], g.get(name, "log_probs_prev"),
+                                               g.get(name, "y_prev"), lens)
+        K = p["K"]
+        assert np.array_equal(y[:, :, :K], g.get(name, "y_next")[:, :, :K]) and y.shape == g.get(name, "y_next").shape
+        assert np.array_equal(ln, g.get(name, "y_next_lens")) and np.array_equal(src, g.get(name, "next_src"))
+        assert np.array_equal(lp, g.get(name, "log_probs_next"))
+    for name in g.names("walk"):
+        lens = g.get(name, "y_prev_lens") if g.has(name, "y_prev_lens") else None
+        y, lp = O.random_walk_advance(g.get(name, "log_probs_t"), g.get(name, "log_probs_prev"), g.get(name, "y_prev"),
+                                      g.get(name, "y_t"), lens)
+        assert np.array_equal(y, g.get(name, "y_next"))
+        assert np.allclose(lp, g.get(name, "log_probs_next"), rtol=1e-6, atol=1e-7)

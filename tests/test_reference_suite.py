@@ -19,10 +19,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_PKG = os.path.join(ROOT, "baseline", "_ref")
 REF_TESTS = os.path.join(ROOT, "oracle", "_ref", "tests")
 EXPECTED_CASES = 310  # per device: what `pytest tests/test_string.py -m cpu` collects upstream
+# tests/test_decoding.py: the step functions of the N-best producers AND the reference's own
+# BeamSearch / RandomWalk modules running on them (install() rebinds the names their loops call)
+DECODING_SELECT = "beam_search or random_walk"
+EXPECTED_DECODING = 9  # per device (+ 3 cases the reference itself marks xfail under trace)
+EXPECTED_ADVANCE = 2  # test_beam_search_advance_greedy, test_beam_search_advance
 
 
-def _run(marker):
-    if not (os.path.isfile(os.path.join(REF_TESTS, "test_string.py"))
+def _run(marker, test_file="test_string.py", select=None, expected=EXPECTED_CASES):
+    if not (os.path.isfile(os.path.join(REF_TESTS, test_file))
             and os.path.isdir(os.path.join(REF_PKG, "pydrobert"))):
         pytest.skip("reference copy absent (oracle/make_ref.sh needs /root/reference)")
     env = dict(os.environ)
@@ -30,13 +35,13 @@ def _run(marker):
                                         + ([env["PYTHONPATH"]] if env.get("PYTHONPATH") else []))
     cmd = [sys.executable, "-m", "pytest", "-p", "ref_suite_plugin", "-p", "no:cacheprovider", "-q",
            "-W", "ignore", "--rootdir", REF_TESTS, "-c", os.path.join(REF_TESTS, "pytest.ini"),
-           os.path.join(REF_TESTS, "test_string.py"), "-m", marker]
+           os.path.join(REF_TESTS, test_file), "-m", marker] + (["-k", select] if select else [])
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, cwd=REF_TESTS, timeout=3000)
     tail = (r.stdout + r.stderr)[-4000:]
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
-    assert m and int(m.group(1)) == EXPECTED_CASES, tail
-    assert "failed" not in r.stdout.splitlines()[-1], tail
+    assert m and int(m.group(1)) == expected, tail
+    assert not re.search(r"\b\d+ failed", r.stdout.splitlines()[-1]), tail
 
 
 def test_reference_suite_on_emulator():
@@ -46,9 +51,19 @@ def test_reference_suite_on_emulator():
     if torch.cuda.is_available():
         pytest.skip("GPU present: the gpu-marked run below is the gate")
     _run("cpu")
+    # (the step-function cases only: the reference's BeamSearch / RandomWalk module cases train a
+    # language model first, which takes minutes on the emulator; the GPU run below has them all)
+    _run("cpu", "test_decoding.py", "beam_search_advance or random_walk_advance", EXPECTED_ADVANCE)
 
 
 @pytest.mark.gpu
 def test_reference_suite_on_b200():
     """-m gpu: the same 310 cases with CUDA tensors on the real kernels."""
     _run("gpu")
+
+
+@pytest.mark.gpu
+def test_reference_decoding_steps_on_b200():
+    """-m gpu: the reference's beam-search / random-walk tests (step functions and its own
+    BeamSearch / RandomWalk modules) on the step kernels."""
+    _run("gpu", "test_decoding.py", DECODING_SELECT, EXPECTED_DECODING)
