@@ -38,3 +38,10 @@ assert _rm.MinimumErrorRateLoss is b200lev.modules.MinimumErrorRateLoss
 def pytest_report_header(config):
     return "reference names rebound to b200lev ({})".format(
         "CUDA: " + torch.cuda.get_device_name(0) if torch.cuda.is_available() else "SIMT emulator")
+
+
+def pytest_runtest_setup(item):
+    # the reference's statistical cases (e.g. test_random_walk: a 10 000-step sample mean within
+    # 1e-2) draw from the global generator without seeding it: pin it per test so that a run of
+    # this suite is reproducible
+    torch.manual_seed(int(os.environ.get("B200LEV_REF_SUITE_SEED", "1")))
