@@ -151,38 +151,66 @@ __device__ __forceinline__ void lev_cta_strip(const LevParams& p, const int pair
 
     // one wavefront step; ALL = every lane has a row to update (32 <= s <= steps), which
     // removes the divergent branch from the steady state
-    auto step = [&](auto ALL, const int s) {
-        constexpr bool all_active = decltype(ALL)::value;
-        // ---- flow control (warp-uniform): next LEV_CTA_PUB rows of the left boundary ----
+    // the three parts of a wavefront step.  flow / publish only act on every LEV_CTA_PUB-th
+    // row; the steady state below runs them at fixed places of an unrolled block of rows.
+    auto flow = [&](const int s) {  // wait for the next LEV_CTA_PUB rows of the left boundary
         if (!first && (s & (LEV_CTA_PUB - 1)) == 1 && s <= steps) {
             const int need = min(s + LEV_CTA_PUB - 1, steps);
             while (lev_ld_volatile_shared(done_in) < need) __nanosleep(32);
             LEV_CTA_FENCE();
         }
+    };
+    auto publish = [&](const int s) {  // rows <= s - 31 of this strip's boundary are out
+        if (!last) {
+            const int i31 = s - 31;
+            if (i31 >= 1 && ((i31 & (LEV_CTA_PUB - 1)) == 0 || i31 == steps)) {
+                __syncwarp();
+                if (is31) {
+                    LEV_CTA_FENCE();
+                    lev_st_volatile_shared(done + k, i31);
+                }
+            }
+        }
+    };
+    // ALL = every lane has a row to update (32 <= s <= steps): no divergent branch.  Lane 0's
+    // left neighbour is the boundary column: EVERY lane reads that word (one broadcast LDS) and
+    // selects, instead of lane 0 branching away to fetch it.
+    // PRE: the boundary word(s) and the token of this row were loaded ahead (steady-state blocks)
+    auto core = [&](auto ALL, const int s, auto PRE, const int pre_v, const int pre_a, const int pre_b,
+                    const int pre_ht) {
+        constexpr bool all_active = decltype(ALL)::value;
+        constexpr bool pre = decltype(PRE)::value;
+        (void)pre_a; (void)pre_b;
         const V sh_v = __shfl_up_sync(LEV_FULL_MASK, v[C - 1], 1);
         // past the last row lane 0 is idle; whatever it reads there is never used
-        V hand_v = sh_v;
-        if (is0) hand_v = first ? BIG : as_v(lev_lds32_sync(in_v_a + 4u * (unsigned)s));
+        const V bnd_v = first ? BIG : as_v(pre ? pre_v : lev_lds32_sync(in_v_a + 4u * (unsigned)s));
+        const V hand_v = is0 ? bnd_v : sh_v;
         const V diag_v = pl_v;
         pl_v = hand_v;
         V hand_m = (V)0, diag_m = (V)0, hand_ob = BIG, hand_oj = (V)0;
         if (COUNT) {
-            hand_m = __shfl_up_sync(LEV_FULL_MASK, m[C - 1], 1);
-            if (is0) hand_m = first ? (V)0 : as_v(lev_lds32_sync(in_a_a + 4u * (unsigned)s));
+            const V sh_m = __shfl_up_sync(LEV_FULL_MASK, m[C - 1], 1);
+            const V bnd_m = first ? (V)0 : as_v(pre ? pre_a : lev_lds32_sync(in_a_a + 4u * (unsigned)s));
+            hand_m = is0 ? bnd_m : sh_m;
             diag_m = pl_m;
             pl_m = hand_m;
         }
         if (FLT_COST) {
-            hand_ob = __shfl_up_sync(LEV_FULL_MASK, ob, 1);
-            hand_oj = __shfl_up_sync(LEV_FULL_MASK, oj, 1);
-            if (is0) {
-                hand_ob = first ? BIG : as_v(lev_lds32_sync(in_a_a + 4u * (unsigned)s));
-                hand_oj = first ? (V)0 : as_v(lev_lds32_sync(in_b_a + 4u * (unsigned)s));
-            }
+            const V sh_ob = __shfl_up_sync(LEV_FULL_MASK, ob, 1);
+            const V sh_oj = __shfl_up_sync(LEV_FULL_MASK, oj, 1);
+            const V bnd_ob = first ? BIG : as_v(pre ? pre_a : lev_lds32_sync(in_a_a + 4u * (unsigned)s));
+            const V bnd_oj = first ? (V)0 : as_v(pre ? pre_b : lev_lds32_sync(in_b_a + 4u * (unsigned)s));
+            hand_ob = is0 ? bnd_ob : sh_ob;
+            hand_oj = is0 ? bnd_oj : sh_oj;
         }
         (void)hand_m; (void)diag_m; (void)hand_ob; (void)hand_oj;
-        const int ht = ht_next;
-        ht_next = lev_lds32(hyp_a + 4u * (unsigned)(s + 1));
+        int ht;
+        if (pre) {
+            ht = pre_ht;
+        } else {
+            ht = ht_next;
+            ht_next = lev_lds32(hyp_a + 4u * (unsigned)(s + 1));
+        }
         const bool active = all_active || (unsigned)(s - lane - 1) < (unsigned)steps;
         if (active) {
             if (COUNT) {  // SM:292-314
@@ -259,25 +287,38 @@ __device__ __forceinline__ void lev_cta_strip(const LevParams& p, const int pair
                 orow[(int64_t)s * p.out_si] = val;
             }
         }
-        // ---- publish (warp-uniform test on s): rows <= s - 31 of this strip's boundary ----
-        if (!last) {
-            const int i31 = s - 31;
-            if (i31 >= 1 && ((i31 & (LEV_CTA_PUB - 1)) == 0 || i31 == steps)) {
-                __syncwarp();
-                if (is31) {
-                    LEV_CTA_FENCE();
-                    lev_st_volatile_shared(done + k, i31);
-                }
-            }
-        }
+    };
+    auto step = [&](auto ALL, const int s) {
+        flow(s);
+        core(ALL, s, std::false_type(), 0, 0, 0, 0);
+        publish(s);
     };
 #ifdef LEV_CTA_CLOCK
     const long long clk0 = clock64();
 #endif
     int s = 1;
-    for (; s <= 31 && s <= nsteps; ++s) step(std::false_type(), s);   // ramp-up
-    for (; s <= steps; ++s) step(std::true_type(), s);                // steady state
-    for (; s <= nsteps; ++s) step(std::false_type(), s);              // ramp-down
+    for (; s <= 32 && s <= nsteps; ++s) {  // ramp-up (and row 32, so that blocks start at s = 1 mod PUB)
+        if (s <= 31 || s > steps)
+            step(std::false_type(), s);
+        else
+            step(std::true_type(), s);
+    }
+    // steady state in blocks of LEV_CTA_PUB rows starting at s = 1 (mod PUB): one wait for the
+    // left boundary at the top, the progress word published after the row with s - 31 = 0 (mod
+    // PUB) -- fixed places, so the rows themselves carry no flow-control tests
+    static_assert(LEV_CTA_PUB == 8, "the block below assumes 31 = PUB - 1 (mod PUB)");
+    // (fetching the block's boundary words and tokens up front instead of one shared-memory
+    // load per row was measured too: no gain, 17 more registers)
+    for (; s + LEV_CTA_PUB - 1 <= steps; s += LEV_CTA_PUB) {
+        flow(s);
+#pragma unroll
+        for (int u = 0; u < LEV_CTA_PUB; ++u) {
+            core(std::true_type(), s + u, std::false_type(), 0, 0, 0, 0);
+            if (u == LEV_CTA_PUB - 2) publish(s + u);  // s + u - 31 = 0 (mod PUB)
+        }
+    }
+    for (; s <= steps; ++s) step(std::true_type(), s);    // what is left of the steady state
+    for (; s <= nsteps; ++s) step(std::false_type(), s);  // ramp-down
 #ifdef LEV_CTA_CLOCK
     if (lane == 0 && pair == 0) {  // debug: cycles of this strip's step loop
         p.gmeta[2 + 2 * k] = (int)(clock64() - clk0);
