@@ -330,7 +330,7 @@ __device__ __forceinline__ void lev_cta_strip(const LevParams& p, const int pair
 }
 
 template <typename V, bool COUNT, int MODE>
-__global__ void __launch_bounds__(512) lev_cta_kernel(const LevParams p, const LevCtaGeom geo) {
+__global__ void __launch_bounds__(128, 4) lev_cta_kernel(const LevParams p, const LevCtaGeom geo) {
     LEV_DYN_SMEM(int, smem);
     if (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) return;  // stand-by lev_warp_kernel takes over
     constexpr int NCH = LevCtaChan<V, COUNT>::NCH;
@@ -404,8 +404,10 @@ static int lev_cta_launch_one(const LevParams& p, cudaStream_t st) {
     // enough warps to cover a row with C = 1 strips, at most 4: with C up to 16 columns per
     // lane four concurrent strips span 2048 columns, and 2-3 CTAs share an SM
     int NW = (p.R + 1 + 31) / 32;
-    int maxw = 4;
-    if (const char* e = getenv("B200LEV_CTA_WARPS")) maxw = atoi(e);  // tuning experiments
+    // (8 / 16 / 32 warps per pair were measured on config 5: 8 ties with 4 on 256 pairs and loses
+    // 30 % on 1184, more warps lose everywhere -- the strips of a pair run at the pace of the
+    // first one, so extra warps only add pipeline fill)
+    const int maxw = 4;
     geo.NW = NW < 2 ? 2 : (NW > maxw ? maxw : NW);
     geo.Smax = (p.R + 1 + 511) / 512;
     if (geo.Smax < geo.NW) geo.Smax = geo.NW;
