@@ -530,6 +530,7 @@ extern "C" int b200lev_completion_count(const b200lev_tokens_t* ref, const b200l
     if (cudaMemsetAsync(dbits, 0, sizeof(uint32_t) * (size_t)L.Hout * L.P * L.Wd, st) != cudaSuccess)
         return lev_check_cuda("memset");
     p.uid = uid;
+    p.ndist = ndist;
     p.dbits = dbits;
     p.Wd = (int)L.Wd;
     p.umax = umax;

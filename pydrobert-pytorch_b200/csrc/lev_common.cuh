@@ -128,6 +128,7 @@ struct LevParams {
     int Hout;
     // MASK
     const int32_t* uid;  // [Nref][Rp] rank of ref[j] among the pair's distinct tokens
+    const int32_t* ndist;  // [Nref] number of distinct tokens of the reference
     uint32_t* dbits;     // [Hout][P][Wd]
     int Wd;
     int* umax;

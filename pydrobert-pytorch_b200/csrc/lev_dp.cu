@@ -33,11 +33,17 @@
 template <typename V, bool COUNT, int MODE>
 struct LevBufs {
     static constexpr bool FLT_COST = !std::is_same<V, int>::value && !COUNT;
-    static constexpr int NB = (COUNT ? 2 : (FLT_COST ? 3 : 1)) + (MODE == LEV_MODE_MASK ? 1 : 0);
+    // MASK: + row minima + the chained bitmap word handed from strip to strip
+    static constexpr int NB = (COUNT ? 2 : (FLT_COST ? 3 : 1)) + (MODE == LEV_MODE_MASK ? 2 : 0);
 };
 
 // One pair on one warp.  PASS: 0 = the only pass (FINAL/PREFIX) or the row-minimum
-// pass of MASK; 1 = the equality pass of MASK.
+// pass of MASK; 1 = the equality pass of MASK, one global atomicOr per flagged position;
+// 2 = the equality pass for references with at most 32 distinct tokens: the row's bitmap is
+// ONE word, OR-ed along the lane chain with the shuffle that also carries the boundary cell
+// (and from strip to strip through a shared-memory column), and stored once per row by the
+// last lane -- no atomics, no divergent branch per cell, and the largest set size (SM:510-511)
+// falls out of the same word.  Returns that size (valid on lane 31).
 // tokens that do not fit in int32 (B200LEV_FLAG_WIDE_TOKENS): read the caller's tensors
 // directly and compare in 64 bits.  Slow (strided gathers) but exact; uniform per launch.
 __device__ __forceinline__ int64_t lev_load_raw(const void* base, int elem_bytes, int64_t idx) {
@@ -50,7 +56,7 @@ __device__ __forceinline__ int64_t lev_load_raw(const void* base, int elem_bytes
 }
 
 template <typename V, bool COUNT, int MODE, int C, int PASS, bool WIDE>
-__device__ __forceinline__ void lev_warp_pair(const LevParams& p, const int pair, const int r,
+__device__ __forceinline__ int lev_warp_pair(const LevParams& p, const int pair, const int r,
                                               const int h, const int steps,
                                               const int* __restrict__ hyp_s_,
                                               V* __restrict__ bufs, const int Hs) {
@@ -60,7 +66,9 @@ __device__ __forceinline__ void lev_warp_pair(const LevParams& p, const int pair
     constexpr bool FLT_COST = !IS_INT && !COUNT;
     constexpr bool RMIN = (MODE == LEV_MODE_MASK && PASS == 0);
     constexpr bool EQ = (MODE == LEV_MODE_MASK && PASS == 1);
+    constexpr bool EQC = (MODE == LEV_MODE_MASK && PASS == 2);
     constexpr int W = 32 * C;
+    int set_max = 0;  // EQC: largest number of distinct next tokens over the rows (lane 31)
     const int lane = threadIdx.x & 31;
     const int S = (r + W) / W;  // ceil((r + 1) / W)
     const int refcol = pair / p.ref_group;
@@ -71,8 +79,9 @@ __device__ __forceinline__ void lev_warp_pair(const LevParams& p, const int pair
     V* __restrict__ bnd_v = bufs;
     V* __restrict__ bnd_a = bufs + Hs;      // COUNT: counts ; FLT_COST: run-origin value
     V* __restrict__ bnd_b = bufs + 2 * Hs;  // FLT_COST: fl(origin * del)
-    V* __restrict__ rowmin = bufs + (LevBufs<V, COUNT, MODE>::NB - 1) * Hs;  // MASK only
-    (void)bnd_a; (void)bnd_b; (void)rowmin;
+    V* __restrict__ rowmin = bufs + (LevBufs<V, COUNT, MODE>::NB - 2) * Hs;  // MASK only
+    unsigned* __restrict__ bitcol = reinterpret_cast<unsigned*>(bufs + (LevBufs<V, COUNT, MODE>::NB - 1) * Hs);
+    (void)bnd_a; (void)bnd_b; (void)rowmin; (void)bitcol;
 
     for (int k = 0; k < S; ++k) {
         const bool first = (k == 0), last = (k == S - 1);
@@ -97,8 +106,12 @@ __device__ __forceinline__ void lev_warp_pair(const LevParams& p, const int pair
                 rt[c] = (j >= 1) ? (Tok)rtok[j - 1] : (Tok)0;
             ud[c] = -1;
             if (EQ) ud[c] = (j >= 0 && j < r) ? p.uid[(int64_t)refcol * p.Rp + j] : -1;
+            // EQC: the bit of this column's token (ranks < 32), 0 for columns that are no target
+            if (EQC) ud[c] = (j >= 0 && j < r) ? (int)(1u << (p.uid[(int64_t)refcol * p.Rp + j] & 31)) : 0;
         }
         (void)m; (void)jd; (void)ud;
+        unsigned bitrun = 0u;  // EQC chain register
+        (void)bitrun;
         // chain registers: what this lane publishes to lane+1 at the next step
         V ob = BIG, oj = (V)0, rmrun = BIG;
         (void)ob; (void)oj; (void)rmrun;
@@ -132,7 +145,12 @@ __device__ __forceinline__ void lev_warp_pair(const LevParams& p, const int pair
                     const V sh_rm = __shfl_up_sync(LEV_FULL_MASK, rmrun, 1);
                     in_rm = (lane == 0) ? (first ? BIG : rowmin[32 + s]) : sh_rm;
                 }
-                (void)in_m; (void)diag_m; (void)in_ob; (void)in_oj; (void)in_rm;
+                unsigned in_bits = 0u;
+                if (EQC) {
+                    const unsigned sh_b = __shfl_up_sync(LEV_FULL_MASK, bitrun, 1);
+                    in_bits = (lane == 0) ? (first ? 0u : bitcol[32 + s]) : sh_b;
+                }
+                (void)in_m; (void)diag_m; (void)in_ob; (void)in_oj; (void)in_rm; (void)in_bits;
                 const int i = s - lane;  // the row this lane updates now
                 if (i >= 1 && i <= steps) {
                     const Tok ht = hyp_s[32 + i - 1];
@@ -206,7 +224,23 @@ __device__ __forceinline__ void lev_warp_pair(const LevParams& p, const int pair
                                          1u << (ud[c] & 31));
                         }
                     }
+                    if (EQC) {  // the same test, branch-free, into the row's one-word bitmap
+                        const V mn = rowmin[32 + i];
+                        unsigned bits = in_bits;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) bits |= v[c] == mn ? (unsigned)ud[c] : 0u;
+                        bitrun = bits;
+                    }
                     if (lane == 31) {
+                        if (EQC) {
+                            if (!last) {
+                                bitcol[32 + i] = bitrun;
+                            } else {
+                                p.dbits[((int64_t)i * p.P + pair) * p.Wd] = bitrun;
+                                const int cnt = __popc(bitrun);
+                                set_max = cnt > set_max ? cnt : set_max;
+                            }
+                        }
                         if (!last) {
                             bnd_v[32 + i] = v[C - 1];
                             if (COUNT) bnd_a[32 + i] = m[C - 1];
@@ -227,14 +261,21 @@ __device__ __forceinline__ void lev_warp_pair(const LevParams& p, const int pair
             p.out[pair] = lev_finalize((float)(COUNT ? m[C - 1] : v[C - 1]), p, r, h > 0);
         __syncwarp();
     }
+    return set_max;
 }
 
+// Returns -1 when the largest target set still has to be counted from the bitmaps in global
+// memory (atomic pass), else that size as lane 31 saw it (chained pass).
 template <typename V, bool COUNT, int MODE, int C, bool WIDE = false>
-__device__ __forceinline__ void lev_warp_pair_all(const LevParams& p, int pair, int r, int h,
-                                                  int steps, const int* hyp_s, V* bufs, int Hs) {
+__device__ __forceinline__ int lev_warp_pair_all(const LevParams& p, int pair, int r, int h,
+                                                 int steps, const int* hyp_s, V* bufs, int Hs,
+                                                 bool one_word) {
     lev_warp_pair<V, COUNT, MODE, C, 0, WIDE>(p, pair, r, h, steps, hyp_s, bufs, Hs);
-    if (MODE == LEV_MODE_MASK)
+    if (MODE == LEV_MODE_MASK) {
+        if (one_word) return lev_warp_pair<V, COUNT, MODE, C, 2, WIDE>(p, pair, r, h, steps, hyp_s, bufs, Hs);
         lev_warp_pair<V, COUNT, MODE, C, 1, WIDE>(p, pair, r, h, steps, hyp_s, bufs, Hs);
+    }
+    return -1;
 }
 
 // CMASK: bit c set => the kernel carries a C = 2^c variant (1, 2, 4, 8); each pair
@@ -270,17 +311,20 @@ __global__ void __launch_bounds__(256) lev_warp_kernel(const LevParams p) {
         }
         __syncwarp();
         const int cols = r + 1;
+        // MASK: a reference with at most 32 distinct tokens keeps a row's bitmap in one word
+        const bool one_word = MODE == LEV_MODE_MASK && p.ndist[pair / p.ref_group] <= 32;
+        int set_max = -1;
         if (wide)
-            lev_warp_pair_all<V, COUNT, MODE, (CMASK & 8) ? 8 : ((CMASK & 4) ? 4 : ((CMASK & 2) ? 2 : 1)), true>(
-                p, pair, r, h, steps, hyp_s, bufs, Hs);
+            set_max = lev_warp_pair_all<V, COUNT, MODE, (CMASK & 8) ? 8 : ((CMASK & 4) ? 4 : ((CMASK & 2) ? 2 : 1)), true>(
+                p, pair, r, h, steps, hyp_s, bufs, Hs, one_word);
         else if ((CMASK & 1) && (cols <= 32 || !(CMASK & 14)))
-            lev_warp_pair_all<V, COUNT, MODE, 1>(p, pair, r, h, steps, hyp_s, bufs, Hs);
+            set_max = lev_warp_pair_all<V, COUNT, MODE, 1>(p, pair, r, h, steps, hyp_s, bufs, Hs, one_word);
         else if ((CMASK & 2) && (cols <= 64 || !(CMASK & 12)))
-            lev_warp_pair_all<V, COUNT, MODE, 2>(p, pair, r, h, steps, hyp_s, bufs, Hs);
+            set_max = lev_warp_pair_all<V, COUNT, MODE, 2>(p, pair, r, h, steps, hyp_s, bufs, Hs, one_word);
         else if ((CMASK & 4) && (cols <= 128 || !(CMASK & 8)))
-            lev_warp_pair_all<V, COUNT, MODE, 4>(p, pair, r, h, steps, hyp_s, bufs, Hs);
+            set_max = lev_warp_pair_all<V, COUNT, MODE, 4>(p, pair, r, h, steps, hyp_s, bufs, Hs, one_word);
         else if (CMASK & 8)
-            lev_warp_pair_all<V, COUNT, MODE, 8>(p, pair, r, h, steps, hyp_s, bufs, Hs);
+            set_max = lev_warp_pair_all<V, COUNT, MODE, 8>(p, pair, r, h, steps, hyp_s, bufs, Hs, one_word);
 
         if (MODE == LEV_MODE_PREFIX) {
             // SM:279-285 (row 0) and SM:379-386 (tail := padding)
@@ -299,14 +343,19 @@ __global__ void __launch_bounds__(256) lev_warp_kernel(const LevParams p) {
                 atomicOr(p.dbits + (int64_t)pair * p.Wd + (u >> 5), 1u << (u & 31));
             }
             // SM:510-511: largest target set of this pair -> global maximum U
-            __threadfence();
-            __syncwarp();
             int mx = 0;
-            for (int i = lane; i <= steps && i < p.Hout; i += 32) {
-                const uint32_t* row = p.dbits + ((int64_t)i * p.P + pair) * p.Wd;
-                int cnt = 0;
-                for (int w = 0; w < p.Wd; ++w) cnt += __popc(__ldcg(row + w));
-                mx = cnt > mx ? cnt : mx;
+            if (one_word) {  // lane 31 counted the rows' words as it stored them; row 0 holds one token
+                mx = __shfl_sync(LEV_FULL_MASK, set_max, 31);
+                if (r > 0 && p.Hout > 0 && mx < 1) mx = 1;
+            } else {
+                __threadfence();
+                __syncwarp();
+                for (int i = lane; i <= steps && i < p.Hout; i += 32) {
+                    const uint32_t* row = p.dbits + ((int64_t)i * p.P + pair) * p.Wd;
+                    int cnt = 0;
+                    for (int w = 0; w < p.Wd; ++w) cnt += __popc(__ldcg(row + w));
+                    mx = cnt > mx ? cnt : mx;
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {

@@ -466,3 +466,12 @@ def test_decode_steps_golden_and_oracle(F, golden_decode):
     and the oracle."""
     assert PC.check_golden_decode(F, DEV, golden_decode) == 26
     PC.check_decode_vs_oracle(F, DEV)
+
+
+def test_completion_many_distinct_tokens(F):
+    """Mask mode with more than 32 distinct reference tokens (bitmaps of several words, the
+    atomic equality pass) next to the one-word chained pass (few distinct tokens), single- and
+    multi-strip references."""
+    for R, H, N, V in ((40, 45, 7, 1000), (300, 40, 3, 2000), (70, 30, 5, 40), (300, 35, 2, 20)):
+        PC.check_vs_oracle(F, DEV, seed=R + V, R=R, H=H, N=N, V=V, costs=(1, 1, 1), include_eos=True,
+                           norm=False, exclude_last=False, min_frac=0.5)
