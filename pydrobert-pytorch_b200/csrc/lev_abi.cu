@@ -525,7 +525,7 @@ extern "C" int b200lev_completion_count(const b200lev_tokens_t* ref, const b200l
     int64_t* dtok = (int64_t*)(ws + L.off_dtok);
     int32_t* ndist = (int32_t*)(ws + L.off_ndist);
     uint32_t* dbits = (uint32_t*)(ws + L.off_dbits);
-    rc = lev_launch_uid(ref, p.ref_len, uid, dtok, ndist, L.Rp, st);
+    rc = lev_launch_uid(ref, p.ref_tok, p.wide_flag, p.ref_len, uid, dtok, ndist, L.Rp, st);
     if (rc) return rc;
     if (cudaMemsetAsync(dbits, 0, sizeof(uint32_t) * (size_t)L.Hout * L.P * L.Wd, st) != cudaSuccess)
         return lev_check_cuda("memset");

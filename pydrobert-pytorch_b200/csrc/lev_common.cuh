@@ -198,7 +198,8 @@ int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
                       cudaStream_t st, void* after_uid, bool short_form);
 // 0: off, 1: forced (tests; runs whatever the references look like), 2: device-selected
 int lev_bitvec_mode();
-int lev_launch_uid(const b200lev_tokens_t* ref, const int32_t* ref_len, int32_t* uid,
+int lev_launch_uid(const b200lev_tokens_t* ref, const int32_t* packed, const int* state,
+                   const int32_t* ref_len, int32_t* uid,
                    int64_t* dtok, int32_t* ndist, int64_t Rp, cudaStream_t st);
 int lev_launch_completion_fill(const uint32_t* dbits, const int64_t* dtok, int64_t Rp,
                                int64_t Hout, int64_t P, int64_t Wd, int ref_group, int64_t U,
