@@ -206,6 +206,16 @@ lev_completion_fill_kernel(const uint32_t* __restrict__ dbits, const int64_t* __
             // then + 64 ...; the counts of the rows travel by shuffle.  All of it in 32 bits
             // (a run is 32 U elements) with the divisions by U hoisted out of the loop.
             const int Ui = (int)U, Usi = (int)Us, total = 32 * Ui;
+            if (((i * out_si + (int64_t)n0 * U) & 1) != 0) {
+                // the run starts on an odd element (odd U times odd row count): 8-byte stores
+                for (int e = lane; e < total; e += 32) {
+                    const int rw = e / Ui, kk = e - rw * Ui;
+                    const int c = __shfl_sync(__activemask(), cnt, rw);
+                    dst[e] = kk < c ? buf[rw * Usi + kk] : padding;
+                }
+                __syncwarp();
+                continue;
+            }
             const int q64 = 64 / Ui, r64 = 64 - q64 * Ui;
             int row = (2 * lane) / Ui, k = 2 * lane - row * Ui;
             for (int e = 2 * lane; e - 2 * lane < total; e += 64) {

@@ -654,3 +654,12 @@ def test_completion_many_distinct_tokens(F, dev):
     for R, H, N, V in ((40, 45, 7, 1000), (300, 40, 3, 2000), (70, 30, 5, 40), (300, 35, 2, 20)):
         PC.check_vs_oracle(F, dev, seed=R + V, R=R, H=H, N=N, V=V, costs=(1, 1, 1), include_eos=True,
                            norm=False, exclude_last=False, min_frac=0.5)
+
+
+@pytest.mark.parametrize("N", [33, 37, 64, 65, 97])
+def test_completion_target_writer_alignment(F, dev, N):
+    """The target writer stores 16 bytes per lane where a warp's run of 32 rows starts on an even
+    element, and 8 bytes where it does not (odd set size x odd batch size): both must be exact."""
+    for V in (3, 4, 7):
+        PC.check_vs_oracle(F, dev, seed=N + V, R=21, H=19, N=N, V=V, costs=(1, 1, 1), include_eos=True,
+                           norm=False, exclude_last=False, min_frac=0.3)
