@@ -423,7 +423,10 @@ def main():
     dev = torch.device("cuda", local)
     numa_node = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        # (a short collective timeout: a rank that falls out of step must fail, not hang the box)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
         # one process per GPU: keep this rank's host buffers on its GPU's NUMA node
         numa_node = D.bind_host_to_gpu(local)
     L = _abi.lib()
@@ -506,9 +509,21 @@ def main():
     if rank == 0 and not args.no_clock_sampler:
         sampler.start()
     soak_s = 0.5
-    t_soak = time.perf_counter()
-    while time.perf_counter() - t_soak < soak_s:
-        timed_loop(step, 10)
+
+    def soak(seconds):
+        """The same step, untimed, for about `seconds` -- by a step COUNT every rank agrees on (a
+        wall-clock loop would run a different number of steps, hence of all-reduces, per rank)."""
+        t10, _ = timed_loop(step, 10)
+        t = torch.tensor([t10], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n = int(min(max(seconds * 1e3 / max(float(t.item()), 1e-3), 10), 20000))
+        done = 0
+        while done < n:
+            timed_loop(step, min(100, n - done))
+            done += min(100, n - done)
+
+    soak(soak_s)
     barrier()
     # the sampler polls up to the first timed step and again from the last one on, while the same
     # step keeps running (untimed): the clocks are those of this load, read within milliseconds of
@@ -519,9 +534,7 @@ def main():
     ms, out = timed_loop(step, args.steps)
     cells_step = sum(batches[(first_turn + k) % len(batches)][2] for k in range(args.steps)) / args.steps
     sampler.pause(False)
-    t_soak = time.perf_counter()
-    while time.perf_counter() - t_soak < 0.25:
-        timed_loop(step, 10)
+    soak(0.25)
     barrier()
     clocks = sampler.stop(0, None) if rank == 0 else None
     if clocks is not None:
@@ -555,7 +568,7 @@ def main():
     # cfg2: the same call with the bit-vector kernels switched off -- north_star's target is
     # quoted on the wavefront kernel, so it is measured live next to the path that ships
     wave = None
-    if bitvec:
+    if bitvec and wl.cfg == 2:
         saved = os.environ.get("B200LEV_BITVEC")
         os.environ["B200LEV_BITVEC"] = "0"
         try:
