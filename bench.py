@@ -394,6 +394,41 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+def measure_sharded_scoring(torch, dist, D, dev, rank, world, steps):
+    """BASELINE config 4 as a secondary line of a multi-GPU run of another config: the million
+    pairs cut over the ranks, every step = shard -> error_rate + device sums -> ONE all-reduce of
+    the 24-byte fp64 totals.  Same protocol as the main measurement (warm-up, barrier, K steps
+    between events, max over ranks); the totals are checked in the run."""
+    wl = Workload(4)
+    lo, hi = D.shard_bounds(wl.sat_pairs, rank, world)
+    ref_np, hyp_np, cells = wl.make(hi - lo, seed=900 + rank)
+    ref, hyp = torch.from_numpy(ref_np).to(dev), torch.from_numpy(hyp_np).to(dev)
+    acc = None
+    for _ in range(5):
+        er, acc = D.bulk_error_rate(ref, hyp, eos=-1)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        er, acc = D.bulk_error_rate(ref, hyp, eos=-1)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    c = torch.tensor([float(cells)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    tot = acc.cpu().tolist()
+    ok = int(tot[2]) == wl.sat_pairs
+    return {"workload": wl.name, "scaling": "strong", "pairs_total": wl.sat_pairs, "ms_per_step": ms,
+            "pairs_per_s": wl.sat_pairs / (ms * 1e-3), "gcups": float(c.item()) / (ms * 1e-3) / 1e9,
+            "collective": "one all_reduce(sum) of 3 fp64 values per step on the NCCL stream",
+            "all_reduced_pair_count_is_global": ok, "wer": tot[0] / max(tot[1], 1.0)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -676,6 +711,11 @@ def main():
         assert check["slice_matches_oracle"], "cfg4: per-pair errors differ from the oracle"
         assert int(acc[2]) == total_pairs, "cfg4: the all-reduced pair count is not the global one"
 
+    # ---- multi-GPU runs of the other configs also carry config 4 with its all-reduce ---------
+    sharded = None
+    if world > 1 and wl.cfg != 4:
+        sharded = measure_sharded_scoring(torch, dist, D, dev, rank, world, max(args.steps, 20))
+
     # ---- reduce over ranks ---------------------------------------------------------------
     dom_ms = float(prof[7] if bitvec else prof[3])
     stats = torch.tensor([ms, ms_e2e, dom_ms, ms_e2e_16 or 0.0], dtype=torch.float64, device=dev)
@@ -811,6 +851,8 @@ def main():
                 "h2d_bytes_per_step": in_bytes // 4, "d2h_bytes_per_step": out_bytes,
                 "note": "same public call, same pairs, host tensors of dtype int16 instead of int64 "
                         "(results asserted equal)"}
+        if sharded is not None:
+            line["sharded_scoring_cfg4"] = sharded
         if lit is not None:
             line["literal"] = lit
         if check is not None:

@@ -71,6 +71,11 @@ def golden_ctc():
 
 
 @pytest.fixture(scope="session")
+def golden_seqlp_packed():
+    return Golden("seqlp_packed.npz")
+
+
+@pytest.fixture(scope="session")
 def golden_decode():
     return Golden("decode.npz")
 

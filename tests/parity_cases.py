@@ -700,3 +700,23 @@ def check_decode_vs_oracle(F, dev, seed=0):
         y, _, lp, _ = F.beam_search_advance(lt.unsqueeze(1), 1, lp, y)
     mx, am = logits.max(2)
     assert torch.equal(y.squeeze(2), am) and torch.allclose(lp.squeeze(1), mx.sum(0))
+
+
+def check_golden_seqlp_packed(F, dev, golden):
+    """sequence_log_probs with PackedSequence logits (_decoding.py:1551-1586) against the
+    reference's outputs and gradients (fp32: 2e-6 relative + 2e-6 absolute)."""
+    n = 0
+    for name in golden.names("ps"):
+        p = golden.params[name]
+        data = torch.from_numpy(golden.get(name, "data")).to(dev).requires_grad_(True)
+        parts = list(data.split(p["lens"]))
+        packed = torch.nn.utils.rnn.pack_sequence(parts, enforce_sorted=p["enforce_sorted"])
+        hyp = torch.from_numpy(golden.get(name, "hyp")).to(dev)
+        out = F.sequence_log_probs(packed, hyp, p["dim"])
+        assert np.allclose(out.detach().cpu().numpy(), golden.get(name, "out"), rtol=2e-6, atol=2e-6), name
+        (grad,) = torch.autograd.grad(out, data, torch.from_numpy(golden.get(name, "grad_out")).to(dev))
+        assert np.allclose(grad.cpu().numpy(), golden.get(name, "grad"), rtol=2e-6, atol=2e-6), name
+        n += 1
+    with pytest.raises(RuntimeError, match="either a Tensor or PackedSequence"):
+        F.sequence_log_probs([1, 2], torch.zeros(2, 2, dtype=torch.long))
+    return n

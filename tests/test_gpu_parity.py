@@ -663,3 +663,7 @@ def test_completion_target_writer_alignment(F, dev, N):
     for V in (3, 4, 7):
         PC.check_vs_oracle(F, dev, seed=N + V, R=21, H=19, N=N, V=V, costs=(1, 1, 1), include_eos=True,
                            norm=False, exclude_last=False, min_frac=0.3)
+
+
+def test_sequence_log_probs_packed(F, dev, golden_seqlp_packed):
+    assert PC.check_golden_seqlp_packed(F, dev, golden_seqlp_packed) == 6

@@ -475,3 +475,7 @@ def test_completion_many_distinct_tokens(F):
     for R, H, N, V in ((40, 45, 7, 1000), (300, 40, 3, 2000), (70, 30, 5, 40), (300, 35, 2, 20)):
         PC.check_vs_oracle(F, DEV, seed=R + V, R=R, H=H, N=N, V=V, costs=(1, 1, 1), include_eos=True,
                            norm=False, exclude_last=False, min_frac=0.5)
+
+
+def test_sequence_log_probs_packed(F, golden_seqlp_packed):
+    assert PC.check_golden_seqlp_packed(F, DEV, golden_seqlp_packed) == 6
