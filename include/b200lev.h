@@ -205,6 +205,14 @@ int b200lev_mwer_backward(const float *er, const void *log_probs, int32_t dtype,
  */
 int b200lev_err_sum(const float *er, const int32_t *ref_lens, int64_t P, int32_t ref_group,
                     double *acc, void *stream);
+
+/* b200lev_final followed by b200lev_err_sum in one call: `out` as b200lev_final, and
+ * acc[0] += sum(out), acc[1] += sum over pairs of the reference length, acc[2] += #pairs (fp64,
+ * device).  Where the short-reference kernel serves the call the sums are accumulated inside it
+ * (no second kernel): the per-batch body of command_line.py:1124-1147. */
+int b200lev_final_sums(const b200lev_tokens_t *ref, const b200lev_tokens_t *hyp,
+                       const b200lev_opts_t *opts, float *out, void *workspace,
+                       size_t workspace_bytes, int32_t *flags, double *acc, void *stream);
 /* pointers into a workspace laid out by b200lev_final/prefix/completion_count */
 const int32_t *b200lev_workspace_ref_lens(const b200lev_tokens_t *ref,
                                           const b200lev_tokens_t *hyp, const void *workspace);

@@ -66,6 +66,7 @@ SIGNATURES = {
                                             c_i32, c_vp, c_vp, c_vp]),
     "b200lev_mwer_backward": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i64, c_i64, c_i64, c_i64, c_i32,
                                              c_i32, c_vp, c_vp, c_vp]),
+    "b200lev_final_sums": (ctypes.c_int, [_PT, _PT, _PO, c_vp, c_vp, c_sz, c_vp, c_vp, c_vp]),
     "b200lev_err_sum": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "b200lev_workspace_ref_lens": (c_vp, [_PT, _PT, c_vp]),
     "b200lev_workspace_hyp_lens": (c_vp, [_PT, _PT, c_vp]),

@@ -616,10 +616,9 @@ def error_sums(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: bool, 
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         out = torch.empty(n, dtype=torch.float32, device=dev)
         st = _stream(dev)
-        _abi.check(L.b200lev_final(ctypes.byref(rt), ctypes.byref(ht), ctypes.byref(o),
-                                   out.data_ptr(), ws.data_ptr(), nbytes, flags.data_ptr(), st))
-        lens = L.b200lev_workspace_ref_lens(ctypes.byref(rt), ctypes.byref(ht), ws.data_ptr())
-        _abi.check(L.b200lev_err_sum(out.data_ptr(), lens, n, ref_group, acc.data_ptr(), st))
+        _abi.check(L.b200lev_final_sums(ctypes.byref(rt), ctypes.byref(ht), ctypes.byref(o),
+                                        out.data_ptr(), ws.data_ptr(), nbytes, flags.data_ptr(),
+                                        acc.data_ptr(), st))
     return pl.back(out), acc, pl.back(flags)
 
 

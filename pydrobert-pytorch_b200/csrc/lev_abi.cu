@@ -325,7 +325,8 @@ static int lev_fork_join(const LevFork&, cudaStream_t) { return B200LEV_OK; }
 static int lev_try_bitvec(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
                           const b200lev_opts_t* o, const LevLayout& L, char* ws, int32_t* flags,
                           cudaStream_t st, int mode, float* out, int64_t out_si, int64_t out_sn,
-                          int Hout, LevFork* fork, bool* forked) {
+                          int Hout, LevFork* fork, bool* forked, double* acc = nullptr,
+                          bool* sums_done = nullptr) {
     *forked = false;
     if (!L.off_bv_ref) return 0;
     LevParams tmp;
@@ -350,14 +351,20 @@ static int lev_try_bitvec(const b200lev_tokens_t* ref, const b200lev_tokens_t* h
                                      (int32_t*)(ws + L.off_hyp_len), ws + L.off_bv_ref,
                                      ws + L.off_hyp_tok, ws + L.off_slots, forced ? nullptr : state,
                                      flags, out, out_si, Hout, st, *forked ? fork->after_uid : nullptr,
-                                     short_form);
+                                     short_form, acc);
     if (rc) return rc;
+    if (sums_done != nullptr)
+        *sums_done = short_form && mode == LEV_MODE_FINAL && acc != nullptr && !(getenv("B200LEV_BVS_SUMS") && atoi(getenv("B200LEV_BVS_SUMS")) == 0);
     return forced ? 1 : 2;
 }
 
+extern "C" int b200lev_err_sum(const float* er, const int32_t* ref_lens, int64_t P, int32_t ref_group,
+                               double* acc, void* stream);
+
 static int lev_final_impl(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
                           const b200lev_opts_t* opts, float* out, void* workspace,
-                          size_t workspace_bytes, int32_t* flags, void* stream, bool do_pack) {
+                          size_t workspace_bytes, int32_t* flags, void* stream, bool do_pack,
+                          double* acc = nullptr) {
     int rc = lev_check_tokens(ref, hyp, opts);
     if (rc) return rc;
     if (hyp->N == 0) return B200LEV_OK;
@@ -379,10 +386,16 @@ static int lev_final_impl(const b200lev_tokens_t* ref, const b200lev_tokens_t* h
     bool forked = false;
     std::lock_guard<std::mutex> fork_lock(g_fork_mu);
     if (do_pack) {
+        bool sums_done = false;
         bv = lev_try_bitvec(ref, hyp, &o, L, lev_ws_base(workspace), flags, st, LEV_MODE_FINAL, out,
-                            0, 1, 0, &fork, &forked);
+                            0, 1, 0, &fork, &forked, acc, &sums_done);
         if (bv < 0) return bv;
-        if (bv == 1) return B200LEV_OK;
+        if (bv == 1) {
+            if (acc != nullptr && !sums_done)
+                return b200lev_err_sum(out, (const int32_t*)(lev_ws_base(workspace) + L.off_ref_len), hyp->N,
+                                       o.ref_group, acc, stream);
+            return B200LEV_OK;
+        }
     }
     cudaStream_t side = lev_fork_begin(fork, forked && bv == 2);
     cudaStream_t cs = side ? side : st;  // the wavefront chain's stream
@@ -397,7 +410,21 @@ static int lev_final_impl(const b200lev_tokens_t* ref, const b200lev_tokens_t* h
         const int jr = lev_fork_join(fork, st);
         if (rc == B200LEV_OK) rc = jr;
     }
+    if (rc == B200LEV_OK && acc != nullptr)
+        rc = b200lev_err_sum(out, (const int32_t*)(lev_ws_base(workspace) + L.off_ref_len), hyp->N,
+                             o.ref_group, acc, stream);
     return rc;
+}
+
+extern "C" int b200lev_final_sums(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
+                                  const b200lev_opts_t* opts, float* out, void* workspace,
+                                  size_t workspace_bytes, int32_t* flags, double* acc, void* stream) {
+    if (!acc) {
+        lev_set_error("NULL accumulator");
+        return B200LEV_ERR_ARG;
+    }
+    if (hyp && hyp->N == 0) return B200LEV_OK;
+    return lev_final_impl(ref, hyp, opts, out, workspace, workspace_bytes, flags, stream, true, acc);
 }
 
 extern "C" int b200lev_final(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,

@@ -592,7 +592,7 @@ int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
                       const b200lev_opts_t* o, int mode, float mult, int32_t* ref_len,
                       int32_t* hyp_len, void* uid_ref, void* uid_hyp, void* lead,
                       int32_t* state, int32_t* flags, float* out, int64_t out_si, int Hout,
-                      cudaStream_t st, void* after_uid, bool short_form) {
+                      cudaStream_t st, void* after_uid, bool short_form, double* acc) {
     LevBvArgs a;
     memset(&a, 0, sizeof(a));
     a.ref = ref->data;
@@ -624,6 +624,7 @@ int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
     a.padding = (float)o->padding;
     a.out = out;
     a.out_si = out_si;
+    a.acc = (short_form && mode == LEV_MODE_FINAL && !(getenv("B200LEV_BVS_SUMS") && atoi(getenv("B200LEV_BVS_SUMS")) == 0)) ? acc : nullptr;
     if (short_form) {  // R <= 64: lane = pair, reference in registers, no tables (lev_bvshort.cu)
         if (getenv("B200LEV_TRACE"))
             fprintf(stderr, "b200lev: short bit-vector kernel, mode %d, R=%d H=%d P=%d\n", mode, a.R, a.H, a.P);

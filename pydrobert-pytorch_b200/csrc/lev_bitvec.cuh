@@ -29,6 +29,7 @@ struct LevBvArgs {
     float mult, padding;
     float* out;
     int64_t out_si;  // prefix: elements between output rows (pairs are adjacent)
+    double* acc;     // FINAL, short-reference kernel: += [sum(out), sum(ref_len per pair), #pairs] (may be NULL)
 };
 
 // Bucketed hash: 4 ways per bucket, one 128-bit read of the keys and one 32-bit read of the

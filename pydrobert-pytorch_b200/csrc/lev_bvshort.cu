@@ -26,17 +26,24 @@
 
 constexpr int LEV_BVS_WARPS = 4;
 
+template <int P>
+struct LevPath {
+    static constexpr int value = P;
+};
+
 // 16 reference positions per step pair: register k of a word holds the low halves of the tokens
-// at positions k (bits 0-15) and k + 16 (bits 16-31).  XOR with the hypothesis token's low half
-// in both lanes, clamp every half to 0 / 1 (VIMNMX.U16x2: 1 = differs) and shift the pair into
-// the accumulator with an integer multiply-add (FMA pipe): after k = 15 .. 0 bit j of the
-// accumulator says "position j differs" -- 2 ALU + 1 FMA instruction per TWO positions.
-__device__ __forceinline__ unsigned lev_bvs_neq16(const unsigned (&half)[16], unsigned vv) {
+// at positions k (bits 0-15) and k + 16 (bits 16-31).  `nvv` carries the NEGATED low half of the
+// hypothesis token in both halves: one DPX instruction (VIADDMNMX.U16x2) adds it to both
+// positions modulo 65 536 and clamps each half to 0 / 1 (1 = differs), an integer multiply-add
+// (FMA pipe) shifts the pair into the accumulator: after k = 15 .. 0 bit j of the accumulator
+// says "position j differs" -- 1 ALU + 1 FMA instruction per TWO positions.
+__device__ __forceinline__ unsigned lev_bvs_neg16(unsigned half) { return ((0u - half) & 0xffffu) * 0x00010001u; }
+__device__ __forceinline__ unsigned lev_bvs_neq16(const unsigned (&half)[16], unsigned nvv) {
     unsigned acc0 = 0u, acc1 = 0u;  // two chains of 8
 #pragma unroll
-    for (int k = 15; k >= 8; --k) acc1 = acc1 * 2u + __vminu2(half[k] ^ vv, 0x00010001u);
+    for (int k = 15; k >= 8; --k) acc1 = acc1 * 2u + __viaddmin_u16x2(half[k], nvv, 0x00010001u);
 #pragma unroll
-    for (int k = 7; k >= 0; --k) acc0 = acc0 * 2u + __vminu2(half[k] ^ vv, 0x00010001u);
+    for (int k = 7; k >= 0; --k) acc0 = acc0 * 2u + __viaddmin_u16x2(half[k], nvv, 0x00010001u);
     // acc1 holds positions 8..15 / 24..31 at bits 0..7 / 16..23: move them up by 8
     return acc0 + acc1 * 256u;
 }
@@ -65,6 +72,22 @@ __device__ __forceinline__ void lev_bvs_step(const unsigned (&eq)[W], unsigned (
 }
 
 // KIND: 0 = final value, 1 = prefix rows, 2 = prefix rows with exclude_last.
+// command_line.py:1135-1147: the totals of the bulk-scoring command, folded into the kernel that
+// produced the values (fp64 sums; of integers when the values are counts, so exact in any order);
+// three atomics per CTA.  Kept out of line: inlined, it costs the DP loop above it 18 registers.
+__device__ __forceinline__ void lev_bvs_totals(double sum_out, int sum_len, double* acc, int64_t P, bool first) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        sum_out += __shfl_xor_sync(LEV_FULL_MASK, sum_out, d);
+        sum_len += __shfl_xor_sync(LEV_FULL_MASK, sum_len, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(acc + 0, sum_out);
+        atomicAdd(acc + 1, (double)sum_len);
+        if (first) atomicAdd(acc + 2, (double)P);
+    }
+}
+
 template <typename TT, int W, int KIND>
 __global__ void __launch_bounds__(32 * LEV_BVS_WARPS, W == 1 ? 4 : 3) lev_bv_short_kernel(const LevBvArgs a) {
     constexpr bool PREFIX = KIND != 0, EXCL = KIND == 2;
@@ -75,6 +98,14 @@ __global__ void __launch_bounds__(32 * LEV_BVS_WARPS, W == 1 ? 4 : 3) lev_bv_sho
     const int R = a.R, H = a.H, Hm1 = a.H - 1;
     const int eos_lo = (int)a.eos, eos_hi = (int)(a.eos >> 32);
     const int haseos_m = a.has_eos ? -1 : 0, incl_m = a.include_eos ? -1 : 0;
+    // bulk scoring: this thread's share of the totals lives in shared memory (one slot per
+    // thread), not in registers carried through the DP loop
+    __shared__ double sums[LEV_BVS_WARPS * 32];
+    __shared__ int lens[LEV_BVS_WARPS * 32];
+    if (!PREFIX) {
+        sums[threadIdx.x] = 0.0;
+        lens[threadIdx.x] = 0;
+    }
     for (int64_t block = (int64_t)blockIdx.x * LEV_BVS_WARPS + (threadIdx.x >> 5); block < nblocks;
          block += (int64_t)gridDim.x * LEV_BVS_WARPS) {
         // lanes past the batch shadow its last pair (they compute and store the same values)
@@ -178,7 +209,12 @@ __global__ void __launch_bounds__(32 * LEV_BVS_WARPS, W == 1 ? 4 : 3) lev_bv_sho
         const bool narrow_warp = !__any_sync(LEV_FULL_MASK, outside != 0u);
         const bool wide_warp = (sizeof(TT) == 8 && __any_sync(LEV_FULL_MASK, wacc != 0)) || (!HAVE_HI && !narrow_warp);
 
-        auto position = [&](const TT tok, const int t) {
+        // PATH 0: every token of the warp's references sits in one 65 536-wide window (low halves
+        // decide); 1: low and high halves; 2 (rare): exact compares against the cached column.
+        // One copy of the hypothesis loop per path keeps the hot one contiguous in the
+        // instruction cache.
+        auto position = [&](auto path, const TT tok, const int t) {
+            constexpr int PATH = decltype(path)::value;
             const int64_t x = (int64_t)tok;
             const int v = (int)x, hi = (int)(x >> 32);
             int e = v ^ eos_lo;
@@ -197,26 +233,25 @@ __global__ void __launch_bounds__(32 * LEV_BVS_WARPS, W == 1 ? 4 : 3) lev_bv_sho
             unsigned eq[W];
 #pragma unroll
             for (int w = 0; w < W; ++w) eq[w] = 0u;
-            if (!wide_warp) {
-                const unsigned vlo = ((unsigned)v & 0xffffu) * 0x00010001u;
-                if (narrow_warp) {
-                    // every reference token of the lane lies in [base, base + 65536): a token in
-                    // the same window is equal iff the low halves are, one outside equals none
-                    // (that also covers a 64-bit token outside int32, whose low word is garbage)
-                    bool tok_ok = ((unsigned)(v - base) >> 16) == 0u;
-                    if (sizeof(TT) == 8) tok_ok = tok_ok && hi == (v >> 31);
+            if (PATH == 0) {
+                // every reference token of the lane lies in [base, base + 65536): a token in
+                // the same window is equal iff the low halves are, one outside equals none
+                // (that also covers a 64-bit token outside int32, whose low word is garbage)
+                const unsigned nlo = lev_bvs_neg16((unsigned)v & 0xffffu);
+                bool tok_ok = ((unsigned)(v - base) >> 16) == 0u;
+                if (sizeof(TT) == 8) tok_ok = tok_ok && hi == (v >> 31);
 #pragma unroll
-                    for (int w = 0; w < W; ++w)
-                        if (w == 0 || R > 32) eq[w] = tok_ok ? ~lev_bvs_neq16(rlo[w], vlo) : 0u;
-                } else {
-                    const bool tok_ok = sizeof(TT) < 8 || hi == (v >> 31);
-                    const unsigned vhi = ((unsigned)v >> 16) * 0x00010001u;
+                for (int w = 0; w < W; ++w)
+                    if (w == 0 || R > 32) eq[w] = tok_ok ? ~lev_bvs_neq16(rlo[w], nlo) : 0u;
+            } else if (PATH == 1) {
+                const unsigned nlo = lev_bvs_neg16((unsigned)v & 0xffffu);
+                const unsigned nhi = lev_bvs_neg16((unsigned)v >> 16);
+                const bool tok_ok = sizeof(TT) < 8 || hi == (v >> 31);
 #pragma unroll
-                    for (int w = 0; w < W; ++w)
-                        if (w == 0 || R > 32)
-                            eq[w] = tok_ok ? ~(lev_bvs_neq16(rlo[w], vlo) | lev_bvs_neq16(rhi[HAVE_HI ? w : 0], vhi)) : 0u;
-                }
-            } else {  // rare: exact compares against the (cached) reference column
+                for (int w = 0; w < W; ++w)
+                    if (w == 0 || R > 32)
+                        eq[w] = tok_ok ? ~(lev_bvs_neq16(rlo[w], nlo) | lev_bvs_neq16(rhi[HAVE_HI ? w : 0], nhi)) : 0u;
+            } else {
 #pragma unroll
                 for (int w = 0; w < W; ++w)
                     for (int jj = 0; jj < 32 && 32 * w + jj < rlen; ++jj)
@@ -240,58 +275,66 @@ __global__ void __launch_bounds__(32 * LEV_BVS_WARPS, W == 1 ? 4 : 3) lev_bv_sho
         if (H > 0) {
             auto ld = [&](int t) { return lev_ldg_stream(hsrc + (int64_t)(t < Hm1 ? t : Hm1) * hst); };
             int t0 = 0;
-            bool done = false;
-            if (W == 1) {
-                // two chunk buffers, rotated by NAME (the loop body is two trips): a chunk is loaded
-                // two trips before it is used and nothing touches it in between -- a rotation by
-                // register moves waits for the loads it moves; more trips per body would push the
-                // loop out of the instruction cache
-                TT bA[CH], bB[CH];
-#pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    bA[k] = ld(k);
-                    bB[k] = ld(CH + k);
-                }
-                auto trip = [&](TT (&buf)[CH]) {  // CH positions from `buf`, then its next chunk
-                    if (!done) {
-#pragma unroll
-                        for (int k = 0; k < CH; ++k) position(buf[k], t0 + k);
-#pragma unroll
-                        for (int k = 0; k < CH; ++k) buf[k] = ld(t0 + 2 * CH + k);
-                        t0 += CH;
-                        // every hypothesis of the warp has ended, or the last row is out
-                        done = t0 >= T_end || !__any_sync(LEV_FULL_MASK, live_m != 0);
-                    }
-                };
-#pragma unroll 1
-                while (!done) {
-                    trip(bA);
-                    trip(bB);
-                }
-            } else {
-                // two-word references are short of registers and long on code: one trip per loop
-                // body, the buffers rotate through register moves
-                TT cur[CH], n1[CH], n2[CH];
-#pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    cur[k] = ld(k);
-                    n1[k] = ld(CH + k);
-                }
-#pragma unroll 1
-                while (!done) {
-#pragma unroll
-                    for (int k = 0; k < CH; ++k) n2[k] = ld(t0 + 2 * CH + k);
-#pragma unroll
-                    for (int k = 0; k < CH; ++k) position(cur[k], t0 + k);
+            auto hypothesis = [&](auto path) {
+                bool done = false;
+                if (W == 1) {
+                    // two chunk buffers, rotated by NAME (the loop body is two trips): a chunk is
+                    // loaded two trips before it is used and nothing touches it in between -- a
+                    // rotation by register moves waits for the loads it moves; more trips per body
+                    // would push the loop out of the instruction cache
+                    TT bA[CH], bB[CH];
 #pragma unroll
                     for (int k = 0; k < CH; ++k) {
-                        cur[k] = n1[k];
-                        n1[k] = n2[k];
+                        bA[k] = ld(k);
+                        bB[k] = ld(CH + k);
                     }
-                    t0 += CH;
-                    done = t0 >= T_end || !__any_sync(LEV_FULL_MASK, live_m != 0);
+                    auto trip = [&](TT (&buf)[CH]) {  // CH positions from `buf`, then its next chunk
+                        if (!done) {
+#pragma unroll
+                            for (int k = 0; k < CH; ++k) position(path, buf[k], t0 + k);
+#pragma unroll
+                            for (int k = 0; k < CH; ++k) buf[k] = ld(t0 + 2 * CH + k);
+                            t0 += CH;
+                            // every hypothesis of the warp has ended, or the last row is out
+                            done = t0 >= T_end || !__any_sync(LEV_FULL_MASK, live_m != 0);
+                        }
+                    };
+#pragma unroll 1
+                    while (!done) {
+                        trip(bA);
+                        trip(bB);
+                    }
+                } else {
+                    // two-word references are short of registers and long on code: one trip per
+                    // loop body, the buffers rotate through register moves
+                    TT cur[CH], n1[CH], n2[CH];
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) {
+                        cur[k] = ld(k);
+                        n1[k] = ld(CH + k);
+                    }
+#pragma unroll 1
+                    while (!done) {
+#pragma unroll
+                        for (int k = 0; k < CH; ++k) n2[k] = ld(t0 + 2 * CH + k);
+#pragma unroll
+                        for (int k = 0; k < CH; ++k) position(path, cur[k], t0 + k);
+#pragma unroll
+                        for (int k = 0; k < CH; ++k) {
+                            cur[k] = n1[k];
+                            n1[k] = n2[k];
+                        }
+                        t0 += CH;
+                        done = t0 >= T_end || !__any_sync(LEV_FULL_MASK, live_m != 0);
+                    }
                 }
-            }
+            };
+            if (wide_warp)  // (all three conditions are warp-uniform)
+                hypothesis(LevPath<2>{});
+            else if (narrow_warp)
+                hypothesis(LevPath<0>{});
+            else if (HAVE_HI)
+                hypothesis(LevPath<1>{});
             tdone = t0 < T_end ? t0 : T_end;
         }
         if (PREFIX) {
@@ -312,6 +355,17 @@ __global__ void __launch_bounds__(32 * LEV_BVS_WARPS, W == 1 ? 4 : 3) lev_bv_sho
             float val = __fmul_rn((float)score, a.mult);
             if (a.norm) val = (rlen == 0) ? (hlen > 0 ? 1.0f : 0.0f) : val / (float)rlen;
             a.out[pc] = val;
+            if (a.acc != nullptr) {
+                if (pair < a.P) {  // (lanes shadowing the last pair do not count twice)
+                    sums[threadIdx.x] += (double)val;
+                    lens[threadIdx.x] += rlen;
+                }
+                // the warp's last block: its totals go out from inside the loop (code after the
+                // loop costs the loop ~20 registers)
+                if (block + (int64_t)gridDim.x * LEV_BVS_WARPS >= nblocks)
+                    lev_bvs_totals(sums[threadIdx.x], lens[threadIdx.x], a.acc, a.P,
+                                   blockIdx.x == 0 && threadIdx.x < 32);
+            }
         }
         a.hyp_len[pc] = hlen;
         if (pc % a.ref_group == 0) a.ref_len[rcol] = rlen;
@@ -332,7 +386,8 @@ bool lev_bvshort_supports(int elem_bytes, int64_t R) {
 template <typename TT, int W>
 static void lev_bvs_launch_w(const LevBvArgs& a, cudaStream_t st) {
     int64_t n = ((int64_t)a.P + 32 * LEV_BVS_WARPS - 1) / (32 * LEV_BVS_WARPS);
-    const int64_t cap = (int64_t)148 * 16;
+    int64_t cap = (int64_t)148 * 16;
+    if (const char* e = getenv("B200LEV_BVS_CTAS")) cap = atoll(e) > 0 ? atoll(e) : cap;  // (tests: many blocks per warp)
     const dim3 grid((unsigned)(n < cap ? n : cap)), block(32 * LEV_BVS_WARPS);
     if (a.mode != LEV_MODE_PREFIX)
         lev_launch(lev_bv_short_kernel<TT, W, 0>, grid, block, 0, st, a);

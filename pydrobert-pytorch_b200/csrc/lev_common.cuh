@@ -195,7 +195,7 @@ int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
                       const b200lev_opts_t* o, int mode, float mult, int32_t* ref_len,
                       int32_t* hyp_len, void* uid_ref, void* uid_hyp, void* lead,
                       int32_t* state, int32_t* flags, float* out, int64_t out_si, int Hout,
-                      cudaStream_t st, void* after_uid, bool short_form);
+                      cudaStream_t st, void* after_uid, bool short_form, double* acc);
 // 0: off, 1: forced (tests; runs whatever the references look like), 2: device-selected
 int lev_bitvec_mode();
 int lev_launch_uid(const b200lev_tokens_t* ref, const int32_t* packed, const int* state,

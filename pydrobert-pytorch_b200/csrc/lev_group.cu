@@ -24,8 +24,8 @@
 // PACKED path: when K0 found all tokens inside a 65536-wide window (their low 16 bits are
 // then injective) and costs/lengths keep every value below LEVG_BIG16, TWO pairs share
 // each register, one per 16-bit half, and the 2-wide DPX instructions do the work.  Per 2
-// cells: LOP3 (token xor), VIMNMX.U16x2 (-> 0/1 per half), IMAD (diag + neq*sub, FMA
-// pipe), 2 x VIADDMNMX.S16x2.  Otherwise the 32-bit cell update of lev_dp.cu runs.
+// cells: VIADDMNMX.U16x2 (token + negated row token, clamped -> 0/1 per half), IMAD (diag +
+// neq*sub, FMA pipe), 2 x VIADDMNMX.S16x2.  Otherwise the 32-bit cell update of lev_dp.cu runs.
 //
 // Integer costs only (cost row, or (cost, count) rows for the error-rate family);
 // FINAL and PREFIX modes.  Everything else stays on lev_dp.cu.
@@ -197,12 +197,15 @@ __device__ __forceinline__ void levg_run16(const LevParams& p, const int G, cons
         pl = in;
         const int i = s - gl;
         if ((unsigned)(i - 1) < (unsigned)maxsteps) {
-            const unsigned ht = (unsigned)hypA[i - 1] | ((unsigned)hypB[i - 1] << 16);
+            // the row's two tokens, NEGATED per half: rt + (-ht) modulo 65 536 is zero where equal,
+            // and the DPX add-and-clamp below turns it into the 0 / 1 "differs" in one instruction
+            const unsigned htA = hypA[i - 1], htB = hypB[i - 1];
+            const unsigned nht = ((0u - htA) & 0xffffu) | ((0u - htB) << 16);
             unsigned lf = in;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const unsigned up = v[c];
-                const unsigned n01 = __vminu2(rt[c] ^ ht, 0x00010001u);
+                const unsigned n01 = __viaddmin_u16x2(rt[c], nht, 0x00010001u);
                 const unsigned sb = n01 * subc + dg;
                 const unsigned t = __viaddmin_s16x2(up, ins2, sb);
                 lf = __viaddmin_s16x2(lf, del2, t);

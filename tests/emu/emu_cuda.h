@@ -268,6 +268,10 @@ static inline unsigned __vimin3_s16x2(unsigned a, unsigned b, unsigned c) {
 static inline unsigned __vmins2(unsigned a, unsigned b) {
     return __emu_pack16(std::min(__emu_lo16(a), __emu_lo16(b)), std::min(__emu_hi16(a), __emu_hi16(b)));
 }
+static inline unsigned __viaddmin_u16x2(unsigned a, unsigned b, unsigned c) {  // halves add modulo 65536
+    unsigned lo = std::min((a + b) & 0xffffu, c & 0xffffu), hi = std::min(((a >> 16) + (b >> 16)) & 0xffffu, c >> 16);
+    return lo | (hi << 16);
+}
 static inline unsigned __vminu2(unsigned a, unsigned b) {
     unsigned lo = std::min(a & 0xffffu, b & 0xffffu), hi = std::min(a >> 16, b >> 16);
     return lo | (hi << 16);

@@ -177,6 +177,38 @@ def bv_form(request, monkeypatch):
     return request.param
 
 
+@pytest.mark.parametrize("costs", [(1, 1, 1), (3, 3, 4)])
+@pytest.mark.parametrize("group", [1, 3])
+def test_final_sums_every_kernel_form(F, bv_form, costs, group, monkeypatch):
+    """b200lev_final_sums (the bulk-scoring step, command_line.py:1124-1147): the fp64 totals are
+    the same whether the short-reference kernel accumulates them itself or b200lev_err_sum follows
+    the fused / wavefront kernels -- odd pair counts (lanes shadowing the last pair), references
+    shared by `group` hypotheses, normalised and raw values."""
+    from b200lev import _ops
+
+    monkeypatch.setenv("B200LEV_BITVEC", "1")
+    monkeypatch.setenv("B200LEV_BITVEC_MIN_PAIRS", "1")
+    monkeypatch.setenv("B200LEV_BVS_CTAS", "2")  # several blocks of pairs per warp
+    rng = np.random.default_rng(11)
+    for R, H, n_ref in ((20, 25, 37), (30, 9, 1100), (64, 30, 45), (90, 40, 33)):
+        ref = PC.random_tokens(rng, R, n_ref, 12, -1, -2, min_len=0)
+        hyp = PC.random_tokens(rng, H, n_ref * group, 12, -1, -2, min_len=0)
+        for norm in (False, True):
+            exp = PC.O.error_rate(np.repeat(ref, group, axis=1), hyp, eos=-1, include_eos=False,
+                                  norm=norm, ins_cost=costs[0], del_cost=costs[1], sub_cost=costs[2])
+            er, acc, _ = _ops.error_sums(torch.from_numpy(ref), torch.from_numpy(hyp), -1, False, False,
+                                         float(costs[0]), float(costs[1]), float(costs[2]), norm, True,
+                                         group)
+            PC.assert_same(er, exp, True, f"sums {R}x{H} norm={norm}")
+            ref_lens = np.where((ref == -1).any(0), (ref == -1).argmax(0), R)
+            got = acc.tolist()
+            assert got[1:] == [float(ref_lens.sum() * group), float(n_ref * group)]
+            if norm:  # fp64 sums of rounded quotients: order-dependent in the last bits
+                assert abs(got[0] - float(exp.astype(np.float64).sum())) < 1e-9
+            else:
+                assert got[0] == float(exp.astype(np.float64).sum())
+
+
 @pytest.mark.parametrize("shape", [(1, 9, 33), (20, 25, 70), (32, 40, 64), (33, 30, 31), (64, 70, 40),
                                    (65, 20, 45), (96, 101, 35), (101, 101, 40), (128, 60, 34)])
 @pytest.mark.parametrize("costs", [(1, 1, 1), (3, 3, 3), (0.5, 0.5, 0.5)])
