@@ -132,34 +132,43 @@ __global__ void __launch_bounds__(32 * LEV_BVS_WARPS, W == 1 ? 4 : 3) lev_bv_sho
             for (int w = 0; w < W; ++w) {
                 eos_bits[w] = 0u;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    rlo[w][k] = 0u;
-                    if (HAVE_HI) rhi[w][k] = 0u;
-                }
+                for (int k = 0; k < 16; ++k) rlo[w][k] = 0u;
             }
             // batches of RB positions: the RB loads are issued back to back (one exposed DRAM
-            // latency per batch, not per token), then packed
+            // latency per batch, not per token), then packed.  The column is walked with a running
+            // pointer (a 64-bit add per position instead of a 64-bit multiply-add); positions past
+            // R repeat position R - 1: they change neither the window nor the FIRST eos, and bits
+            // at or above r are never read
             constexpr int RB = W == 1 ? 16 : 8;  // (two-word references are short of registers)
-            const int Rm1 = R - 1;
+            const TT* __restrict__ rp = rsrc;
 #pragma unroll
             for (int j0 = 0; j0 < 32 * W; j0 += RB) {
                 if (j0 < R) {  // (warp-uniform)
                     TT raw[RB];
+                    if (j0 + RB < R) {
 #pragma unroll
-                    for (int k = 0; k < RB; ++k)
-                        raw[k] = rsrc[(int64_t)(j0 + k < Rm1 ? j0 + k : Rm1) * rst];
+                        for (int k = 0; k < RB; ++k) {
+                            raw[k] = *rp;
+                            rp += rst;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < RB; ++k) {
+                            raw[k] = *rp;
+                            if (j0 + k < R - 1) rp += rst;
+                        }
+                    }
 #pragma unroll
                     for (int k = 0; k < RB; ++k) {
                         const int j = j0 + k;
                         const int64_t x = (int64_t)raw[k];
                         const int lo = (int)x, hi = (int)(x >> 32);
-                        // (positions past R repeat position R - 1: they change neither the window
-                        // nor the FIRST eos, and bits at or above r are never read)
                         if (j == 0) base = lo - 32768;
                         outside |= (unsigned)(lo - base) >> 16;
-                        const int sh = (j & 16);  // which half of register (j & 15) of word j / 32
-                        rlo[j >> 5][j & 15] |= ((unsigned)lo & 0xffffu) << sh;
-                        if (HAVE_HI) rhi[HAVE_HI ? (j >> 5) : 0][j & 15] |= ((unsigned)lo >> 16) << sh;
+                        if ((j & 16) == 0)
+                            rlo[j >> 5][j & 15] = (unsigned)lo & 0xffffu;
+                        else  // the upper half of the register position j - 16 opened
+                            rlo[j >> 5][j & 15] = __byte_perm(rlo[j >> 5][j & 15], (unsigned)lo, 0x5410);
                         int e = lo ^ eos_lo;
                         if (sizeof(TT) == 8) {
                             wacc |= hi ^ (lo >> 31);
@@ -209,6 +218,18 @@ __global__ void __launch_bounds__(32 * LEV_BVS_WARPS, W == 1 ? 4 : 3) lev_bv_sho
         const bool narrow_warp = !__any_sync(LEV_FULL_MASK, outside != 0u);
         const bool wide_warp = (sizeof(TT) == 8 && __any_sync(LEV_FULL_MASK, wacc != 0)) || (!HAVE_HI && !narrow_warp);
 
+        if (HAVE_HI && !narrow_warp && !wide_warp) {
+            // (uncommon) some lane's reference leaves its window: the high halves of the tokens
+            // join the compare; they are packed here, from the (cached) column, not in the prologue
+            // every warp pays for
+#pragma unroll
+            for (int k = 0; k < 16; ++k) rhi[0][k] = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int lo = (int)(int64_t)rsrc[(int64_t)(j < R - 1 ? j : R - 1) * rst];
+                rhi[0][j & 15] |= ((unsigned)lo >> 16) << (j & 16);
+            }
+        }
         // PATH 0: every token of the warp's references sits in one 65 536-wide window (low halves
         // decide); 1: low and high halves; 2 (rare): exact compares against the cached column.
         // One copy of the hypothesis loop per path keeps the hot one contiguous in the
@@ -236,21 +257,23 @@ __global__ void __launch_bounds__(32 * LEV_BVS_WARPS, W == 1 ? 4 : 3) lev_bv_sho
             if (PATH == 0) {
                 // every reference token of the lane lies in [base, base + 65536): a token in
                 // the same window is equal iff the low halves are, one outside equals none
-                // (that also covers a 64-bit token outside int32, whose low word is garbage)
+                // (that also covers a 64-bit token outside int32, whose low word is garbage).
+                // The compare runs regardless and is masked afterwards: no branch per position
                 const unsigned nlo = lev_bvs_neg16((unsigned)v & 0xffffu);
-                bool tok_ok = ((unsigned)(v - base) >> 16) == 0u;
-                if (sizeof(TT) == 8) tok_ok = tok_ok && hi == (v >> 31);
+                const bool tok_ok = sizeof(TT) == 8 ? (uint64_t)(x - (int64_t)base) < 65536ull
+                                                    : (unsigned)(v - base) < 65536u;
+                const unsigned ok_m = tok_ok ? ~0u : 0u;
 #pragma unroll
                 for (int w = 0; w < W; ++w)
-                    if (w == 0 || R > 32) eq[w] = tok_ok ? ~lev_bvs_neq16(rlo[w], nlo) : 0u;
+                    if (w == 0 || R > 32) eq[w] = ~lev_bvs_neq16(rlo[w], nlo) & ok_m;
             } else if (PATH == 1) {
                 const unsigned nlo = lev_bvs_neg16((unsigned)v & 0xffffu);
                 const unsigned nhi = lev_bvs_neg16((unsigned)v >> 16);
-                const bool tok_ok = sizeof(TT) < 8 || hi == (v >> 31);
+                const unsigned ok_m = (sizeof(TT) < 8 || hi == (v >> 31)) ? ~0u : 0u;
 #pragma unroll
                 for (int w = 0; w < W; ++w)
                     if (w == 0 || R > 32)
-                        eq[w] = tok_ok ? ~(lev_bvs_neq16(rlo[w], nlo) | lev_bvs_neq16(rhi[HAVE_HI ? w : 0], nhi)) : 0u;
+                        eq[w] = ~(lev_bvs_neq16(rlo[w], nlo) | lev_bvs_neq16(rhi[HAVE_HI ? w : 0], nhi)) & ok_m;
             } else {
 #pragma unroll
                 for (int w = 0; w < W; ++w)
@@ -273,7 +296,26 @@ __global__ void __launch_bounds__(32 * LEV_BVS_WARPS, W == 1 ? 4 : 3) lev_bv_sho
         const int T_end = PREFIX ? (a.Hout > H ? a.Hout : H) : H;
         int tdone = 0;
         if (H > 0) {
-            auto ld = [&](int t) { return lev_ldg_stream(hsrc + (int64_t)(t < Hm1 ? t : Hm1) * hst); };
+            // the hypothesis column is walked CH tokens at a time with a running pointer (rows past
+            // H - 1 repeat row H - 1: nothing reads them)
+            const TT* __restrict__ hp = hsrc;
+            int tl = 0;  // the row `hp` points at
+            auto ld_chunk = [&](TT (&buf)[CH]) {
+                if (tl + CH < H) {  // (warp-uniform)
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) {
+                        buf[k] = lev_ldg_stream(hp);
+                        hp += hst;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) {
+                        buf[k] = lev_ldg_stream(hp);
+                        if (tl + k < Hm1) hp += hst;
+                    }
+                }
+                tl += CH;
+            };
             int t0 = 0;
             auto hypothesis = [&](auto path) {
                 bool done = false;
@@ -283,17 +325,13 @@ __global__ void __launch_bounds__(32 * LEV_BVS_WARPS, W == 1 ? 4 : 3) lev_bv_sho
                     // rotation by register moves waits for the loads it moves; more trips per body
                     // would push the loop out of the instruction cache
                     TT bA[CH], bB[CH];
-#pragma unroll
-                    for (int k = 0; k < CH; ++k) {
-                        bA[k] = ld(k);
-                        bB[k] = ld(CH + k);
-                    }
+                    ld_chunk(bA);
+                    ld_chunk(bB);
                     auto trip = [&](TT (&buf)[CH]) {  // CH positions from `buf`, then its next chunk
                         if (!done) {
 #pragma unroll
                             for (int k = 0; k < CH; ++k) position(path, buf[k], t0 + k);
-#pragma unroll
-                            for (int k = 0; k < CH; ++k) buf[k] = ld(t0 + 2 * CH + k);
+                            ld_chunk(buf);
                             t0 += CH;
                             // every hypothesis of the warp has ended, or the last row is out
                             done = t0 >= T_end || !__any_sync(LEV_FULL_MASK, live_m != 0);
@@ -308,15 +346,11 @@ __global__ void __launch_bounds__(32 * LEV_BVS_WARPS, W == 1 ? 4 : 3) lev_bv_sho
                     // two-word references are short of registers and long on code: one trip per
                     // loop body, the buffers rotate through register moves
                     TT cur[CH], n1[CH], n2[CH];
-#pragma unroll
-                    for (int k = 0; k < CH; ++k) {
-                        cur[k] = ld(k);
-                        n1[k] = ld(CH + k);
-                    }
+                    ld_chunk(cur);
+                    ld_chunk(n1);
 #pragma unroll 1
                     while (!done) {
-#pragma unroll
-                        for (int k = 0; k < CH; ++k) n2[k] = ld(t0 + 2 * CH + k);
+                        ld_chunk(n2);
 #pragma unroll
                         for (int k = 0; k < CH; ++k) position(path, cur[k], t0 + k);
 #pragma unroll
