@@ -210,7 +210,6 @@ __global__ void __launch_bounds__(32 * LEV_BVS_WARPS, W == 1 ? 4 : 3) lev_bv_sho
             pv[w] = ~0u;
             mv[w] = 0u;
         }
-        int score = rlen;
         float scoref = (float)rlen;
         int live_m = -1, prev_m = -1, nin = 0;
         float prev_val = PREFIX ? value_of(scoref, 0.0f) : 0.0f;
@@ -281,15 +280,30 @@ __global__ void __launch_bounds__(32 * LEV_BVS_WARPS, W == 1 ? 4 : 3) lev_bv_sho
                         if ((int64_t)rsrc[(int64_t)(32 * w + jj) * rst] == x) eq[w] |= 1u << jj;
             }
             unsigned ph[W], mh[W];
-            lev_bvs_step<W>(eq, pv, mv, ph, mh);
-            const unsigned up = (((top_hi ? ph[W - 1] : ph[0]) >> top_sh) & 1u) | empty_up;
-            const unsigned down = ((top_hi ? mh[W - 1] : mh[0]) >> top_sh) & 1u & ~empty_up;
             if (PREFIX) {
+                lev_bvs_step<W>(eq, pv, mv, ph, mh);
+                const unsigned up = (((top_hi ? ph[W - 1] : ph[0]) >> top_sh) & 1u) | empty_up;
+                const unsigned down = ((top_hi ? mh[W - 1] : mh[0]) >> top_sh) & 1u & ~empty_up;
                 scoref += __int_as_float((int)(up * 0x3f800000u));
                 scoref -= __int_as_float((int)(down * 0x3f800000u));
                 prev_val = value_of(scoref, bias);
             } else {
-                score += ((int)up - (int)down) & in_m;
+                // FINAL: no score is carried.  The column state (the vertical deltas) freezes at the
+                // lane's last counted token, and D[r][h] = h + #(+1 deltas) - #(-1 deltas) among the
+                // first r positions is read off it after the loop: 2 selects per word and step
+                // instead of 6 instructions of score keeping
+                unsigned npv[W], nmv[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    npv[w] = pv[w];
+                    nmv[w] = mv[w];
+                }
+                lev_bvs_step<W>(eq, npv, nmv, ph, mh);
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    pv[w] = (npv[w] & (unsigned)in_m) | (pv[w] & ~(unsigned)in_m);
+                    mv[w] = (nmv[w] & (unsigned)in_m) | (mv[w] & ~(unsigned)in_m);
+                }
             }
         };
 
@@ -386,6 +400,13 @@ __global__ void __launch_bounds__(32 * LEV_BVS_WARPS, W == 1 ? 4 : 3) lev_bv_sho
         const int hlen = nin;
         if (a.has_eos && a.include_eos && live_m != 0) myflags |= B200LEV_FLAG_HYP_NO_EOS;
         if (!PREFIX) {  // SM:390-405
+            int score = hlen;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                const int nb = rlen - 32 * w;  // positions of the reference in this word
+                const unsigned m = nb >= 32 ? ~0u : (nb > 0 ? (1u << nb) - 1u : 0u);
+                score += __popc(pv[w] & m) - __popc(mv[w] & m);
+            }
             float val = __fmul_rn((float)score, a.mult);
             if (a.norm) val = (rlen == 0) ? (hlen > 0 ? 1.0f : 0.0f) : val / (float)rlen;
             a.out[pc] = val;
