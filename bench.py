@@ -53,7 +53,7 @@ import numpy as np  # noqa: E402
 OPS_PER_CELL = 5  # compare, select/add, add, add, 3-input min
 NBEST = 8
 PROF_SLOTS = ("pack_ref", "pack_hyp", "bucketing", "dp", "prefix_finalize", "standby_wide",
-              "bitvec_probe_or_uid", "bitvec_dp", "completion_uid", "completion_fill", "err_sum")
+              "bitvec_probe_or_uid", "bitvec_dp", "completion_uid", "completion_fill", "err_sum", "mask_packed")
 
 
 # ---------------------------------------------------------------------------------------------

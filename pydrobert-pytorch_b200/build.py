@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "b200lev")
 LIB = os.path.join(OUT_DIR, "libb200lev.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["lev_abi.cu", "lev_pack.cu", "lev_dp.cu", "lev_group.cu", "lev_bitvec.cu", "lev_bvfused.cu", "lev_bvshort.cu", "lev_cta.cu", "lev_completion.cu", "lev_loss.cu", "lev_seqlp.cu", "lev_ragged.cu", "lev_decode.cu"]
+SOURCES = ["lev_abi.cu", "lev_pack.cu", "lev_dp.cu", "lev_group.cu", "lev_bitvec.cu", "lev_bvfused.cu", "lev_bvshort.cu", "lev_cta.cu", "lev_completion.cu", "lev_loss.cu", "lev_seqlp.cu", "lev_ragged.cu", "lev_decode.cu", "lev_mask16.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

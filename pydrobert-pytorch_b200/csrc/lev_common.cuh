@@ -141,6 +141,7 @@ struct LevParams {
     int64_t ref_st, ref_sn, hyp_st, hyp_sn;
     int ref_eb, hyp_eb;
     int only_if_wide;  // lev_warp_kernel: exit unless the wide-token flag is set
+    int mask16;        // MASK: lev_mask16_kernel ran first; lev_warp_kernel skips the pairs it took
     int bv_check;      // the bit-vector kernels ran first: exit if they took the batch
     // group kernel tables (workspace)
     int* ghist;
@@ -154,11 +155,30 @@ struct LevParams {
     int nbins;
 };
 
+
+#if defined(__CUDACC__) || defined(B200LEV_EMU)
+// K0's token range (state[1] = max(u), state[2] = max(~u), u = token + 2^31): all tokens of the
+// call lie in one 65 536-wide window, so their low 16 bits tell them apart
+__device__ __forceinline__ bool lev_tokens_narrow(const int* state) {
+    const unsigned umax = (unsigned)state[1], umin = ~(unsigned)state[2];
+    return umax < umin || umax - umin < 65536u;
+}
+// the packed mask kernel (lev_mask16.cu) and lev_warp_kernel split a mask-mode batch by these
+// two rules: the first is per call, the second per pair
+__device__ __forceinline__ bool lev_mask16_tokens_ok(const int* state) {
+    return !(state[0] & B200LEV_FLAG_WIDE_TOKENS) && lev_tokens_narrow(state);
+}
+__device__ __forceinline__ bool lev_mask16_takes(const LevParams& p, int pair) {
+    return p.ndist[pair / p.ref_group] <= 32;
+}
+#endif
+
 // optional per-kernel timing (b200lev_profile): CUDA events recorded on the launch stream
 // around each phase; slots of b200lev_profile_read()
 enum LevProfSlot { LEV_PROF_PACK_REF = 0, LEV_PROF_PACK_HYP, LEV_PROF_SORT, LEV_PROF_DP,
                    LEV_PROF_FINALIZE, LEV_PROF_STANDBY, LEV_PROF_BV_UID, LEV_PROF_BV_DP,
-                   LEV_PROF_COMP_UID, LEV_PROF_COMP_FILL, LEV_PROF_ERR_SUM, LEV_PROF_NSLOTS };
+                   LEV_PROF_COMP_UID, LEV_PROF_COMP_FILL, LEV_PROF_ERR_SUM, LEV_PROF_MASK16,
+                   LEV_PROF_NSLOTS };
 void lev_prof_begin(int slot, cudaStream_t st);
 void lev_prof_end(int slot, cudaStream_t st);
 
@@ -174,6 +194,7 @@ int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int inc
 int lev_launch_dp(const LevParams& p, int mode, bool count_mode, bool float_path,
                   cudaStream_t st);
 int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t st);
+int lev_launch_mask16(const LevParams& p, bool float_path, cudaStream_t st);
 int lev_launch_cta(const LevParams& p, int mode, bool count_mode, bool float_path, cudaStream_t st);
 // lanes per pair if the shapes admit the group kernel (its histogram is then built at
 // pack time), else 0

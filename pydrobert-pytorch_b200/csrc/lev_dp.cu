@@ -295,7 +295,9 @@ __global__ void __launch_bounds__(256) lev_warp_kernel(const LevParams p) {
     const bool wide = (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) != 0;
     if (p.only_if_wide && !wide) return;  // the group kernel already did the work
     if (p.bv_check && lev_bv_took(p.wide_flag)) return;
+    const bool mask16 = MODE == LEV_MODE_MASK && p.mask16 && lev_mask16_tokens_ok(p.wide_flag);
     for (int pair = blockIdx.x * wpc + warp; pair < p.P; pair += gridDim.x * wpc) {
+        if (mask16 && lev_mask16_takes(p, pair)) continue;  // lev_mask16_kernel's pair
         const int r = p.ref_len[pair / p.ref_group];
         const int h = p.hyp_len[pair];
         const int steps = p.exclude_last ? (h > 0 ? h - 1 : 0) : h;  // SM:286-288
@@ -409,6 +411,14 @@ int lev_launch_dp(const LevParams& p_, int mode, bool count_mode, bool float_pat
     if (p_.P <= 0) return B200LEV_OK;
     LevParams p = p_;
     p.only_if_wide = 0;
+    p.mask16 = 0;
+    if (mode == LEV_MODE_MASK) {
+        // integer costs, r <= 255: the packed two-pairs-per-warp kernel first; the warp kernel
+        // below takes what it leaves (per pair, decided on the device)
+        const int took = lev_launch_mask16(p, float_path || count_mode, st);
+        if (took < 0) return took;
+        p.mask16 = took;
+    }
     if (!float_path) {
         // large batches of short/mid pairs: length-bucketed group kernel (lev_group.cu);
         // this kernel then only runs if K0 flagged tokens wider than 32 bits

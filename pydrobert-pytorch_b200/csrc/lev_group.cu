@@ -47,12 +47,7 @@ struct LevGroupGeom {
     int wpc;        // warps per CTA
 };
 
-// device-side choice between the packed and the 32-bit build (see lev_pack.cu):
-// state[1] = max(u), state[2] = max(~u), u = token + 2^31
-__device__ __forceinline__ bool levg_tokens_narrow(const int* state) {
-    const unsigned umax = (unsigned)state[1], umin = ~(unsigned)state[2];
-    return umax < umin || umax - umin < 65536u;
-}
+// device-side choice between the packed and the 32-bit build (see lev_pack.cu): lev_tokens_narrow
 
 // IEEE-754 correctly rounded a / b from the correctly rounded reciprocal y = RN(1/b)
 // (Markstein): q0 = RN(a*y), r = a - b*q0 (exact in an FMA), q = RN(q0 + r*y).  Valid for
@@ -272,7 +267,7 @@ lev_sort_kernel(const LevParams p, const LevGroupGeom geo, const int count_mode)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (p.bv_check && lev_bv_took(p.wide_flag)) return;
     if (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) return;
-    const bool packed = !count_mode && geo.allow16 && levg_tokens_narrow(p.wide_flag);
+    const bool packed = !count_mode && geo.allow16 && lev_tokens_narrow(p.wide_flag);
     const int PPT = (32 / geo.G) * (packed ? 2 : 1);
     const int H1 = p.H + 1;
     // every CTA repeats the (tiny) scan: histogram -> shared memory (all threads), then one
@@ -379,7 +374,7 @@ __global__ void __launch_bounds__(128, LEVG_MIN_CTAS) lev_group_kernel(const Lev
     // 65536-wide window and small values -> PACKED; else the 32-bit build.
     if (p.bv_check && lev_bv_took(p.wide_flag)) return;
     if (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) return;
-    if ((!COUNT && geo.allow16 && levg_tokens_narrow(p.wide_flag)) != PACKED) return;
+    if ((!COUNT && geo.allow16 && lev_tokens_narrow(p.wide_flag)) != PACKED) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int G = geo.G, PPW = 32 / G, RW = geo.row_words;
     const int PPT = PACKED ? 2 * PPW : PPW;  // pairs per task (<= 32)
@@ -508,7 +503,7 @@ __global__ void __launch_bounds__(256)
 lev_prefix_finalize_kernel(const LevParams p, const LevGroupGeom geo) {
     if (p.bv_check && lev_bv_took(p.wide_flag)) return;
     if (*p.wide_flag & B200LEV_FLAG_WIDE_TOKENS) return;  // lev_warp_kernel wrote `out` itself
-    const bool packed = !COUNT && geo.allow16 && levg_tokens_narrow(p.wide_flag);
+    const bool packed = !COUNT && geo.allow16 && lev_tokens_narrow(p.wide_flag);
     const int tid = threadIdx.x;
     if (p.out_sn == 1) {
         // lane = pair: a lane walks 32 rows of ITS pair's raw values (128-bit loads, the row's

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "pydrobert-pytorch_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libb200lev_emu.so")
-SOURCES = ["lev_abi.cu", "lev_pack.cu", "lev_dp.cu", "lev_group.cu", "lev_bitvec.cu", "lev_bvfused.cu", "lev_bvshort.cu", "lev_cta.cu", "lev_completion.cu", "lev_loss.cu", "lev_seqlp.cu", "lev_ragged.cu", "lev_decode.cu"]
+SOURCES = ["lev_abi.cu", "lev_pack.cu", "lev_dp.cu", "lev_group.cu", "lev_bitvec.cu", "lev_bvfused.cu", "lev_bvshort.cu", "lev_cta.cu", "lev_completion.cu", "lev_loss.cu", "lev_seqlp.cu", "lev_ragged.cu", "lev_decode.cu", "lev_mask16.cu"]
 FLAGS = ["-O1", "-g", "-std=c++17", "-fPIC", "-fno-fast-math", "-ffp-contract=off", "-w",
          "-include", os.path.join(HERE, "emu_cuda.h"), "-I", HERE]
 

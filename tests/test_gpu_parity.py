@@ -656,6 +656,22 @@ def test_completion_many_distinct_tokens(F, dev):
                            norm=False, exclude_last=False, min_frac=0.5)
 
 
+@pytest.mark.parametrize("costs", [(1, 1, 1), (2, 3, 4)])
+def test_completion_packed_mask_kernel(F, dev, costs, monkeypatch):
+    """lev_mask16.cu (two pairs per warp, 16-bit DPX) forced on for small batches -- see the
+    emulator test of the same name -- and on a batch large enough to take it by default."""
+    monkeypatch.setenv("B200LEV_MASK16_MIN_PAIRS", "1")
+    for R, H, N, V, spread in ((20, 25, 7, 6, 1), (63, 100, 5, 20, 1), (64, 70, 4, 30, 1), (127, 40, 3, 25, 1),
+                               (200, 150, 5, 30, 1), (255, 140, 2, 12, 1), (60, 70, 9, 45, 1),
+                               (50, 40, 5, 10, 70001)):
+        for excl in (False, True):
+            PC.check_vs_oracle(F, dev, seed=R + H, R=R, H=H, N=N, V=V, costs=costs, include_eos=not excl,
+                               norm=False, exclude_last=excl, min_frac=0.0, spread=spread)
+    monkeypatch.delenv("B200LEV_MASK16_MIN_PAIRS")
+    PC.check_vs_oracle(F, dev, seed=3, R=40, H=36, N=2500, V=24, costs=costs, include_eos=True, norm=False,
+                       exclude_last=False, min_frac=0.2)
+
+
 @pytest.mark.parametrize("N", [33, 37, 64, 65, 97])
 def test_completion_target_writer_alignment(F, dev, N):
     """The target writer stores 16 bytes per lane where a warp's run of 32 rows starts on an even

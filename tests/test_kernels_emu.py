@@ -509,5 +509,21 @@ def test_completion_many_distinct_tokens(F):
                            norm=False, exclude_last=False, min_frac=0.5)
 
 
+@pytest.mark.parametrize("costs", [(1, 1, 1), (2, 3, 4)])
+def test_completion_packed_mask_kernel(F, costs, monkeypatch):
+    """lev_mask16.cu forced on for small batches: every column count C (r + 1 <= 64 / 128 / 256),
+    odd batch sizes (a duo with one pair), rows beyond the 64-row ring of the equality sheet,
+    pairs of very different lengths sharing a warp, exclude_last, mixed batches where references
+    with more than 32 distinct tokens stay on lev_warp_kernel, and tokens spread beyond one 16-bit
+    window (the whole batch stays there)."""
+    monkeypatch.setenv("B200LEV_MASK16_MIN_PAIRS", "1")
+    for R, H, N, V, spread in ((20, 25, 7, 6, 1), (63, 100, 5, 20, 1), (64, 70, 4, 30, 1), (127, 40, 3, 25, 1),
+                               (200, 150, 5, 30, 1), (255, 140, 2, 12, 1), (60, 70, 9, 45, 1),
+                               (50, 40, 5, 10, 70001)):
+        for excl in (False, True):
+            PC.check_vs_oracle(F, DEV, seed=R + H, R=R, H=H, N=N, V=V, costs=costs, include_eos=not excl,
+                               norm=False, exclude_last=excl, min_frac=0.0, spread=spread)
+
+
 def test_sequence_log_probs_packed(F, golden_seqlp_packed):
     assert PC.check_golden_seqlp_packed(F, DEV, golden_seqlp_packed) == 6
