@@ -32,6 +32,14 @@ __device__ __forceinline__ unsigned levm_neg2(unsigned a, unsigned b) {  // (-a,
 
 constexpr int LEVM_RING = 64;  // rows of the sheet: 32 in flight (the skew) + 32 being converted
 
+template <int N>
+struct LevmCols {
+    static constexpr int value = N;
+};
+
+// One pass over the duo's DP with C columns per lane.  PASS 0 leaves the NEGATED row minima of
+// both pairs in rowmin_s (what pass 1 adds to a cell to test it); PASS 1 fills the sheet and calls
+// convert(first_row) whenever 32 rows of it are complete.
 template <int C, int PASS, typename Convert>
 __device__ __forceinline__ void levm_pass(const LevParams& p, const int lane, const int rA, const int rB,
                                           const int pairA, const int pairB, const int maxsteps,
@@ -58,71 +66,78 @@ __device__ __forceinline__ void levm_pass(const LevParams& p, const int lane, co
     (void)rmrun;
     unsigned short* __restrict__ sheet16 = reinterpret_cast<unsigned short*>(sheet_s);
     const int nsteps = maxsteps + 31;
-    for (int s = 1; s <= nsteps; ++s) {
-        const unsigned sh = __shfl_up_sync(LEV_FULL_MASK, v[C - 1], 1);
-        const unsigned in = (lane == 0) ? BIG2 : sh;
-        unsigned dg = pl;
-        pl = in;
-        unsigned in_rm = BIG2;
-        if (PASS == 0) {
-            const unsigned sh_rm = __shfl_up_sync(LEV_FULL_MASK, rmrun, 1);
-            in_rm = (lane == 0) ? BIG2 : sh_rm;
-        }
-        const int i = s - lane;  // the row this lane updates now
-        if ((unsigned)(i - 1) < (unsigned)maxsteps) {
-            const unsigned nht = nht_s[i - 1];  // both pairs' row tokens, negated per half
-            unsigned lf = in;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const unsigned up = v[c];
-                const unsigned n01 = __viaddmin_u16x2(rt[c], nht, 0x00010001u);  // 1 = tokens differ
-                const unsigned sb = n01 * subc + dg;                              // SM:293
-                const unsigned t = __viaddmin_s16x2(up, ins2, sb);                // SM:292, 316
-                lf = __viaddmin_s16x2(lf, del2, t);                               // SM:317
-                dg = up;
-                v[c] = lf;
+    int i = 1 - lane;  // the row this lane updates at step s = 1
+    // steps in blocks of 32: after the block that ends with step s0 + 31 the rows up to s0 are
+    // complete in every lane
+    for (int s0 = 0; s0 < nsteps; s0 += 32) {
+        const int nk = nsteps - s0 < 32 ? nsteps - s0 : 32;
+#pragma unroll 1
+        for (int k = 0; k < nk; ++k, ++i) {
+            const unsigned sh = __shfl_up_sync(LEV_FULL_MASK, v[C - 1], 1);
+            const unsigned in = (lane == 0) ? BIG2 : sh;
+            unsigned dg = pl;
+            pl = in;
+            unsigned in_rm = BIG2;
+            if (PASS == 0) {
+                const unsigned sh_rm = __shfl_up_sync(LEV_FULL_MASK, rmrun, 1);
+                in_rm = (lane == 0) ? BIG2 : sh_rm;
             }
-            if (PASS == 0) {  // SM:332-333: running minimum of row i over the columns up to mine
-                unsigned rm = in_rm;
+            if ((unsigned)(i - 1) < (unsigned)maxsteps) {
+                const unsigned nht = nht_s[i - 1];  // both pairs' row tokens, negated per half
+                unsigned lf = in;
 #pragma unroll
-                for (int c = 0; c < C; ++c) rm = __vminu2(rm, v[c]);
-                rmrun = rm;
-                if (lane == 31) rowmin_s[i] = rm;
-            } else {  // SM:334, 349-354: which of my cells sit on the row minimum
-                const unsigned mn = rowmin_s[i];
-                const unsigned nmn = levm_neg2(mn & 0xffffu, mn >> 16);
-                unsigned acc = 0u;
+                for (int c = 0; c < C; ++c) {
+                    const unsigned up = v[c];
+                    const unsigned n01 = __viaddmin_u16x2(rt[c], nht, 0x00010001u);  // 1 = tokens differ
+                    const unsigned sb = n01 * subc + dg;                              // SM:293
+                    const unsigned t = __viaddmin_s16x2(up, ins2, sb);                // SM:292, 316
+                    lf = __viaddmin_s16x2(lf, del2, t);                               // SM:317
+                    dg = up;
+                    v[c] = lf;
+                }
+                if (PASS == 0) {  // SM:332-333: running minimum of row i over the columns up to mine
+                    unsigned rm = in_rm;
 #pragma unroll
-                for (int c = 0; c < C; ++c) acc = acc * 2u + __viaddmin_u16x2(v[c], nmn, 0x00010001u);
-                const unsigned eq = ~acc;  // bit C - 1 - c of a half: cell c equals the minimum
-                sheet16[(i & (LEVM_RING - 1)) * (2 * LEVM_SHEET_WORDS) + lane] =
-                    (unsigned short)((eq & ((1u << C) - 1u)) | (((eq >> 16) & ((1u << C) - 1u)) << 8));
+                    for (int c = 0; c < C; ++c) rm = __vminu2(rm, v[c]);
+                    rmrun = rm;
+                    if (lane == 31) rowmin_s[i] = levm_neg2(rm & 0xffffu, rm >> 16);
+                } else {  // SM:334, 349-354: which of my cells sit on the row minimum
+                    const unsigned nmn = rowmin_s[i];
+                    unsigned acc = 0u;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) acc = acc * 2u + __viaddmin_u16x2(v[c], nmn, 0x00010001u);
+                    // bit C - 1 - c of a half of ~acc: cell c equals the minimum; A -> byte 0, B -> byte 1
+                    const unsigned eq = ~acc & (((1u << C) - 1u) * 0x00010001u);
+                    sheet16[(i & (LEVM_RING - 1)) * (2 * LEVM_SHEET_WORDS) + lane] =
+                        (unsigned short)__byte_perm(eq, 0u, 0x4420);
+                }
             }
         }
-        if (PASS == 1 && (s & 31) == 31 && s >= 63) {
-            // rows s - 62 .. s - 31 are complete (lane 31 has just done row s - 31): 32 rows, lane = row
+        if (PASS == 1 && s0 >= 32 && nk == 32) {
+            // rows s0 - 31 .. s0 are complete (lane 31 has just done row s0): 32 rows, lane = row
             __syncwarp();
-            convert(s - 62);
+            convert(s0 - 31);
             __syncwarp();
         }
     }
-    if (PASS == 1) {  // the rows the loop did not flush: from the last flushed row + 1 to maxsteps
+    if (PASS == 1) {  // the rows the loop did not flush
         __syncwarp();
-        const int flushed = nsteps >= 63 ? ((nsteps - 31) & ~31) : 0;  // rows 1 .. flushed are out
+        const int full = nsteps / 32;                      // whole blocks of steps
+        const int flushed = full >= 2 ? 32 * (full - 1) : 0;  // rows 1 .. flushed are out
         for (int first = flushed + 1; first <= maxsteps; first += 32) convert(first);
     }
 }
 
-template <int C>
+template <int CMAX>
 __global__ void __launch_bounds__(256) lev_mask16_kernel(const LevParams p, const int Hs) {
     LEV_DYN_SMEM(unsigned, smem);
     if (!lev_mask16_tokens_ok(p.wide_flag)) return;  // lev_warp_kernel keeps the whole batch
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    const int per_warp = Hs * 2 + LEVM_RING * LEVM_SHEET_WORDS + (2 * 32 * C) / 4;
+    const int per_warp = Hs * 2 + LEVM_RING * LEVM_SHEET_WORDS + (2 * 32 * CMAX) / 4;
     unsigned* nht_s = smem + (size_t)warp * per_warp;  // [Hs]  negated row tokens of both pairs
-    unsigned* rowmin_s = nht_s + Hs;                    // [Hs]  row minima of both pairs
+    unsigned* rowmin_s = nht_s + Hs;                    // [Hs]  negated row minima of both pairs
     unsigned* sheet_s = rowmin_s + Hs;                  // [64][17] equality masks, [row & 63][lane]
-    unsigned char* rank_s = reinterpret_cast<unsigned char*>(sheet_s + LEVM_RING * LEVM_SHEET_WORDS);  // [2][32 C]
+    unsigned char* rank_s = reinterpret_cast<unsigned char*>(sheet_s + LEVM_RING * LEVM_SHEET_WORDS);  // [2][32 CMAX]
     const int nduo = (p.P + 1) / 2;
     for (int duo = blockIdx.x * wpc + warp; duo < nduo; duo += gridDim.x * wpc) {
         int pairA = 2 * duo, pairB = 2 * duo + 1;
@@ -146,52 +161,67 @@ __global__ void __launch_bounds__(256) lev_mask16_kernel(const LevParams p, cons
             const int32_t* __restrict__ uA = p.uid + (int64_t)refA * p.Rp;
             const int32_t* __restrict__ uB = p.uid + (int64_t)refB * p.Rp;
             for (int j = lane; j < rA; j += 32) rank_s[j] = (unsigned char)uA[j];
-            for (int j = lane; j < rB; j += 32) rank_s[32 * C + j] = (unsigned char)uB[j];
+            for (int j = lane; j < rB; j += 32) rank_s[32 * CMAX + j] = (unsigned char)uB[j];
         }
         __syncwarp();
-        // ---- the sheet -> bitmaps over distinct tokens, lane = row (32 rows from `first`) -------
         int mx = 0;
-        auto convert = [&](const int first) {
-            const int i = first + lane;
-            if (i > maxsteps) return;
-            unsigned bitsA = 0u, bitsB = 0u;
-            const unsigned* __restrict__ row = sheet_s + (i & (LEVM_RING - 1)) * LEVM_SHEET_WORDS;
+        // the duo's column count: the longer reference decides (warp-uniform), one copy of the
+        // two passes per count
+        auto run = [&](auto cols) {
+            constexpr int C = decltype(cols)::value;
+            // ---- the sheet -> bitmaps over distinct tokens, lane = row (32 rows from `first`) ---
+            auto convert = [&](const int first) {
+                const int i = first + lane;
+                if (i > maxsteps) return;
+                unsigned bitsA = 0u, bitsB = 0u;
+                const unsigned* __restrict__ row = sheet_s + (i & (LEVM_RING - 1)) * LEVM_SHEET_WORDS;
 #pragma unroll 4
-            for (int k = 0; k < 16; ++k) {
-                unsigned w = row[k];
-                while (w != 0u) {  // (rare: a row has a handful of minimal cells)
-                    const int b = 31 - __clz((int)w);
-                    w ^= 1u << b;
-                    const int l = 2 * k + (b >> 4);          // the lane that set it
-                    const int c = C - 1 - (b & 7);           // its cell
-                    const int j = l * C + c + 1 - 32 * C;    // column minus r
-                    if (b & 8) {
-                        const int jj = j + rB;
-                        if (jj >= 0 && jj < rB) bitsB |= 1u << rank_s[32 * C + jj];
-                    } else {
-                        const int jj = j + rA;
-                        if (jj >= 0 && jj < rA) bitsA |= 1u << rank_s[jj];
+                for (int k = 0; k < 16; ++k) {
+                    unsigned w = row[k];
+                    while (w != 0u) {  // (rare: a row has a handful of minimal cells)
+                        const int b = 31 - __clz((int)w);
+                        w ^= 1u << b;
+                        const int l = 2 * k + (b >> 4);        // the lane that set it
+                        const int c = C - 1 - (b & 7);         // its cell
+                        const int j = l * C + c + 1 - 32 * C;  // column minus r
+                        if (b & 8) {
+                            const int jj = j + rB;
+                            if (jj >= 0 && jj < rB) bitsB |= 1u << rank_s[32 * CMAX + jj];
+                        } else {
+                            const int jj = j + rA;
+                            if (jj >= 0 && jj < rA) bitsA |= 1u << rank_s[jj];
+                        }
                     }
                 }
-            }
-            if (i < p.Hout) {
-                if (pairA >= 0 && i <= stepsA) {
-                    p.dbits[((int64_t)i * p.P + pairA) * p.Wd] = bitsA;
-                    const int cnt = __popc(bitsA);
-                    mx = cnt > mx ? cnt : mx;
+                if (i < p.Hout) {
+                    if (pairA >= 0 && i <= stepsA) {
+                        p.dbits[((int64_t)i * p.P + pairA) * p.Wd] = bitsA;
+                        const int cnt = __popc(bitsA);
+                        mx = cnt > mx ? cnt : mx;
+                    }
+                    if (pairB >= 0 && i <= stepsB) {
+                        p.dbits[((int64_t)i * p.P + pairB) * p.Wd] = bitsB;
+                        const int cnt = __popc(bitsB);
+                        mx = cnt > mx ? cnt : mx;
+                    }
                 }
-                if (pairB >= 0 && i <= stepsB) {
-                    p.dbits[((int64_t)i * p.P + pairB) * p.Wd] = bitsB;
-                    const int cnt = __popc(bitsB);
-                    mx = cnt > mx ? cnt : mx;
-                }
-            }
+            };
+            auto nothing = [](int) {};
+            levm_pass<C, 0>(p, lane, rA, rB, pairA, pairB, maxsteps, nht_s, rowmin_s, sheet_s, nothing);
+            __syncwarp();
+            levm_pass<C, 1>(p, lane, rA, rB, pairA, pairB, maxsteps, nht_s, rowmin_s, sheet_s, convert);
+            __syncwarp();
         };
-        auto nothing = [](int) {};
-        levm_pass<C, 0>(p, lane, rA, rB, pairA, pairB, maxsteps, nht_s, rowmin_s, sheet_s, nothing);
-        __syncwarp();
-        levm_pass<C, 1>(p, lane, rA, rB, pairA, pairB, maxsteps, nht_s, rowmin_s, sheet_s, convert);
-        __syncwarp();
+        const int rmax = rA > rB ? rA : rB;
+        const int cneed = (rmax + 32) / 32;  // ceil((r + 1) / 32)
+        if (CMAX >= 8 && cneed > 7) run(LevmCols<(CMAX >= 8 ? 8 : CMAX)>{});
+        else if (CMAX >= 7 && cneed > 6) run(LevmCols<(CMAX >= 7 ? 7 : CMAX)>{});
+        else if (CMAX >= 6 && cneed > 5) run(LevmCols<(CMAX >= 6 ? 6 : CMAX)>{});
+        else if (CMAX >= 5 && cneed > 4) run(LevmCols<(CMAX >= 5 ? 5 : CMAX)>{});
+        else if (CMAX >= 4 && cneed > 3) run(LevmCols<(CMAX >= 4 ? 4 : CMAX)>{});
+        else if (CMAX >= 3 && cneed > 2) run(LevmCols<(CMAX >= 3 ? 3 : CMAX)>{});
+        else if (CMAX >= 2 && cneed > 1) run(LevmCols<(CMAX >= 2 ? 2 : CMAX)>{});
+        else run(LevmCols<1>{});
         // SM:271-278: prefix 0 points at reference position 0 whenever the reference is non-empty
         if (lane == 0 && p.Hout > 0) {
             if (pairA >= 0 && rA > 0) {
@@ -199,7 +229,7 @@ __global__ void __launch_bounds__(256) lev_mask16_kernel(const LevParams p, cons
                 mx = mx < 1 ? 1 : mx;
             }
             if (pairB >= 0 && rB > 0) {
-                p.dbits[(int64_t)pairB * p.Wd] = 1u << rank_s[32 * C];
+                p.dbits[(int64_t)pairB * p.Wd] = 1u << rank_s[32 * CMAX];
                 mx = mx < 1 ? 1 : mx;
             }
         }
@@ -232,7 +262,7 @@ int lev_launch_mask16(const LevParams& p, bool float_path, cudaStream_t st) {
     const size_t budget = 56 * 1024;  // four CTAs per SM
     if (per_warp > budget) return 0;
     int wpc = (int)(budget / per_warp);
-    if (wpc > 8) wpc = 8;
+    if (wpc > 4) wpc = 4;  // small CTAs: a batch is often a single wave, and whole CTAs are what the SMs share out
     const size_t smem = per_warp * wpc;
     const int64_t nduo = ((int64_t)p.P + 1) / 2;
     int64_t blocks = (nduo + wpc - 1) / wpc;
