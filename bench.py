@@ -809,7 +809,11 @@ def main():
             kname = {1: "lev_group_kernel<cost,FINAL,packed16>", 3: "lev_warp_kernel<int,MASK> (two passes)",
                      4: "lev_group_kernel<cost,FINAL,packed16>", 5: "lev_cta_kernel<int,PREFIX> (TMA-staged)",
                      2: "lev_group_kernel<cost,PREFIX,packed16>"}[wl.cfg]
-            roofline = int32_roofline(kname, float(prof[3]),
+            dp_ms = float(prof[3])
+            if wl.cfg == 3 and len(prof) > 11 and prof[11] > dp_ms:
+                # mask mode on the packed kernel (lev_warp_kernel only takes what it leaves)
+                kname, dp_ms = "lev_mask16_kernel<8> (two passes, two pairs per warp, 16x2 DPX)", float(prof[11])
+            roofline = int32_roofline(kname, dp_ms,
                                       "algorithmic 5 INT32 ops/cell (SURVEY 8d) on the wavefront DP kernel",
                                       kname.split("<")[0])
             if pack_ms > 0:
