@@ -579,7 +579,8 @@ extern "C" int b200lev_completion_fill(const b200lev_tokens_t* ref, const b200le
     }
     const char* ws = lev_ws_base(workspace);
     return lev_launch_completion_fill((const uint32_t*)(ws + L.off_dbits),
-                                      (const int64_t*)(ws + L.off_dtok), L.Rp, L.Hout, L.P, L.Wd,
+                                      (const int64_t*)(ws + L.off_dtok), (const int*)(ws + L.off_flags), L.Rp,
+                                      L.Hout, L.P, L.Wd,
                                       opts->ref_group, U, opts->padding, out, out_stride_i,
                                       out_stride_n, (cudaStream_t)stream);
 }

@@ -163,6 +163,14 @@ __device__ __forceinline__ bool lev_tokens_narrow(const int* state) {
     const unsigned umax = (unsigned)state[1], umin = ~(unsigned)state[2];
     return umax < umin || umax - umin < 65536u;
 }
+// Mask mode, small alphabets (character-level targets): when every token of the call lies in a
+// window of 32 values, "token - smallest token" IS an order-preserving index into a one-word
+// bitmap -- no sort per reference, no rank -> token table (lev_completion.cu)
+__device__ __forceinline__ bool lev_tokens_direct(const int* state, int* tmin) {
+    const unsigned umax = (unsigned)state[1], umin = ~(unsigned)state[2];
+    *tmin = (int)(umin ^ 0x80000000u);
+    return !(state[0] & B200LEV_FLAG_WIDE_TOKENS) && umax >= umin && umax - umin < 32u;
+}
 // the packed mask kernel (lev_mask16.cu) and lev_warp_kernel split a mask-mode batch by these
 // two rules: the first is per call, the second per pair
 __device__ __forceinline__ bool lev_mask16_tokens_ok(const int* state) {
@@ -222,7 +230,7 @@ int lev_bitvec_mode();
 int lev_launch_uid(const b200lev_tokens_t* ref, const int32_t* packed, const int* state,
                    const int32_t* ref_len, int32_t* uid,
                    int64_t* dtok, int32_t* ndist, int64_t Rp, cudaStream_t st);
-int lev_launch_completion_fill(const uint32_t* dbits, const int64_t* dtok, int64_t Rp,
+int lev_launch_completion_fill(const uint32_t* dbits, const int64_t* dtok, const int* state, int64_t Rp,
                                int64_t Hout, int64_t P, int64_t Wd, int ref_group, int64_t U,
                                int64_t padding, int64_t* out, int64_t out_si, int64_t out_sn,
                                cudaStream_t st);

@@ -33,6 +33,17 @@ lev_uid_kernel(const TT* __restrict__ tok, int64_t st, int64_t sn, const int32_t
     const int64_t n = blockIdx.x;
     const int r = ref_len[n];
     const int tid = threadIdx.x, nt = blockDim.x;
+    {
+        // a call whose tokens span fewer than 32 values: the bit of a token is its offset from
+        // the smallest one (ascending bit order is still ascending token order, duplicates still
+        // collapse); lev_completion_fill turns bits back into tokens by the same rule
+        int tmin;
+        if (lev_tokens_direct(state, &tmin)) {
+            for (int j = tid; j < r; j += nt) uid[n * Rp + j] = packed[n * Rp + j] - tmin;
+            if (tid == 0) ndist[n] = 32;
+            return;
+        }
+    }
     // the smallest power of two that holds this reference (uniform per CTA)
     int m = 32;
     while (m < r) m <<= 1;
@@ -155,16 +166,16 @@ int lev_launch_uid(const b200lev_tokens_t* ref, const int32_t* packed, const int
 
 // One thread per (hypothesis prefix i, pair n) lists the distinct next tokens of its row.
 // STAGED: the 32 rows of a warp are ONE contiguous run of 32 * U values in the output (rows of
-// consecutive n are adjacent), most of it padding.  Each lane enumerates the few set bits of its
-// row into shared memory and publishes the count; then the warp writes the run with 128-bit
-// stores, 512 contiguous bytes per store instruction (a value is the staged token if its slot
-// is below the row's count, else `padding`, which never passes through shared memory).  A
-// thread writing its own U values directly touches 32 different sectors per instruction, a
-// quarter of each: 2.4 TB/s of the 7 TB/s a plain fill reaches on this part.
+// consecutive n are adjacent), most of it padding.  The warp keeps an image of that run in
+// shared memory: it fills the image with `padding` (128-bit stores), each lane drops the few
+// tokens of its row into it, and the image goes out with 128-bit loads and stores, 512
+// contiguous bytes per instruction -- no per-element index arithmetic at all.  A thread writing
+// its own U values directly touches 32 different sectors per instruction, a quarter of each:
+// 2.4 TB/s of the 7 TB/s a plain fill reaches on this part.
 template <bool STAGED>
 __global__ void __launch_bounds__(256)
 lev_completion_fill_kernel(const uint32_t* __restrict__ dbits, const int64_t* __restrict__ dtok,
-                           int64_t Rp, int Hout, int P, int Wd, int ref_group, int64_t U, int64_t padding,
+                           const int* __restrict__ state, int64_t Rp, int Hout, int P, int Wd, int ref_group, int64_t U, int64_t padding,
                            int64_t* __restrict__ out, int64_t out_si, int64_t out_sn) {
     LEV_DYN_SMEM(int64_t, lev_fill_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -174,96 +185,97 @@ lev_completion_fill_kernel(const uint32_t* __restrict__ dbits, const int64_t* __
     const int n0 = n - lane;
     if (n0 >= P) return;
     const bool live = n < P;
-    const int64_t Us = U | 1;  // odd row pitch: the lanes' 8-byte stores spread over the banks
-    int64_t* __restrict__ buf = lev_fill_smem + (int64_t)warp * 32 * Us;
+    const int Ui = (int)U;
+    const int total2 = 16 * Ui;  // 16-byte pieces of a run of 32 rows
+    int64_t* __restrict__ img = lev_fill_smem + (int64_t)warp * 32 * U;
     // staged only when the warp's 32 rows are one contiguous piece of the output
     const bool run = STAGED && out_sn == U && n0 + 31 < P;
     const int64_t* __restrict__ dt = dtok + (int64_t)((live ? n : n0) / ref_group) * Rp;
+    const longlong2 pad2 = make_longlong2(padding, padding);
+    int tmin;
+    const bool direct = lev_tokens_direct(state, &tmin);  // bit b of word 0 = token tmin + b
+    // The two global reads of a row depend on each other (bitmap word -> token table) and both
+    // miss L1: the first word of the NEXT prefix's bitmap is fetched an iteration ahead, and the
+    // table look-ups go out four at a time before the first of them is used.
+    uint32_t word0 = (live && (int)blockIdx.y < Hout) ? dbits[((int64_t)blockIdx.y * P + n) * Wd] : 0u;
     for (int i = blockIdx.y; i < Hout; i += gridDim.y) {
-    int64_t* __restrict__ o = run ? buf + (int64_t)lane * Us : out + i * out_si + n * out_sn;
-    int cnt = 0;
-    if (live) {
-        const uint32_t* __restrict__ w = dbits + ((int64_t)i * P + n) * Wd;
-        int k = 0;
-        const int Ui = (int)U;
-        for (int q = 0; q < Wd && k < Ui; ++q) {
-            uint32_t bits = w[q];
-            while (bits && k < Ui) {
-                const int b = __ffs((int)bits) - 1;
-                bits &= bits - 1;
-                o[k++] = dt[q * 32 + b];
-            }
+        const uint32_t w0 = word0;
+        if (live && i + (int)gridDim.y < Hout) word0 = dbits[((int64_t)(i + gridDim.y) * P + n) * Wd];
+        if (STAGED && run) {
+            longlong2* __restrict__ img2 = reinterpret_cast<longlong2*>(img);
+            for (int e = lane; e < total2; e += 32) img2[e] = pad2;
+            __syncwarp();
         }
-        cnt = k;
-        if (!run)
-            for (; k < Ui; ++k) o[k] = padding;
-    }
-    if (STAGED) {
-        __syncwarp();
-        if (run) {
-            int64_t* __restrict__ dst = out + i * out_si + (int64_t)n0 * U;
-            // element e of the run = slot k of row `row`; lane handles e = 2 lane, 2 lane + 1,
-            // then + 64 ...; the counts of the rows travel by shuffle.  All of it in 32 bits
-            // (a run is 32 U elements) with the divisions by U hoisted out of the loop.
-            const int Ui = (int)U, Usi = (int)Us, total = 32 * Ui;
-            if (((i * out_si + (int64_t)n0 * U) & 1) != 0) {
+        int64_t* __restrict__ o = run ? img + lane * Ui : out + i * out_si + n * out_sn;
+        if (live) {
+            const uint32_t* __restrict__ w = dbits + ((int64_t)i * P + n) * Wd;
+            int k = 0;
+            for (int q = 0; q < Wd && k < Ui; ++q) {
+                uint32_t bits = q == 0 ? w0 : w[q];
+                const int64_t* __restrict__ dq = dt + q * 32;
+                if (direct) {  // (q == 0: such bitmaps have one word in use)
+                    while (bits && k < Ui) {
+                        o[k++] = (int64_t)tmin + (__ffs((int)bits) - 1);
+                        bits &= bits - 1u;
+                    }
+                }
+                while (bits && k < Ui) {
+                    int64_t t[4];
+                    int nb = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool ok = bits != 0u;
+                        const int b = ok ? __ffs((int)bits) - 1 : 0;
+                        bits &= bits - 1u;  // (0 stays 0)
+                        t[j] = dq[b];       // (slot 0 of the table always exists)
+                        nb += ok ? 1 : 0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < nb && k < Ui) o[k++] = t[j];
+                }
+            }
+            if (!run)
+                for (; k < Ui; ++k) o[k] = padding;
+        }
+        if (STAGED && run) {
+            __syncwarp();
+            const int64_t first = i * out_si + (int64_t)n0 * U;
+            if ((first & 1) == 0) {
+                const longlong2* __restrict__ img2 = reinterpret_cast<const longlong2*>(img);
+                longlong2* __restrict__ dst2 = reinterpret_cast<longlong2*>(out + first);
+                for (int e = lane; e < total2; e += 32) dst2[e] = img2[e];
+            } else {
                 // the run starts on an odd element (odd U times odd row count): 8-byte stores
-                for (int e = lane; e < total; e += 32) {
-                    const int rw = e / Ui, kk = e - rw * Ui;
-                    const int c = __shfl_sync(__activemask(), cnt, rw);
-                    dst[e] = kk < c ? buf[rw * Usi + kk] : padding;
-                }
-                __syncwarp();
-                continue;
+                int64_t* __restrict__ dst = out + first;
+                for (int e = lane; e < 2 * total2; e += 32) dst[e] = img[e];
             }
-            const int q64 = 64 / Ui, r64 = 64 - q64 * Ui;
-            int row = (2 * lane) / Ui, k = 2 * lane - row * Ui;
-            for (int e = 2 * lane; e - 2 * lane < total; e += 64) {
-                const bool in = e < total;  // (total is even: a pair never straddles the end)
-                const int r0 = in ? row : 0;
-                int r1 = r0, k1 = k + 1;
-                if (k1 >= Ui) {
-                    k1 = 0;
-                    r1 = r0 + 1;
-                }
-                r1 = r1 > 31 ? 31 : r1;  // (only the unused second half of a final pair)
-                const int c0 = __shfl_sync(LEV_FULL_MASK, cnt, r0);
-                const int c1 = __shfl_sync(LEV_FULL_MASK, cnt, r1);
-                if (in) {
-                    longlong2 v;
-                    v.x = k < c0 ? buf[r0 * Usi + k] : padding;
-                    v.y = k1 < c1 ? buf[r1 * Usi + k1] : padding;
-                    *reinterpret_cast<longlong2*>(dst + e) = v;
-                }
-                k += r64;
-                row += q64;
-                if (k >= Ui) {
-                    k -= Ui;
-                    ++row;
-                }
-            }
+            __syncwarp();  // the image is reused by the next prefix
         }
-        __syncwarp();  // the staging rows are reused by the next prefix
-    }
     }
 }
 
-int lev_launch_completion_fill(const uint32_t* dbits, const int64_t* dtok, int64_t Rp,
+int lev_launch_completion_fill(const uint32_t* dbits, const int64_t* dtok, const int* state, int64_t Rp,
                                int64_t Hout, int64_t P, int64_t Wd, int ref_group, int64_t U,
                                int64_t padding, int64_t* out, int64_t out_si, int64_t out_sn,
                                cudaStream_t st) {
     if (Hout <= 0 || P <= 0 || U <= 0) return B200LEV_OK;
-    dim3 block(256), grid((unsigned)((P + 255) / 256), (unsigned)(Hout < 65535 ? Hout : 65535));
-    const size_t smem = (size_t)8 * 32 * (size_t)(U | 1) * sizeof(int64_t);
+    // (a CTA walks several prefixes once the grid holds a few waves)
+    const int64_t gx = (P + 255) / 256;
+    int64_t gy = (148 * 16 + gx - 1) / gx;
+    if (gy > Hout) gy = Hout;
+    if (gy > 65535) gy = 65535;
+    dim3 block(256), grid((unsigned)gx, (unsigned)gy);
+    const size_t smem = (size_t)8 * 32 * (size_t)U * sizeof(int64_t);
     lev_prof_begin(LEV_PROF_COMP_FILL, st);
     if (smem <= 96 * 1024) {
         auto kern = lev_completion_fill_kernel<true>;
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        lev_launch(kern, grid, block, smem, st, dbits, dtok, Rp, (int)Hout, (int)P, (int)Wd, ref_group, U, padding,
+        lev_launch(kern, grid, block, smem, st, dbits, dtok, state, Rp, (int)Hout, (int)P, (int)Wd, ref_group, U, padding,
                    out, out_si, out_sn);
     } else {
-        lev_launch(lev_completion_fill_kernel<false>, grid, block, 0, st, dbits, dtok, Rp, (int)Hout, (int)P,
+        lev_launch(lev_completion_fill_kernel<false>, grid, block, 0, st, dbits, dtok, state, Rp, (int)Hout, (int)P,
                    (int)Wd, ref_group, U, padding, out, out_si, out_sn);
     }
     lev_prof_end(LEV_PROF_COMP_FILL, st);

@@ -469,6 +469,25 @@ def check_ctc_masked_classes(F, dev):
 # ---------------------------------------------------------------------------------------
 # fill_after_eos and the nn.Module shells under nojit / trace / script
 # ---------------------------------------------------------------------------------------
+def check_completion_small_alphabets(F, dev, seed=0):
+    """optimal_completion where the call's tokens span 31 / 32 / 33 / 40 values, around zero and
+    far from it: up to 32 the bitmaps index tokens by their offset from the smallest one
+    (lev_tokens_direct), above that by their rank in the sorted reference -- same outputs."""
+    rng = np.random.default_rng(seed)
+    for lo in (-17, 0, 5, 1 << 20, -(1 << 30)):
+        for span in (2, 31, 32, 33, 40):
+            R, H, N = 37, 33, 21
+            ref = rng.integers(lo, lo + span, size=(R, N)).astype(np.int64)
+            hyp = rng.integers(lo, lo + span, size=(H, N)).astype(np.int64)
+            ref[0, 0], ref[1, 0] = lo, lo + span - 1  # the whole span is present
+            eos = lo + 1
+            for kw in (dict(eos=eos, include_eos=True), dict(eos=None), dict(eos=eos, include_eos=False, exclude_last=True)):
+                exp = O.optimal_completion(ref, hyp, **kw)
+                act = F.optimal_completion(torch.from_numpy(ref).to(dev), torch.from_numpy(hyp).to(dev),
+                                           warn=False, **kw)
+                assert_same(act, exp, True, f"small alphabet lo={lo} span={span} {kw}")
+
+
 def check_fill_after_eos(F, dev, seed=0):
     """SM:30-42 against the oracle: every axis, negative axes, integer and float fills, a
     broadcast ``value`` tensor, float "tokens" (the reference's trace placeholders), 1-D and

@@ -672,6 +672,12 @@ def test_completion_packed_mask_kernel(F, dev, costs, monkeypatch):
                        exclude_last=False, min_frac=0.2)
 
 
+def test_completion_small_alphabets(F, dev, monkeypatch):
+    PC.check_completion_small_alphabets(F, dev)
+    monkeypatch.setenv("B200LEV_MASK16_MIN_PAIRS", "1")
+    PC.check_completion_small_alphabets(F, dev, seed=1)
+
+
 @pytest.mark.parametrize("N", [33, 37, 64, 65, 97])
 def test_completion_target_writer_alignment(F, dev, N):
     """The target writer stores 16 bytes per lane where a warp's run of 32 rows starts on an even

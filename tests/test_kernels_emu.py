@@ -525,5 +525,11 @@ def test_completion_packed_mask_kernel(F, costs, monkeypatch):
                                norm=False, exclude_last=excl, min_frac=0.0, spread=spread)
 
 
+def test_completion_small_alphabets(F, monkeypatch):
+    PC.check_completion_small_alphabets(F, DEV)
+    monkeypatch.setenv("B200LEV_MASK16_MIN_PAIRS", "1")
+    PC.check_completion_small_alphabets(F, DEV, seed=1)
+
+
 def test_sequence_log_probs_packed(F, golden_seqlp_packed):
     assert PC.check_golden_seqlp_packed(F, DEV, golden_seqlp_packed) == 6
