@@ -199,10 +199,16 @@ __device__ __forceinline__ int lev_warp_pair(const LevParams& p, const int pair,
                     } else {
                         // integer costs: 4 INT32 instructions per cell
                         int dg = (int)diag_v, lf = (int)in_v;
+                        // (32-bit tokens: "differs" as 0 / 1 from one DPX add-and-clamp, times the
+                        // cost on the FMA pipe -- 3 ALU-pipe instructions per cell; 64-bit tokens
+                        // keep the compare)
+                        const unsigned nht = 0u - (unsigned)ht;
+                        (void)nht;
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
                             const int up = (int)v[c];
-                            const int sb = dg + ((rt[c] != ht) ? (int)subc : 0);
+                            const int sb = WIDE ? dg + ((rt[c] != ht) ? (int)subc : 0)
+                                                : dg + (int)(__viaddmin_u32((unsigned)rt[c], nht, 1u) * (unsigned)subc);
                             const int t = __viaddmin_s32(up, (int)insc, sb);
                             lf = __viaddmin_s32(lf, (int)delc, t);
                             dg = up;

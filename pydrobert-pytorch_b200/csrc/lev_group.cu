@@ -128,11 +128,11 @@ __device__ __forceinline__ void levg_run32(const LevParams& p, const int G, cons
                 }
             } else {
                 int dg = diag_v, lf = in_v;
+                const unsigned nht = 0u - (unsigned)ht;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const int up = v[c];
-                    int sb = dg;
-                    if (rt[c] != ht) sb += subc;
+                    const int sb = dg + (int)(__viaddmin_u32((unsigned)rt[c], nht, 1u) * (unsigned)subc);
                     const int t = __viaddmin_s32(up, insc, sb);
                     lf = __viaddmin_s32(lf, delc, t);
                     dg = up;

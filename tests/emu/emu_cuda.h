@@ -233,6 +233,7 @@ static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 static inline int __viaddmin_s32(int a, int b, int c) { return std::min(a + b, c); }
+static inline unsigned __viaddmin_u32(unsigned a, unsigned b, unsigned c) { return std::min(a + b, c); }
 static inline int __viaddmax_s32(int a, int b, int c) { return std::max(a + b, c); }
 static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift) {
     shift &= 31;
