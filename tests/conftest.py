@@ -33,6 +33,17 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(autouse=True)
+def _small_unit_cost_batches_on_the_wavefront_kernels(monkeypatch):
+    """The library sends EVERY unit-cost batch with references of at most 64 tokens to the
+    short-reference bit-vector kernel (B200LEV_BVSHORT_MIN_PAIRS defaults to 1).  Most tests here
+    use tiny unit-cost batches to exercise the pack / wavefront / group / CTA kernels, so the suite
+    runs with the threshold at 64; the `bv_form` tests (and the reference's own suite, which sets
+    nothing) cover the default."""
+    if "B200LEV_BVSHORT_MIN_PAIRS" not in os.environ:
+        monkeypatch.setenv("B200LEV_BVSHORT_MIN_PAIRS", "64")
+
+
 class Golden:
     """Accessor for one tests/golden/*.npz fixture (written by make_golden.py)."""
 

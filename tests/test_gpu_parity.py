@@ -183,7 +183,7 @@ def test_cfg4_bulk_slice_and_sums(F, dev):
     from b200lev import dist as D
 
     rng = np.random.default_rng(4)
-    P, T, V = 100_000, 31, 10000
+    P, T, V = 100_003, 31, 10000  # (not a multiple of 32: the last warp shadows the last pair)
     ref = PC.random_tokens(rng, T, P, V, -1, -2, min_len=9)
     hyp = PC.random_tokens(rng, T, P, V, -1, -2, min_len=9)
     exp = O.error_rate(ref, hyp, eos=-1, include_eos=False, norm=False)

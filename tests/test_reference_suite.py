@@ -31,6 +31,7 @@ def _run(marker, test_file="test_string.py", select=None, expected=EXPECTED_CASE
             and os.path.isdir(os.path.join(REF_PKG, "pydrobert"))):
         pytest.skip("reference copy absent (oracle/make_ref.sh needs /root/reference)")
     env = dict(os.environ)
+    env.pop("B200LEV_BVSHORT_MIN_PAIRS", None)  # the reference's own suite runs at the library's defaults
     env["PYTHONPATH"] = os.pathsep.join([REF_PKG, os.path.join(ROOT, "tests")]
                                         + ([env["PYTHONPATH"]] if env.get("PYTHONPATH") else []))
     cmd = [sys.executable, "-m", "pytest", "-p", "ref_suite_plugin", "-p", "no:cacheprovider", "-q",
