@@ -89,7 +89,7 @@ __device__ __forceinline__ void lev_bvs_totals(double sum_out, int sum_len, doub
 }
 
 template <typename TT, int W, int KIND>
-__global__ void __launch_bounds__(32 * LEV_BVS_WARPS, W == 1 ? 4 : 3) lev_bv_short_kernel(const LevBvArgs a) {
+__global__ void __launch_bounds__(32 * LEV_BVS_WARPS, 4) lev_bv_short_kernel(const LevBvArgs a) {
     constexpr bool PREFIX = KIND != 0, EXCL = KIND == 2;
     constexpr int CH = 4;
     const int lane = threadIdx.x & 31;
