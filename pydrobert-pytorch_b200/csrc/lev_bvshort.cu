@@ -89,7 +89,7 @@ __device__ __forceinline__ void lev_bvs_totals(double sum_out, int sum_len, doub
 }
 
 template <typename TT, int W, int KIND>
-__global__ void __launch_bounds__(32 * LEV_BVS_WARPS, 4) lev_bv_short_kernel(const LevBvArgs a) {
+__global__ void __launch_bounds__(32 * LEV_BVS_WARPS, W == 1 ? 5 : 4) lev_bv_short_kernel(const LevBvArgs a) {
     constexpr bool PREFIX = KIND != 0, EXCL = KIND == 2;
     constexpr int CH = 4;
     const int lane = threadIdx.x & 31;
@@ -441,7 +441,7 @@ bool lev_bvshort_supports(int elem_bytes, int64_t R) {
 template <typename TT, int W>
 static void lev_bvs_launch_w(const LevBvArgs& a, cudaStream_t st) {
     int64_t n = ((int64_t)a.P + 32 * LEV_BVS_WARPS - 1) / (32 * LEV_BVS_WARPS);
-    int64_t cap = (int64_t)148 * 16;
+    int64_t cap = (int64_t)148 * (W == 1 ? 20 : 16);  // whole waves of the resident CTAs (5 / 4 per SM)
     if (const char* e = getenv("B200LEV_BVS_CTAS")) cap = atoll(e) > 0 ? atoll(e) : cap;  // (tests: many blocks per warp)
     const dim3 grid((unsigned)(n < cap ? n : cap)), block(32 * LEV_BVS_WARPS);
     if (a.mode != LEV_MODE_PREFIX)
