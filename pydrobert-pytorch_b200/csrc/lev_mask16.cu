@@ -71,7 +71,7 @@ __device__ __forceinline__ void levm_pass(const LevParams& p, const int lane, co
     // complete in every lane
     for (int s0 = 0; s0 < nsteps; s0 += 32) {
         const int nk = nsteps - s0 < 32 ? nsteps - s0 : 32;
-#pragma unroll 1
+#pragma unroll 2
         for (int k = 0; k < nk; ++k, ++i) {
             const unsigned sh = __shfl_up_sync(LEV_FULL_MASK, v[C - 1], 1);
             const unsigned in = (lane == 0) ? BIG2 : sh;
