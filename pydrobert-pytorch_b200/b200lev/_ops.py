@@ -593,14 +593,14 @@ def ragged_to_padded(flat: Tensor, offsets: Tensor, sel: Optional[Tensor], first
     return out
 
 
-@torch.library.custom_op("b200lev::error_sums", mutates_args=())
-def error_sums(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: bool, batch_first: bool,
-               ins_cost: float, del_cost: float, sub_cost: float, norm: bool,
-               return_mistakes: bool, ref_group: int) -> Tuple[Tensor, Tensor, Tensor]:
+def error_sums_impl(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: bool, batch_first: bool,
+                    ins_cost: float, del_cost: float, sub_cost: float, norm: bool,
+                    return_mistakes: bool, ref_group: int) -> Tuple[Tensor, Tensor, Tensor]:
     """Bulk scoring (command_line.py:1124-1147 without the per-utterance host reads):
     ``(er, acc, flags)`` with ``er`` the per-pair values of ``string_matching`` and
     ``acc = [sum(er), sum(ref_lens), #pairs]`` in fp64 ON THE COMPUTE DEVICE, ready for a
-    single all-reduce.  The reference lengths come from the same packing pass as the DP."""
+    single all-reduce.  One C call (``b200lev_final_sums``); where the short-reference kernel
+    serves it, one kernel."""
     R, H, n = _shapes(ref, hyp, batch_first, ref_group)
     ref, hyp = _as_tokens(ref), _as_tokens(hyp)
     pl = _host.Placement(ref, hyp)
@@ -610,8 +610,11 @@ def error_sums(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: bool, 
         rt, ht = _tok_struct(ref, batch_first), _tok_struct(hyp, batch_first)
         o = _opts(eos, include_eos, ins_cost, del_cost, sub_cost, norm, False, 0,
                   return_mistakes, ref_group)
-        flags = torch.zeros(1, dtype=torch.int32, device=dev)
-        acc = torch.zeros(3, dtype=torch.float64, device=dev)
+        # one zero fill for both: the totals, and behind them the warning flags (a step of a
+        # strongly scaled scoring job is a few tens of microseconds: every launch counts)
+        zeroed = torch.zeros(4, dtype=torch.float64, device=dev)
+        acc = zeroed[:3]
+        flags = zeroed[3:].view(torch.int32)[:1]
         nbytes = L.b200lev_workspace_bytes(ctypes.byref(rt), ctypes.byref(ht), 0, 0)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         out = torch.empty(n, dtype=torch.float32, device=dev)
@@ -620,6 +623,19 @@ def error_sums(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: bool, 
                                         out.data_ptr(), ws.data_ptr(), nbytes, flags.data_ptr(),
                                         acc.data_ptr(), st))
     return pl.back(out), acc, pl.back(flags)
+
+
+def _error_sums_op(ref: Tensor, hyp: Tensor, eos: Optional[int], include_eos: bool, batch_first: bool,
+                   ins_cost: float, del_cost: float, sub_cost: float, norm: bool,
+                   return_mistakes: bool, ref_group: int) -> Tuple[Tensor, Tensor, Tensor]:
+    # (the returns of a registered op may not share storage: totals and flags are views of one
+    # zero-filled block in the plain function)
+    er, acc, flags = error_sums_impl(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost,
+                                     sub_cost, norm, return_mistakes, ref_group)
+    return er, acc.clone(), flags.clone()
+
+
+error_sums = torch.library.custom_op("b200lev::error_sums", _error_sums_op, mutates_args=())
 
 
 @error_sums.register_fake
