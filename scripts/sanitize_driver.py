@@ -57,7 +57,8 @@ def nbest_case(what):
          O.prefix_error_rates(rx, h, eos=0), what)
 
 
-which = sys.argv[1:] or ["warp", "group", "cta", "bitvec2", "fused", "completion", "loss", "seqlp", "ragged"]
+which = sys.argv[1:] or ["warp", "group", "cta", "bitvec2", "fused", "short", "completion", "mask16", "loss", "seqlp",
+                         "ragged"]
 if "warp" in which:  # K1: warp per pair (lev_dp.cu), integer and float costs
     run({"B200LEV_BITVEC": "0", "B200LEV_CTA_KERNEL": "0"}, lambda: prefix_case(70, 80, 9, 7, "K1 warp kernel"))
     run({"B200LEV_BITVEC": "0"}, lambda: prefix_case(40, 45, 5, 7, "K1 float costs", ins_cost=0.7, del_cost=1.1, sub_cost=1.3)
@@ -75,6 +76,29 @@ if "fused" in which:  # fused bit-vector kernel + probe
     run({"B200LEV_BITVEC": "1", "B200LEV_BITVEC_MIN_PAIRS": "1"}, lambda: nbest_case("fused bit-vector kernel"))
     run({"B200LEV_BITVEC_MIN_PAIRS": "1", "B200LEV_GROUP_MIN_PAIRS": "1"},
         lambda: nbest_case("device-selected (probe + fork)"))
+if "short" in which:  # short-reference bit-vector kernel: one and two words, prefix rows, bulk totals
+    from b200lev import dist as D
+
+    run({"B200LEV_BVSHORT_MIN_PAIRS": "1"}, lambda: prefix_case(30, 35, 70, 12, "short-reference kernel, one word"))
+    run({"B200LEV_BVSHORT_MIN_PAIRS": "1"}, lambda: prefix_case(60, 50, 45, 300, "short-reference kernel, two words"))
+
+    def bulk():
+        r, h = toks(31, 1100, 500, eos=-1), toks(31, 1100, 500, eos=-1)
+        er, acc = D.bulk_error_rate(torch.from_numpy(r).to(dev), torch.from_numpy(h).to(dev), eos=-1)
+        exp = np.asarray(O.error_rate(r, h, eos=-1, include_eos=False, norm=False))
+        same(er, exp, "bulk scoring: per-pair values")
+        assert acc.tolist()[0] == float(exp.astype(np.float64).sum()) and acc.tolist()[2] == 1100.0
+        print("ok bulk scoring: totals inside the short-reference kernel", flush=True)
+
+    run({"B200LEV_BVS_CTAS": "2"}, bulk)
+if "mask16" in which:  # packed two-pairs-per-warp mask kernel: ring of equality masks in shared memory
+    def packed(R, H, N, V, what):
+        r, h = toks(R, N, V), toks(H, N, V)
+        same(F.optimal_completion(torch.from_numpy(r).to(dev), torch.from_numpy(h).to(dev), eos=0, warn=False),
+             O.optimal_completion(r, h, eos=0), what)
+
+    run({"B200LEV_MASK16_MIN_PAIRS": "1"}, lambda: packed(70, 150, 7, 9, "packed mask kernel, small alphabet (no table)"))
+    run({"B200LEV_MASK16_MIN_PAIRS": "1"}, lambda: packed(200, 90, 5, 45, "packed mask kernel + warp kernel, rank table"))
 if "completion" in which:
     r, h = toks(40, 6, 9), toks(45, 6, 9)
     same(F.optimal_completion(torch.from_numpy(r).to(dev), torch.from_numpy(h).to(dev), eos=0, warn=False),
