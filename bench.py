@@ -766,13 +766,15 @@ def main():
                 f"lev_bv_short_kernel<int64,W={1 if wl.T <= 32 else 2},{'PREFIX' if wl.cfg == 2 else 'FINAL'}>",
                 float(prof[7]),
                 "algorithmic 5 INT32 ops/cell (SURVEY 8d); the match masks come from 16-bit packed compares "
-                "against the reference registers (2 ALU + 1 FMA instruction per two positions), the "
-                "recurrence is Myers' bit-vector step; the same kernel reads both raw int64 token tensors "
-                "(roofline_hbm)", "lev_bv_short_kernel")
+                "against the reference registers (one DPX add-and-clamp + one FMA-pipe shift per two "
+                "positions), the recurrence is Myers' bit-vector step; the same kernel reads both raw int64 "
+                "token tensors (roofline_hbm)" + ("; config 4: the totals are accumulated in this kernel" if wl.cfg == 4 else ""),
+                "lev_bv_short_kernel" if wl.T <= 32 else "lev_bv_short_kernel_cfg1")
             extra["roofline_hbm"] = hbm_roofline(
                 "lev_bv_short_kernel (its memory side)", float(prof[7]), in_bytes + out_bytes + 8 * P,
-                "reads both raw int64 token tensors once, writes the results + lengths", "lev_bv_short_kernel")
-            launches = 1 + (1 if wl.cfg == 4 else 0)
+                "reads both raw int64 token tensors once, writes the results + lengths",
+                "lev_bv_short_kernel" if wl.T <= 32 else "lev_bv_short_kernel_cfg1")
+            launches = 1  # (config 4 included: b200lev_final_sums accumulates inside the kernel)
         elif bitvec:
             fused = os.environ.get("B200LEV_BV_FUSED", "1") != "0"
             if fused:
