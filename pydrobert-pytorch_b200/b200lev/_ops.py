@@ -42,12 +42,37 @@ def _as_tokens(t: Tensor) -> Tensor:
     return t.to(torch.long)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream(dev: torch.device) -> int:
+    """The caller's current stream on `dev` as a raw handle (a small call is host-bound: the
+    Stream object torch.cuda.current_stream builds costs 6 us of a 40 us call)."""
+    if _raw_stream is not None:
+        return _raw_stream(dev.index if dev.index is not None else torch.cuda.current_device())
     return torch.cuda.current_stream(dev).cuda_stream
 
 
-def _DeviceGuard(dev: torch.device):
-    return torch.cuda.device(dev)
+class _DeviceGuard:
+    """`with torch.cuda.device(dev)` that does nothing when `dev` is current already."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, dev: torch.device):
+        self.idx = -1 if dev.index is None else dev.index
+        self.prev = -1
+
+    def __enter__(self):
+        if self.idx >= 0:
+            prev = torch.cuda.current_device()
+            if prev != self.idx:
+                torch.cuda.set_device(self.idx)
+                self.prev = prev
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def _tok_struct(t: Tensor, batch_first: bool) -> _abi.Tokens:

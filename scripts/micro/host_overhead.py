@@ -17,11 +17,15 @@ import b200lev.functional as F
 import bench
 
 dev = torch.device("cuda", 0)
-wl = bench.Workload(2)
-for pairs in (131072, 512):
+cases = [(2, 131072, "prefix_error_rates"), (2, 512, "prefix_error_rates"), (1, 32, "error_rate")]
+if len(sys.argv) > 1:
+    cases = [c for c in cases if str(c[1]) in sys.argv[1:]]
+for cfg, pairs, fn in cases:
+    wl = bench.Workload(cfg)
     r, h, cells = wl.make(pairs, 1)
     tr, th = torch.from_numpy(r).to(dev), torch.from_numpy(h).to(dev)
-    f = lambda: F.prefix_error_rates(tr, th, eos=0, warn=False)
+    f = (lambda: F.prefix_error_rates(tr, th, eos=0, warn=False)) if fn == "prefix_error_rates" else (
+        lambda: F.error_rate(tr, th, eos=0, warn=False))
     for _ in range(10):
         f()
     torch.cuda.synchronize()
@@ -43,4 +47,4 @@ for _ in range(300):
     f()
 pr.disable()
 torch.cuda.synchronize()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
