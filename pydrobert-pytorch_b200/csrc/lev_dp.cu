@@ -160,12 +160,15 @@ __device__ __forceinline__ int lev_warp_pair(const LevParams& p, const int pair,
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
                             const V uc = v[c], um = m[c];
-                            const bool neq = rt[c] != ht;
-                            const V sub_c = dc + (neq ? subc : (V)0);  // SM:293
+                            // (integer cells, 32-bit tokens: "differs" from one DPX add-and-clamp, the cost and count terms by
+                            // multiply / add instead of two selects)
+                            const V neq01 = (IS_INT && !WIDE) ? (V)(int)__viaddmin_u32((unsigned)rt[c], 0u - (unsigned)ht, 1u)
+                                                   : (rt[c] != ht ? (V)1 : (V)0);
+                            const V sub_c = IS_INT ? dc + neq01 * subc : dc + (neq01 != (V)0 ? subc : (V)0);  // SM:293
                             const V ins_c = uc + insc;                 // SM:292
                             const bool ps = ins_c >= sub_c;            // SM:296
                             V cc = ps ? sub_c : ins_c;
-                            V mm = ps ? dm + (neq ? (V)1 : (V)0) : um + (V)1;  // SM:299-301
+                            V mm = ps ? dm + neq01 : um + (V)1;  // SM:299-301
                             const V del_c = lc + delc;                          // SM:308
                             const bool keep = del_c >= cc;                      // SM:309
                             cc = keep ? cc : del_c;

@@ -106,15 +106,16 @@ __device__ __forceinline__ void levg_run32(const LevParams& p, const int G, cons
             const int ht = hyp_row[i - 1];
             if (COUNT) {  // SM:292-314
                 int dc = diag_v, dm = diag_m, lc = in_v, lm = in_m;
+                const unsigned nht = 0u - (unsigned)ht;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const int uc = v[c], um = m[c];
-                    const bool neq = rt[c] != ht;
-                    const int sub_c = dc + (neq ? subc : 0);
+                    const int neq = (int)__viaddmin_u32((unsigned)rt[c], nht, 1u);  // 1 = tokens differ (DPX)
+                    const int sub_c = dc + neq * subc;
                     const int ins_c = uc + insc;
                     const bool ps = ins_c >= sub_c;
                     int cc = ps ? sub_c : ins_c;
-                    int mm = ps ? dm + (neq ? 1 : 0) : um + 1;
+                    int mm = ps ? dm + neq : um + 1;
                     const int del_c = lc + delc;
                     const bool keep = del_c >= cc;
                     cc = keep ? cc : del_c;
