@@ -804,8 +804,8 @@ def main():
                 w = int32_roofline(
                     "lev_group_kernel<cost,PREFIX,packed16> (B200LEV_BITVEC=0: the wavefront path, taken "
                     "by every batch the bit-vector path declines)", wave["kernel_ms"],
-                    "algorithmic 5 INT32 ops/cell (SURVEY 8d); the kernel issues 2.5 instructions per cell "
-                    "(2 cells per 16x2 DPX instruction)", "lev_group_kernel")
+                    "algorithmic 5 INT32 ops/cell (SURVEY 8d); the kernel issues 2 instructions per cell "
+                    "(3 ALU-pipe DPX + 1 FMA-pipe instruction per two cells)", "lev_group_kernel")
                 w.update({"whole_call_ms": wave["ms_per_step"],
                           "whole_call_gcups": cells / (wave["ms_per_step"] * 1e-3) / 1e9,
                           "pack_ms": wave["pack_ms"],
