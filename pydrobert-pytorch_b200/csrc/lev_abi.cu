@@ -333,10 +333,13 @@ static int lev_try_bitvec(const b200lev_tokens_t* ref, const b200lev_tokens_t* h
     memset(&tmp, 0, sizeof(tmp));
     bool cm, fp;
     lev_classify_costs(o, L.R, L.H, &tmp, &cm, &fp);
-    bool short_form = false;
-    if (!lev_bitvec_eligible(ref, hyp, mode, cm, fp, tmp.ins_i, tmp.del_i, tmp.sub_i, out_sn, &short_form)) return 0;
-    // the short-reference kernel takes any batch: nothing to select on the device, no chain behind it
-    const bool forced = lev_bitvec_mode() == 1 || short_form;
+    bool short_form = false, grouped = false;
+    if (!lev_bitvec_eligible(ref, hyp, mode, cm, fp, tmp.ins_i, tmp.del_i, tmp.sub_i, out_sn, o->ref_group,
+                             &short_form, &grouped))
+        return 0;
+    // the short-reference kernel takes any batch, the fused kernel any batch whose references the
+    // caller declared shared: nothing to select on the device, no chain behind them
+    const bool forced = lev_bitvec_mode() == 1 || short_form || grouped;
     int32_t* state = (int32_t*)(ws + L.off_flags);
     if (!forced) {
         // device-selected: only where the wavefront fallback is the group path, whose kernels

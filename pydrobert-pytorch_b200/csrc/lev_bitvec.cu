@@ -534,16 +534,27 @@ static int64_t lev_bvshort_min_pairs() {
     return v;
 }
 
+// `grouped`: the call says how its references are shared (ref_group hypotheses per reference,
+// _string.py:1426/1439 -- minimum_error_rate_loss): with 8 or more a block of 32 pairs holds at
+// most 4 - 5 references, which is what the fused kernel's tables are built for, so there is
+// nothing to probe and no stand-by chain to enqueue; such a call is worth it from a few warps on.
 bool lev_bitvec_eligible(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp, int mode,
                          bool count_mode, bool float_path, int ins_i, int del_i, int sub_i,
-                         int64_t out_sn, bool* short_form) {
+                         int64_t out_sn, int ref_group, bool* short_form, bool* grouped) {
     *short_form = false;
+    *grouped = false;
     if (lev_bitvec_mode() == 0) return false;
     if (mode != LEV_MODE_FINAL && mode != LEV_MODE_PREFIX) return false;
     if (count_mode || float_path || ins_i != 1 || del_i != 1 || sub_i != 1) return false;
     if (ref->T > 128 || ref->T < 1 || hyp->T >= (1 << 20)) return false;
     *short_form = lev_bvshort_supports(ref->elem_bytes, ref->T) && hyp->N >= lev_bvshort_min_pairs();
-    if (!*short_form && hyp->N < lev_bv_min_pairs()) return false;
+    {
+        const char* e = getenv("B200LEV_BV_FUSED");
+        const char* g = getenv("B200LEV_BV_GROUPED");
+        *grouped = !*short_form && ref_group >= 8 && hyp->N >= 128 && !(e != nullptr && atoi(e) == 0) &&
+                   !(g != nullptr && atoi(g) == 0) && lev_bvfused_supports(ref->elem_bytes);
+    }
+    if (!*short_form && !*grouped && hyp->N < lev_bv_min_pairs()) return false;
     if (ref->elem_bytes != hyp->elem_bytes) return false;
     if (ref->stride_t >= ((int64_t)1 << 31) || hyp->stride_t >= ((int64_t)1 << 31) ||
         ref->stride_t < 0 || hyp->stride_t < 0)

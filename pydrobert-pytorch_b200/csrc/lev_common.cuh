@@ -219,7 +219,7 @@ __device__ __forceinline__ bool lev_bv_took(const int* state) {
 // unit-cost bit-vector path (lev_bitvec.cu)
 bool lev_bitvec_eligible(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp, int mode,
                          bool count_mode, bool float_path, int ins_i, int del_i, int sub_i,
-                         int64_t out_sn, bool* short_form);
+                         int64_t out_sn, int ref_group, bool* short_form, bool* grouped);
 int lev_bitvec_launch(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
                       const b200lev_opts_t* o, int mode, float mult, int32_t* ref_len,
                       int32_t* hyp_len, void* uid_ref, void* uid_hyp, void* lead,

@@ -239,6 +239,35 @@ def check_nbest_batch(F, dev, seed, R, H, n_utts, nbest, V=30, shared=True, wide
         assert_same(act, exp, True, f"{func} nbest seed={seed} shared={shared}")
 
 
+def check_grouped_references(F, dev, seed=0):
+    """minimum_error_rate_loss on batches whose group size (samples per reference) is 8 or more:
+    the call declares its references shared, so the fused bit-vector kernel takes it without a
+    probe (lev_bitvec_eligible: grouped) -- group sizes that divide 32, that do not (a block of 32
+    pairs then holds 5 references: two table passes), references of 65 .. 128 tokens (longer or
+    shorter ones go elsewhere), sub_avg on and off, and the error rates themselves through the
+    registered op."""
+    from b200lev import _ops
+
+    rng = np.random.default_rng(seed)
+    for R, H, N, M in ((70, 60, 16, 8), (100, 101, 12, 12), (128, 90, 15, 9), (65, 70, 5, 32), (96, 40, 9, 16)):
+        ref = random_tokens(rng, R, N, 40, 0, -1, 0, 0.1)
+        hyp = random_tokens(rng, H, N * M, 40, 0, -1, 0, 0.1)
+        exp_er = O.error_rate(np.repeat(ref, M, axis=1), hyp, eos=0, include_eos=True, norm=True)
+        er, _ = _ops.string_matching_impl(torch.from_numpy(ref).to(dev), torch.from_numpy(hyp).to(dev), 0, True,
+                                          False, 1.0, 1.0, 1.0, True, False, False, 0, True, M)
+        assert_same(er, exp_er, True, f"grouped error rates R={R} M={M}")
+        lp = rng.standard_normal((N, M)).astype(np.float32)
+        for sub_avg in (True, False):
+            exp_loss, exp_grad = O.minimum_error_rate_loss(lp, ref, hyp.reshape(H, N, M), eos=0, sub_avg=sub_avg)
+            x = torch.from_numpy(lp).to(dev).requires_grad_(True)
+            loss = F.minimum_error_rate_loss(x, torch.from_numpy(ref).to(dev),
+                                             torch.from_numpy(hyp.reshape(H, N, M)).to(dev), eos=0,
+                                             sub_avg=sub_avg, warn=False)
+            loss.backward()
+            np.testing.assert_allclose(loss.item(), exp_loss, rtol=2e-6, atol=1e-7)
+            np.testing.assert_allclose(x.grad.cpu().numpy(), exp_grad, rtol=2e-5, atol=1e-7)
+
+
 # ---- sequence_log_probs ("next #1", _decoding.py:1516-1548) --------------------------------
 # tolerances: fp64 1e-12; fp32 2e-6 relative (+2e-6 absolute: log_softmax of ~10-magnitude
 # logits in fp32); bf16 / fp16 one unit in the last place of the result (each step is rounded

@@ -672,6 +672,12 @@ def test_completion_packed_mask_kernel(F, dev, costs, monkeypatch):
                        exclude_last=False, min_frac=0.2)
 
 
+def test_grouped_references_take_the_fused_kernel(F, dev, monkeypatch):
+    PC.check_grouped_references(F, dev)
+    monkeypatch.setenv("B200LEV_BV_GROUPED", "0")  # the same batches through the wavefront kernels
+    PC.check_grouped_references(F, dev, seed=1)
+
+
 def test_completion_small_alphabets(F, dev, monkeypatch):
     PC.check_completion_small_alphabets(F, dev)
     monkeypatch.setenv("B200LEV_MASK16_MIN_PAIRS", "1")

@@ -89,6 +89,12 @@ def test_n_best_shared_reference(F):
     np.testing.assert_allclose(x.grad.numpy(), exp_grad, rtol=2e-5, atol=1e-7)
 
 
+def test_grouped_references_take_the_fused_kernel(F, monkeypatch):
+    PC.check_grouped_references(F, DEV)
+    monkeypatch.setenv("B200LEV_BV_GROUPED", "0")  # the same batches through the wavefront kernels
+    PC.check_grouped_references(F, DEV, seed=1)
+
+
 def test_warnings(F):
     PC.check_warnings(F, DEV)
 
