@@ -15,13 +15,17 @@
 //   * per hypothesis token the match mask Eq of Myers' recurrence is built by comparing the
 //     token with every reference register, two positions per instruction (16-bit halves,
 //     lev_bvs_neq16): no table, no hashing, unrelated references cost the same as shared ones;
-//   * one Myers step (1 or 2 words, reference LEFT-aligned: bit j = position j, the score is
-//     read at bit r - 1) per hypothesis row; eos / length logic (SM:195-228), freezing
-//     (SM:286-288), scaling, exact division by r and padding exactly as in lev_bvfused.cu.
+//   * one Myers step (1 or 2 words, reference LEFT-aligned: bit j = position j) per hypothesis
+//     row; prefix modes read the score at bit r - 1 after every step, the final mode freezes the
+//     column state at the lane's last counted token and reads the distance off it once
+//     (population counts); eos / length logic (SM:195-228), freezing (SM:286-288), scaling,
+//     exact division by r and padding exactly as in lev_bvfused.cu;
+//   * b200lev_final_sums: the totals of the bulk-scoring command (command_line.py:1135-1147)
+//     are accumulated here too, so that call is this one kernel.
 //
-// Per DP cell that is ~1.5 ALU instructions (the packed wavefront kernel issues 2.5), and it is
-// the WHOLE call.  Taken unconditionally (no probe, no stand-by chain) whenever
-// lev_bitvec_eligible holds and R <= 64.
+// Per DP cell that is about one ALU-pipe instruction (the packed wavefront kernel issues 1.5
+// and half an FMA-pipe one), and it is the WHOLE call.  Taken unconditionally (no probe, no
+// stand-by chain) whenever lev_bitvec_eligible holds and R <= 64.
 #include "lev_bitvec.cuh"
 
 constexpr int LEV_BVS_WARPS = 4;

@@ -17,9 +17,10 @@
 // lane 31 for row i, read by lane 0 of the next strip 31 steps earlier in its own
 // schedule, so one buffer per channel suffices).
 //
-// Per cell the integer path issues 4 INT32 instructions:
-//   ISETP (token compare), predicated IADD (diag + sub), VIADDMNMX (min(up+ins, .)),
-//   VIADDMNMX (min(left+del, .))            -- the DPX fused add+min of sm_90+/sm_100.
+// Per cell the integer path issues 3 ALU-pipe instructions and one on the FMA pipe:
+//   VIADDMNMX.U32 (token + negated row token clamped to 0 / 1 = "differs"), IMAD (diag +
+//   differs * sub), VIADDMNMX (min(up+ins, .)), VIADDMNMX (min(left+del, .))
+//                                           -- the DPX fused add+min of sm_90+/sm_100.
 //
 // Modes: FINAL (one value per pair), PREFIX (value at column r after every row),
 // MASK (row minima in pass A, equality bits in pass B; bits are set per DISTINCT
