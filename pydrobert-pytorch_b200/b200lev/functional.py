@@ -289,6 +289,9 @@ def hard_optimal_completion_distillation_loss(
     code = _reduction_code(reduction)
     optimals = _optimal_completion(ref, hyp, eos, include_eos, batch_first, ins_cost, del_cost,
                                    sub_cost, ignore_index, True, warn)  # SM:1216-1228
+    if not torch.jit.is_scripting():
+        if not _ops.needs_dispatcher():
+            return _ops.ocd_loss_eager(logits, optimals, weight, ignore_index, code, 1 if batch_first else 0)
     loss, _, _ = torch.ops.b200lev.ocd_loss(logits, optimals, weight, ignore_index, code,
                                             1 if batch_first else 0)
     return loss
@@ -343,6 +346,9 @@ def minimum_error_rate_loss(
         ref2 = ref if ref.dim() == 2 else ref.reshape(ref.size(0), -1)
     er = _string_matching(ref2, hyp2, eos, include_eos, batch_first, ins_cost, del_cost, sub_cost,
                           warn, norm, False, False, 0, True, group)  # SM:1451-1462
+    if not torch.jit.is_scripting():
+        if not _ops.needs_dispatcher():
+            return _ops.mwer_loss_eager(er, log_probs, sub_avg, code)
     return torch.ops.b200lev.mwer_loss(er, log_probs, sub_avg, code)
 
 
