@@ -501,12 +501,27 @@ def _ctc_setup(ctx, inputs, output):
     ctx.save_for_backward(logits, arg, row_lse, length)
 
 
+def _ctc_probs_backward(g_max: Tensor, probs: Tensor, arg: Tensor, length: Tensor) -> Tensor:
+    """is_probs=True: max_ is the PRODUCT of the chosen probabilities over the valid steps
+    (_decoding.py:527, 540-553).  Its gradient is torch's own, taken through that product on the
+    chosen entries (zeros among them included) -- a handful of small torch ops, off the hot path."""
+    outer, T, inner, V = probs.shape
+    dev = probs.device
+    with torch.enable_grad():
+        x = probs.detach().requires_grad_(True)
+        chosen = x.gather(3, arg.to(dev).view(outer, T, inner, 1)).squeeze(3)  # (outer, T, inner)
+        steps = torch.arange(T, device=dev).view(1, T, 1)
+        valid = steps < length.to(dev).view(outer, 1, inner)
+        prod = chosen.masked_fill(~valid, 1.0).prod(1)  # (outer, inner)
+        (grad,) = torch.autograd.grad(prod, x, g_max.to(device=dev, dtype=prod.dtype).view(outer, inner))
+    return grad
+
+
 def _ctc_backward(ctx, g_max, g_paths, g_lens, g_arg, g_lse, g_len):
-    if ctx.is_probs:
-        raise _abi.B200LevError("ctc_greedy_search: the gradient of the path probability is implemented "
-                                "for logits only (is_probs=False)")
     logits, arg, row_lse, length = ctx.saved_tensors
     outer, T, inner, _ = logits.shape
+    if ctx.is_probs:
+        return _ctc_probs_backward(g_max, logits, arg, length), None, None, None
     # d max_ / d logits = g * (onehot(arg max) - softmax) on the valid steps: the same kernel as
     # sequence_log_probs' backward with the greedy path as the hypothesis
     return (sequence_log_probs_backward(g_max, logits, arg.view(outer, T, inner), row_lse, length),

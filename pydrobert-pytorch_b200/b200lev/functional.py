@@ -447,6 +447,7 @@ def sequence_log_probs(logits: Any, hyp: torch.Tensor, dim: int = 0, eos: Option
     raise RuntimeError("logits must be either a Tensor or PackedSequence")
 
 
+@script
 def ctc_greedy_search(logits: torch.Tensor, in_lens: Optional[torch.Tensor] = None, blank_idx: int = -1,
                       batch_first: bool = False, is_probs: bool = False
                       ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -455,7 +456,7 @@ def ctc_greedy_search(logits: torch.Tensor, in_lens: Optional[torch.Tensor] = No
     score ``max_ (N,)`` (sum of the chosen log-probabilities; product of the chosen
     probabilities with ``is_probs``), ``paths`` (``(T, N)`` / ``(N, T)`` long: blanks and repeats
     removed, compacted to the front) and ``out_lens (N,)``.  Equal maxima resolve to the lowest
-    class index.  ``max_`` is differentiable w.r.t. ``logits`` when ``is_probs`` is false."""
+    class index.  ``max_`` is differentiable w.r.t. ``logits``."""
     if logits.dim() != 3:
         raise RuntimeError("logits must be 3-dimensional")
     V = logits.size(2)
@@ -469,16 +470,22 @@ def ctc_greedy_search(logits: torch.Tensor, in_lens: Optional[torch.Tensor] = No
     blank = (blank_idx + V) % V
     N = logits.size(0) if batch_first else logits.size(1)
     T = logits.size(1) if batch_first else logits.size(0)
-    if in_lens is not None and tuple(in_lens.shape) != (N,):
-        raise RuntimeError(f"in_lens must have shape ({N},), got {tuple(in_lens.shape)}")
-    outer, inner = (N, 1) if batch_first else (1, N)
+    if in_lens is not None:
+        if in_lens.dim() != 1 or in_lens.size(0) != N:
+            raise RuntimeError(f"in_lens must have shape ({N},)")
+    outer = N if batch_first else 1
+    inner = 1 if batch_first else N
     logits4 = logits.contiguous().view(outer, T, inner, V)
-    if _ops.needs_dispatcher() or _ops.wants_grad(logits):
-        max_, paths, out_lens, _, _, _ = _ops.ctc_greedy_search(logits4, in_lens, blank, is_probs)
-    else:
-        max_, paths, out_lens, _, _, _ = _ops.ctc_greedy_search_impl(logits4, in_lens, blank, is_probs)
-    shape = (N, T) if batch_first else (T, N)
-    return max_.view(N), paths.view(shape), out_lens.view(N)
+    if not torch.jit.is_scripting():
+        if not (_ops.needs_dispatcher() or _ops.wants_grad(logits)):
+            max_, paths, out_lens, _, _, _ = _ops.ctc_greedy_search_impl(logits4, in_lens, blank, is_probs)
+            if batch_first:
+                return max_.view(N), paths.view(N, T), out_lens.view(N)
+            return max_.view(N), paths.view(T, N), out_lens.view(N)
+    max_, paths, out_lens, _, _, _ = torch.ops.b200lev.ctc_greedy_search(logits4, in_lens, blank, is_probs)
+    if batch_first:
+        return max_.view(N), paths.view(N, T), out_lens.view(N)
+    return max_.view(N), paths.view(T, N), out_lens.view(N)
 
 
 @script

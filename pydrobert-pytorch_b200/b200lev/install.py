@@ -15,10 +15,9 @@ from . import functional as _F
 from . import modules as _M
 
 # sequence_log_probs / SequenceLogProbabilities are not TorchScript (the reference scripts its
-# Union[Tensor, PackedSequence] signature), ctc_greedy_search / CTCGreedySearch differentiate
-# logits only (not is_probs=True): they are offered by name but not rebound behind the
+# Union[Tensor, PackedSequence] signature): offered by name but not rebound behind the
 # reference's back
-_NOT_REBOUND = ("sequence_log_probs", "SequenceLogProbabilities", "ctc_greedy_search", "CTCGreedySearch")
+_NOT_REBOUND = ("sequence_log_probs", "SequenceLogProbabilities")
 _FUNCS = tuple(n for n in _F.__all__ if n not in _NOT_REBOUND)
 _CLASSES = tuple(n for n in _M.__all__ if n not in _NOT_REBOUND)
 _saved = {}

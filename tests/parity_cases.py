@@ -478,6 +478,33 @@ def check_ctc_vs_oracle(F, dev, seed, T, N, V, batch_first, dtype=torch.float32,
                                atol=atol * max(1.0, float(np.abs(g).max())))
 
 
+def check_ctc_probs_gradient(F, dev, seed=0):
+    """is_probs=True: the path probability is a product over the valid steps; its gradient equals
+    torch's through the reference formula (_decoding.py:527-553), zeros among the chosen
+    probabilities included, both layouts."""
+    g = torch.Generator().manual_seed(seed)
+    T, N, V = 9, 6, 7
+    p = torch.rand(T, N, V, generator=g).softmax(2)
+    p[2, 1, :] = 0.0
+    p[2, 1, 3] = 1.0
+    p[4, 2, :] = 0.0  # a step whose maximum is zero: the product is zero, its gradient is not
+    lens = torch.tensor([9, 3, 7, 1, 6, 9])
+    w = torch.rand(N, generator=g)
+    for batch_first in (False, True):
+        src = p.transpose(0, 1).contiguous() if batch_first else p
+        x = src.clone().to(dev).requires_grad_(True)
+        m, _, _ = F.ctc_greedy_search(x, lens.to(dev), batch_first=batch_first, is_probs=True)
+        (ga,) = torch.autograd.grad(m, x, w.to(dev))
+        y = src.clone().requires_grad_(True)
+        yy = y if batch_first else y.transpose(0, 1)
+        mx, _ = yy.max(2)
+        mask = torch.arange(T).unsqueeze(0) < lens.unsqueeze(1)
+        mref = mx.masked_fill(~mask, 1.0).prod(1)
+        (gb,) = torch.autograd.grad(mref, y, w)
+        assert torch.allclose(m.detach().cpu(), mref.detach(), rtol=1e-6, atol=1e-8)
+        assert torch.allclose(ga.cpu(), gb, rtol=1e-5, atol=1e-8), (ga.cpu() - gb).abs().max()
+
+
 def check_ctc_masked_classes(F, dev):
     """-inf logits (masked classes), including rows that START with -inf vectors and a class
     count that leaves a scalar tail: arg max, lengths and score against the oracle."""

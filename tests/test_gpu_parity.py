@@ -547,6 +547,10 @@ def test_completion_fill_staged_rows(F, dev, N, batch_first):
                        batch_first=batch_first, exclude_last=True, min_frac=0.0, padding=-7)
 
 
+def test_ctc_probs_gradient(F, dev):
+    PC.check_ctc_probs_gradient(F, dev)
+
+
 def test_ctc_masked_classes(F, dev):
     PC.check_ctc_masked_classes(F, dev)
 

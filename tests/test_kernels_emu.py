@@ -474,8 +474,8 @@ def test_ctc_low_precision_ties_and_errors(F):
         F.ctc_greedy_search(torch.zeros(3, 4, 5), torch.zeros(3, dtype=torch.long))
     p = torch.full((3, 2, 4), 0.25, requires_grad=True)
     m, _, _ = F.ctc_greedy_search(p, None, -1, False, True)
-    with pytest.raises(_abi.B200LevError, match="logits only"):
-        m.sum().backward()
+    m.sum().backward()  # (is_probs=True: the product's gradient, check_ctc_probs_gradient)
+    assert torch.allclose(p.grad[:, :, 0], torch.full((3, 2), 0.0625)) and float(p.grad[:, :, 1:].abs().sum()) == 0.0
     m, paths, lens = F.ctc_greedy_search(torch.zeros(0, 2, 4))
     assert m.tolist() == [0.0, 0.0] and paths.shape == (0, 2) and lens.tolist() == [0, 0]
     import b200lev.modules as M
@@ -493,6 +493,10 @@ def test_completion_fill_staged_rows(F, N, batch_first):
                        batch_first=batch_first, exclude_last=False, min_frac=0.3)
     PC.check_vs_oracle(F, DEV, seed=N + 1, R=14, H=6, N=N, V=3, costs=(1, 2, 3), include_eos=False,
                        batch_first=batch_first, exclude_last=True, min_frac=0.0, padding=-7)
+
+
+def test_ctc_probs_gradient(F):
+    PC.check_ctc_probs_gradient(F, DEV)
 
 
 def test_ctc_masked_classes(F):

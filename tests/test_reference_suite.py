@@ -24,6 +24,7 @@ EXPECTED_CASES = 310  # per device: what `pytest tests/test_string.py -m cpu` co
 DECODING_SELECT = "beam_search or random_walk"
 EXPECTED_DECODING = 9  # per device (+ 3 cases the reference itself marks xfail under trace)
 EXPECTED_ADVANCE = 2  # test_beam_search_advance_greedy, test_beam_search_advance
+EXPECTED_CTC = 38  # test_ctc_greedy_search (nojit / trace / script) + test_ctc_greedy_search_ignores_padding
 
 
 def _run(marker, test_file="test_string.py", select=None, expected=EXPECTED_CASES):
@@ -55,6 +56,7 @@ def test_reference_suite_on_emulator():
     # (the step-function cases only: the reference's BeamSearch / RandomWalk module cases train a
     # language model first, which takes minutes on the emulator; the GPU run below has them all)
     _run("cpu", "test_decoding.py", "beam_search_advance or random_walk_advance", EXPECTED_ADVANCE)
+    _run("cpu", "test_decoding.py", "ctc_greedy", EXPECTED_CTC)
 
 
 @pytest.mark.gpu
@@ -68,3 +70,9 @@ def test_reference_decoding_steps_on_b200():
     """-m gpu: the reference's beam-search / random-walk tests (step functions and its own
     BeamSearch / RandomWalk modules) on the step kernels."""
     _run("gpu", "test_decoding.py", DECODING_SELECT, EXPECTED_DECODING)
+
+
+@pytest.mark.gpu
+def test_reference_ctc_greedy_search_on_b200():
+    """-m gpu: the reference's CTCGreedySearch tests (plain, traced, scripted) on lev_ctc kernels."""
+    _run("gpu", "test_decoding.py", "ctc_greedy", EXPECTED_CTC)
