@@ -374,6 +374,7 @@ def _prod(sizes: Tuple[int, ...]) -> int:
     return n
 
 
+@script
 def _sequence_log_probs_tensor(logits: torch.Tensor, hyp: torch.Tensor, dim: int,
                                eos: Optional[int]) -> torch.Tensor:
     """_decoding.py:1516-1548"""
@@ -384,34 +385,43 @@ def _sequence_log_probs_tensor(logits: torch.Tensor, hyp: torch.Tensor, dim: int
             "got {})".format(-hyp_dim, hyp_dim - 1, dim)
         )
     dim = (hyp_dim + dim) % hyp_dim
-    if logits.dim() != hyp_dim + 1 or tuple(logits.shape[:-1]) != tuple(hyp.shape):
+    if logits.dim() != hyp_dim + 1 or logits.shape[:-1] != hyp.shape:
         raise RuntimeError(
             "logits must have the shape of hyp plus a class axis: got {} and {}".format(
-                tuple(logits.shape), tuple(hyp.shape)))
+                logits.shape, hyp.shape))
     if not logits.is_floating_point():
         raise RuntimeError("logits must be floating point")
-    outer, inner = _prod(tuple(hyp.shape[:dim])), _prod(tuple(hyp.shape[dim + 1:]))
-    T, V = hyp.shape[dim], logits.shape[-1]
+    outer, inner = 1, 1
+    for i in range(dim):
+        outer *= hyp.size(i)
+    for i in range(dim + 1, hyp_dim):
+        inner *= hyp.size(i)
+    T, V = hyp.size(dim), logits.size(-1)
+    out_shape = hyp.shape[:dim] + hyp.shape[dim + 1:]
     logits4 = logits.contiguous().view(outer, T, inner, V)
     hyp3 = hyp.to(torch.long).contiguous().view(outer, T, inner)
-    if _ops.needs_dispatcher() or _ops.wants_grad(logits):
-        out, _, _ = _ops.sequence_log_probs(logits4, hyp3, eos)
-    else:
-        out, _, _ = _ops.sequence_log_probs_impl(logits4, hyp3, eos)
-    return out.view(tuple(hyp.shape[:dim]) + tuple(hyp.shape[dim + 1:]))
+    if not torch.jit.is_scripting():
+        if not (_ops.needs_dispatcher() or _ops.wants_grad(logits)):
+            out, _, _ = _ops.sequence_log_probs_impl(logits4, hyp3, eos)
+            return out.view(out_shape)
+    out, _, _ = torch.ops.b200lev.sequence_log_probs(logits4, hyp3, eos)
+    return out.view(out_shape)
 
 
-def _sequence_log_probs_packed(logits: torch.nn.utils.rnn.PackedSequence, hyp: torch.Tensor,
-                               dim: int) -> torch.Tensor:
-    """_decoding.py:1551-1586: ``logits`` is a PackedSequence of per-step distributions
-    ``(sum(lens), V)`` and ``hyp`` the ``(T, N)`` (``dim == 0``) or ``(N, T)`` (``dim == 1``)
-    token matrix of the same sequences in their original order.
+@script
+def _sequence_log_probs_packed(
+        logits: Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]],
+        hyp: torch.Tensor, dim: int) -> torch.Tensor:
+    """_decoding.py:1551-1586: ``logits`` is a PackedSequence (data ``(sum(lens), V)``, batch
+    sizes per step, sorting permutations) of per-step distributions and ``hyp`` the ``(T, N)``
+    (``dim == 0``) or ``(N, T)`` (``dim == 1``) token matrix of the same sequences in their
+    original order.
 
-    The packed data is a ragged view of the padded ``(T, N, V)`` tensor: a step that a sequence
+    The packed data is a ragged view of a padded ``(T, N, V)`` tensor: a step that a sequence
     does not have contributes nothing.  That is exactly what the tensor kernel does with a
-    token outside ``[0, V)``, so the packed rows are scattered into a padded logits tensor,
-    the steps beyond a sequence's length get token -1, and the tensor path does the rest
-    (its backward hands the padded gradient back through the same index map)."""
+    token outside ``[0, V)``, so the packed rows are gathered into the padded layout (one
+    ``index_select``: its backward scatters the padded gradient back), the steps beyond a
+    sequence's length get token -1, and the tensor path does the rest."""
     hyp_dim = hyp.dim()
     if dim < -hyp_dim or dim > hyp_dim - 1:
         raise RuntimeError(
@@ -421,17 +431,37 @@ def _sequence_log_probs_packed(logits: torch.nn.utils.rnn.PackedSequence, hyp: t
     if hyp_dim != 2:
         raise RuntimeError("hyp must be 2 dimensional when logits is a PackedSequence")
     dim = (hyp_dim + dim) % hyp_dim
-    padded, lens = torch.nn.utils.rnn.pad_packed_sequence(logits, batch_first=bool(dim))
-    T = padded.size(dim)
-    hyp = hyp.narrow(dim, 0, T) if hyp.size(dim) >= T else hyp
-    steps = torch.arange(T, device=hyp.device)
-    lens = lens.to(hyp.device)
-    beyond = (steps.unsqueeze(1) >= lens.unsqueeze(0)) if dim == 0 else \
-        (steps.unsqueeze(0) >= lens.unsqueeze(1))
-    hyp = hyp.masked_fill(beyond, -1)
-    return _sequence_log_probs_tensor(padded, hyp, dim, None)
+    data, batch_sizes, sidxs, uidxs = logits
+    dev = data.device
+    bs = batch_sizes.to(device=dev, dtype=torch.long)  # (T,) sequences alive at step t, descending
+    T = bs.size(0)
+    N = hyp.size(1 - dim)
+    if T == 0 or N == 0:
+        return torch.zeros(N, dtype=data.dtype, device=dev)
+    # row of `data` that holds step t of the n-th LONGEST sequence (clamped where it has none)
+    first = torch.cumsum(bs, 0) - bs
+    n_idx = torch.arange(N, device=dev)
+    alive = n_idx.unsqueeze(0) < bs.unsqueeze(1)  # (T, N)
+    rows = first.unsqueeze(1) + torch.min(n_idx.unsqueeze(0), (bs - 1).clamp_min(0).unsqueeze(1))
+    padded = data.index_select(0, rows.flatten()).view(T, N, data.size(1))
+    # the hypotheses in the same (sorted) order, steps x sequences, -1 beyond a sequence's length
+    h = hyp.to(dev)
+    if dim == 1:
+        h = h.t()
+    if sidxs is not None:
+        h = h.index_select(1, sidxs.to(dev))
+    if h.size(0) >= T:
+        h = h[:T]
+    else:
+        h = torch.cat([h, h.new_full((T - h.size(0), N), -1)], 0)
+    h = h.masked_fill(~alive, -1)
+    out = _sequence_log_probs_tensor(padded, h, 0, None)
+    if uidxs is not None:
+        out = out.index_select(0, uidxs.to(dev))
+    return out
 
 
+@script
 def sequence_log_probs(logits: Any, hyp: torch.Tensor, dim: int = 0, eos: Optional[int] = None
                        ) -> torch.Tensor:
     """Functional version of SequenceLogProbabilities (_decoding.py:1516-1633): joint
@@ -442,7 +472,8 @@ def sequence_log_probs(logits: Any, hyp: torch.Tensor, dim: int = 0, eos: Option
     Differentiable with respect to ``logits``."""
     if isinstance(logits, torch.Tensor):
         return _sequence_log_probs_tensor(logits, hyp, dim, eos)
-    if isinstance(logits, torch.nn.utils.rnn.PackedSequence):
+    elif torch.jit.isinstance(
+            logits, Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]):
         return _sequence_log_probs_packed(logits, hyp, dim)
     raise RuntimeError("logits must be either a Tensor or PackedSequence")
 

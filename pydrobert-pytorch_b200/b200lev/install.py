@@ -14,10 +14,7 @@ import importlib
 from . import functional as _F
 from . import modules as _M
 
-# sequence_log_probs / SequenceLogProbabilities are not TorchScript (the reference scripts its
-# Union[Tensor, PackedSequence] signature): offered by name but not rebound behind the
-# reference's back
-_NOT_REBOUND = ("sequence_log_probs", "SequenceLogProbabilities")
+_NOT_REBOUND = ()  # (every functional and module of the family is rebound)
 _FUNCS = tuple(n for n in _F.__all__ if n not in _NOT_REBOUND)
 _CLASSES = tuple(n for n in _M.__all__ if n not in _NOT_REBOUND)
 _saved = {}

@@ -7,7 +7,7 @@ forward calls the functional of the same name, which dispatches to the sm_100a k
 """
 
 import abc
-from typing import Optional, Tuple
+from typing import Any, Optional, Tuple
 
 import torch
 
@@ -295,7 +295,8 @@ class MinimumErrorRateLoss(torch.nn.Module):
 
 
 class SequenceLogProbabilities(torch.nn.Module):
-    """Calculate joint log probability of sequences (_decoding.py:1636-1721), tensor inputs"""
+    """Calculate joint log probability of sequences (_decoding.py:1636-1721); `logits` is a
+    tensor or a PackedSequence"""
 
     __constants__ = "dim", "eos"
     dim: int
@@ -315,7 +316,7 @@ class SequenceLogProbabilities(torch.nn.Module):
             s += f", eos={self.eos}"
         return s
 
-    def forward(self, logits: torch.Tensor, hyp: torch.Tensor) -> torch.Tensor:
+    def forward(self, logits: Any, hyp: torch.Tensor) -> torch.Tensor:
         return F.sequence_log_probs(logits, hyp, self.dim, self.eos)
 
 

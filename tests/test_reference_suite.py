@@ -25,6 +25,7 @@ DECODING_SELECT = "beam_search or random_walk"
 EXPECTED_DECODING = 9  # per device (+ 3 cases the reference itself marks xfail under trace)
 EXPECTED_ADVANCE = 2  # test_beam_search_advance_greedy, test_beam_search_advance
 EXPECTED_CTC = 38  # test_ctc_greedy_search (nojit / trace / script) + test_ctc_greedy_search_ignores_padding
+EXPECTED_SEQLP = 12  # test_sequence_log_probs: tensor (4 step axes) and PackedSequence inputs x nojit / trace / script
 
 
 def _run(marker, test_file="test_string.py", select=None, expected=EXPECTED_CASES):
@@ -57,6 +58,7 @@ def test_reference_suite_on_emulator():
     # language model first, which takes minutes on the emulator; the GPU run below has them all)
     _run("cpu", "test_decoding.py", "beam_search_advance or random_walk_advance", EXPECTED_ADVANCE)
     _run("cpu", "test_decoding.py", "ctc_greedy", EXPECTED_CTC)
+    _run("cpu", "test_decoding.py", "sequence_log_probs", EXPECTED_SEQLP)
 
 
 @pytest.mark.gpu
@@ -76,3 +78,10 @@ def test_reference_decoding_steps_on_b200():
 def test_reference_ctc_greedy_search_on_b200():
     """-m gpu: the reference's CTCGreedySearch tests (plain, traced, scripted) on lev_ctc kernels."""
     _run("gpu", "test_decoding.py", "ctc_greedy", EXPECTED_CTC)
+
+
+@pytest.mark.gpu
+def test_reference_sequence_log_probs_on_b200():
+    """-m gpu: the reference's SequenceLogProbabilities tests (tensor and PackedSequence logits; plain,
+    traced, scripted) on lev_seqlp kernels."""
+    _run("gpu", "test_decoding.py", "sequence_log_probs", EXPECTED_SEQLP)
