@@ -207,14 +207,15 @@ static int lev_prepare(const b200lev_tokens_t* ref, const b200lev_tokens_t* hyp,
         lev_prof_begin(LEV_PROF_PACK_REF, st);
         int rc = lev_launch_pack(ref, o->has_eos, o->eos, o->include_eos, ref_tok, L.Rp, nullptr, 0,
                                  ref_len, flags, state, B200LEV_FLAG_REF_NO_EOS, nullptr, 1, 0,
-                                 nullptr, bv_check, st);
+                                 nullptr, bv_check, st, (int32_t*)(ws + L.off_split_ref));
         lev_prof_end(LEV_PROF_PACK_REF, st);
         if (rc) return rc;
         lev_prof_begin(LEV_PROF_PACK_HYP, st);
         rc = lev_launch_pack(hyp, o->has_eos, o->eos, o->include_eos, hyp_tok, L.Hp,
                              (uint16_t*)(ws + L.off_hyp_tok16), L.Hp16, hyp_len, flags, state,
                              B200LEV_FLAG_HYP_NO_EOS, ref_len, o->ref_group, G,
-                             G ? (int*)(ws + L.off_ghist) : nullptr, bv_check, st);
+                             G ? (int*)(ws + L.off_ghist) : nullptr, bv_check, st,
+                             (int32_t*)(ws + L.off_split_hyp));
         lev_prof_end(LEV_PROF_PACK_HYP, st);
         if (rc) return rc;
     }

@@ -55,6 +55,8 @@ struct LevLayout {
     // bit-vector path (lev_bitvec.cu): 16-byte uid chunks [ceil(R/16)][P]; the hypothesis
     // chunks [ceil(H/16)][P] reuse the packed-hypothesis region, which that path leaves idle
     size_t off_bv_ref;
+    // pack kernel, few long sequences: [N first-eos words][ceil(N / 32) tickets] per side
+    size_t off_split_ref, off_split_hyp;
     size_t bytes;
 };
 
@@ -102,6 +104,8 @@ static inline LevLayout lev_layout(const b200lev_tokens_t* ref, const b200lev_to
         L.off_ndist = take(sizeof(int32_t) * (size_t)L.Nref);
         L.off_dbits = take(sizeof(uint32_t) * (size_t)L.Hout * L.P * L.Wd);
     }
+    L.off_split_ref = take(sizeof(int32_t) * (size_t)(L.Nref + (L.Nref + 31) / 32));
+    L.off_split_hyp = take(sizeof(int32_t) * (size_t)(L.P + (L.P + 31) / 32));
     L.bytes = o;
     return L;
 }
@@ -198,7 +202,8 @@ int lev_check_cuda(const char* what);
 int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int include_eos,
                     int32_t* packed, int64_t Tp, uint16_t* packed16, int64_t Tp16, int32_t* lens,
                     int32_t* flags, int32_t* state, int missing_flag, const int32_t* ref_len,
-                    int ref_group, int G, int* ghist, int bv_check, cudaStream_t st);
+                    int ref_group, int G, int* ghist, int bv_check, cudaStream_t st,
+                    int32_t* split_scratch = nullptr);  // [N + ceil(N / 32)] words, or NULL
 int lev_launch_dp(const LevParams& p, int mode, bool count_mode, bool float_path,
                   cudaStream_t st);
 int lev_launch_group(const LevParams& p, int mode, bool count_mode, cudaStream_t st);

@@ -44,6 +44,13 @@ struct LevPackArgs {
     int bv_check;  // exit if the bit-vector kernels, enqueued first, took the batch
     int slice;     // positions per warp and chunk: 32, or 16 / 8 for T <= 64 / 32
     int hist_bins;  // > 0: a CTA walks many blocks and collects the histogram in shared memory
+    // few, long sequences (N / 32 CTAs would leave most SMs idle): `split` CTAs share a block of
+    // 32 sequences, each taking split_len positions (a multiple of the 128-position chunk).
+    // They meet in split_first[n] (first eos - T, atomicMin on zeroes) and split_ticket[block];
+    // the CTA that draws the last ticket runs the owner epilogue.  split = 1: off.
+    int split, split_len;
+    int* split_first;
+    int* split_ticket;
 };
 
 // ---- epilogue pieces shared by both layouts ----------------------------------------------
@@ -182,7 +189,10 @@ __global__ void __launch_bounds__(128, 8) lev_pack_seqfirst_kernel(const LevPack
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     // a CTA walks blocks of 32 sequences (a few each: the grid stays small, so that standing by
     // for the bit-vector path costs a 1000-CTA launch and not one of N / 32 CTAs)
-    for (int64_t n0 = (int64_t)blockIdx.x * 32; n0 < a.N; n0 += (int64_t)gridDim.x * 32) {
+    const int64_t nitems = ((a.N + 31) / 32) * a.split;
+    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int64_t n0 = (item / a.split) * 32;
+    const int t_lo = (int)(item % a.split) * a.split_len;
     const int64_t n = n0 + lane;
     const bool valid_seq = n < a.N;
     const int rows = (int)(a.N - n0 < 32 ? a.N - n0 : 32);
@@ -205,7 +215,8 @@ __global__ void __launch_bounds__(128, 8) lev_pack_seqfirst_kernel(const LevPack
     }
     __syncthreads();
     const int sw = a.slice, chunk = 4 * sw;
-    for (int tb = 0; tb < Ti; tb += chunk) {
+    const int t_hi = (a.split > 1 && t_lo + a.split_len < Ti) ? t_lo + a.split_len : Ti;
+    for (int tb = t_lo; tb < t_hi; tb += chunk) {
         const int t0 = tb + sw * w;
         const TT* sp = seq + (int64_t)t0 * st;
         int* trow = &tile[lane][sw * w];
@@ -224,7 +235,7 @@ __global__ void __launch_bounds__(128, 8) lev_pack_seqfirst_kernel(const LevPack
         }
 #undef LEV_PACK_SLICE
         __syncthreads();
-        if (threadIdx.x == 0 && tb + chunk >= Ti) {
+        if (threadIdx.x == 0 && tb + chunk >= t_hi) {
             // a recent copy of the range words; the load completes under the row stores
             cur_u = lev_ldg_l2(reinterpret_cast<const unsigned*>(a.state) + 1);
             cur_n = lev_ldg_l2(reinterpret_cast<const unsigned*>(a.state) + 2);
@@ -254,7 +265,7 @@ __global__ void __launch_bounds__(128, 8) lev_pack_seqfirst_kernel(const LevPack
         // rare: a low-word match may be a wide token (or eos itself is wide) -- rescan this
         // lane's slices with the exact comparison
         seen.first = Ti;
-        for (int tb = 0; tb < Ti; tb += chunk)
+        for (int tb = t_lo; tb < t_hi; tb += chunk)
             for (int t = tb + sw * w; t < Ti && t < tb + sw * w + sw; ++t)
                 if ((int64_t)seq[(int64_t)t * st] == a.eos) {
                     seen.first = t < seen.first ? t : seen.first;
@@ -274,7 +285,22 @@ __global__ void __launch_bounds__(128, 8) lev_pack_seqfirst_kernel(const LevPack
     }
     __syncthreads();
     if (w == 0) {
-        int flags = valid_seq ? lev_pack_owner(a, ref_len, n, first_s[lane], a.hist_bins ? cta_hist : nullptr) : 0;
+        int first = first_s[lane];
+        bool owner = valid_seq;
+        if (a.split > 1) {
+            if (valid_seq && first < Ti) atomicMin(&a.split_first[n], first - Ti);
+            __threadfence();
+            __syncwarp();
+            int ticket = 0;
+            if (lane == 0) ticket = atomicAdd(&a.split_ticket[n0 >> 5], 1);
+            ticket = __shfl_sync(LEV_FULL_MASK, ticket, 0);
+            owner = owner && ticket == a.split - 1;  // every other slice of these rows has published
+            if (owner) {
+                __threadfence();
+                first = Ti + __ldcg(&a.split_first[n]);
+            }
+        }
+        int flags = owner ? lev_pack_owner(a, ref_len, n, first, a.hist_bins ? cta_hist : nullptr) : 0;
         unsigned umax = blk_u, nmax = blk_n;
         lev_pack_warp_reduce(flags, umax, nmax);
         if (lane == 0) lev_pack_publish(a, flags | blk_flags, umax, nmax, cur_u, cur_n);
@@ -399,7 +425,7 @@ __global__ void __launch_bounds__(128) lev_pack_rows_kernel(const LevPackArgs a)
 int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int include_eos,
                     int32_t* packed, int64_t Tp, uint16_t* packed16, int64_t Tp16, int32_t* lens,
                     int32_t* flags, int32_t* state, int missing_flag, const int32_t* ref_len,
-                    int ref_group, int G, int* ghist, int bv_check, cudaStream_t st) {
+                    int ref_group, int G, int* ghist, int bv_check, cudaStream_t st, int32_t* split_scratch) {
     if (t->N <= 0) return B200LEV_OK;
     if (t->T >= (int64_t)1 << 30) {
         lev_set_error("sequence dimension %lld too long", (long long)t->T);
@@ -449,8 +475,32 @@ int lev_launch_pack(const b200lev_tokens_t* t, int has_eos, int64_t eos, int inc
             smem = sizeof(int) * (size_t)bins;
         }
     }
-    const dim3 grid((unsigned)nblk, 1, 1);
     const bool warpseq = seqfirst && t->T <= 64;
+    // few, long sequences: several CTAs per block of 32 sequences, split along the sequence axis
+    a.split = 1;
+    a.split_len = 0;
+    a.split_first = a.split_ticket = nullptr;
+    {
+        int64_t want = 148 * 4;  // CTAs that keep the machine busy
+        if (const char* e = getenv("B200LEV_PACK_SPLIT")) want = atoll(e);  // tests; 0 = off
+        const int64_t nchunks = (t->T + LEV_PACK_CHUNK - 1) / LEV_PACK_CHUNK;
+        if (seqfirst && !warpseq && split_scratch != nullptr && nchunks >= 2 && 4 * nblk <= want) {  // (less than a CTA per SM)
+            int64_t S = (want + nblk - 1) / nblk;
+            S = S < nchunks ? S : nchunks;
+            const int64_t per = (nchunks + S - 1) / S;  // chunks per slice
+            S = (nchunks + per - 1) / per;
+            if (S > 1) {
+                a.split = (int)S;
+                a.split_len = (int)(per * LEV_PACK_CHUNK);
+                a.split_first = split_scratch;
+                a.split_ticket = split_scratch + t->N;
+                if (cudaMemsetAsync(split_scratch, 0, sizeof(int32_t) * (size_t)(t->N + nblk), st) != cudaSuccess)
+                    return lev_check_cuda("memset");
+                nblk *= S;
+            }
+        }
+    }
+    const dim3 grid((unsigned)nblk, 1, 1);
     if (warpseq) {  // a warp per 32 sequences: 4 blocks per CTA and iteration
         int64_t n = ((t->N + 31) / 32 + 3) / 4;
         const bool many = n > cap && (bv_check || n >= 8 * cap);

@@ -193,10 +193,9 @@ def check_errors(F, dev):
                                   reduction="bad")
 
 
-def check_wide_tokens(F, dev):
+def check_wide_tokens(F, dev, R=70, H=40, N=9):
     """Tokens that differ only above bit 31 must not compare equal (64-bit path)."""
     rng = np.random.default_rng(11)
-    R, H, N = 70, 40, 9
     ref = random_tokens(rng, R, N, 4, 0, -1, min_len=20)
     hyp = random_tokens(rng, H, N, 4, 0, -1, min_len=20)
     big = np.int64(1) << 32

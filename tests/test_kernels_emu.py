@@ -309,6 +309,20 @@ def test_pack_persistent_ctas_and_cta_histogram(F, monkeypatch):
                            include_eos=True, norm=True, min_frac=0.1)
 
 
+@pytest.mark.parametrize("want", ["592", "5", "0"])
+def test_pack_split_along_the_sequence_axis(F, want, monkeypatch):
+    """Few, long sequences: several pack CTAs share a block of 32 sequences, each taking a range
+    of positions; first-eos positions meet in the workspace, the CTA with the last ticket writes
+    the lengths (eos early / late / missing, tokens outside int32, N over two blocks)."""
+    monkeypatch.setenv("B200LEV_PACK_SPLIT", want)
+    monkeypatch.setenv("B200LEV_BITVEC", "0")
+    for R, H, N in ((300, 520, 3), (1000, 260, 40)):
+        for include_eos in (True, False):
+            PC.check_vs_oracle(F, DEV, seed=R + N, R=R, H=H, N=N, V=7, costs=(1, 2, 3), do_mask=False,
+                               include_eos=include_eos, norm=True, min_frac=0.05)
+    PC.check_wide_tokens(F, DEV, R=300, H=390, N=5)
+
+
 def test_group_kernel_n_best_and_wide(F, monkeypatch):
     monkeypatch.setenv("B200LEV_GROUP_MIN_PAIRS", "1")
     test_n_best_shared_reference(F)
