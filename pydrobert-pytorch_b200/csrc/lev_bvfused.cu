@@ -185,11 +185,14 @@ __device__ __forceinline__ void lev_bvf_block(const LevBvArgs& a, int4* keys4, u
                             (int64_t)(t < nrows - 1 ? t : nrows - 1) * stride);
     };
     auto prefetch_hyp = [&](int64_t blk, int t_first) { prefetch16(a.hyp, blk * 32, a.P, hst, t_first, H); };
-    auto prefetch_ref = [&](int64_t blk, int t_first) {
-        prefetch16(a.ref, (blk * 32) / a.ref_group, (a.P + a.ref_group - 1) / a.ref_group, rst, t_first, a.R);
+    // (the two divisions are taken once per block, not once per prefetch inside the stream loop)
+    const int64_t ref_ncols = (a.P + a.ref_group - 1) / a.ref_group;
+    const int64_t next_ref_col = next_block >= 0 ? (next_block * 32) / a.ref_group : 0;
+    auto prefetch_ref = [&](int64_t first_col, int t_first) {
+        prefetch16(a.ref, first_col, ref_ncols, rst, t_first, a.R);
     };
     if (first_block) {  // (later blocks were announced by the block before them)
-        for (int t = 0; t < a.R; t += 16) prefetch_ref(block, t);
+        for (int t = 0; t < a.R; t += 16) prefetch_ref((block * 32) / a.ref_group, t);
         prefetch_hyp(block, 0);
         prefetch_hyp(block, 16);
     }
@@ -369,29 +372,43 @@ __device__ __forceinline__ void lev_bvf_block(const LevBvArgs& a, int4* keys4, u
         const int T_end = PREFIX ? (a.Hout > H ? a.Hout : H) : H;  // positions to visit
         int tdone = 0;  // positions (= output rows) done by the stream
         if (H > 0 && __any_sync(LEV_FULL_MASK, fast)) {
-            auto ld = [&](int t) { return lev_ldg_stream(hsrc + (int64_t)(t < Hm1 ? t : Hm1) * hst); };
+            // the column is read strictly in order, CH rows at a time: a running pointer and
+            // `row k of the chunk` offsets (one IMAD.WIDE per load instead of a clamp and a 64-bit
+            // multiply-add); only the chunks that reach past the last row clamp per load
+            const TT* __restrict__ hp = hsrc;
+            int tl = 0;  // first row of the next chunk
+            auto ld_chunk = [&](TT (&buf)[CH]) {
+                if (tl + CH <= H) {  // (warp-uniform)
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) buf[k] = lev_ldg_stream(hp + (int64_t)k * hst);
+                    hp += (int64_t)CH * hst;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) {
+                        const int t = tl + k;
+                        buf[k] = lev_ldg_stream(hsrc + (int64_t)(t < Hm1 ? t : Hm1) * hst);
+                    }
+                }
+                tl += CH;
+            };
             // four chunk buffers rotate: the loads of a chunk are issued three trips (12
             // positions, > 1000 issue slots of this warp) before its tokens are looked up; the
             // rotation's register moves run on the FMA pipe
             TT cur[CH], n1[CH], n2[CH], n3[CH];
-#pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                cur[k] = ld(k);
-                n1[k] = ld(CH + k);
-                n2[k] = ld(2 * CH + k);
-            }
+            ld_chunk(cur);
+            ld_chunk(n1);
+            ld_chunk(n2);
             int t0 = 0;
 #pragma unroll 1
             for (; t0 < T_end; t0 += CH) {
                 if ((t0 & 15) == 0) {
                     prefetch_hyp(block, t0 + 32);
                     if (next_block >= 0) {  // announce the next block of this warp
-                        if (t0 < a.R) prefetch_ref(next_block, t0);
+                        if (t0 < a.R) prefetch_ref(next_ref_col, t0);
                         if (t0 < 32) prefetch_hyp(next_block, t0);
                     }
                 }
-#pragma unroll
-                for (int k = 0; k < CH; ++k) n3[k] = ld(t0 + 3 * CH + k);
+                ld_chunk(n3);
                 if (fast) {
 #pragma unroll
                     for (int k = 0; k < CH; ++k) position(cur[k], t0 + k, row_hashed);
@@ -441,7 +458,7 @@ __device__ __forceinline__ void lev_bvf_block(const LevBvArgs& a, int4* keys4, u
         }
     }
     if (next_block >= 0) {  // whatever of the next block's first rows the stream did not announce
-        for (int t = 0; t < a.R; t += 16) prefetch_ref(next_block, t);
+        for (int t = 0; t < a.R; t += 16) prefetch_ref(next_ref_col, t);
         prefetch_hyp(next_block, 0);
         prefetch_hyp(next_block, 16);
     }

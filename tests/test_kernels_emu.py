@@ -316,7 +316,7 @@ def test_pack_split_along_the_sequence_axis(F, want, monkeypatch):
     the lengths (eos early / late / missing, tokens outside int32, N over two blocks)."""
     monkeypatch.setenv("B200LEV_PACK_SPLIT", want)
     monkeypatch.setenv("B200LEV_BITVEC", "0")
-    for R, H, N in ((300, 520, 3), (1000, 260, 40)):
+    for R, H, N in ((300, 390, 3), (520, 260, 34)):
         for include_eos in (True, False):
             PC.check_vs_oracle(F, DEV, seed=R + N, R=R, H=H, N=N, V=7, costs=(1, 2, 3), do_mask=False,
                                include_eos=include_eos, norm=True, min_frac=0.05)

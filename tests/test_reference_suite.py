@@ -28,7 +28,7 @@ EXPECTED_CTC = 38  # test_ctc_greedy_search (nojit / trace / script) + test_ctc_
 EXPECTED_SEQLP = 12  # test_sequence_log_probs: tensor (4 step axes) and PackedSequence inputs x nojit / trace / script
 
 
-def _run(marker, test_file="test_string.py", select=None, expected=EXPECTED_CASES):
+def _run(marker, test_file="test_string.py", select=None, expected=EXPECTED_CASES, workers=0):
     if not (os.path.isfile(os.path.join(REF_TESTS, test_file))
             and os.path.isdir(os.path.join(REF_PKG, "pydrobert"))):
         pytest.skip("reference copy absent (oracle/make_ref.sh needs /root/reference)")
@@ -39,6 +39,15 @@ def _run(marker, test_file="test_string.py", select=None, expected=EXPECTED_CASE
     cmd = [sys.executable, "-m", "pytest", "-p", "ref_suite_plugin", "-p", "no:cacheprovider", "-q",
            "-W", "ignore", "--rootdir", REF_TESTS, "-c", os.path.join(REF_TESTS, "pytest.ini"),
            os.path.join(REF_TESTS, test_file), "-m", marker] + (["-k", select] if select else [])
+    if workers > 1:
+        # the emulator runs one kernel thread: spread the cases over single-threaded workers
+        # (eight torch threads per worker would fight over the cores instead)
+        try:
+            import xdist  # noqa: F401
+            cmd += ["-n", str(workers)]
+            env["OMP_NUM_THREADS"] = env["MKL_NUM_THREADS"] = "1"
+        except ImportError:
+            pass
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, cwd=REF_TESTS, timeout=3000)
     tail = (r.stdout + r.stderr)[-4000:]
     assert r.returncode == 0, tail
@@ -53,7 +62,7 @@ def test_reference_suite_on_emulator():
 
     if torch.cuda.is_available():
         pytest.skip("GPU present: the gpu-marked run below is the gate")
-    _run("cpu")
+    _run("cpu", workers=min(6, os.cpu_count() or 1))
     # (the step-function cases only: the reference's BeamSearch / RandomWalk module cases train a
     # language model first, which takes minutes on the emulator; the GPU run below has them all)
     _run("cpu", "test_decoding.py", "beam_search_advance or random_walk_advance", EXPECTED_ADVANCE)
