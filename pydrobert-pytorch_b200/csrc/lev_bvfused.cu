@@ -32,6 +32,25 @@
 #include "lev_bitvec.cuh"
 
 constexpr int LEV_BVF_WARPS = 4;
+// tuning switches (scripts/gpu_ab.sh builds one library per setting)
+#ifndef LEV_BVF_NBUF
+#define LEV_BVF_NBUF 4  // chunk buffers of the hypothesis stream: loads run NBUF - 1 trips ahead
+#endif
+#ifndef LEV_BVF_CH
+#define LEV_BVF_CH 4  // hypothesis positions per loop trip
+#endif
+#ifndef LEV_BVF_PRED_ST
+#define LEV_BVF_PRED_ST 1  // 1: the row store as one predicated instruction, no branch
+#endif
+#ifndef LEV_BVF_SCAN_PTR
+#define LEV_BVF_SCAN_PTR 1  // 1: the reference scan reads through a running pointer
+#endif
+#ifndef LEV_BVF_PF_AHEAD
+#define LEV_BVF_PF_AHEAD 32  // rows the L2 prefetch runs ahead of the hypothesis stream
+#endif
+#ifndef LEV_BVF_LD_PLAIN
+#define LEV_BVF_LD_PLAIN 0  // 1: plain loads instead of evict-first ones in the hypothesis stream
+#endif
 
 // ---- the match-mask table of one pass: M[(R + 1)][NT][W], row R stays zero (no match) ----
 template <int W>
@@ -119,17 +138,31 @@ __device__ __forceinline__ LevBvfScan lev_bvf_scan(const LevBvArgs& a, const TT*
         if (live < DH) eos_bits &= live > 0 ? (1u << live) - 1u : 0u;
         if (eos_bits != 0 && s.first_eos == a.R) s.first_eos = t0 + __ffs((int)eos_bits) - 1;
     };
-    auto row = [&](int t) { return rsrc[(int64_t)(t < Rm1 ? t : Rm1) * rst]; };
-    TT bufA[DH], bufB[DH];
+    // the column is read in order, DH rows at a time: a running pointer and `row k of the batch`
+    // offsets; only the batches that reach past the last row clamp per load
+    const TT* __restrict__ rp = rsrc;
+    int tl = 0;  // first row of the next batch
+    auto ld_batch = [&](TT (&buf)[DH]) {
+        if (LEV_BVF_SCAN_PTR && tl + DH <= a.R) {  // (warp-uniform)
 #pragma unroll
-    for (int k = 0; k < DH; ++k) bufA[k] = row(k);
+            for (int k = 0; k < DH; ++k) buf[k] = rp[(int64_t)k * rst];
+            rp += (int64_t)DH * rst;
+        } else {
+#pragma unroll
+            for (int k = 0; k < DH; ++k) {
+                const int t = tl + k;
+                buf[k] = rsrc[(int64_t)(t < Rm1 ? t : Rm1) * rst];
+            }
+        }
+        tl += DH;
+    };
+    TT bufA[DH], bufB[DH];
+    ld_batch(bufA);
 #pragma unroll 1
     for (int t0 = 0; t0 < a.R; t0 += 2 * DH) {
-#pragma unroll
-        for (int k = 0; k < DH; ++k) bufB[k] = row(t0 + DH + k);
+        ld_batch(bufB);
         observe(bufA, t0);
-#pragma unroll
-        for (int k = 0; k < DH; ++k) bufA[k] = row(t0 + 2 * DH + k);
+        ld_batch(bufA);
         observe(bufB, t0 + DH);
     }
     if (!a.has_eos) s.first_eos = a.R;
@@ -161,7 +194,7 @@ __device__ __forceinline__ void lev_bvf_block(const LevBvArgs& a, int4* keys4, u
     // hypothesis positions per loop trip: small on purpose -- the stream loop (~100 instructions
     // per position) has to stay inside the instruction caches next to the scan and build loops
     // of the warps that are in another phase (ncu: no_instruction was the top stall at 8)
-    constexpr int CH = 4;
+    constexpr int CH = LEV_BVF_CH;
     const int64_t pair = block * 32 + lane;
     const int64_t pc = pair < a.P ? pair : (int64_t)a.P - 1;
     const int64_t rcol = pc / a.ref_group;
@@ -322,7 +355,11 @@ __device__ __forceinline__ void lev_bvf_block(const LevBvArgs& a, int4* keys4, u
             if (PREFIX) {
                 // row t is a value iff t <= h (t < h with exclude_last: token t must exist)
                 const int c_m = EXCL ? in_m : prev_m;
+#if LEV_BVF_PRED_ST
+                lev_st_f32_if(t < a.Hout, orow, c_m != 0 ? prev_val : a.padding);
+#else
                 if (t < a.Hout) *orow = c_m != 0 ? prev_val : a.padding;
+#endif
                 orow += a.out_si;
                 prev_m = in_m;
             }
@@ -380,7 +417,8 @@ __device__ __forceinline__ void lev_bvf_block(const LevBvArgs& a, int4* keys4, u
             auto ld_chunk = [&](TT (&buf)[CH]) {
                 if (tl + CH <= H) {  // (warp-uniform)
 #pragma unroll
-                    for (int k = 0; k < CH; ++k) buf[k] = lev_ldg_stream(hp + (int64_t)k * hst);
+                    for (int k = 0; k < CH; ++k)
+                        buf[k] = LEV_BVF_LD_PLAIN ? hp[(int64_t)k * hst] : lev_ldg_stream(hp + (int64_t)k * hst);
                     hp += (int64_t)CH * hst;
                 } else {
 #pragma unroll
@@ -391,34 +429,32 @@ __device__ __forceinline__ void lev_bvf_block(const LevBvArgs& a, int4* keys4, u
                 }
                 tl += CH;
             };
-            // four chunk buffers rotate: the loads of a chunk are issued three trips (12
-            // positions, > 1000 issue slots of this warp) before its tokens are looked up; the
+            // NBUF chunk buffers rotate: the loads of a chunk are issued NBUF - 1 trips before its
+            // tokens are looked up (4 buffers: 12 positions, > 1000 issue slots of this warp); the
             // rotation's register moves run on the FMA pipe
-            TT cur[CH], n1[CH], n2[CH], n3[CH];
-            ld_chunk(cur);
-            ld_chunk(n1);
-            ld_chunk(n2);
+            constexpr int NBUF = LEV_BVF_NBUF;
+            TT buf[NBUF][CH];
+#pragma unroll
+            for (int b = 0; b < NBUF - 1; ++b) ld_chunk(buf[b]);
             int t0 = 0;
 #pragma unroll 1
             for (; t0 < T_end; t0 += CH) {
                 if ((t0 & 15) == 0) {
-                    prefetch_hyp(block, t0 + 32);
+                    prefetch_hyp(block, t0 + LEV_BVF_PF_AHEAD);
                     if (next_block >= 0) {  // announce the next block of this warp
                         if (t0 < a.R) prefetch_ref(next_ref_col, t0);
                         if (t0 < 32) prefetch_hyp(next_block, t0);
                     }
                 }
-                ld_chunk(n3);
+                ld_chunk(buf[NBUF - 1]);
                 if (fast) {
 #pragma unroll
-                    for (int k = 0; k < CH; ++k) position(cur[k], t0 + k, row_hashed);
+                    for (int k = 0; k < CH; ++k) position(buf[0][k], t0 + k, row_hashed);
                 }
 #pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    cur[k] = n1[k];
-                    n1[k] = n2[k];
-                    n2[k] = n3[k];
-                }
+                for (int b = 0; b < NBUF - 1; ++b)
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) buf[b][k] = buf[b + 1][k];
                 // every hypothesis of this pass has ended: the remaining rows are padding
                 if ((t0 & 12) == 12 && !__any_sync(LEV_FULL_MASK, fast && live_m != 0)) {
                     t0 += CH;

@@ -100,6 +100,17 @@ __device__ __forceinline__ void lev_sts32(lev_saddr a, int v) {
 __device__ __forceinline__ void lev_prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+// a store under a predicate: no branch (and no convergence barrier pair) around one instruction
+__device__ __forceinline__ void lev_st_f32_if(bool p, float* ptr, float v) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.s32 q, %0, 0;\n"
+        "@q st.global.f32 [%1], %2;\n"
+        "}" ::"r"((int)p),
+        "l"(ptr), "f"(v)
+        : "memory");
+}
 // hide a pointer's derivation from the optimiser, so that the addresses built from it stay
 // "pointer + small constant x stride" (one IMAD.WIDE each) instead of being re-derived
 #define LEV_OPAQUE_PTR(p) asm volatile("" : "+l"(p))

@@ -383,6 +383,7 @@ static inline void lev_launch(void (*k)(KArgs...), dim3 grid, dim3 block, size_t
 #define LEV_SPIN_YIELD() emu::yield()
 #define LEV_OPAQUE_PTR(p) asm volatile("" : "+r"(p))
 static inline void lev_prefetch_l2(const void*) {}
+static inline void lev_st_f32_if(bool p, float* ptr, float v) { if (p) *ptr = v; }
 static inline unsigned lev_ldg_l2(const unsigned* p) { return *p; }
 template <typename T>
 static inline T lev_ldg_stream(const T* p) { return *p; }
