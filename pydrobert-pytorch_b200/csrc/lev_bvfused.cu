@@ -48,6 +48,12 @@ constexpr int LEV_BVF_WARPS = 4;
 #ifndef LEV_BVF_PF_AHEAD
 #define LEV_BVF_PF_AHEAD 32  // rows the L2 prefetch runs ahead of the hypothesis stream
 #endif
+#ifndef LEV_BVF_DYNAMIC
+#define LEV_BVF_DYNAMIC 1  // 1: after its first block a warp claims blocks from a global counter
+#endif
+#ifndef LEV_BVF_PROBE_BLOCKS
+#define LEV_BVF_PROBE_BLOCKS 1024  // blocks of 32 pairs the probe samples at most
+#endif
 #ifndef LEV_BVF_LD_PLAIN
 #define LEV_BVF_LD_PLAIN 0  // 1: plain loads instead of evict-first ones in the hypothesis stream
 #endif
@@ -507,7 +513,8 @@ __device__ __forceinline__ void lev_bvf_block(const LevBvArgs& a, int4* keys4, u
     __syncwarp();  // the next block of this warp reuses the tables
 }
 
-// Warps are independent and walk the blocks of 32 pairs with a grid stride.  Per warp: keys
+// Warps are independent: each takes the block of 32 pairs of its own index, then claims further
+// blocks from a global counter (LEV_BVF_DYNAMIC; a grid stride without it).  Per warp: keys
 // [nb][NT] int4 (4 ways), posw [nb][NT] words (4 position bytes), M [(R + 1)][NT][W] words.
 template <typename TT, int W, int KIND>
 __global__ void __launch_bounds__(32 * LEV_BVF_WARPS, 3) lev_bv_fused_kernel(const LevBvArgs a) {
@@ -523,9 +530,33 @@ __global__ void __launch_bounds__(32 * LEV_BVF_WARPS, 3) lev_bv_fused_kernel(con
     const int64_t nblocks = ((int64_t)a.P + 31) / 32;
     const int64_t stride = (int64_t)gridDim.x * LEV_BVF_WARPS;
     const int64_t first = (int64_t)blockIdx.x * LEV_BVF_WARPS + warp;
+#if LEV_BVF_DYNAMIC
+    // The first block of a warp is its own; further ones are claimed from a counter (the first
+    // word of the uid region, which this form leaves idle; zeroed by the probe or a memset), one
+    // block AHEAD so that the stream of the current block can announce the next one to L2.  A
+    // warp's blocks take different times (ragged hypotheses, table retries): equal shares leave
+    // the last warps of an SM running alone at a third of the occupancy.
+    int* counter = reinterpret_cast<int*>(a.ref_uid);
+    auto claim = [&]() -> int64_t {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(counter, 1);
+        c = __shfl_sync(LEV_FULL_MASK, c, 0);
+        const int64_t b = stride + c;
+        return b < nblocks ? b : -1;
+    };
+    int64_t block = first < nblocks ? first : -1;
+    bool first_block = true;
+    while (block >= 0) {
+        const int64_t next = claim();
+        lev_bvf_block<TT, W, KIND>(a, keys4, posw, M, nb, tab_words, block, next, first_block, lane);
+        block = next;
+        first_block = false;
+    }
+#else
     for (int64_t block = first; block < nblocks; block += stride)
         lev_bvf_block<TT, W, KIND>(a, keys4, posw, M, nb, tab_words, block,
                                    block + stride < nblocks ? block + stride : -1, block == first, lane);
+#endif
 }
 
 // ---- the probe: is this an n-best shaped batch? ---------------------------------------------
@@ -536,6 +567,9 @@ __global__ void __launch_bounds__(128) lev_bv_probe_kernel(const LevBvArgs a, co
                                                            const int64_t nsample) {
     const int lane = threadIdx.x & 31;
     const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+#if LEV_BVF_DYNAMIC
+    if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<int*>(a.ref_uid) = 0;  // the block counter
+#endif
     if (s >= nsample) return;
     const int64_t block = s * stride;
     const int64_t pair = block * 32 + lane;
@@ -564,7 +598,8 @@ __global__ void __launch_bounds__(128) lev_bv_probe_kernel(const LevBvArgs a, co
 // big batch takes 2-3 blocks, and a full machine during the early rounds beats equal shares)
 static unsigned lev_bvf_grid(int64_t P, int per_sm) {
     const int64_t n = (P + 32 * LEV_BVF_WARPS - 1) / (32 * LEV_BVF_WARPS);
-    const int64_t cap = (int64_t)148 * per_sm;
+    int64_t cap = (int64_t)148 * per_sm;
+    if (const char* e = getenv("B200LEV_BVF_CTAS")) cap = atoll(e) > 0 ? atoll(e) : cap;  // tests
     return (unsigned)(n < cap ? n : cap);
 }
 
@@ -603,7 +638,7 @@ bool lev_bvfused_supports(int elem_bytes) { return elem_bytes == 8 || elem_bytes
 int lev_bvfused_launch(const LevBvArgs& a, int elem_bytes, cudaStream_t st, void* after_probe) {
     if (a.check_state) {
         const int64_t nblocks = ((int64_t)a.P + 31) / 32;
-        const int64_t stride = (nblocks + 4095) / 4096;
+        const int64_t stride = (nblocks + LEV_BVF_PROBE_BLOCKS - 1) / LEV_BVF_PROBE_BLOCKS;
         const int64_t nsample = (nblocks + stride - 1) / stride;
         const dim3 grid((unsigned)((nsample + 3) / 4)), block(128);
         lev_prof_begin(LEV_PROF_BV_UID, st);
@@ -616,6 +651,9 @@ int lev_bvfused_launch(const LevBvArgs& a, int elem_bytes, cudaStream_t st, void
         const int rc = lev_check_cuda("lev_bv_probe_kernel");
         if (rc) return rc;
     }
+#if LEV_BVF_DYNAMIC
+    if (!a.check_state && cudaMemsetAsync(a.ref_uid, 0, sizeof(int), st) != cudaSuccess) return lev_check_cuda("memset");
+#endif
 #ifndef B200LEV_EMU
     if (after_probe != nullptr && cudaEventRecord((cudaEvent_t)after_probe, st) != cudaSuccess)
         return lev_check_cuda("cudaEventRecord");

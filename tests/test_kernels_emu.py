@@ -263,6 +263,23 @@ def test_bitvec_device_selected(F, bv_form, shape, shared, monkeypatch):
                          wide=True)
 
 
+@pytest.mark.parametrize("shared", [True, False], ids=["nbest", "unrelated_refs"])
+def test_fused_kernel_claims_blocks_from_the_counter(F, shared, monkeypatch):
+    """Big batches: a warp of the fused kernel takes the block of its own index, then claims further
+    blocks of 32 pairs from a global counter (forced here with a one-CTA grid: 12 blocks, 4 warps),
+    in the forced mode (the counter zeroed by a memset) and the device-selected one (by the probe)."""
+    monkeypatch.setenv("B200LEV_BV_SHORT", "0")
+    monkeypatch.setenv("B200LEV_BVF_CTAS", "1")
+    monkeypatch.setenv("B200LEV_BITVEC_MIN_PAIRS", "1")
+    monkeypatch.setenv("B200LEV_GROUP_MIN_PAIRS", "1")
+    for mode in ("1", None):
+        if mode is None:
+            monkeypatch.delenv("B200LEV_BITVEC", raising=False)
+        else:
+            monkeypatch.setenv("B200LEV_BITVEC", mode)
+        PC.check_nbest_batch(F, DEV, seed=5, R=70, H=45, n_utts=47, nbest=8, shared=shared)
+
+
 def test_bitvec_degenerate_shapes(F, bv_form, monkeypatch):
     """Forced bit-vector path on the shapes the reference's tests poke at: empty hypotheses,
     one-token references, batches that are not a multiple of 32, all-eos columns."""
