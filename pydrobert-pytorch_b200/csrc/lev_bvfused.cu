@@ -31,7 +31,13 @@
 // exact-compare loop.
 #include "lev_bitvec.cuh"
 
-constexpr int LEV_BVF_WARPS = 4;
+#ifndef LEV_BVF_WARPS_PER_CTA
+#define LEV_BVF_WARPS_PER_CTA 4
+#endif
+#ifndef LEV_BVF_CTAS_PER_SM
+#define LEV_BVF_CTAS_PER_SM 3  // resident CTAs per SM the launch bounds and the grid are sized for
+#endif
+constexpr int LEV_BVF_WARPS = LEV_BVF_WARPS_PER_CTA;
 // tuning switches (scripts/gpu_ab.sh builds one library per setting)
 #ifndef LEV_BVF_NBUF
 #define LEV_BVF_NBUF 4  // chunk buffers of the hypothesis stream: loads run NBUF - 1 trips ahead
@@ -517,7 +523,7 @@ __device__ __forceinline__ void lev_bvf_block(const LevBvArgs& a, int4* keys4, u
 // blocks from a global counter (LEV_BVF_DYNAMIC; a grid stride without it).  Per warp: keys
 // [nb][NT] int4 (4 ways), posw [nb][NT] words (4 position bytes), M [(R + 1)][NT][W] words.
 template <typename TT, int W, int KIND>
-__global__ void __launch_bounds__(32 * LEV_BVF_WARPS, 3) lev_bv_fused_kernel(const LevBvArgs a) {
+__global__ void __launch_bounds__(32 * LEV_BVF_WARPS, LEV_BVF_CTAS_PER_SM) lev_bv_fused_kernel(const LevBvArgs a) {
     if (a.check_state && !lev_bv_took(a.state)) return;  // the probe handed the batch back
     LEV_DYN_SMEM(int, smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -608,7 +614,7 @@ static void lev_bvf_launch_w(const LevBvArgs& a, cudaStream_t st) {
     const int nb = 1 << a.slots_log2;
     const int tab_words = ((a.R + 1) * W * LEV_BV_NT + 3) & ~3;
     const size_t smem = sizeof(int) * (size_t)(nb * LEV_BV_NT * 5 + tab_words) * LEV_BVF_WARPS;
-    const dim3 grid(lev_bvf_grid(a.P, 3)), block(32 * LEV_BVF_WARPS);
+    const dim3 grid(lev_bvf_grid(a.P, LEV_BVF_CTAS_PER_SM)), block(32 * LEV_BVF_WARPS);
     auto go = [&](auto kern) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         lev_launch(kern, grid, block, smem, st, a);
