@@ -326,7 +326,7 @@ def test_pack_persistent_ctas_and_cta_histogram(F, monkeypatch):
                            include_eos=True, norm=True, min_frac=0.1)
 
 
-@pytest.mark.parametrize("want", ["592", "5", "0"])
+@pytest.mark.parametrize("want", ["592", "5"])
 def test_pack_split_along_the_sequence_axis(F, want, monkeypatch):
     """Few, long sequences: several pack CTAs share a block of 32 sequences, each taking a range
     of positions; first-eos positions meet in the workspace, the CTA with the last ticket writes
