@@ -263,6 +263,10 @@ int lev_launch_mask16(const LevParams& p, bool float_path, cudaStream_t st) {
     if (per_warp > budget) return 0;
     int wpc = (int)(budget / per_warp);
     if (wpc > 4) wpc = 4;  // small CTAs: a batch is often a single wave, and whole CTAs are what the SMs share out
+    if (const char* e = getenv("B200LEV_MASK16_WPC")) {  // tuning: warps per CTA
+        const int w = atoi(e);
+        if (w >= 1 && w < wpc) wpc = w;
+    }
     const size_t smem = per_warp * wpc;
     const int64_t nduo = ((int64_t)p.P + 1) / 2;
     int64_t blocks = (nduo + wpc - 1) / wpc;
